@@ -1,0 +1,1173 @@
+/*
+ * claw_oracle.c -- CPU restatement of PyClaw's finite-volume time-step hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in pyclaw_b200/ (the product) may import,
+ * link or call this file.  It exists so that tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs have an independent checker that
+ * follows the reference's arithmetic order statement by statement.
+ *
+ * The reference's own Fortran cannot be built in this image (no Fortran compiler),
+ * so this is a "port" oracle.  It is pinned against the reference's golden files
+ * (tests/test_oracle_golden.py): test/sb_density, test/acoustics2D_solution,
+ * test/ac_sc_solution and the two 1-D scalars of test/test_examples.py.
+ *
+ * Layout follows the reference: Fortran order q(meqn, 1-mbc:mx+mbc, 1-mbc:my+mbc),
+ * i.e. component fastest.  Strict IEEE double: compile with -ffp-contract=off.
+ *
+ * Reference files restated (all under /root/reference):
+ *   src/fortran/1d/classic/step1.f:4-142, limiter.f:4-60, philim.f:4-58
+ *   src/fortran/2d/classic/flux2.f:5-193, step2.f:2-241, step2ds.f:2-248
+ *   src/fortran/1d/sharpclaw/flux1.f90:2-195 (and the 2-D twin),
+ *   src/fortran/1d/sharpclaw/reconstruct.f90:120-185 (old weno5), weno.f90:5-102
+ *   src/fortran/2d/sharpclaw/flux2.f90:2-96
+ *   development/rp_approaches/rpn2_euler_5wave.f:5-302, rpt2_euler_5wave.f:4-98
+ * Riemann solvers that live in the external clawpack/riemann repository (un-vendored,
+ * un-pinned) are restated from their published algorithm:
+ *   rp1/rpn2/rpt2 acoustics, rp1/rpn2/rpt2 advection, rpn2/rpt2 shallow Roe + efix.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RP_ACOUSTICS 1
+#define RP_ADVECTION 2
+#define RP_EULER5 3
+#define RP_SHALLOW 4
+
+#define WENO_PYWENO_F32 0 /* weno.f90 literals read as REAL(4), as gfortran does */
+#define WENO_PYWENO_F64 1 /* same formulas, literals read as doubles            */
+#define WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)              */
+
+typedef struct {
+    int rp_id;
+    int ndim;
+    double p[8];
+    /* acoustics: p[0]=rho p[1]=bulk p[2]=cc p[3]=zz ; advection: p[0]=u p[1]=v ;
+       euler: p[0]=gamma p[1]=gamma1 ; shallow: p[0]=grav */
+    /* common /comroe/ twin: filled by rpn2, read by rpt2 on the same slice */
+    int nroe;
+    double *u2v2, *u, *v, *enth, *a, *g1a2, *euv, *h;
+} rp_ctx;
+
+static void ctx_alloc(rp_ctx *c, int n)
+{
+    c->nroe = n;
+    c->u2v2 = (double *)calloc(n, sizeof(double));
+    c->u = (double *)calloc(n, sizeof(double));
+    c->v = (double *)calloc(n, sizeof(double));
+    c->enth = (double *)calloc(n, sizeof(double));
+    c->a = (double *)calloc(n, sizeof(double));
+    c->g1a2 = (double *)calloc(n, sizeof(double));
+    c->euv = (double *)calloc(n, sizeof(double));
+    c->h = (double *)calloc(n, sizeof(double));
+}
+static void ctx_free(rp_ctx *c)
+{
+    free(c->u2v2); free(c->u); free(c->v); free(c->enth);
+    free(c->a); free(c->g1a2); free(c->euv); free(c->h);
+}
+
+static inline double dmax2(double a, double b) { return (a > b) ? a : b; }
+static inline double dmin2(double a, double b) { return (a < b) ? a : b; }
+
+/* slice indexing: Fortran index i in [1-mbc, maxm+mbc] -> offset i+mbc-1 */
+#define IX(i) ((i) + mbc - 1)
+#define Q2(arr, m, i) arr[(m) + meqn * IX(i)]
+#define WV(m, mw, i) wave[(m) + meqn * ((mw) + mwaves * IX(i))]
+#define SP(mw, i) s[(mw) + mwaves * IX(i)]
+
+/* ------------------------------------------------------------------------- */
+/* Normal Riemann solvers.  ixy = 0 means "1-D problem" (rp1).               */
+/* Interface i has left state qr(:,i-1) and right state ql(:,i); loops run   */
+/* i = 2-mbc .. mx+mbc exactly as in the Fortran.                            */
+/* ------------------------------------------------------------------------- */
+
+/* clawpack/riemann rp1_acoustics.f / rpn2_acoustics.f (external) */
+static void rpn_acoustics(const rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                          const double *ql, const double *qr,
+                          double *wave, double *s, double *amdq, double *apdq)
+{
+    const double cc = c->p[2], zz = c->p[3];
+    int mu, mv;
+    if (ixy <= 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double delta1 = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        double delta2 = Q2(ql, mu, i) - Q2(qr, mu, i - 1);
+        double a1 = (-delta1 + zz * delta2) / (2.0 * zz);
+        double a2 = (delta1 + zz * delta2) / (2.0 * zz);
+        WV(0, 0, i) = -a1 * zz;
+        WV(mu, 0, i) = a1;
+        if (meqn == 3) WV(mv, 0, i) = 0.0;
+        SP(0, i) = -cc;
+        WV(0, 1, i) = a2 * zz;
+        WV(mu, 1, i) = a2;
+        if (meqn == 3) WV(mv, 1, i) = 0.0;
+        SP(1, i) = cc;
+    }
+    for (int m = 0; m < meqn; m++)
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            Q2(amdq, m, i) = SP(0, i) * WV(m, 0, i);
+            Q2(apdq, m, i) = SP(1, i) * WV(m, 1, i);
+        }
+}
+
+/* clawpack/riemann rp1_advection.f / rpn2_advection.f (external) */
+static void rpn_advection(const rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                          const double *ql, const double *qr,
+                          double *wave, double *s, double *amdq, double *apdq)
+{
+    const double sp = (ixy <= 1) ? c->p[0] : c->p[1];
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        WV(0, 0, i) = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        SP(0, i) = sp;
+        Q2(amdq, 0, i) = dmin2(SP(0, i), 0.0) * WV(0, 0, i);
+        Q2(apdq, 0, i) = dmax2(SP(0, i), 0.0) * WV(0, 0, i);
+    }
+}
+
+/* development/rp_approaches/rpn2_euler_5wave.f:5-302 */
+static void rpn_euler5(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                       const double *ql, const double *qr,
+                       double *wave, double *s, double *amdq, double *apdq)
+{
+    const double gamma = c->p[0], gamma1 = c->p[1];
+    int mu, mv;
+    if (ixy == 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
+    double *u = c->u, *v = c->v, *enth = c->enth, *a = c->a, *g1a2 = c->g1a2,
+           *euv = c->euv, *u2v2 = c->u2v2;
+    /* :87-104 Roe averages */
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int k = IX(i);
+        double rhsqrtl = sqrt(Q2(qr, 0, i - 1));
+        double rhsqrtr = sqrt(Q2(ql, 0, i));
+        double pl = gamma1 * (Q2(qr, 3, i - 1) -
+                              0.5 * (Q2(qr, 1, i - 1) * Q2(qr, 1, i - 1) +
+                                     Q2(qr, 2, i - 1) * Q2(qr, 2, i - 1)) / Q2(qr, 0, i - 1));
+        double pr = gamma1 * (Q2(ql, 3, i) -
+                              0.5 * (Q2(ql, 1, i) * Q2(ql, 1, i) +
+                                     Q2(ql, 2, i) * Q2(ql, 2, i)) / Q2(ql, 0, i));
+        double rhsq2 = rhsqrtl + rhsqrtr;
+        u[k] = (Q2(qr, mu, i - 1) / rhsqrtl + Q2(ql, mu, i) / rhsqrtr) / rhsq2;
+        v[k] = (Q2(qr, mv, i - 1) / rhsqrtl + Q2(ql, mv, i) / rhsqrtr) / rhsq2;
+        enth[k] = (((Q2(qr, 3, i - 1) + pl) / rhsqrtl + (Q2(ql, 3, i) + pr) / rhsqrtr)) / rhsq2;
+        u2v2[k] = u[k] * u[k] + v[k] * v[k];
+        double a2 = gamma1 * (enth[k] - .5 * u2v2[k]);
+        a[k] = sqrt(a2);
+        g1a2[k] = gamma1 / a2;
+        euv[k] = enth[k] - u2v2[k];
+    }
+    /* :110-163 wave strengths and waves */
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int k = IX(i);
+        double d1 = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        double d2 = Q2(ql, mu, i) - Q2(qr, mu, i - 1);
+        double d3 = Q2(ql, mv, i) - Q2(qr, mv, i - 1);
+        double d4 = Q2(ql, 3, i) - Q2(qr, 3, i - 1);
+        double a3 = g1a2[k] * (euv[k] * d1 + u[k] * d2 + v[k] * d3 - d4);
+        double a2 = d3 - v[k] * d1;
+        double a4 = (d2 + (a[k] - u[k]) * d1 - a[k] * a3) / (2.0 * a[k]);
+        double a1 = d1 - a3 - a4;
+        WV(0, 0, i) = a1;
+        WV(mu, 0, i) = a1 * (u[k] - a[k]);
+        WV(mv, 0, i) = a1 * v[k];
+        WV(3, 0, i) = a1 * (enth[k] - u[k] * a[k]);
+        WV(4, 0, i) = 0.0;
+        SP(0, i) = u[k] - a[k];
+        WV(0, 1, i) = 0.0;
+        WV(mu, 1, i) = 0.0;
+        WV(mv, 1, i) = a2;
+        WV(3, 1, i) = a2 * v[k];
+        WV(4, 1, i) = 0.0;
+        SP(1, i) = u[k];
+        WV(0, 2, i) = a3;
+        WV(mu, 2, i) = a3 * u[k];
+        WV(mv, 2, i) = a3 * v[k];
+        WV(3, 2, i) = a3 * 0.5 * u2v2[k];
+        WV(4, 2, i) = 0.0;
+        SP(2, i) = u[k];
+        WV(0, 3, i) = a4;
+        WV(mu, 3, i) = a4 * (u[k] + a[k]);
+        WV(mv, 3, i) = a4 * v[k];
+        WV(3, 3, i) = a4 * (enth[k] + u[k] * a[k]);
+        WV(4, 3, i) = 0.0;
+        SP(3, i) = u[k] + a[k];
+        WV(0, 4, i) = 0.0;
+        WV(mu, 4, i) = 0.0;
+        WV(mv, 4, i) = 0.0;
+        WV(3, 4, i) = 0.0;
+        WV(4, 4, i) = Q2(ql, 4, i) - Q2(qr, 4, i - 1);
+        SP(4, i) = u[k];
+    }
+    /* :205-286 entropy fix (efix = .true., :60) */
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double rhoim1 = Q2(qr, 0, i - 1);
+        double pim1 = gamma1 * (Q2(qr, 3, i - 1) -
+                                0.5 * (Q2(qr, mu, i - 1) * Q2(qr, mu, i - 1) +
+                                       Q2(qr, mv, i - 1) * Q2(qr, mv, i - 1)) / rhoim1);
+        double cim1 = sqrt(gamma * pim1 / rhoim1);
+        double s0 = Q2(qr, mu, i - 1) / rhoim1 - cim1;
+        if (s0 >= 0.0 && SP(0, i) > 0.0) {
+            for (int m = 0; m < meqn; m++) Q2(amdq, m, i) = 0.0;
+            continue;
+        }
+        double rho1 = Q2(qr, 0, i - 1) + WV(0, 0, i);
+        double rhou1 = Q2(qr, mu, i - 1) + WV(mu, 0, i);
+        double rhov1 = Q2(qr, mv, i - 1) + WV(mv, 0, i);
+        double en1 = Q2(qr, 3, i - 1) + WV(3, 0, i);
+        double p1 = gamma1 * (en1 - 0.5 * (rhou1 * rhou1 + rhov1 * rhov1) / rho1);
+        double c1 = sqrt(gamma * p1 / rho1);
+        double s1 = rhou1 / rho1 - c1;
+        double sfract;
+        if (s0 < 0.0 && s1 > 0.0)
+            sfract = s0 * (s1 - SP(0, i)) / (s1 - s0);
+        else if (SP(0, i) < 0.0)
+            sfract = SP(0, i);
+        else
+            sfract = 0.0;
+        for (int m = 0; m < meqn; m++) Q2(amdq, m, i) = sfract * WV(m, 0, i);
+        if (SP(1, i) >= 0.0) continue;
+        for (int m = 0; m < meqn; m++) {
+            Q2(amdq, m, i) = Q2(amdq, m, i) + SP(1, i) * WV(m, 1, i);
+            Q2(amdq, m, i) = Q2(amdq, m, i) + SP(2, i) * WV(m, 2, i);
+            Q2(amdq, m, i) = Q2(amdq, m, i) + SP(4, i) * WV(m, 4, i);
+        }
+        double rhoi = Q2(ql, 0, i);
+        double pi = gamma1 * (Q2(ql, 3, i) -
+                              0.5 * (Q2(ql, mu, i) * Q2(ql, mu, i) +
+                                     Q2(ql, mv, i) * Q2(ql, mv, i)) / rhoi);
+        double ci = sqrt(gamma * pi / rhoi);
+        double s3 = Q2(ql, mu, i) / rhoi + ci;
+        double rho2 = Q2(ql, 0, i) - WV(0, 3, i);
+        double rhou2 = Q2(ql, mu, i) - WV(mu, 3, i);
+        double rhov2 = Q2(ql, mv, i) - WV(mv, 3, i);
+        double en2 = Q2(ql, 3, i) - WV(3, 3, i);
+        double p2 = gamma1 * (en2 - 0.5 * (rhou2 * rhou2 + rhov2 * rhov2) / rho2);
+        double c2 = sqrt(gamma * p2 / rho2);
+        double s2 = rhou2 / rho2 + c2;
+        if (s2 < 0.0 && s3 > 0.0)
+            sfract = s2 * (s3 - SP(3, i)) / (s3 - s2);
+        else if (SP(3, i) < 0.0)
+            sfract = SP(3, i);
+        else
+            continue;
+        for (int m = 0; m < meqn; m++)
+            Q2(amdq, m, i) = Q2(amdq, m, i) + sfract * WV(m, 3, i);
+    }
+    /* :291-298 */
+    for (int m = 0; m < meqn; m++)
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            double df = 0.0;
+            for (int mw = 0; mw < mwaves; mw++) df = df + SP(mw, i) * WV(m, mw, i);
+            Q2(apdq, m, i) = df - Q2(amdq, m, i);
+        }
+}
+
+/* clawpack/riemann rpn2_shallow_roe_with_efix.f (external) */
+static void rpn_shallow(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                        const double *ql, const double *qr,
+                        double *wave, double *s, double *amdq, double *apdq)
+{
+    const double grav = c->p[0];
+    int mu, mv;
+    if (ixy == 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
+    double *u = c->u, *v = c->v, *a = c->a, *h = c->h;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int k = IX(i);
+        h[k] = (Q2(qr, 0, i - 1) + Q2(ql, 0, i)) * 0.50;
+        double hsqrtl = sqrt(Q2(qr, 0, i - 1));
+        double hsqrtr = sqrt(Q2(ql, 0, i));
+        double hsq2 = hsqrtl + hsqrtr;
+        u[k] = (Q2(qr, mu, i - 1) / hsqrtl + Q2(ql, mu, i) / hsqrtr) / hsq2;
+        v[k] = (Q2(qr, mv, i - 1) / hsqrtl + Q2(ql, mv, i) / hsqrtr) / hsq2;
+        a[k] = sqrt(grav * h[k]);
+    }
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int k = IX(i);
+        double d1 = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        double d2 = Q2(ql, mu, i) - Q2(qr, mu, i - 1);
+        double d3 = Q2(ql, mv, i) - Q2(qr, mv, i - 1);
+        double a1 = ((u[k] + a[k]) * d1 - d2) * (0.50 / a[k]);
+        double a2 = -v[k] * d1 + d3;
+        double a3 = (-(u[k] - a[k]) * d1 + d2) * (0.50 / a[k]);
+        WV(0, 0, i) = a1;
+        WV(mu, 0, i) = a1 * (u[k] - a[k]);
+        WV(mv, 0, i) = a1 * v[k];
+        SP(0, i) = u[k] - a[k];
+        WV(0, 1, i) = 0.0;
+        WV(mu, 1, i) = 0.0;
+        WV(mv, 1, i) = a2;
+        SP(1, i) = u[k];
+        WV(0, 2, i) = a3;
+        WV(mu, 2, i) = a3 * (u[k] + a[k]);
+        WV(mv, 2, i) = a3 * v[k];
+        SP(2, i) = u[k] + a[k];
+    }
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double him1 = Q2(qr, 0, i - 1);
+        double s0 = Q2(qr, mu, i - 1) / him1 - sqrt(grav * him1);
+        if (s0 > 0.0 && SP(0, i) > 0.0) {
+            for (int m = 0; m < 3; m++) Q2(amdq, m, i) = 0.0;
+            continue;
+        }
+        double h1 = Q2(qr, 0, i - 1) + WV(0, 0, i);
+        double hu1 = Q2(qr, mu, i - 1) + WV(mu, 0, i);
+        double s1 = hu1 / h1 - sqrt(grav * h1);
+        double sfract;
+        if (s0 < 0.0 && s1 > 0.0)
+            sfract = s0 * ((s1 - SP(0, i)) / (s1 - s0));
+        else if (SP(0, i) < 0.0)
+            sfract = SP(0, i);
+        else
+            sfract = 0.0;
+        for (int m = 0; m < 3; m++) Q2(amdq, m, i) = sfract * WV(m, 0, i);
+        if (SP(1, i) > 0.0) continue;
+        for (int m = 0; m < 3; m++)
+            Q2(amdq, m, i) = Q2(amdq, m, i) + SP(1, i) * WV(m, 1, i);
+        double hi = Q2(ql, 0, i);
+        double s03 = Q2(ql, mu, i) / hi + sqrt(grav * hi);
+        double h3 = Q2(ql, 0, i) - WV(0, 2, i);
+        double hu3 = Q2(ql, mu, i) - WV(mu, 2, i);
+        double s3 = hu3 / h3 + sqrt(grav * h3);
+        if (s3 < 0.0 && s03 > 0.0)
+            sfract = s3 * ((s03 - SP(2, i)) / (s03 - s3));
+        else if (SP(2, i) < 0.0)
+            sfract = SP(2, i);
+        else
+            continue;
+        for (int m = 0; m < 3; m++)
+            Q2(amdq, m, i) = Q2(amdq, m, i) + sfract * WV(m, 2, i);
+    }
+    for (int m = 0; m < 3; m++)
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            double df = 0.0;
+            for (int mw = 0; mw < mwaves; mw++) df = df + SP(mw, i) * WV(m, mw, i);
+            Q2(apdq, m, i) = df - Q2(amdq, m, i);
+        }
+}
+
+static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                const double *ql, const double *qr,
+                double *wave, double *s, double *amdq, double *apdq)
+{
+    switch (c->rp_id) {
+    case RP_ACOUSTICS: rpn_acoustics(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
+    case RP_ADVECTION: rpn_advection(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
+    case RP_EULER5: rpn_euler5(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
+    case RP_SHALLOW: rpn_shallow(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Transverse Riemann solvers                                                */
+/* ------------------------------------------------------------------------- */
+static void rpt(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                const double *asdq, double *bmasdq, double *bpasdq)
+{
+    int mu, mv;
+    if (ixy == 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
+    (void)mwaves;
+    if (c->rp_id == RP_ACOUSTICS) {
+        /* clawpack/riemann rpt2_acoustics.f (external) */
+        const double cc = c->p[2], zz = c->p[3];
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            double a1 = (-Q2(asdq, 0, i) + zz * Q2(asdq, mv, i)) / (2.0 * zz);
+            double a2 = (Q2(asdq, 0, i) + zz * Q2(asdq, mv, i)) / (2.0 * zz);
+            Q2(bmasdq, 0, i) = cc * a1 * zz;
+            Q2(bmasdq, mu, i) = 0.0;
+            Q2(bmasdq, mv, i) = -cc * a1;
+            Q2(bpasdq, 0, i) = cc * a2 * zz;
+            Q2(bpasdq, mu, i) = 0.0;
+            Q2(bpasdq, mv, i) = cc * a2;
+        }
+    } else if (c->rp_id == RP_ADVECTION) {
+        /* clawpack/riemann rpt2_advection.f (external) */
+        double stran = (ixy == 1) ? c->p[1] : c->p[0];
+        double stranm = dmin2(stran, 0.0), stranp = dmax2(stran, 0.0);
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            Q2(bmasdq, 0, i) = stranm * Q2(asdq, 0, i);
+            Q2(bpasdq, 0, i) = stranp * Q2(asdq, 0, i);
+        }
+    } else if (c->rp_id == RP_EULER5) {
+        /* development/rp_approaches/rpt2_euler_5wave.f:4-98 */
+        double *u = c->u, *v = c->v, *enth = c->enth, *a = c->a, *g1a2 = c->g1a2,
+               *euv = c->euv, *u2v2 = c->u2v2;
+        double waveb[5][4], sb[4];
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            int k = IX(i);
+            double a3 = g1a2[k] * (euv[k] * Q2(asdq, 0, i) + u[k] * Q2(asdq, mu, i) +
+                                   v[k] * Q2(asdq, mv, i) - Q2(asdq, 3, i));
+            double a2 = Q2(asdq, mu, i) - u[k] * Q2(asdq, 0, i);
+            double a4 = (Q2(asdq, mv, i) + (a[k] - v[k]) * Q2(asdq, 0, i) - a[k] * a3) / (2.0 * a[k]);
+            double a1 = Q2(asdq, 0, i) - a3 - a4;
+            waveb[0][0] = a1;
+            waveb[mu][0] = a1 * u[k];
+            waveb[mv][0] = a1 * (v[k] - a[k]);
+            waveb[3][0] = a1 * (enth[k] - v[k] * a[k]);
+            waveb[4][0] = 0.0;
+            sb[0] = v[k] - a[k];
+            waveb[0][1] = a3;
+            waveb[mu][1] = a3 * u[k] + a2;
+            waveb[mv][1] = a3 * v[k];
+            waveb[3][1] = a3 * 0.5 * u2v2[k] + a2 * u[k];
+            waveb[4][1] = 0.0;
+            sb[1] = v[k];
+            waveb[0][2] = a4;
+            waveb[mu][2] = a4 * u[k];
+            waveb[mv][2] = a4 * (v[k] + a[k]);
+            waveb[3][2] = a4 * (enth[k] + v[k] * a[k]);
+            waveb[4][2] = 0.0;
+            sb[2] = v[k] + a[k];
+            waveb[0][3] = 0.0;
+            waveb[mu][3] = 0.0;
+            waveb[mv][3] = 0.0;
+            waveb[3][3] = 0.0;
+            waveb[4][3] = Q2(asdq, 4, i);
+            sb[3] = v[k];
+            for (int m = 0; m < meqn; m++) {
+                Q2(bmasdq, m, i) = 0.0;
+                Q2(bpasdq, m, i) = 0.0;
+                for (int mw = 0; mw < 4; mw++) {
+                    Q2(bmasdq, m, i) = Q2(bmasdq, m, i) + dmin2(sb[mw], 0.0) * waveb[m][mw];
+                    Q2(bpasdq, m, i) = Q2(bpasdq, m, i) + dmax2(sb[mw], 0.0) * waveb[m][mw];
+                }
+            }
+        }
+    } else if (c->rp_id == RP_SHALLOW) {
+        /* clawpack/riemann rpt2_shallow_roe_with_efix.f (external) */
+        double *u = c->u, *v = c->v, *a = c->a;
+        double waveb[3][3], sb[3];
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            int k = IX(i);
+            double a1 = (0.50 / a[k]) * ((v[k] + a[k]) * Q2(asdq, 0, i) - Q2(asdq, mv, i));
+            double a2 = Q2(asdq, mu, i) - u[k] * Q2(asdq, 0, i);
+            double a3 = (0.50 / a[k]) * (-(v[k] - a[k]) * Q2(asdq, 0, i) + Q2(asdq, mv, i));
+            waveb[0][0] = a1;
+            waveb[mu][0] = a1 * u[k];
+            waveb[mv][0] = a1 * (v[k] - a[k]);
+            sb[0] = v[k] - a[k];
+            waveb[0][1] = 0.0;
+            waveb[mu][1] = a2;
+            waveb[mv][1] = 0.0;
+            sb[1] = v[k];
+            waveb[0][2] = a3;
+            waveb[mu][2] = a3 * u[k];
+            waveb[mv][2] = a3 * (v[k] + a[k]);
+            sb[2] = v[k] + a[k];
+            for (int m = 0; m < meqn; m++) {
+                Q2(bmasdq, m, i) = 0.0;
+                Q2(bpasdq, m, i) = 0.0;
+                for (int mw = 0; mw < 3; mw++) {
+                    Q2(bmasdq, m, i) = Q2(bmasdq, m, i) + dmin2(sb[mw], 0.0) * waveb[m][mw];
+                    Q2(bpasdq, m, i) = Q2(bpasdq, m, i) + dmax2(sb[mw], 0.0) * waveb[m][mw];
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* philim.f:4-58 and limiter.f:4-60                                          */
+/* ------------------------------------------------------------------------- */
+static double philim(double a, double b, int meth)
+{
+    double r = b / a;
+    switch (meth) {
+    case 1: return dmax2(0.0, dmin2(1.0, r));
+    case 2: return dmax2(dmax2(0.0, dmin2(1.0, 2.0 * r)), dmin2(2.0, r));
+    case 3: return (r + fabs(r)) / (1.0 + fabs(r));
+    case 4: {
+        double c = (1.0 + r) / 2.0;
+        return dmax2(0.0, dmin2(dmin2(c, 2.0), 2.0 * r));
+    }
+    default: return r;
+    }
+}
+
+static void limiter(int maxm, int meqn, int mwaves, int mbc, int mx,
+                    double *wave, const double *s, const int *mthlim)
+{
+    (void)maxm;
+    for (int mw = 0; mw < mwaves; mw++) {
+        if (mthlim[mw] == 0) continue;
+        double dotr = 0.0;
+        for (int i = 0; i <= mx + 1; i++) {
+            double wnorm2 = 0.0;
+            double dotl = dotr;
+            dotr = 0.0;
+            for (int m = 0; m < meqn; m++) {
+                wnorm2 = wnorm2 + WV(m, mw, i) * WV(m, mw, i);
+                dotr = dotr + WV(m, mw, i) * WV(m, mw, i + 1);
+            }
+            if (i == 0) continue;
+            if (wnorm2 == 0.0) continue;
+            double wlimitr;
+            if (SP(mw, i) > 0.0)
+                wlimitr = philim(wnorm2, dotl, mthlim[mw]);
+            else
+                wlimitr = philim(wnorm2, dotr, mthlim[mw]);
+            for (int m = 0; m < meqn; m++) WV(m, mw, i) = wlimitr * WV(m, mw, i);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* step1.f:4-142.  q(meqn, 1-mbc:mx+mbc) updated in place; returns cfl.      */
+/* method = {dt_variable, order, trans, verbosity, 0, mcapa(1-based or 0), maux} */
+/* ------------------------------------------------------------------------- */
+double oracle_step1(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
+                    int maux, int mx, double *q, const double *aux, double dx, double dt,
+                    const int *method, const int *mthlim)
+{
+    rp_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.rp_id = rp_id; c.ndim = 1;
+    memcpy(c.p, rp_params, 8 * sizeof(double));
+    int n = mx + 2 * mbc;
+    ctx_alloc(&c, n);
+    double *f = (double *)calloc((size_t)meqn * n, sizeof(double));
+    double *s = (double *)calloc((size_t)mwaves * n, sizeof(double));
+    double *wave = (double *)calloc((size_t)meqn * mwaves * n, sizeof(double));
+    double *amdq = (double *)calloc((size_t)meqn * n, sizeof(double));
+    double *apdq = (double *)calloc((size_t)meqn * n, sizeof(double));
+    double *dtdx = (double *)calloc(n, sizeof(double));
+    int limit = 0;
+    for (int mw = 0; mw < mwaves; mw++) if (mthlim[mw] > 0) limit = 1;
+    int mcapa = method[5];
+    for (int i = 1 - mbc; i <= mx + mbc; i++) {
+        if (mcapa > 0) dtdx[IX(i)] = dt / (dx * aux[(mcapa - 1) + maux * IX(i)]);
+        else dtdx[IX(i)] = dt / dx;
+    }
+    rpn(&c, 0, meqn, mwaves, mbc, mx, q, q, wave, s, amdq, apdq);
+    /* forall: first statement for all (i,m), then the second (:93-96) */
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(q, m, i) = Q2(q, m, i) - dtdx[IX(i)] * Q2(apdq, m, i);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(q, m, i - 1) = Q2(q, m, i - 1) - dtdx[IX(i - 1)] * Q2(amdq, m, i);
+    double cfl = 0.0;
+    for (int mw = 0; mw < mwaves; mw++)
+        for (int i = 1; i <= mx + 1; i++)
+            cfl = dmax2(dmax2(cfl, dtdx[IX(i)] * SP(mw, i)), -dtdx[IX(i - 1)] * SP(mw, i));
+    if (method[1] != 1) {
+        for (int k = 0; k < meqn * n; k++) f[k] = 0.0;
+        if (limit) limiter(mx, meqn, mwaves, mbc, mx, wave, s, mthlim);
+        for (int i = 1; i <= mx + 1; i++)
+            for (int m = 0; m < meqn; m++)
+                for (int mw = 0; mw < mwaves; mw++) {
+                    double dtdxave = 0.5 * (dtdx[IX(i - 1)] + dtdx[IX(i)]);
+                    Q2(f, m, i) = Q2(f, m, i) + 0.5 * fabs(SP(mw, i)) *
+                                  (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
+                }
+        /* :136-138 (f(m,mx+2) is zero) */
+        for (int i = 1; i <= mx + 1; i++)
+            for (int m = 0; m < meqn; m++)
+                Q2(q, m, i) = Q2(q, m, i) - dtdx[IX(i)] * (Q2(f, m, i + 1) - Q2(f, m, i));
+    }
+    free(f); free(s); free(wave); free(amdq); free(apdq); free(dtdx);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* ------------------------------------------------------------------------- */
+/* flux2.f:5-193                                                             */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    double *wave, *s, *amdq, *apdq, *cqxx, *bmasdq, *bpasdq;
+    double *q1d, *qadd, *fadd, *gadd, *dtdx1d, *dtdy1d;
+} work2;
+
+static void work2_alloc(work2 *w, int n, int meqn, int mwaves)
+{
+    w->wave = (double *)calloc((size_t)n * meqn * mwaves, sizeof(double));
+    w->s = (double *)calloc((size_t)n * mwaves, sizeof(double));
+    w->amdq = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->apdq = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->cqxx = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->bmasdq = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->bpasdq = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->q1d = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->qadd = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->fadd = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->gadd = (double *)calloc((size_t)n * meqn * 2, sizeof(double));
+    w->dtdx1d = (double *)calloc(n, sizeof(double));
+    w->dtdy1d = (double *)calloc(n, sizeof(double));
+}
+static void work2_free(work2 *w)
+{
+    free(w->wave); free(w->s); free(w->amdq); free(w->apdq); free(w->cqxx);
+    free(w->bmasdq); free(w->bpasdq); free(w->q1d); free(w->qadd); free(w->fadd);
+    free(w->gadd); free(w->dtdx1d); free(w->dtdy1d);
+}
+
+#define GADD(m, k, i) gadd[(m) + meqn * ((k) + 2 * IX(i))]
+
+static double flux2(rp_ctx *c, int ixy, int maxm, int meqn, int mwaves, int mbc, int mx,
+                    const double *q1d, const double *dtdx1d, const int *method,
+                    const int *mthlim, work2 *w)
+{
+    double *wave = w->wave, *s = w->s, *amdq = w->amdq, *apdq = w->apdq, *cqxx = w->cqxx;
+    double *bmasdq = w->bmasdq, *bpasdq = w->bpasdq;
+    double *qadd = w->qadd, *fadd = w->fadd, *gadd = w->gadd;
+    (void)maxm;
+    int limit = 0;
+    for (int mw = 0; mw < mwaves; mw++) if (mthlim[mw] > 0) limit = 1;
+    for (int i = 1 - mbc; i <= mx + mbc; i++)
+        for (int m = 0; m < meqn; m++) {
+            Q2(qadd, m, i) = 0.0;
+            Q2(fadd, m, i) = 0.0;
+            GADD(m, 0, i) = 0.0;
+            GADD(m, 1, i) = 0.0;
+        }
+    rpn(c, ixy, meqn, mwaves, mbc, mx, q1d, q1d, wave, s, amdq, apdq);
+    /* :103-106 forall with two statements */
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(qadd, m, i) = Q2(qadd, m, i) - dtdx1d[IX(i)] * Q2(apdq, m, i);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(qadd, m, i - 1) = Q2(qadd, m, i - 1) - dtdx1d[IX(i - 1)] * Q2(amdq, m, i);
+    double cfl1d = 0.0;
+    for (int mw = 0; mw < mwaves; mw++)
+        for (int i = 1; i <= mx + 1; i++)
+            cfl1d = dmax2(dmax2(cfl1d, dtdx1d[IX(i)] * SP(mw, i)), -dtdx1d[IX(i - 1)] * SP(mw, i));
+    if (method[1] != 1) {
+        if (limit) limiter(maxm, meqn, mwaves, mbc, mx, wave, s, mthlim);
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            double dtdxave = 0.5 * (dtdx1d[IX(i - 1)] + dtdx1d[IX(i)]);
+            for (int m = 0; m < meqn; m++) {
+                Q2(cqxx, m, i) = 0.0;
+                for (int mw = 0; mw < mwaves; mw++)
+                    Q2(cqxx, m, i) = Q2(cqxx, m, i) +
+                                     fabs(SP(mw, i)) * (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
+                Q2(fadd, m, i) = Q2(fadd, m, i) + 0.5 * Q2(cqxx, m, i);
+            }
+        }
+    }
+    if (method[2] <= 0) return cfl1d;
+    if (method[1] > 1 && method[2] == 2) {
+        for (int i = 1; i <= mx + 1; i++)
+            for (int m = 0; m < meqn; m++) {
+                Q2(amdq, m, i) = Q2(amdq, m, i) + Q2(cqxx, m, i);
+                Q2(apdq, m, i) = Q2(apdq, m, i) - Q2(cqxx, m, i);
+            }
+    }
+    rpt(c, ixy, meqn, mwaves, mbc, mx, amdq, bmasdq, bpasdq);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++) {
+            GADD(m, 0, i - 1) = GADD(m, 0, i - 1) - 0.5 * dtdx1d[IX(i - 1)] * Q2(bmasdq, m, i);
+            GADD(m, 1, i - 1) = GADD(m, 1, i - 1) - 0.5 * dtdx1d[IX(i - 1)] * Q2(bpasdq, m, i);
+        }
+    rpt(c, ixy, meqn, mwaves, mbc, mx, apdq, bmasdq, bpasdq);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++) {
+            GADD(m, 0, i) = GADD(m, 0, i) - 0.5 * dtdx1d[IX(i)] * Q2(bmasdq, m, i);
+            GADD(m, 1, i) = GADD(m, 1, i) - 0.5 * dtdx1d[IX(i)] * Q2(bpasdq, m, i);
+        }
+    return cfl1d;
+}
+
+/* 2-D array indexing, Fortran (m, i, j) with i in [1-mbc, mx+mbc] */
+#define NX (mx + 2 * mbc)
+#define Q3(arr, m, i, j) arr[(m) + (size_t)meqn * (((i) + mbc - 1) + (size_t)NX * ((j) + mbc - 1))]
+#define AUX3(ma, i, j) aux[(ma) + (size_t)maux * (((i) + mbc - 1) + (size_t)NX * ((j) + mbc - 1))]
+
+static void rp_ctx_init(rp_ctx *c, int rp_id, const double *rp_params, int n)
+{
+    memset(c, 0, sizeof(*c));
+    c->rp_id = rp_id; c->ndim = 2;
+    memcpy(c->p, rp_params, 8 * sizeof(double));
+    ctx_alloc(c, n);
+}
+
+/* ------------------------------------------------------------------------- */
+/* step2ds.f:2-248                                                           */
+/* ------------------------------------------------------------------------- */
+double oracle_step2ds(int rp_id, const double *rp_params, int maxm, int meqn, int mwaves,
+                      int maux, int mbc, int mx, int my, const double *qold, double *qnew,
+                      const double *aux, double dx, double dy, double dt,
+                      const int *method, const int *mthlim, int ids)
+{
+    int n = maxm + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    work2 w;
+    work2_alloc(&w, n, meqn, mwaves);
+    int mcapa = method[5];
+    double cfl = 0.0;
+    double dtdx = dt / dx, dtdy = dt / dy;
+    if (mcapa == 0)
+        for (int k = 0; k < n; k++) { w.dtdx1d[k] = dtdx; w.dtdy1d[k] = dtdy; }
+    double *q1d = w.q1d, *qadd = w.qadd, *fadd = w.fadd;
+    if (ids == 1) {
+        for (int j = 1 - mbc; j <= my + mbc; j++) {
+            for (int i = 1 - mbc; i <= mx + mbc; i++)
+                for (int m = 0; m < meqn; m++) Q2(q1d, m, i) = Q3(qold, m, i, j);
+            if (mcapa > 0)
+                for (int i = 1 - mbc; i <= mx + mbc; i++)
+                    w.dtdx1d[IX(i)] = dtdx / AUX3(mcapa - 1, i, j);
+            double cfl1d = flux2(&c, 1, maxm, meqn, mwaves, mbc, mx, q1d, w.dtdx1d, method, mthlim, &w);
+            cfl = dmax2(cfl, cfl1d);
+            if (mcapa == 0) {
+                for (int i = 1; i <= mx; i++)
+                    for (int m = 0; m < meqn; m++)
+                        Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, i) -
+                                            dtdx * (Q2(fadd, m, i + 1) - Q2(fadd, m, i));
+            } else {
+                for (int i = 1; i <= mx; i++)
+                    for (int m = 0; m < meqn; m++)
+                        Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, i) -
+                                            dtdx * (Q2(fadd, m, i + 1) - Q2(fadd, m, i)) /
+                                                AUX3(mcapa - 1, i, j);
+            }
+        }
+    }
+    if (ids == 2) {
+        for (int i = 1 - mbc; i <= mx + mbc; i++) {
+            for (int j = 1 - mbc; j <= my + mbc; j++)
+                for (int m = 0; m < meqn; m++) Q2(q1d, m, j) = Q3(qold, m, i, j);
+            if (mcapa > 0)
+                for (int j = 1 - mbc; j <= my + mbc; j++)
+                    w.dtdy1d[IX(j)] = dtdy / AUX3(mcapa - 1, i, j);
+            double cfl1d = flux2(&c, 2, maxm, meqn, mwaves, mbc, my, q1d, w.dtdy1d, method, mthlim, &w);
+            cfl = dmax2(cfl, cfl1d);
+            if (mcapa == 0) {
+                for (int j = 1; j <= my; j++)
+                    for (int m = 0; m < meqn; m++)
+                        Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, j) -
+                                            dtdy * (Q2(fadd, m, j + 1) - Q2(fadd, m, j));
+            } else {
+                for (int j = 1; j <= my; j++)
+                    for (int m = 0; m < meqn; m++)
+                        Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, j) -
+                                            dtdy * (Q2(fadd, m, j + 1) - Q2(fadd, m, j)) /
+                                                AUX3(mcapa - 1, i, j);
+            }
+        }
+    }
+    work2_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* ------------------------------------------------------------------------- */
+/* step2.f:2-241 (unsplit, with transverse terms).  qnew == qold on entry.    */
+/* ------------------------------------------------------------------------- */
+double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int mwaves,
+                    int maux, int mbc, int mx, int my, const double *qold, double *qnew,
+                    const double *aux, double dx, double dy, double dt,
+                    const int *method, const int *mthlim)
+{
+    int n = maxm + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    work2 w;
+    work2_alloc(&w, n, meqn, mwaves);
+    int mcapa = method[5];
+    double cfl = 0.0;
+    double dtdx = dt / dx, dtdy = dt / dy;
+    if (mcapa == 0)
+        for (int k = 0; k < n; k++) { w.dtdx1d[k] = dtdx; w.dtdy1d[k] = dtdy; }
+    double *q1d = w.q1d, *qadd = w.qadd, *fadd = w.fadd, *gadd = w.gadd;
+    for (int j = 0; j <= my + 1; j++) {
+        for (int m = 0; m < meqn; m++)
+            for (int i = 1 - mbc; i <= mx + mbc; i++) Q2(q1d, m, i) = Q3(qold, m, i, j);
+        if (mcapa > 0)
+            for (int i = 1 - mbc; i <= mx + mbc; i++)
+                w.dtdx1d[IX(i)] = dtdx / AUX3(mcapa - 1, i, j);
+        double cfl1d = flux2(&c, 1, maxm, meqn, mwaves, mbc, mx, q1d, w.dtdx1d, method, mthlim, &w);
+        cfl = dmax2(cfl, cfl1d);
+        if (mcapa == 0) {
+            for (int m = 0; m < meqn; m++)
+                for (int i = 1; i <= mx; i++) {
+                    Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, i) -
+                                        dtdx * (Q2(fadd, m, i + 1) - Q2(fadd, m, i)) -
+                                        dtdy * (GADD(m, 1, i) - GADD(m, 0, i));
+                    Q3(qnew, m, i, j - 1) = Q3(qnew, m, i, j - 1) - dtdy * GADD(m, 0, i);
+                    Q3(qnew, m, i, j + 1) = Q3(qnew, m, i, j + 1) + dtdy * GADD(m, 1, i);
+                }
+        } else {
+            for (int m = 0; m < meqn; m++)
+                for (int i = 1; i <= mx; i++) {
+                    Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, i) -
+                                        (dtdx * (Q2(fadd, m, i + 1) - Q2(fadd, m, i)) +
+                                         dtdy * (GADD(m, 1, i) - GADD(m, 0, i))) /
+                                            AUX3(mcapa - 1, i, j);
+                    Q3(qnew, m, i, j - 1) = Q3(qnew, m, i, j - 1) -
+                                            dtdy * GADD(m, 0, i) / AUX3(mcapa - 1, i, j - 1);
+                    Q3(qnew, m, i, j + 1) = Q3(qnew, m, i, j + 1) +
+                                            dtdy * GADD(m, 1, i) / AUX3(mcapa - 1, i, j + 1);
+                }
+        }
+    }
+    for (int i = 0; i <= mx + 1; i++) {
+        for (int m = 0; m < meqn; m++)
+            for (int j = 1 - mbc; j <= my + mbc; j++) Q2(q1d, m, j) = Q3(qold, m, i, j);
+        if (mcapa > 0)
+            for (int j = 1 - mbc; j <= my + mbc; j++)
+                w.dtdy1d[IX(j)] = dtdy / AUX3(mcapa - 1, i, j);
+        double cfl1d = flux2(&c, 2, maxm, meqn, mwaves, mbc, my, q1d, w.dtdy1d, method, mthlim, &w);
+        cfl = dmax2(cfl, cfl1d);
+        if (mcapa == 0) {
+            for (int m = 0; m < meqn; m++)
+                for (int j = 1; j <= my; j++) {
+                    Q3(qnew, m, i, j) = Q3(qnew, m, i, j) +
+                                        (Q2(qadd, m, j) -
+                                         dtdy * (Q2(fadd, m, j + 1) - Q2(fadd, m, j)) -
+                                         dtdx * (GADD(m, 1, j) - GADD(m, 0, j)));
+                    Q3(qnew, m, i - 1, j) = Q3(qnew, m, i - 1, j) - dtdx * GADD(m, 0, j);
+                    Q3(qnew, m, i + 1, j) = Q3(qnew, m, i + 1, j) + dtdx * GADD(m, 1, j);
+                }
+        } else {
+            for (int m = 0; m < meqn; m++)
+                for (int j = 1; j <= my; j++) {
+                    Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, j) -
+                                        (dtdy * (Q2(fadd, m, j + 1) - Q2(fadd, m, j)) +
+                                         dtdx * (GADD(m, 1, j) - GADD(m, 0, j))) /
+                                            AUX3(mcapa - 1, i, j);
+                    Q3(qnew, m, i - 1, j) = Q3(qnew, m, i - 1, j) -
+                                            dtdx * GADD(m, 0, j) / AUX3(mcapa - 1, i - 1, j);
+                    Q3(qnew, m, i + 1, j) = Q3(qnew, m, i + 1, j) +
+                                            dtdx * GADD(m, 1, j) / AUX3(mcapa - 1, i + 1, j);
+                }
+        }
+    }
+    work2_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* ------------------------------------------------------------------------- */
+/* SharpClaw: WENO5 reconstructions.  Arrays are (meqn, n) with n = mx+2*mbc, */
+/* 1-based position p = i + mbc.  Only positions whose results are consumed   */
+/* by flux1 are computed: p = mbc .. mx+mbc+1.                                */
+/* ------------------------------------------------------------------------- */
+#define QP(arr, m, p) arr[(m) + meqn * ((p)-1)]
+
+/* weno.f90:5-102 (PyWENO generated).  f32lit selects the REAL(4) reading of the
+   kind-less literals. */
+static void weno5_pyweno(const double *q, double *ql, double *qr, int meqn, int mx, int mbc,
+                         int f32lit)
+{
+#define LIT(x) (f32lit ? (double)(x##f) : (double)(x))
+    const double c333 = LIT(3.33333333333333), c1033 = LIT(10.3333333333333),
+                 c366 = LIT(3.66666666666667), c833 = LIT(8.33333333333333),
+                 c633 = LIT(6.33333333333333), c133 = LIT(1.33333333333333),
+                 c433 = LIT(4.33333333333333), c166 = LIT(1.66666666666667);
+    const double d01 = LIT(0.1), d06 = LIT(0.6), d03 = LIT(0.3), eps = LIT(1.0e-36);
+    const double r183 = LIT(1.83333333333333), r116 = LIT(1.16666666666667),
+                 r0333 = LIT(0.333333333333333), r0833 = LIT(0.833333333333333),
+                 r0166 = LIT(0.166666666666667);
+#undef LIT
+    for (int p = mbc; p <= mx + mbc + 1; p++) {
+        for (int m = 0; m < meqn; m++) {
+            double qm2 = QP(q, m, p - 2), qm1 = QP(q, m, p - 1), q0 = QP(q, m, p),
+                   qp1 = QP(q, m, p + 1), qp2 = QP(q, m, p + 2);
+            double sigma0 = ((c333)*q0) * q0 + ((-c1033) * q0) * qp1 + ((c366)*q0) * qp2 +
+                            ((c833)*qp1) * qp1 + ((-c633) * qp1) * qp2 + ((c133)*qp2) * qp2;
+            double sigma1 = ((c133)*qm1) * qm1 + ((-c433) * qm1) * q0 + ((c166)*qm1) * qp1 +
+                            ((c433)*q0) * q0 + ((-c433) * q0) * qp1 + ((c133)*qp1) * qp1;
+            double sigma2 = ((c133)*qm2) * qm2 + ((-c633) * qm2) * qm1 + ((c366)*qm2) * q0 +
+                            ((c833)*qm1) * qm1 + ((-c1033) * qm1) * q0 + ((c333)*q0) * q0;
+            double acc = 0.0;
+            double omega0 = d01 / ((sigma0 + eps) * (sigma0 + eps));
+            acc = acc + omega0;
+            double omega1 = d06 / ((sigma1 + eps) * (sigma1 + eps));
+            acc = acc + omega1;
+            double omega2 = d03 / ((sigma2 + eps) * (sigma2 + eps));
+            acc = acc + omega2;
+            omega0 = omega0 / acc;
+            omega1 = omega1 / acc;
+            omega2 = omega2 / acc;
+            acc = 0.0;
+            double omega3 = d03 / ((sigma0 + eps) * (sigma0 + eps));
+            acc = acc + omega3;
+            double omega4 = d06 / ((sigma1 + eps) * (sigma1 + eps));
+            acc = acc + omega4;
+            double omega5 = d01 / ((sigma2 + eps) * (sigma2 + eps));
+            acc = acc + omega5;
+            omega3 = omega3 / acc;
+            omega4 = omega4 / acc;
+            omega5 = omega5 / acc;
+            double fr0 = (r183)*q0 + (-r116) * qp1 + (r0333)*qp2;
+            double fr1 = (r0333)*qm1 + (r0833)*q0 + (-r0166) * qp1;
+            double fr2 = (-r0166) * qm2 + (r0833)*qm1 + (r0333)*q0;
+            double fr3 = (r0333)*q0 + (r0833)*qp1 + (-r0166) * qp2;
+            double fr4 = (-r0166) * qm1 + (r0833)*q0 + (r0333)*qp1;
+            double fr5 = (r0333)*qm2 + (-r116) * qm1 + (r183)*q0;
+            QP(ql, m, p) = omega0 * fr0 + omega1 * fr1 + omega2 * fr2;
+            QP(qr, m, p) = omega3 * fr3 + omega4 * fr4 + omega5 * fr5;
+        }
+    }
+}
+
+/* reconstruct.f90:120-185 (hand-written weno5, lim_type = 3) */
+static void weno5_old(const double *q, double *ql, double *qr, int meqn, int mx, int mbc,
+                      double *dq1m, double *uu)
+{
+    const double epweno = (double)1.e-36f; /* "1.e-36" is a REAL(4) literal, reconstruct.f90:7 */
+    int mx2 = mx + 2 * mbc;
+    for (int m = 0; m < meqn; m++) {
+        for (int p = 2; p <= mx2; p++) dq1m[p] = QP(q, m, p) - QP(q, m, p - 1);
+        for (int m1 = 1; m1 <= 2; m1++) {
+            int im = (m1 == 1) ? 1 : -1;
+            int ione = im, inone = -im, intwo = -2 * im;
+            for (int p = mbc; p <= mx2 - mbc + 1; p++) {
+                double t1 = im * (dq1m[p + intwo] - dq1m[p + inone]);
+                double t2 = im * (dq1m[p + inone] - dq1m[p]);
+                double t3 = im * (dq1m[p] - dq1m[p + ione]);
+                double e1 = dq1m[p + intwo] - 3. * dq1m[p + inone];
+                double e2 = dq1m[p + inone] + dq1m[p];
+                double e3 = 3. * dq1m[p] - dq1m[p + ione];
+                double tt1 = 13. * (t1 * t1) + 3. * (e1 * e1);
+                double tt2 = 13. * (t2 * t2) + 3. * (e2 * e2);
+                double tt3 = 13. * (t3 * t3) + 3. * (e3 * e3);
+                tt1 = (epweno + tt1) * (epweno + tt1);
+                tt2 = (epweno + tt2) * (epweno + tt2);
+                tt3 = (epweno + tt3) * (epweno + tt3);
+                double s1 = tt2 * tt3;
+                double s2 = 6. * tt1 * tt3;
+                double s3 = 3. * tt1 * tt2;
+                double t0 = 1. / (s1 + s2 + s3);
+                s1 = s1 * t0;
+                s3 = s3 * t0;
+                uu[(m1 - 1) + 2 * p] =
+                    (s1 * (t2 - t1) + (0.5 * s3 - 0.25) * (t3 - t2)) / 3. +
+                    (-QP(q, m, p - 2) + 7. * (QP(q, m, p - 1) + QP(q, m, p)) - QP(q, m, p + 1)) / 12.;
+            }
+        }
+        for (int p = mbc; p <= mx2 - mbc + 1; p++) {
+            QP(qr, m, p - 1) = uu[0 + 2 * p];
+            QP(ql, m, p) = uu[1 + 2 * p];
+        }
+    }
+}
+
+/* flux1.f90:2-195.  Returns cfl; dq1d(meqn, n) receives the increments for i=1..mx
+   (entries outside are left untouched). */
+typedef struct {
+    double *ql, *qr, *wave, *s, *amdq, *apdq, *amdq2, *apdq2, *dtdx, *dq1m, *uu, *q1d, *dq1d;
+} workS;
+static void workS_alloc(workS *w, int n, int meqn, int mwaves)
+{
+    w->ql = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->qr = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->wave = (double *)calloc((size_t)n * meqn * mwaves, sizeof(double));
+    w->s = (double *)calloc((size_t)n * mwaves, sizeof(double));
+    w->amdq = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->apdq = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->amdq2 = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->apdq2 = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->dtdx = (double *)calloc(n, sizeof(double));
+    w->dq1m = (double *)calloc(n + 2, sizeof(double));
+    w->uu = (double *)calloc(2 * (size_t)(n + 2), sizeof(double));
+    w->q1d = (double *)calloc((size_t)n * meqn, sizeof(double));
+    w->dq1d = (double *)calloc((size_t)n * meqn, sizeof(double));
+}
+static void workS_free(workS *w)
+{
+    free(w->ql); free(w->qr); free(w->wave); free(w->s); free(w->amdq); free(w->apdq);
+    free(w->amdq2); free(w->apdq2); free(w->dtdx); free(w->dq1m); free(w->uu);
+    free(w->q1d); free(w->dq1d);
+}
+
+static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, double dxv,
+                       int ixy, int meqn, int mwaves, int mx, int mbc, int weno_variant,
+                       int zero_dq, workS *w)
+{
+    int n = mx + 2 * mbc;
+    double *ql = w->ql, *qr = w->qr, *wave = w->wave, *s = w->s;
+    double *amdq = w->amdq, *apdq = w->apdq, *amdq2 = w->amdq2, *apdq2 = w->apdq2;
+    double *dtdx = w->dtdx;
+    for (int k = 0; k < n; k++) dtdx[k] = dt / dxv;
+    if (zero_dq)
+        for (int k = 0; k < n * meqn; k++) dq1d[k] = 0.0;
+    /* positions never reconstructed hold the cell average so that the Riemann
+       solver sees finite data there (the Fortran leaves them uninitialised; the
+       results at those interfaces are never consumed). */
+    memcpy(ql, q1d, sizeof(double) * n * meqn);
+    memcpy(qr, q1d, sizeof(double) * n * meqn);
+    if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
+    else weno5_pyweno(q1d, ql, qr, meqn, mx, mbc, weno_variant == WENO_PYWENO_F32);
+    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq);
+    double cfl = 0.0;
+    for (int mw = 0; mw < mwaves; mw++)
+        for (int i = 1; i <= mx + 1; i++)
+            cfl = dmax2(dmax2(cfl, dtdx[IX(i)] * SP(mw, i)), -dtdx[IX(i - 1)] * SP(mw, i));
+    /* :170-175 swap so that interface i of the second solve is the in-cell problem */
+    for (int i = 1 - mbc + 1; i <= mx + mbc; i++)
+        for (int m = 0; m < meqn; m++) {
+            Q2(qr, m, i - 1) = Q2(ql, m, i);
+            Q2(ql, m, i) = Q2(qr, m, i);
+        }
+    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq2, apdq2);
+    for (int i = 1; i <= mx; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(dq1d, m, i) = Q2(dq1d, m, i) -
+                             dtdx[IX(i)] * (Q2(amdq, m, i + 1) + Q2(apdq, m, i) +
+                                            Q2(amdq2, m, i) + Q2(apdq2, m, i));
+    return cfl;
+}
+
+/* 1-D entry: sharpclaw1.flux1(q,auxbc,dt,t,ixy,mx,mbc,maxnx) -> (dq1d, cfl); dq1d zero on entry */
+double oracle_sc_flux1(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
+                       int mx, const double *q, double *dq, double dx, double dt, int weno_variant)
+{
+    int n = mx + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    c.ndim = 1;
+    workS w;
+    workS_alloc(&w, n, meqn, mwaves);
+    double cfl = sc_flux1(&c, q, dq, dt, dx, 0, meqn, mwaves, mx, mbc, weno_variant, 0, &w);
+    workS_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* 2d/sharpclaw/flux2.f90:2-96 ; dq must be zero on entry (f2py optional => zeros) */
+double oracle_sc_flux2(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
+                       int mx, int my, const double *q, double *dq, double dx, double dy,
+                       double dt, int weno_variant)
+{
+    int maxm = mx > my ? mx : my;
+    int n = maxm + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    workS w;
+    workS_alloc(&w, n, meqn, mwaves);
+    double cfl = 0.0;
+    double *q1d = w.q1d, *dq1d = w.dq1d;
+    for (int j = 0; j <= my + 1; j++) {
+        for (int i = 1 - mbc; i <= mx + mbc; i++)
+            for (int m = 0; m < meqn; m++) Q2(q1d, m, i) = Q3(q, m, i, j);
+        double cfl1d = sc_flux1(&c, q1d, dq1d, dt, dx, 1, meqn, mwaves, mx, mbc, weno_variant, 1, &w);
+        cfl = dmax2(cfl, cfl1d);
+        for (int i = 1; i <= mx; i++)
+            for (int m = 0; m < meqn; m++)
+                Q3(dq, m, i, j) = Q3(dq, m, i, j) + Q2(dq1d, m, i);
+    }
+    for (int i = 0; i <= mx + 1; i++) {
+        for (int j = 1 - mbc; j <= my + mbc; j++)
+            for (int m = 0; m < meqn; m++) Q2(q1d, m, j) = Q3(q, m, i, j);
+        double cfl1d = sc_flux1(&c, q1d, dq1d, dt, dy, 2, meqn, mwaves, my, mbc, weno_variant, 1, &w);
+        cfl = dmax2(cfl, cfl1d);
+        for (int j = 1; j <= my; j++)
+            for (int m = 0; m < meqn; m++)
+                Q3(dq, m, i, j) = Q3(dq, m, i, j) + Q2(dq1d, m, j);
+    }
+    workS_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Host-parallel drivers for the CPU baseline: the grid is cut into y-slabs   */
+/* with mbc ghost rows each (what PetClaw's DMDA does with MPI ranks), every  */
+/* slab runs the serial routine above.  Results are identical to the serial   */
+/* call because each cell update is a pure function of its neighbourhood.     */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int kind; /* 0 = classic step2/step2ds, 1 = sharpclaw flux2 */
+    int rp_id; const double *rp_params;
+    int meqn, mwaves, maux, mbc, mx, my;
+    const double *qold; double *qnew; const double *aux;
+    double dx, dy, dt;
+    const int *method; const int *mthlim;
+    int dimsplit, weno_variant;
+    int nslabs, sl;
+    double cfl;
+} slab_job;
+
+static void *slab_run(void *arg)
+{
+    slab_job *jb = (slab_job *)arg;
+    int meqn = jb->meqn, maux = jb->maux, mbc = jb->mbc, mx = jb->mx, my = jb->my;
+    size_t rowq = (size_t)meqn * NX, rowa = (size_t)maux * NX;
+    int j0 = (int)((long long)my * jb->sl / jb->nslabs);       /* first interior row, 0-based */
+    int j1 = (int)((long long)my * (jb->sl + 1) / jb->nslabs); /* one past the last */
+    int myl = j1 - j0;
+    size_t nq = rowq * (size_t)(myl + 2 * mbc);
+    if (jb->kind == 0) {
+        int maxm = mx > myl ? mx : myl;
+        double *qo = (double *)malloc(nq * sizeof(double));
+        double *qn = (double *)malloc(nq * sizeof(double));
+        memcpy(qo, jb->qold + rowq * (size_t)j0, nq * sizeof(double));
+        memcpy(qn, qo, nq * sizeof(double));
+        const double *auxl = (maux > 0) ? jb->aux + rowa * (size_t)j0 : jb->aux;
+        if (jb->dimsplit) {
+            double cx = oracle_step2ds(jb->rp_id, jb->rp_params, maxm, meqn, jb->mwaves, maux, mbc,
+                                       mx, myl, qo, qn, auxl, jb->dx, jb->dy, jb->dt,
+                                       jb->method, jb->mthlim, 1);
+            double cy = oracle_step2ds(jb->rp_id, jb->rp_params, maxm, meqn, jb->mwaves, maux, mbc,
+                                       mx, myl, qn, qn, auxl, jb->dx, jb->dy, jb->dt,
+                                       jb->method, jb->mthlim, 2);
+            jb->cfl = dmax2(cx, cy);
+        } else {
+            jb->cfl = oracle_step2(jb->rp_id, jb->rp_params, maxm, meqn, jb->mwaves, maux, mbc,
+                                   mx, myl, qo, qn, auxl, jb->dx, jb->dy, jb->dt,
+                                   jb->method, jb->mthlim);
+        }
+        memcpy(jb->qnew + rowq * (size_t)(j0 + mbc), qn + rowq * (size_t)mbc,
+               rowq * (size_t)myl * sizeof(double));
+        free(qo); free(qn);
+    } else {
+        double *dql = (double *)calloc(nq, sizeof(double));
+        jb->cfl = oracle_sc_flux2(jb->rp_id, jb->rp_params, meqn, jb->mwaves, mbc, mx, myl,
+                                  jb->qold + rowq * (size_t)j0, dql, jb->dx, jb->dy, jb->dt,
+                                  jb->weno_variant);
+        memcpy(jb->qnew + rowq * (size_t)(j0 + mbc), dql + rowq * (size_t)mbc,
+               rowq * (size_t)myl * sizeof(double));
+        free(dql);
+    }
+    return NULL;
+}
+
+static double run_slabs(slab_job *proto, int nslabs)
+{
+    if (nslabs < 1) nslabs = 1;
+    if (nslabs > proto->my) nslabs = proto->my;
+    slab_job *jobs = (slab_job *)malloc(sizeof(slab_job) * nslabs);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nslabs);
+    for (int sl = 0; sl < nslabs; sl++) {
+        jobs[sl] = *proto;
+        jobs[sl].nslabs = nslabs;
+        jobs[sl].sl = sl;
+        if (nslabs == 1) slab_run(&jobs[sl]);
+        else pthread_create(&th[sl], NULL, slab_run, &jobs[sl]);
+    }
+    double cfl = 0.0;
+    for (int sl = 0; sl < nslabs; sl++) {
+        if (nslabs > 1) pthread_join(th[sl], NULL);
+        cfl = dmax2(cfl, jobs[sl].cfl);
+    }
+    free(jobs); free(th);
+    return cfl;
+}
+
+double oracle_step2_slabs(int rp_id, const double *rp_params, int meqn, int mwaves, int maux,
+                          int mbc, int mx, int my, const double *qold, double *qnew,
+                          const double *aux, double dx, double dy, double dt,
+                          const int *method, const int *mthlim, int nslabs, int dimsplit)
+{
+    slab_job jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.kind = 0; jb.rp_id = rp_id; jb.rp_params = rp_params;
+    jb.meqn = meqn; jb.mwaves = mwaves; jb.maux = maux; jb.mbc = mbc; jb.mx = mx; jb.my = my;
+    jb.qold = qold; jb.qnew = qnew; jb.aux = aux; jb.dx = dx; jb.dy = dy; jb.dt = dt;
+    jb.method = method; jb.mthlim = mthlim; jb.dimsplit = dimsplit;
+    return run_slabs(&jb, nslabs);
+}
+
+double oracle_sc_flux2_slabs(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
+                             int mx, int my, const double *q, double *dq, double dx, double dy,
+                             double dt, int weno_variant, int nslabs)
+{
+    slab_job jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.kind = 1; jb.rp_id = rp_id; jb.rp_params = rp_params;
+    jb.meqn = meqn; jb.mwaves = mwaves; jb.maux = 0; jb.mbc = mbc; jb.mx = mx; jb.my = my;
+    jb.qold = q; jb.qnew = dq; jb.dx = dx; jb.dy = dy; jb.dt = dt; jb.weno_variant = weno_variant;
+    return run_slabs(&jb, nslabs);
+}

@@ -1,0 +1,136 @@
+"""
+Problem definitions shared by the oracle tests (numpy) and the GPU parity tests.
+
+Each returns plain numpy initial data in the reference's layout ``q[m,i(,j)]`` plus the
+parameters the reference's test apps use:
+  test/acoustics/1d/homogeneous/acoustics.py, test/acoustics/2d/homogeneous/acoustics.py,
+  test/euler/2d/shockbubble.py, apps/shallow/2d/shallow2D.py (all under /root/reference).
+"""
+import numpy as np
+
+GAMMA = 1.4
+GAMMA1 = GAMMA - 1.
+
+
+def centers(lower, upper, n):
+    d = (upper - lower) / float(n)
+    return np.array([lower + (i + 0.5) * d for i in range(n)]), d
+
+
+def acoustics1d(mx=100):
+    x, dx = centers(0.0, 1.0, mx)
+    rho, bulk = 1.0, 1.0
+    zz, cc = np.sqrt(rho * bulk), np.sqrt(rho / bulk)
+    q = np.zeros((2, mx), order="F")
+    beta, gamma, x0 = 100, 0, 0.75
+    q[0, :] = np.exp(-beta * (x - x0) ** 2) * np.cos(gamma * (x - x0))
+    return dict(q=q, d=[dx], params=[rho, bulk, cc, zz], dt_initial=dx / cc * 0.1,
+                tfinal=1.0, nout=5)
+
+
+def acoustics2d(mx=100, my=100, width=0.2):
+    x, dx = centers(-1.0, 1.0, mx)
+    y, dy = centers(-1.0, 1.0, my)
+    Y, X = np.meshgrid(y, x)
+    r = np.sqrt(X ** 2 + Y ** 2)
+    q = np.zeros((3, mx, my), order="F")
+    q[0] = (np.abs(r - 0.5) <= width) * (1. + np.cos(np.pi * (r - 0.5) / width))
+    rho, bulk = 1.0, 4.0
+    cc = np.sqrt(bulk / rho)
+    zz = rho * cc
+    return dict(q=q, d=[dx, dy], params=[rho, bulk, cc, zz],
+                dt_initial=min(dx, dy) / cc * 0.45, tfinal=0.12, nout=10)
+
+
+def shock_state(pinf=5.):
+    rinf = (GAMMA1 + pinf * (GAMMA + 1.)) / ((GAMMA + 1.) + GAMMA1 * pinf)
+    vinf = 1. / np.sqrt(GAMMA) * (pinf - 1.) / np.sqrt(0.5 * ((GAMMA + 1.) / GAMMA) * pinf + 0.5 * GAMMA1 / GAMMA)
+    einf = 0.5 * rinf * vinf ** 2 + pinf / GAMMA1
+    return rinf, vinf, einf
+
+
+def shockbubble(mx=160, my=40, xupper=2.0, yupper=0.5, x0=0.5, y0=0., r0=0.2, rhoin=0.1):
+    x, dx = centers(0.0, xupper, mx)
+    y, dy = centers(0.0, yupper, my)
+    Y, X = np.meshgrid(y, x)
+    r = np.sqrt((X - x0) ** 2 + (Y - y0) ** 2)
+    q = np.zeros((5, mx, my), order="F")
+    q[0] = rhoin * (r <= r0) + 1. * (r > r0)
+    q[3] = (1. * (r <= r0) + 1. * (r > r0)) / GAMMA1
+    q[4] = 1. * (r <= r0)
+    aux = np.zeros((1, mx, my), order="F")
+    for j, yc in enumerate(y):
+        aux[0, :, j] = yc
+    return dict(q=q, aux=aux, d=[dx, dy], params=[GAMMA, GAMMA1], dt_initial=0.005,
+                tfinal=0.2, nout=1, limiters=[4, 4, 4, 4, 2])
+
+
+def shockbc_numpy(idim, t, qbc, mbc):
+    """test/euler/2d/shockbubble.py:41-57 on a numpy qbc."""
+    rinf, vinf, einf = shock_state()
+    for i in range(mbc):
+        qbc[0, i, ...] = rinf
+        qbc[1, i, ...] = rinf * vinf
+        qbc[2, i, ...] = 0.
+        qbc[3, i, ...] = einf
+        qbc[4, i, ...] = 0.
+
+
+def euler_rad_src(xp, q, aux, dt):
+    """test/euler/2d/shockbubble.py:59-94; ``xp`` is numpy or torch (same op order)."""
+    dt2 = dt / 2.
+    ndim = 2
+    rad = aux[0]
+    rho = q[0]
+    u = q[1] / rho
+    v = q[2] / rho
+    press = GAMMA1 * (q[3] - 0.5 * rho * (u ** 2 + v ** 2))
+    qstar = xp.empty_like(q)
+    qstar[0] = q[0] - dt2 * (ndim - 1) / rad * q[2]
+    qstar[1] = q[1] - dt2 * (ndim - 1) / rad * rho * u * v
+    qstar[2] = q[2] - dt2 * (ndim - 1) / rad * rho * v * v
+    qstar[3] = q[3] - dt2 * (ndim - 1) / rad * v * (q[3] + press)
+    rho = qstar[0]
+    u = qstar[1] / rho
+    v = qstar[2] / rho
+    press = GAMMA1 * (qstar[3] - 0.5 * rho * (u ** 2 + v ** 2))
+    q[0] = q[0] - dt * (ndim - 1) / rad * qstar[2]
+    q[1] = q[1] - dt * (ndim - 1) / rad * rho * u * v
+    q[2] = q[2] - dt * (ndim - 1) / rad * rho * v * v
+    q[3] = q[3] - dt * (ndim - 1) / rad * v * (qstar[3] + press)
+
+
+def shallow2d(mx=150, my=150, rad=0.5, hl=2., hr=1.):
+    x, dx = centers(-2.5, 2.5, mx)
+    y, dy = centers(-2.5, 2.5, my)
+    Y, X = np.meshgrid(y, x)
+    r = np.sqrt(X ** 2 + Y ** 2)
+    q = np.zeros((3, mx, my), order="F")
+    q[0] = hl * (r <= rad) + hr * (r > rad)
+    return dict(q=q, d=[dx, dy], params=[1.0], tfinal=2.5, nout=10)
+
+
+def random_state(rp, shape, seed=0):
+    """Seeded, physically admissible random data for kernel-level parity tests."""
+    rng = np.random.RandomState(seed)
+    if rp == "acoustics":
+        meqn = 2 if len(shape) == 1 else 3
+        q = rng.uniform(-1, 1, (meqn,) + tuple(shape))
+    elif rp == "advection":
+        q = rng.uniform(0, 1, (1,) + tuple(shape))
+    elif rp == "euler":
+        q = np.empty((5,) + tuple(shape))
+        rho = rng.uniform(0.2, 2.0, shape)
+        u = rng.uniform(-1.5, 1.5, shape)
+        v = rng.uniform(-1.5, 1.5, shape)
+        p = rng.uniform(0.2, 3.0, shape)
+        q[0], q[1], q[2] = rho, rho * u, rho * v
+        q[3] = p / GAMMA1 + 0.5 * rho * (u * u + v * v)
+        q[4] = rng.uniform(0, 1, shape)
+    elif rp == "shallow":
+        q = np.empty((3,) + tuple(shape))
+        h = rng.uniform(0.5, 2.0, shape)
+        q[0], q[1], q[2] = h, h * rng.uniform(-2.0, 2.0, shape), h * rng.uniform(-2.0, 2.0, shape)
+    else:
+        raise ValueError(rp)
+    return np.asfortranarray(q)

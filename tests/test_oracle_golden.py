@@ -1,0 +1,117 @@
+"""
+Pins the CPU oracle (oracle/claw_oracle.c + oracle/pyclaw_oracle.py) against the
+reference's own golden files and known-answer scalars (test/test_examples.py).
+Tolerances are the reference's own, or tighter where the oracle is bit-exact.
+"""
+import os
+
+import numpy as np
+
+import problems
+from oracle import pyclaw_oracle as po
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_acoustics1d_classic_scalar():
+    # test/test_examples.py:59-66 : 0.00104856594174 within 1e-5
+    pb = problems.acoustics1d(100)
+    s = po.OracleSolver("classic", 1, po.RP_ACOUSTICS, pb["params"], 2)
+    s.limiters = [4, 4]
+    s.dt_initial = pb["dt_initial"]
+    s.bc_lower[0] = s.bc_upper[0] = po.BC_PERIODIC
+    frames = s.run(pb["q"], None, pb["d"], pb["tfinal"], pb["nout"])
+    err = pb["d"][0] * np.sum(np.abs(frames[-1].reshape(-1) - frames[0].reshape(-1)))
+    assert s.total["numsteps"] == 120 and s.total["rejected"] == 0
+    assert abs(err - 0.00104856594174) < 1e-14   # all printed digits
+
+
+def test_acoustics1d_sharpclaw_scalar():
+    # test/test_examples.py:125-150 : 0.000298935748775 within 1e-5
+    pb = problems.acoustics1d(100)
+    for variant, tol in ((po.WENO_PYWENO_F64, 1e-12), (po.WENO_PYWENO_F32, 1e-5), (po.WENO_OLD, 1e-5)):
+        s = po.OracleSolver("sharpclaw", 1, po.RP_ACOUSTICS, pb["params"], 2)
+        s.weno_variant = variant
+        s.dt_initial = pb["dt_initial"]
+        s.bc_lower[0] = s.bc_upper[0] = po.BC_PERIODIC
+        frames = s.run(pb["q"], None, pb["d"], pb["tfinal"], pb["nout"])
+        err = pb["d"][0] * np.sum(np.abs(frames[-1].reshape(-1) - frames[0].reshape(-1)))
+        assert abs(err - 0.000298935748775) < tol, (variant, err)
+
+
+def _acoustics2d(kind):
+    pb = problems.acoustics2d()
+    s = po.OracleSolver(kind, 2, po.RP_ACOUSTICS, pb["params"], 2)
+    s.cfl_max, s.cfl_desired = 0.5, 0.45
+    if kind == "classic":
+        s.dim_split = True
+        s.limiters = [4, 4]
+    s.bc_lower = [po.BC_OUTFLOW] * 2
+    s.bc_upper = [po.BC_OUTFLOW] * 2
+    s.dt_initial = pb["dt_initial"]
+    return pb, s
+
+
+def test_acoustics2d_classic_golden():
+    # test/test_examples.py:239-254 : Frobenius norm < 1e-14 vs test/acoustics2D_solution
+    pb, s = _acoustics2d("classic")
+    frames = s.run(pb["q"], None, pb["d"], pb["tfinal"], pb["nout"])
+    gold = np.loadtxt(os.path.join(GOLD, "acoustics2D_solution"))
+    assert s.total["numsteps"] == 30
+    assert np.linalg.norm(frames[-1][0] - gold) < 2e-14
+    assert np.max(np.abs(frames[-1][0] - gold)) < 1e-15
+
+
+def test_acoustics2d_sharpclaw_golden():
+    # test/test_examples.py:333-376 : Frobenius norm < 1e-4 vs test/ac_sc_solution.
+    # The hand-written weno5 (reconstruct.f90:120-185) reproduces it to round-off; the
+    # PyWENO form with REAL(4) literals (what gfortran compiles) is inside the 1e-4.
+    gold = np.loadtxt(os.path.join(GOLD, "ac_sc_solution"))
+    for variant, tol in ((po.WENO_OLD, 1e-12), (po.WENO_PYWENO_F64, 1e-9), (po.WENO_PYWENO_F32, 1e-4)):
+        pb, s = _acoustics2d("sharpclaw")
+        s.weno_variant = variant
+        frames = s.run(pb["q"], None, pb["d"], pb["tfinal"], pb["nout"])
+        assert np.linalg.norm(frames[-1][0] - gold) < tol, variant
+
+
+def test_shockbubble_golden_bit_exact():
+    # test/test_examples.py:385-397 : max abs < 1e-12 vs test/sb_density ; oracle is bit-exact
+    pb = problems.shockbubble()
+    s = po.OracleSolver("classic", 2, po.RP_EULER5, pb["params"], 5)
+    s.cfl_max, s.cfl_desired = 0.5, 0.45
+    s.limiters = pb["limiters"]
+    s.dt_initial = pb["dt_initial"]
+    s.dim_split = True
+    s.bc_lower = [po.BC_CUSTOM, po.BC_REFLECTING]
+    s.bc_upper = [po.BC_OUTFLOW, po.BC_OUTFLOW]
+    s.user_bc_lower = problems.shockbc_numpy
+    s.step_src = lambda solver, state, dt: problems.euler_rad_src(np, state["q"], state["aux"], dt)
+    frames = s.run(pb["q"], pb["aux"], pb["d"], pb["tfinal"], pb["nout"])
+    gold = np.loadtxt(os.path.join(GOLD, "sb_density"))
+    assert s.total["numsteps"] == 170 and s.total["rejected"] == 1
+    assert np.max(np.abs(frames[-1][0] - gold)) == 0.0
+
+
+def test_slab_threads_identical():
+    # the host-parallel baseline driver must reproduce the serial oracle bit for bit
+    q = problems.random_state("euler", (37, 29), seed=3)
+    mbc = 2
+    for dimsplit in (True, False):
+        outs = []
+        for nth in (1, 4):
+            s = po.OracleSolver("classic", 2, po.RP_EULER5, [1.4, 0.4], 5)
+            s.limiters = [4, 4, 4, 4, 2]
+            s.dim_split = dimsplit
+            s.order_trans = 2
+            s.bc_lower = [po.BC_OUTFLOW, po.BC_PERIODIC]
+            s.bc_upper = [po.BC_OUTFLOW, po.BC_PERIODIC]
+            s.nthreads = nth
+            s.setup(q, None, [0.01, 0.01])
+            st = {"q": q.copy("F"), "t": 0.0}
+            s.dt = 0.001
+            if nth == 1:
+                s.nthreads = 1
+            s._hyperbolic_classic(st)
+            outs.append((st["q"].copy(), s.cfl))
+        assert np.array_equal(outs[0][0], outs[1][0])
+        assert outs[0][1] == outs[1][1]
