@@ -1,0 +1,165 @@
+/*
+ * clawb200.h -- C ABI of libclawb200.so: PyClaw's finite-volume time-step hot path as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one routine of the
+ * reference's f2py extension modules (classic1 / classic2 / sharpclaw1 / sharpclaw2,
+ * built per application by /root/reference/Makefile.rules:1-26 and called from
+ * src/pyclaw/clawpack.py and src/pyclaw/sharpclaw.py).  Signatures use plain pointers
+ * and sizes only.  Two families:
+ *
+ *   *_device entry points  take DEVICE pointers in the library's native layout
+ *       (structure of arrays, q[m][j][i], i fastest, ghost cells in place) plus a
+ *       cudaStream_t passed as void*.  They are asynchronous and never synchronise.
+ *       The Courant number is max-accumulated into a device double (`cfl_dev`) that
+ *       the caller clears with clawb200_cfl_reset() at the start of a step.
+ *
+ *   *_host entry points    take HOST pointers in the reference's own layout
+ *       (Fortran order q(meqn, 1-mbc:mx+mbc, 1-mbc:my+mbc), what f2py hands to the
+ *       Fortran) and return the Courant number by value; they copy in, run the same
+ *       kernels, copy out and synchronise.  They are what a maintainer binds in place
+ *       of `classic2.step2(...)` etc..
+ *
+ * Ownership: the caller owns every q / aux buffer; the library never frees or
+ * reallocates them.  Scratch for the *_host calls is owned by the library and cached
+ * per calling thread.  All functions return 0 on success and a negative code on
+ * error (clawb200_last_error() gives the message); nothing aborts the process --
+ * the Fortran `stop` statements (step2.f:58-63, rpn2_euler_5wave.f:54-58) have no
+ * equivalent here.
+ */
+#ifndef CLAWB200_H
+#define CLAWB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLAWB200_MAXWAVES 8
+
+/* Riemann solver ids (the reference selects the solver at link time through RP_SOURCE
+ * in each application's Makefile, e.g. apps/euler/2d/shockbubble/Makefile:3). */
+#define CLAWB200_RP_ACOUSTICS 1 /* rp1/rpn2/rpt2_acoustics ; params {rho,bulk,cc,zz}   */
+#define CLAWB200_RP_ADVECTION 2 /* rp1/rpn2/rpt2_advection ; params {u,v}              */
+#define CLAWB200_RP_EULER5 3    /* rpn2/rpt2_euler_5wave   ; params {gamma,gamma1}     */
+#define CLAWB200_RP_SHALLOW 4   /* rpn2/rpt2_shallow_roe_with_efix ; params {grav}     */
+
+/* Boundary condition ids = pyclaw.BC (src/pyclaw/solver.py:17-23) */
+#define CLAWB200_BC_CUSTOM 0
+#define CLAWB200_BC_OUTFLOW 1
+#define CLAWB200_BC_PERIODIC 2
+#define CLAWB200_BC_REFLECTING 3
+
+/* SharpClaw reconstruction variants */
+#define CLAWB200_WENO_PYWENO_F32 0 /* weno.f90:35-98 with its kind-less literals read as REAL(4) */
+#define CLAWB200_WENO_PYWENO_F64 1 /* same formulas, literals read as doubles                    */
+#define CLAWB200_WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)                     */
+
+#define CLAWB200_ERR_INVALID (-1)
+#define CLAWB200_ERR_UNSUPPORTED (-2)
+#define CLAWB200_ERR_CUDA (-3)
+
+/* Problem description: what the reference spreads over the f2py argument lists, the
+ * `method` array (clawpack.py:192-212) and the cparam / ClawParams module state. */
+typedef struct clawb200_problem {
+    int ndim;                      /* 1 or 2 */
+    int meqn, mwaves, maux, mbc;
+    int mx, my;                    /* interior cells (my = 1 in 1-D) */
+    double dx, dy;
+    int method[7];                 /* [dt_variable, order, trans(-1 = dim split), verbosity, 0, mcapa+1, maux] */
+    int mthlim[CLAWB200_MAXWAVES]; /* limiter per wave family (limiter.f / philim.f ids 0-5) */
+    int rp_id;
+    double rp_params[8];
+    /* device layout of q: element (m, i, j) (0-based, ghost cells included) is at
+       m*mstride + j*pitch + i.  Unused by the *_host entry points. */
+    long long mstride;
+    int pitch;
+    int weno_variant;              /* SharpClaw only */
+} clawb200_problem;
+
+int clawb200_version(void);
+const char *clawb200_last_error(void);
+
+/* ---- device-pointer entry points ------------------------------------------------ */
+
+/* cfl_dev <- 0 (stream ordered). */
+int clawb200_cfl_reset(double *cfl_dev, void *stream);
+
+/* classic1.step1 (src/fortran/1d/classic/step1.f:4-142; called at clawpack.py:323).
+ * q_in has its ghost cells filled; q_out receives cells 1..mx. q_in != q_out. */
+int clawb200_step1(const clawb200_problem *p, const double *q_in, double *q_out,
+                   const double *aux, double dt, double *cfl_dev, void *stream);
+
+/* classic2.step2ds (src/fortran/2d/classic/step2ds.f:2-248; clawpack.py:538-544).
+ * ids = 1: x-sweeps over every row including ghost rows; ids = 2: y-sweeps.
+ * q_in != q_out (the Fortran's aliased second call becomes a ping-pong). */
+int clawb200_step2ds(const clawb200_problem *p, const double *q_in, double *q_out,
+                     const double *aux, double dt, int ids, double *cfl_dev, void *stream);
+
+/* classic2.step2 (src/fortran/2d/classic/step2.f:2-241; clawpack.py:550-552), unsplit
+ * with transverse propagation.  qold has ghost cells filled; the interior of qnew is
+ * written (qnew need not be initialised). qold != qnew. */
+int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
+                   const double *aux, double dt, double *cfl_dev, void *stream);
+
+/* sharpclaw1.flux1 / sharpclaw2.flux2 (src/fortran/1d/sharpclaw/flux1.f90:2-195,
+ * src/fortran/2d/sharpclaw/flux2.f90:2-96; sharpclaw.py:385,558) fused with the
+ * Runge-Kutta stage update that sharpclaw.py:172-206 performs in numpy.  q is the
+ * stage state with ghost cells filled; dq = dq_hyperbolic(q).  Interior cells of `out`:
+ *   mode 0:  out = q + dq/div                (Euler; SSP33 stage 1; SSP104 stages)
+ *   mode 1:  out = ca*qa + cb*(q + dq)       (SSP33 stages 2 and 3)
+ *   mode 2:  out = (qa + ca*q) + cb*dq       (SSP104 final combination)
+ *   mode 3:  out is not written
+ * If dq_out != NULL the raw dq is stored there as well (used when a dq_src hook is set
+ * and by clawb200_sharpclaw_dq_host).  `cfl_dev` receives this stage's Courant number. */
+#define CLAWB200_STAGE_AXPY 0
+#define CLAWB200_STAGE_CONVEX 1
+#define CLAWB200_STAGE_FINAL104 2
+#define CLAWB200_STAGE_DQ_ONLY 3
+int clawb200_sharpclaw_stage(const clawb200_problem *p, const double *q, const double *qa,
+                             double *out, double *dq_out, const double *aux, double dt,
+                             int mode, double ca, double cb, double div, double *cfl_dev,
+                             void *stream);
+
+/* Solver.qbc_lower / qbc_upper (src/pyclaw/solver.py:384-452) for one side of one
+ * dimension.  narr = number of components of the array (meqn or maux); `negate` is the
+ * component whose sign flips for a reflecting wall (idim+1), or -1 for none (aux). */
+int clawb200_bc_fill(const clawb200_problem *p, double *q, int narr, int idim, int side,
+                     int bctype, int negate, void *stream);
+
+/* Layout converters between the reference's host layout (component fastest) and the
+ * device layout, both on DEVICE memory; nx, ny include ghost cells. */
+int clawb200_aos_to_soa(const double *aos, double *soa, int ncomp, int nx, int ny,
+                        long long mstride, int pitch, void *stream);
+int clawb200_soa_to_aos(const double *soa, double *aos, int ncomp, int nx, int ny,
+                        long long mstride, int pitch, void *stream);
+
+/* Halo pack / unpack for the slab partition (replaces DMDA globalToLocal,
+ * src/petclaw/state.py:254-269): copy `nrows` full padded rows starting at array row
+ * `row0` of every component to / from a contiguous buffer [m][row][i]. */
+int clawb200_halo_pack(const clawb200_problem *p, const double *q, int narr, int row0,
+                       int nrows, double *buf, void *stream);
+int clawb200_halo_unpack(const clawb200_problem *p, double *q, int narr, int row0,
+                         int nrows, const double *buf, void *stream);
+
+/* ---- host-pointer entry points (the f2py signatures) ----------------------------- */
+
+/* (q, cfl) = classic1.step1(mbc, mx, qbc, auxbc, dx, dt, method, mthlim); q updated in place */
+int clawb200_step1_host(const clawb200_problem *p, double *q, const double *aux, double dt,
+                        double *cfl);
+/* (qnew, cfl) = classic2.step2ds(maxm, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method,
+ *                                mthlim, aux1, aux2, aux3, work, ids); qold may equal qnew */
+int clawb200_step2ds_host(const clawb200_problem *p, const double *qold, double *qnew,
+                          const double *aux, double dt, int ids, double *cfl);
+/* (qnew, cfl) = classic2.step2(maxm, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method,
+ *                              mthlim, aux1, aux2, aux3, work) */
+int clawb200_step2_host(const clawb200_problem *p, const double *qold, double *qnew,
+                        const double *aux, double dt, double *cfl);
+/* (dq, cfl) = sharpclaw1.flux1(q, auxbc, dt, t, ixy, mx, mbc, maxnx)   (ndim = 1)
+ * (dq, cfl) = sharpclaw2.flux2(q, auxbc, dt, t, mbc, maxm, mx, my)     (ndim = 2) */
+int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const double *q, double *dq,
+                               const double *aux, double dt, double *cfl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAWB200_H */

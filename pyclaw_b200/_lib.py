@@ -1,0 +1,111 @@
+"""ctypes binding of libclawb200.so (include/clawb200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails,
+an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libclawb200.so")
+
+MAXWAVES = 8
+RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW = 1, 2, 3, 4
+WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
+STAGE_AXPY, STAGE_CONVEX, STAGE_FINAL104, STAGE_DQ_ONLY = 0, 1, 2, 3
+
+
+class ClawB200Error(RuntimeError):
+    pass
+
+
+class Problem(ctypes.Structure):
+    """struct clawb200_problem"""
+    _fields_ = [
+        ("ndim", ctypes.c_int), ("meqn", ctypes.c_int), ("mwaves", ctypes.c_int),
+        ("maux", ctypes.c_int), ("mbc", ctypes.c_int),
+        ("mx", ctypes.c_int), ("my", ctypes.c_int),
+        ("dx", ctypes.c_double), ("dy", ctypes.c_double),
+        ("method", ctypes.c_int * 7),
+        ("mthlim", ctypes.c_int * MAXWAVES),
+        ("rp_id", ctypes.c_int),
+        ("rp_params", ctypes.c_double * 8),
+        ("mstride", ctypes.c_longlong),
+        ("pitch", ctypes.c_int),
+        ("weno_variant", ctypes.c_int),
+    ]
+
+
+def make_problem(ndim, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, rp_params, method=None,
+                 mthlim=None, maux=0, pitch=None, mstride=None, weno_variant=WENO_PYWENO_F32):
+    p = Problem()
+    p.ndim, p.meqn, p.mwaves, p.maux, p.mbc = ndim, meqn, mwaves, maux, mbc
+    p.mx, p.my = mx, (my if ndim > 1 else 1)
+    p.dx, p.dy = dx, (dy if ndim > 1 else 1.0)
+    method = list(method) if method is not None else [1, 2, 0, 0, 0, 0, maux]
+    for i in range(7):
+        p.method[i] = int(method[i])
+    mthlim = list(mthlim) if mthlim is not None else [0] * mwaves
+    for i in range(MAXWAVES):
+        p.mthlim[i] = int(mthlim[i]) if i < len(mthlim) else 0
+    p.rp_id = rp_id
+    for i in range(8):
+        p.rp_params[i] = float(rp_params[i]) if i < len(rp_params) else 0.0
+    nx = mx + 2 * mbc
+    ny = (my + 2 * mbc) if ndim > 1 else 1
+    p.pitch = nx if pitch is None else pitch
+    p.mstride = p.pitch * ny if mstride is None else mstride
+    p.weno_variant = weno_variant
+    return p
+
+
+_lib = None
+_vp, _dp, _i, _d = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_pp = ctypes.POINTER(Problem)
+_dref = ctypes.POINTER(ctypes.c_double)
+
+# name -> argtypes ; every function returns int
+SIGNATURES = {
+    "clawb200_cfl_reset": [_dp, _vp],
+    "clawb200_step1": [_pp, _dp, _dp, _dp, _d, _dp, _vp],
+    "clawb200_step2ds": [_pp, _dp, _dp, _dp, _d, _i, _dp, _vp],
+    "clawb200_step2": [_pp, _dp, _dp, _dp, _d, _dp, _vp],
+    "clawb200_sharpclaw_stage": [_pp, _dp, _dp, _dp, _dp, _dp, _d, _i, _d, _d, _d, _dp, _vp],
+    "clawb200_bc_fill": [_pp, _dp, _i, _i, _i, _i, _i, _vp],
+    "clawb200_aos_to_soa": [_dp, _dp, _i, _i, _i, ctypes.c_longlong, _i, _vp],
+    "clawb200_soa_to_aos": [_dp, _dp, _i, _i, _i, ctypes.c_longlong, _i, _vp],
+    "clawb200_halo_pack": [_pp, _dp, _i, _i, _i, _dp, _vp],
+    "clawb200_halo_unpack": [_pp, _dp, _i, _i, _i, _dp, _vp],
+    "clawb200_step1_host": [_pp, _dp, _dp, _d, _dref],
+    "clawb200_step2ds_host": [_pp, _dp, _dp, _dp, _d, _i, _dref],
+    "clawb200_step2_host": [_pp, _dp, _dp, _dp, _d, _dref],
+    "clawb200_sharpclaw_dq_host": [_pp, _dp, _dp, _dp, _d, _dref],
+}
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ClawB200Error(
+                "libclawb200.so is missing (%s): build it with `python -m pyclaw_b200.build`; "
+                "pyclaw_b200 has no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.clawb200_version.restype = ctypes.c_int
+        L.clawb200_last_error.restype = ctypes.c_char_p
+        for name, args in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = ctypes.c_int
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise ClawB200Error("clawb200 error %d: %s" % (rc, load().clawb200_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,551 @@
+// classic.cuh -- fused wave-propagation sweeps (classic Clawpack) for sm_100a.
+//
+// Replaces, per sweep, the reference's step1 / step2 / step2ds + flux2 + limiter +
+// philim + rpn2 + rpt2 call tree
+//   src/fortran/1d/classic/step1.f:4-142, limiter.f:4-60, philim.f:4-58
+//   src/fortran/2d/classic/step2.f:2-241, step2ds.f:2-248, flux2.f:5-193
+// with kernels that do the Riemann solve, wave limiting, second-order correction,
+// transverse solves and the flux-difference update in one pass over q.
+//
+// Data layout (HBM): structure-of-arrays, q[m][j][i] with i fastest; `pitch` is the
+// row stride and `mstride` the component stride, both in doubles.  Ghost cells are
+// stored in place (mbc on every side), Fortran cell (i,j) lives at
+// (i+mbc-1) + pitch*(j+mbc-1).
+//
+// Two engines, both with one thread per column i so that every global access is a
+// unit-stride, coalesced float64 stream:
+//   * x-engine: a CTA owns a strip of columns and walks down the rows.  Riemann
+//     problems are between neighbouring threads; q rows, waves and the "goes to the
+//     left cell" parts are exchanged through shared memory.  Transverse increments go
+//     to rows j-1 / j+1, i.e. stay in the thread (rolling accumulators).
+//   * y-engine: a thread walks down its own column keeping a rolling window of the
+//     last interfaces in registers; only the transverse increments (which go to the
+//     columns i-1 / i+1) are exchanged through shared memory.
+// The arithmetic order of every cell update is the reference's.
+#pragma once
+#include "rp.cuh"
+
+#define CLAW_MAXWAVES 8
+
+struct SweepArgs {
+    const double *qin;   // Riemann data (qold, ghost cells filled)
+    const double *qbase; // values being updated (== qin for the first sweep)
+    double *qout;
+    long long mstride;
+    int pitch;
+    int mx, my, mbc;
+    double dtdx, dtdy; // dt/dx, dt/dy
+    int order;         // method(2)
+    int trans;         // method(3): -1 dim-split, 0 none, 1 increment, 2 increment+correction
+    int mthlim[CLAW_MAXWAVES];
+    RpParams rp;
+    unsigned long long *cfl_bits; // running max of the Courant number, as ordered bits (cfl >= 0)
+    int rows_per_cta;
+    int jlo, jhi; // first / last output row (Fortran index)
+    int ilo, ihi; // first / last output column
+};
+
+// philim.f:4-58
+__device__ __forceinline__ double philim(double a, double b, int meth)
+{
+    double r = b / a;
+    switch (meth) {
+    case 1: return dmax2(0.0, dmin2(1.0, r));
+    case 2: return dmax2(dmax2(0.0, dmin2(1.0, 2.0 * r)), dmin2(2.0, r));
+    case 3: return (r + fabs(r)) / (1.0 + fabs(r));
+    case 4: {
+        double c = (1.0 + r) / 2.0;
+        return dmax2(0.0, dmin2(dmin2(c, 2.0), 2.0 * r));
+    }
+    default: return r;
+    }
+}
+
+// limiter.f:29-55 for one interface, given the (unlimited) dot products with the
+// neighbouring interfaces.  Entries with RP::nz == false are structurally zero and
+// skipped: adding +0 to a running sum that started at +0 never changes it.
+template <class RP>
+__device__ __forceinline__ void limit_waves(double (&wave)[RP::MEQN][RP::MWAVES],
+                                            const double (&s)[RP::MWAVES],
+                                            const double (&wnorm2)[RP::MWAVES],
+                                            const double (&dotl)[RP::MWAVES],
+                                            const double (&dotr)[RP::MWAVES], const int *mthlim)
+{
+#pragma unroll
+    for (int mw = 0; mw < RP::MWAVES; mw++) {
+        if (mthlim[mw] == 0) continue;
+        if (wnorm2[mw] == 0.0) continue;
+        double wlimitr = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], mthlim[mw]);
+#pragma unroll
+        for (int m = 0; m < RP::MEQN; m++)
+            if (RP::nz(m, mw)) wave[m][mw] = wlimitr * wave[m][mw];
+    }
+}
+
+// flux2.f:127-145: cqxx(m) = sum_mw |s| (1 - |s| dtdxave) wave(m,mw)
+template <class RP>
+__device__ __forceinline__ void second_order(const double (&wave)[RP::MEQN][RP::MWAVES],
+                                             const double (&s)[RP::MWAVES], double dtdxave,
+                                             double (&cqxx)[RP::MEQN])
+{
+#pragma unroll
+    for (int m = 0; m < RP::MEQN; m++) {
+        double c = 0.0;
+#pragma unroll
+        for (int mw = 0; mw < RP::MWAVES; mw++)
+            if (RP::nz(m, mw)) c = c + fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[m][mw];
+        cqxx[m] = c;
+    }
+}
+
+__device__ __forceinline__ void cfl_commit(double cfl, unsigned long long *cfl_bits)
+{
+    // warp-shuffle max, then one atomicMax per warp on the ordered bit pattern
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double other = __shfl_xor_sync(0xffffffffu, cfl, o);
+        cfl = dmax2(cfl, other);
+    }
+    if ((threadIdx.x & 31) == 0 && cfl > 0.0)
+        atomicMax(cfl_bits, (unsigned long long)__double_as_longlong(cfl));
+}
+
+// ---------------------------------------------------------------------------
+// x-engine.  Thread t <-> interface/cell ii = i0-1+t ; cells i0 .. i0+NT-4 are output.
+// TRANS=false: dimensional splitting (step2ds.f ids=1), every row independent.
+// TRANS=true : unsplit (step2.f x-sweeps): slices j0-1 .. j1 are processed for output
+//              rows j0 .. j1-1, contributions applied in the order of SURVEY.md A.3.
+// ---------------------------------------------------------------------------
+template <class RP, bool TRANS, int NT>
+__global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
+{
+    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    constexpr int NC = NT - 3;
+    constexpr int QS = NT + 1;
+    extern __shared__ double sm[];
+    double *qs = sm;                 // [MEQN][NT+1]   staged q row
+    double *ws = qs + MEQN * QS;     // [MEQN*MW][NT]  unlimited waves
+    double *xs = ws + MEQN * MW * NT; // [4*MEQN][NT]   amdq, F, bm(A-), bp(A-) of each interface
+
+    const int t = threadIdx.x;
+    const int i0 = A.ilo + blockIdx.x * NC;
+    const int ii = i0 - 1 + t;
+    const int j0 = A.jlo + blockIdx.y * A.rows_per_cta;
+    const int j1 = min(j0 + A.rows_per_cta, A.jhi + 1);
+    const int mbc = A.mbc;
+    const int imax = A.mx + mbc;
+    const int cload = min(i0 - 2 + t, imax) + mbc - 1;      // array column this thread stages
+    const int cload2 = min(i0 - 2 + NT, imax) + mbc - 1;    // extra column staged by thread 0
+    const bool cell_ok = (t >= 1) && (t <= NC) && (ii <= A.ihi);
+    const bool iface_ok = (ii >= 1) && (ii <= A.mx + 1) && (t >= 1) && (t <= NT - 2);
+    const bool order2 = (A.order != 1);
+    const bool trans2 = order2 && (A.trans == 2);
+    const double dtdx = A.dtdx, dtdy = A.dtdy;
+    const double hdtdx = 0.5 * dtdx;
+
+    double cfl = 0.0;
+    double accPrev[MEQN], pendA[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) { accPrev[m] = 0.0; pendA[m] = 0.0; }
+
+    const int rbeg = TRANS ? j0 - 1 : j0;
+    const int rend = TRANS ? j1 : j1 - 1;
+    for (int r = rbeg; r <= rend; r++) {
+        const long long rowoff = (long long)A.pitch * (r + mbc - 1);
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            qs[m * QS + t] = A.qin[m * A.mstride + rowoff + cload];
+            if (t == 0) qs[m * QS + NT] = A.qin[m * A.mstride + rowoff + cload2];
+        }
+        __syncthreads();
+        double l[MEQN], rr[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
+
+        double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+        RP::solve(A.rp, l, rr, wave, s, amdq, apdq, roe);
+        if (iface_ok) {
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+        }
+        if (order2) {
+#pragma unroll
+            for (int m = 0; m < MEQN; m++)
+#pragma unroll
+                for (int mw = 0; mw < MW; mw++)
+                    if (RP::nz(m, mw)) ws[(m * MW + mw) * NT + t] = wave[m][mw];
+        }
+        __syncthreads();
+
+        double cqxx[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) cqxx[m] = 0.0;
+        if (order2 && t >= 1 && t <= NT - 2) {
+            double wnorm2[MW], dotl[MW], dotr[MW];
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++) {
+                double n2 = 0.0, dl = 0.0, dr = 0.0;
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    if (RP::nz(m, mw)) {
+                        double w = wave[m][mw];
+                        n2 = n2 + w * w;
+                        dl = dl + ws[(m * MW + mw) * NT + t - 1] * w;
+                        dr = dr + w * ws[(m * MW + mw) * NT + t + 1];
+                    }
+                }
+                wnorm2[mw] = n2; dotl[mw] = dl; dotr[mw] = dr;
+            }
+            limit_waves<RP>(wave, s, wnorm2, dotl, dotr, A.mthlim);
+            double dtdxave = 0.5 * (dtdx + dtdx);
+            second_order<RP>(wave, s, dtdxave, cqxx);
+        }
+        double F[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) F[m] = 0.5 * cqxx[m];
+
+        double bmp[MEQN], bpp[MEQN];
+        if (TRANS) {
+            double asdq[MEQN], bmm[MEQN], bpm[MEQN];
+            if (A.trans > 0) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq[m] + cqxx[m]) : amdq[m];
+                RP::transverse(A.rp, roe, asdq, bmm, bpm);
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq[m] - cqxx[m]) : apdq[m];
+                RP::transverse(A.rp, roe, asdq, bmp, bpp);
+            } else { // flux2.f:151 -- gadd stays zero
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp[m] = bpp[m] = 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                xs[(2 * MEQN + m) * NT + t] = bmm[m];
+                xs[(3 * MEQN + m) * NT + t] = bpm[m];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            xs[m * NT + t] = amdq[m];
+            xs[(MEQN + m) * NT + t] = F[m];
+        }
+        __syncthreads();
+
+        if (t <= NT - 2) {
+            const int tn = t + 1;
+            const long long oidx = rowoff + (ii + mbc - 1);
+            if (!TRANS) {
+                // step2ds.f leaves the ghost columns of qnew equal to qold; the y-sweep (and
+                // its CFL number) reads them, so carry them across.
+                if (t < mbc && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+                    const int gc = (blockIdx.x == 0) ? t : (A.mx + mbc + t);
+#pragma unroll
+                    for (int m = 0; m < MEQN; m++) {
+                        if (blockIdx.x == 0)
+                            A.qout[m * A.mstride + rowoff + t] = A.qin[m * A.mstride + rowoff + t];
+                        if (blockIdx.x == gridDim.x - 1)
+                            A.qout[m * A.mstride + rowoff + A.mx + mbc + t] =
+                                A.qin[m * A.mstride + rowoff + A.mx + mbc + t];
+                    }
+                    (void)gc;
+                }
+                if (cell_ok) {
+#pragma unroll
+                    for (int m = 0; m < MEQN; m++) {
+                        double qaddv = (0.0 - dtdx * apdq[m]) - dtdx * xs[m * NT + tn];
+                        double dF = xs[(MEQN + m) * NT + tn] - F[m];
+                        A.qout[m * A.mstride + oidx] = (rr[m] + qaddv) - dtdx * dF;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    double qaddv = (0.0 - dtdx * apdq[m]) - dtdx * xs[m * NT + tn];
+                    double dF = xs[(MEQN + m) * NT + tn] - F[m];
+                    double G1 = (0.0 - hdtdx * xs[(2 * MEQN + m) * NT + tn]) - hdtdx * bmp[m];
+                    double G2 = (0.0 - hdtdx * xs[(3 * MEQN + m) * NT + tn]) - hdtdx * bpp[m];
+                    // row r-1 receives its last x-sweep contribution and is complete
+                    double done = accPrev[m] - dtdy * G1;
+                    if (cell_ok && r - 1 >= j0 && r - 1 < j1)
+                        A.qout[m * A.mstride + oidx - A.pitch] = done;
+                    double acc = rr[m] + pendA[m];
+                    acc = acc + qaddv - dtdx * dF - dtdy * (G2 - G1);
+                    accPrev[m] = acc;
+                    pendA[m] = dtdy * G2;
+                }
+            }
+        }
+    }
+    cfl_commit(cfl, A.cfl_bits);
+}
+
+// ---------------------------------------------------------------------------
+// y-engine.  Thread <-> column; walks rows k = j0-2 .. j1+1 and completes cell k-2
+// at step k.  TRANS=false: step2ds.f ids=2.  TRANS=true: step2.f y-sweeps; qout is
+// updated in place (it already holds the x-sweep result), transverse increments to
+// the neighbouring columns go through shared memory.
+// ---------------------------------------------------------------------------
+template <class RP, bool TRANS, int NT>
+__global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
+{
+    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    constexpr int NC = TRANS ? NT - 2 : NT;
+    extern __shared__ double sm[];
+    double *gs = sm; // [2][2*MEQN][NT]  G1', G2' of the cells in the current row (double buffered)
+
+    const int t = threadIdx.x;
+    const int mbc = A.mbc;
+    const int i0 = A.ilo + blockIdx.x * NC;
+    const int ic = TRANS ? i0 - 1 + t : i0 + t;      // this thread's column (Fortran index)
+    const int icl = min(ic, A.mx + mbc) + mbc - 1;   // clamped array column
+    const bool col_out = TRANS ? (t >= 1 && t <= NC && ic <= A.ihi) : (ic <= A.ihi);
+    const bool col_cfl = TRANS ? (ic >= 0 && ic <= A.mx + 1) : (ic <= A.mx + mbc);
+    const int j0 = A.jlo + blockIdx.y * A.rows_per_cta;
+    const int j1 = min(j0 + A.rows_per_cta, A.jhi + 1);
+    const bool order2 = (A.order != 1);
+    const bool trans2 = order2 && (A.trans == 2);
+    const double dtdx = A.dtdx, dtdy = A.dtdy;
+    const double hdtdy = 0.5 * dtdy;
+
+    double cfl = 0.0;
+    double qm1[MEQN], qm2[MEQN];
+    double wm1[MEQN][MW], sm1[MW], amdq1[MEQN], apdq1[MEQN], roe1[NROE];
+    double norm1[MW], dot1[MW];
+    double apdq2[MEQN], F2[MEQN], bmp2[MEQN], bpp2[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        qm1[m] = qm2[m] = 0.0; amdq1[m] = apdq1[m] = apdq2[m] = F2[m] = bmp2[m] = bpp2[m] = 0.0;
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) wm1[m][mw] = 0.0;
+    }
+#pragma unroll
+    for (int mw = 0; mw < MW; mw++) { sm1[mw] = 0.0; norm1[mw] = 0.0; dot1[mw] = 0.0; }
+#pragma unroll
+    for (int n = 0; n < NROE; n++) roe1[n] = 1.0;
+
+    int buf = 0;
+    for (int k = j0 - 2; k <= j1 + 1; k++) {
+        const long long rowoff = (long long)A.pitch * (k + mbc - 1);
+        double qk[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) qk[m] = A.qin[m * A.mstride + rowoff + icl];
+
+        double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+        double normk[MW], dotk[MW];
+        if (k >= j0 - 1) {
+            RP::solve(A.rp, qm1, qk, wave, s, amdq, apdq, roe);
+            if (col_cfl && k >= 1 && k <= A.my + 1) {
+#pragma unroll
+                for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdy * s[mw]), -dtdy * s[mw]);
+            }
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++) {
+                double n2 = 0.0, d = 0.0;
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    if (RP::nz(m, mw)) {
+                        n2 = n2 + wave[m][mw] * wave[m][mw];
+                        d = d + wm1[m][mw] * wave[m][mw];
+                    }
+                }
+                normk[mw] = n2; dotk[mw] = d;
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                amdq[m] = apdq[m] = 0.0;
+#pragma unroll
+                for (int mw = 0; mw < MW; mw++) wave[m][mw] = 0.0;
+            }
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++) { s[mw] = 0.0; normk[mw] = 0.0; dotk[mw] = 0.0; }
+#pragma unroll
+            for (int n = 0; n < NROE; n++) roe[n] = 1.0;
+        }
+
+        // limit interface k-1 and form its correction flux
+        double cqxx[MEQN], F1[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) cqxx[m] = 0.0;
+        if (order2 && k >= j0 + 1) {
+            limit_waves<RP>(wm1, sm1, norm1, dot1, dotk, A.mthlim);
+            double dtdxave = 0.5 * (dtdy + dtdy);
+            second_order<RP>(wm1, sm1, dtdxave, cqxx);
+        }
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) F1[m] = 0.5 * cqxx[m];
+
+        double bmm[MEQN], bpm[MEQN], bmp1[MEQN], bpp1[MEQN];
+        if (TRANS) {
+            if (A.trans > 0) {
+                double asdq[MEQN];
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq1[m] + cqxx[m]) : amdq1[m];
+                RP::transverse(A.rp, roe1, asdq, bmm, bpm);
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq1[m] - cqxx[m]) : apdq1[m];
+                RP::transverse(A.rp, roe1, asdq, bmp1, bpp1);
+            } else {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp1[m] = bpp1[m] = 0.0;
+            }
+        }
+
+        // complete cell k-2
+        const int jc = k - 2;
+        const bool row_out = (jc >= j0) && (jc < j1);
+        const long long oidx = (long long)A.pitch * (jc + mbc - 1) + icl;
+        if (!TRANS) {
+            if (row_out && col_out) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    double qaddv = (0.0 - dtdy * apdq2[m]) - dtdy * amdq1[m];
+                    double dF = F1[m] - F2[m];
+                    A.qout[m * A.mstride + oidx] = (qm2[m] + qaddv) - dtdy * dF;
+                }
+            }
+        } else {
+            double mainE[MEQN];
+            if (row_out) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    double qaddv = (0.0 - dtdy * apdq2[m]) - dtdy * amdq1[m];
+                    double dF = F1[m] - F2[m];
+                    double G1 = (0.0 - hdtdy * bmm[m]) - hdtdy * bmp2[m];
+                    double G2 = (0.0 - hdtdy * bpm[m]) - hdtdy * bpp2[m];
+                    mainE[m] = (qaddv - dtdy * dF - dtdx * (G2 - G1));
+                    gs[(buf * 2 * MEQN + m) * NT + t] = G1;
+                    gs[(buf * 2 * MEQN + MEQN + m) * NT + t] = G2;
+                }
+            }
+            __syncthreads();
+            if (row_out && col_out) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    double G2l = gs[(buf * 2 * MEQN + MEQN + m) * NT + t - 1];
+                    double G1r = gs[(buf * 2 * MEQN + m) * NT + t + 1];
+                    double q = A.qout[m * A.mstride + oidx];
+                    q = q + dtdx * G2l;
+                    q = q + mainE[m];
+                    q = q - dtdx * G1r;
+                    A.qout[m * A.mstride + oidx] = q;
+                }
+            }
+            buf ^= 1;
+        }
+
+        // shift the window
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            qm2[m] = qm1[m]; qm1[m] = qk[m];
+            apdq2[m] = apdq1[m]; F2[m] = F1[m];
+            amdq1[m] = amdq[m]; apdq1[m] = apdq[m];
+            if (TRANS) { bmp2[m] = bmp1[m]; bpp2[m] = bpp1[m]; }
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++) wm1[m][mw] = wave[m][mw];
+        }
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) { sm1[mw] = s[mw]; norm1[mw] = normk[mw]; dot1[mw] = dotk[mw]; }
+#pragma unroll
+        for (int n = 0; n < NROE; n++) roe1[n] = roe[n];
+    }
+    cfl_commit(cfl, A.cfl_bits);
+}
+
+// ---------------------------------------------------------------------------
+// 1-D step (step1.f:4-142).  Same staging as the x-engine, one "row".
+// Update order: q - dtdx*apdq(i), then - dtdx*amdq(i+1), then - dtdx*(f(i+1)-f(i)).
+// ---------------------------------------------------------------------------
+template <class RP, int NT>
+__global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
+{
+    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    constexpr int NC = NT - 3;
+    constexpr int QS = NT + 1;
+    extern __shared__ double sm[];
+    double *qs = sm;
+    double *ws = qs + MEQN * QS;
+    double *xs = ws + MEQN * MW * NT; // [2*MEQN][NT] amdq, f
+
+    const int t = threadIdx.x;
+    const int i0 = 1 + blockIdx.x * NC;
+    const int ii = i0 - 1 + t;
+    const int mbc = A.mbc;
+    const int imax = A.mx + mbc;
+    const int cload = min(i0 - 2 + t, imax) + mbc - 1;
+    const int cload2 = min(i0 - 2 + NT, imax) + mbc - 1;
+    const bool cell_ok = (t >= 1) && (t <= NC) && (ii <= A.mx);
+    const bool iface_ok = (ii >= 1) && (ii <= A.mx + 1) && (t >= 1) && (t <= NT - 2);
+    const bool order2 = (A.order != 1);
+    const double dtdx = A.dtdx;
+
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        qs[m * QS + t] = A.qin[m * A.mstride + cload];
+        if (t == 0) qs[m * QS + NT] = A.qin[m * A.mstride + cload2];
+    }
+    __syncthreads();
+    double l[MEQN], rr[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
+    double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+    RP::solve(A.rp, l, rr, wave, s, amdq, apdq, roe);
+    double cfl = 0.0;
+    if (iface_ok) {
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+    }
+    if (order2) {
+#pragma unroll
+        for (int m = 0; m < MEQN; m++)
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++)
+                if (RP::nz(m, mw)) ws[(m * MW + mw) * NT + t] = wave[m][mw];
+    }
+    __syncthreads();
+    double f[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) f[m] = 0.0;
+    if (order2 && t >= 1 && t <= NT - 2) {
+        double wnorm2[MW], dotl[MW], dotr[MW];
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) {
+            double n2 = 0.0, dl = 0.0, dr = 0.0;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                if (RP::nz(m, mw)) {
+                    double w = wave[m][mw];
+                    n2 = n2 + w * w;
+                    dl = dl + ws[(m * MW + mw) * NT + t - 1] * w;
+                    dr = dr + w * ws[(m * MW + mw) * NT + t + 1];
+                }
+            }
+            wnorm2[mw] = n2; dotl[mw] = dl; dotr[mw] = dr;
+        }
+        limit_waves<RP>(wave, s, wnorm2, dotl, dotr, A.mthlim);
+        // step1.f:121-128
+        double dtdxave = 0.5 * (dtdx + dtdx);
+#pragma unroll
+        for (int m = 0; m < MEQN; m++)
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++)
+                if (RP::nz(m, mw))
+                    f[m] = f[m] + 0.5 * fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[m][mw];
+    }
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        xs[m * NT + t] = amdq[m];
+        xs[(MEQN + m) * NT + t] = f[m];
+    }
+    __syncthreads();
+    if (cell_ok) {
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            double q = rr[m] - dtdx * apdq[m];
+            q = q - dtdx * xs[m * NT + t + 1];
+            if (order2) q = q - dtdx * (xs[(MEQN + m) * NT + t + 1] - f[m]);
+            A.qout[m * A.mstride + (ii + mbc - 1)] = q;
+        }
+    }
+    cfl_commit(cfl, A.cfl_bits);
+}

@@ -1,0 +1,643 @@
+// clawb200.cu -- C ABI (include/clawb200.h) over the sm_100a kernels in classic.cuh and
+// sharpclaw.cuh.  Built in-tree with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared ...
+// -fmad=false is part of the contract: the reference's Fortran is compiled without FMA
+// contraction and results must match it bit for bit ("hard parts").
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/clawb200.h"
+#include "classic.cuh"
+#include "sharpclaw.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *msg)
+{
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *where)
+{
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return CLAWB200_ERR_CUDA;
+}
+#define CUDA_OK(call)                                             \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+    } while (0)
+
+extern "C" int clawb200_version(void) { return 100; }
+extern "C" const char *clawb200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int clawb200_cfl_reset(double *cfl_dev, void *stream)
+{
+    CUDA_OK(cudaMemsetAsync(cfl_dev, 0, sizeof(double), (cudaStream_t)stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+static int check_problem(const clawb200_problem *p, int ndim)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    if (p->ndim != ndim) return fail(CLAWB200_ERR_INVALID, "wrong ndim for this entry point");
+    if (p->mx < 1 || p->my < 1) return fail(CLAWB200_ERR_INVALID, "mx, my must be positive");
+    if (p->mwaves < 1 || p->mwaves > CLAWB200_MAXWAVES) return fail(CLAWB200_ERR_INVALID, "bad mwaves");
+    if (p->pitch < p->mx + 2 * p->mbc) return fail(CLAWB200_ERR_INVALID, "pitch smaller than padded row");
+    if (p->method[5] != 0)
+        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function (mcapa) not supported by this build");
+    return 0;
+}
+
+static SweepArgs make_args(const clawb200_problem *p, const double *qin, double *qout, double dt,
+                           double *cfl_dev)
+{
+    SweepArgs A;
+    memset(&A, 0, sizeof(A));
+    A.qin = qin; A.qbase = qin; A.qout = qout;
+    A.mstride = p->mstride; A.pitch = p->pitch;
+    A.mx = p->mx; A.my = p->my; A.mbc = p->mbc;
+    A.dtdx = dt / p->dx;
+    A.dtdy = (p->ndim > 1) ? dt / p->dy : 0.0;
+    A.order = p->method[1];
+    A.trans = p->method[2];
+    for (int i = 0; i < CLAW_MAXWAVES; i++) A.mthlim[i] = (i < p->mwaves) ? p->mthlim[i] : 0;
+    for (int i = 0; i < 8; i++) A.rp.p[i] = p->rp_params[i];
+    A.cfl_bits = (unsigned long long *)cfl_dev;
+    return A;
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+constexpr int XNT = 128; // threads per CTA of the x-engine
+constexpr int YNT = 128; // threads per CTA of the y-engine
+
+template <class RP, bool TRANS>
+static int launch_x(SweepArgs A, cudaStream_t st)
+{
+    constexpr int NC = XNT - 3;
+    size_t smem = sizeof(double) * (RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
+    auto k = xsweep_kernel<RP, TRANS, XNT>;
+    CUDA_OK(set_smem(k, smem));
+    int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
+    dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
+    k<<<grid, XNT, smem, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <class RP, bool TRANS>
+static int launch_y(SweepArgs A, cudaStream_t st)
+{
+    constexpr int NC = TRANS ? YNT - 2 : YNT;
+    size_t smem = TRANS ? sizeof(double) * (2 * 2 * RP::MEQN * YNT) : 0;
+    auto k = ysweep_kernel<RP, TRANS, YNT>;
+    CUDA_OK(set_smem(k, smem));
+    int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
+    dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
+    k<<<grid, YNT, smem, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int pick_rows(int nrows, int ncol_ctas)
+{
+    // enough CTAs to fill 148 SMs a few times over, but strips tall enough that the
+    // start-up rows of the streaming engines stay a small fraction of the work
+    int h = 64;
+    while (h > 8 && (long long)ncol_ctas * ((nrows + h - 1) / h) < 148 * 4) h /= 2;
+    return h;
+}
+
+// dispatch on the Riemann solver (the sweep direction is a template parameter of the solver)
+template <bool TRANS>
+static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
+{
+    switch (rp_id) {
+    case CLAWB200_RP_ACOUSTICS: return launch_x<RpAcoustics<2, 1>, TRANS>(A, st);
+    case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS>(A, st);
+    case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS>(A, st);
+    case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS>(A, st);
+    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
+    }
+}
+template <bool TRANS>
+static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
+{
+    switch (rp_id) {
+    case CLAWB200_RP_ACOUSTICS: return launch_y<RpAcoustics<2, 2>, TRANS>(A, st);
+    case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS>(A, st);
+    case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS>(A, st);
+    case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS>(A, st);
+    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
+    }
+}
+
+static int check_rp_shape(const clawb200_problem *p)
+{
+    int meqn = 0, mwaves = 0;
+    switch (p->rp_id) {
+    case CLAWB200_RP_ACOUSTICS: meqn = p->ndim + 1; mwaves = 2; break;
+    case CLAWB200_RP_ADVECTION: meqn = 1; mwaves = 1; break;
+    case CLAWB200_RP_EULER5: meqn = 5; mwaves = 5; break;
+    case CLAWB200_RP_SHALLOW: meqn = 3; mwaves = 3; break;
+    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
+    }
+    if (p->meqn != meqn || p->mwaves != mwaves)
+        return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
+    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SHALLOW) && p->ndim != 2)
+        return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 2-D only");
+    return 0;
+}
+
+extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, double *q_out,
+                              const double *aux, double dt, double *cfl_dev, void *stream)
+{
+    int rc = check_problem(p, 1);
+    if (rc) return rc;
+    if ((rc = check_rp_shape(p))) return rc;
+    if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
+    if (q_in == q_out) return fail(CLAWB200_ERR_INVALID, "q_in and q_out must differ");
+    (void)aux;
+    SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int NT = 128, NC = NT - 3;
+    dim3 grid((p->mx + NC - 1) / NC);
+    switch (p->rp_id) {
+    case CLAWB200_RP_ACOUSTICS: {
+        using RP = RpAcoustics<1, 1>;
+        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
+        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
+    } break;
+    case CLAWB200_RP_ADVECTION: {
+        using RP = RpAdvection<1, 1>;
+        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
+        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
+    } break;
+    default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int clawb200_step2ds(const clawb200_problem *p, const double *q_in, double *q_out,
+                                const double *aux, double dt, int ids, double *cfl_dev,
+                                void *stream)
+{
+    int rc = check_problem(p, 2);
+    if (rc) return rc;
+    if ((rc = check_rp_shape(p))) return rc;
+    if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
+    if (q_in == q_out) return fail(CLAWB200_ERR_INVALID, "q_in and q_out must differ");
+    (void)aux;
+    SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev);
+    A.trans = -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ids == 1) {
+        A.ilo = 1; A.ihi = p->mx;
+        A.jlo = 1 - p->mbc; A.jhi = p->my + p->mbc;
+        A.rows_per_cta = pick_rows(A.jhi - A.jlo + 1, (p->mx + XNT - 4) / (XNT - 3));
+        return dispatch_x<false>(p->rp_id, A, st);
+    } else if (ids == 2) {
+        A.ilo = 1 - p->mbc; A.ihi = p->mx + p->mbc;
+        A.jlo = 1; A.jhi = p->my;
+        A.rows_per_cta = pick_rows(p->my, (p->mx + 2 * p->mbc + YNT - 1) / YNT);
+        return dispatch_y<false>(p->rp_id, A, st);
+    } else
+        return fail(CLAWB200_ERR_INVALID, "ids must be 1 or 2");
+    return 0;
+}
+
+extern "C" int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
+                              const double *aux, double dt, double *cfl_dev, void *stream)
+{
+    int rc = check_problem(p, 2);
+    if (rc) return rc;
+    if ((rc = check_rp_shape(p))) return rc;
+    if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
+    if (qold == qnew) return fail(CLAWB200_ERR_INVALID, "qold and qnew must differ");
+    if (p->method[2] < 0) return fail(CLAWB200_ERR_INVALID, "method[2] < 0 means dimensional splitting: call step2ds");
+    (void)aux;
+    cudaStream_t st = (cudaStream_t)stream;
+    SweepArgs A = make_args(p, qold, qnew, dt, cfl_dev);
+    A.ilo = 1; A.ihi = p->mx; A.jlo = 1; A.jhi = p->my;
+    A.rows_per_cta = pick_rows(p->my, (p->mx + XNT - 4) / (XNT - 3));
+    if ((rc = dispatch_x<true>(p->rp_id, A, st))) return rc;
+    A.rows_per_cta = pick_rows(p->my, (p->mx + YNT - 3) / (YNT - 2));
+    return dispatch_y<true>(p->rp_id, A, st);
+}
+
+// ---------------------------------------------------------------------------
+// Boundary conditions (solver.py:384-452).  One launch per side; the ordering over
+// sides (dim 0 lower, dim 0 upper, dim 1 lower, dim 1 upper) is the caller's, so
+// that custom (user) conditions can be interleaved exactly like the reference does.
+// ---------------------------------------------------------------------------
+__global__ void bc_kernel(double *q, long long mstride, int pitch, int narr, int nx, int ny,
+                          int mbc, int idim, int side, int bctype, int negate)
+{
+    // ghost layer g = 0..mbc-1 counted from the outside for `lower`, from the inside..
+    const int len = (idim == 0) ? ny : nx; // extent along the boundary
+    const long long total = (long long)len * mbc * narr;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
+         id += (long long)gridDim.x * blockDim.x) {
+        int a, g, m;
+        if (idim == 0) { // ghost columns: vary j fastest is uncoalesced either way; keep g fastest
+            g = (int)(id % mbc);
+            a = (int)((id / mbc) % len);
+            m = (int)(id / ((long long)mbc * len));
+        } else { // ghost rows: i fastest (coalesced)
+            a = (int)(id % len);
+            g = (int)((id / len) % mbc);
+            m = (int)(id / ((long long)mbc * len));
+        }
+        const int n = (idim == 0) ? nx : ny; // extent across the boundary (padded)
+        int dst, src;
+        double sign = 1.0;
+        if (side == 0) {
+            dst = g;
+            if (bctype == CLAWB200_BC_OUTFLOW) src = mbc;
+            else if (bctype == CLAWB200_BC_PERIODIC) src = n - 2 * mbc + g;
+            else { src = 2 * mbc - 1 - g; if (m == negate) sign = -1.0; }
+        } else {
+            dst = n - 1 - g;
+            if (bctype == CLAWB200_BC_OUTFLOW) src = n - mbc - 1;
+            else if (bctype == CLAWB200_BC_PERIODIC) src = mbc + (mbc - 1 - g);
+            else { src = n - 2 * mbc + g; if (m == negate) sign = -1.0; }
+        }
+        long long od, os;
+        if (idim == 0) { od = (long long)a * pitch + dst; os = (long long)a * pitch + src; }
+        else { od = (long long)dst * pitch + a; os = (long long)src * pitch + a; }
+        double v = q[m * mstride + os];
+        q[m * mstride + od] = (sign < 0.0) ? -v : v;
+    }
+}
+
+extern "C" int clawb200_bc_fill(const clawb200_problem *p, double *q, int narr, int idim,
+                                int side, int bctype, int negate, void *stream)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    if (idim < 0 || idim >= p->ndim || side < 0 || side > 1)
+        return fail(CLAWB200_ERR_INVALID, "bad idim/side");
+    if (bctype < CLAWB200_BC_OUTFLOW || bctype > CLAWB200_BC_REFLECTING)
+        return fail(CLAWB200_ERR_INVALID, "bc_fill handles outflow, periodic and reflecting only");
+    int nx = p->mx + 2 * p->mbc;
+    int ny = (p->ndim > 1) ? p->my + 2 * p->mbc : 1;
+    long long total = (long long)((idim == 0) ? ny : nx) * p->mbc * narr;
+    int threads = 256;
+    int blocks = (int)((total + threads - 1) / threads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    bc_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(q, p->mstride, p->pitch, narr, nx, ny,
+                                                            p->mbc, idim, side, bctype, negate);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Layout converters (tiled transposes through shared memory): the reference's host
+// layout has the component index fastest, the device layout has i fastest.
+// ---------------------------------------------------------------------------
+template <bool TO_SOA>
+__global__ void layout_kernel(const double *src, double *dst, int ncomp, int nx, int ny,
+                              long long mstride, int pitch)
+{
+    // one CTA converts 128 consecutive cells of one row
+    extern __shared__ double tile[]; // [ncomp][129]
+    const int j = blockIdx.y;
+    const int ibase = blockIdx.x * 128;
+    const int ncell = min(128, nx - ibase);
+    const long long aos0 = ((long long)j * nx + ibase) * ncomp;
+    if (TO_SOA) {
+        for (int e = threadIdx.x; e < ncell * ncomp; e += blockDim.x)
+            tile[(e % ncomp) * 129 + e / ncomp] = src[aos0 + e];
+        __syncthreads();
+        for (int e = threadIdx.x; e < ncell * ncomp; e += blockDim.x) {
+            int m = e / ncell, c = e % ncell;
+            dst[m * mstride + (long long)j * pitch + ibase + c] = tile[m * 129 + c];
+        }
+    } else {
+        for (int e = threadIdx.x; e < ncell * ncomp; e += blockDim.x) {
+            int m = e / ncell, c = e % ncell;
+            tile[m * 129 + c] = src[m * mstride + (long long)j * pitch + ibase + c];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < ncell * ncomp; e += blockDim.x)
+            dst[aos0 + e] = tile[(e % ncomp) * 129 + e / ncomp];
+    }
+}
+
+extern "C" int clawb200_aos_to_soa(const double *aos, double *soa, int ncomp, int nx, int ny,
+                                   long long mstride, int pitch, void *stream)
+{
+    if (ncomp < 1 || ncomp > 32) return fail(CLAWB200_ERR_INVALID, "ncomp out of range");
+    dim3 grid((nx + 127) / 128, ny);
+    layout_kernel<true><<<grid, 128, sizeof(double) * ncomp * 129, (cudaStream_t)stream>>>(
+        aos, soa, ncomp, nx, ny, mstride, pitch);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int clawb200_soa_to_aos(const double *soa, double *aos, int ncomp, int nx, int ny,
+                                   long long mstride, int pitch, void *stream)
+{
+    if (ncomp < 1 || ncomp > 32) return fail(CLAWB200_ERR_INVALID, "ncomp out of range");
+    dim3 grid((nx + 127) / 128, ny);
+    layout_kernel<false><<<grid, 128, sizeof(double) * ncomp * 129, (cudaStream_t)stream>>>(
+        soa, aos, ncomp, nx, ny, mstride, pitch);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Halo pack / unpack for the y-slab partition
+// ---------------------------------------------------------------------------
+template <bool PACK>
+__global__ void halo_kernel(double *q, double *buf, long long mstride, int pitch, int nx, int narr,
+                            int row0, int nrows)
+{
+    const long long total = (long long)narr * nrows * nx;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
+         id += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(id % nx);
+        int r = (int)((id / nx) % nrows);
+        int m = (int)(id / ((long long)nx * nrows));
+        long long qi = m * mstride + (long long)(row0 + r) * pitch + i;
+        if (PACK) buf[id] = q[qi];
+        else q[qi] = buf[id];
+    }
+}
+
+extern "C" int clawb200_halo_pack(const clawb200_problem *p, const double *q, int narr, int row0,
+                                  int nrows, double *buf, void *stream)
+{
+    int nx = p->mx + 2 * p->mbc;
+    long long total = (long long)narr * nrows * nx;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    halo_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((double *)q, buf, p->mstride, p->pitch,
+                                                                nx, narr, row0, nrows);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int clawb200_halo_unpack(const clawb200_problem *p, double *q, int narr, int row0,
+                                    int nrows, const double *buf, void *stream)
+{
+    int nx = p->mx + 2 * p->mbc;
+    long long total = (long long)narr * nrows * nx;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    halo_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(q, (double *)buf, p->mstride, p->pitch,
+                                                                 nx, narr, row0, nrows);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// SharpClaw
+// ---------------------------------------------------------------------------
+constexpr int SNT = 128;
+
+static void weno_constants(ScArgs &A, int variant)
+{
+    const bool f32 = (variant == CLAWB200_WENO_PYWENO_F32);
+#define LIT(x) (f32 ? (double)(x##f) : (double)(x))
+    A.c333 = LIT(3.33333333333333); A.c1033 = LIT(10.3333333333333);
+    A.c366 = LIT(3.66666666666667); A.c833 = LIT(8.33333333333333);
+    A.c633 = LIT(6.33333333333333); A.c133 = LIT(1.33333333333333);
+    A.c433 = LIT(4.33333333333333); A.c166 = LIT(1.66666666666667);
+    A.d01 = LIT(0.1); A.d06 = LIT(0.6); A.d03 = LIT(0.3); A.eps = LIT(1.0e-36);
+    A.r183 = LIT(1.83333333333333); A.r116 = LIT(1.16666666666667);
+    A.r0333 = LIT(0.333333333333333); A.r0833 = LIT(0.833333333333333);
+    A.r0166 = LIT(0.166666666666667);
+#undef LIT
+    A.epweno = (double)1.e-36f; // reconstruct.f90:7, a REAL(4) literal
+}
+
+template <class RPX, class RPY, bool OLD>
+static int sc_launch2(const ScArgs &A, cudaStream_t st)
+{
+    constexpr int NC = SNT - 2;
+    size_t smem = sizeof(double) * (RPX::MEQN * (SNT + 4) + 2 * RPX::MEQN * SNT);
+    auto k = sc2d_kernel<RPX, RPY, OLD, SNT>;
+    CUDA_OK(set_smem(k, smem));
+    dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);
+    k<<<grid, SNT, smem, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <class RP, bool OLD>
+static int sc_launch1(const ScArgs &A, cudaStream_t st)
+{
+    constexpr int NC = SNT - 2;
+    size_t smem = sizeof(double) * (RP::MEQN * (SNT + 4) + 2 * RP::MEQN * SNT);
+    sc1d_kernel<RP, OLD, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *qa, double *out,
+                            double *dq_out, double dt, int mode, double ca, double cb, double div,
+                            double *cfl_dev, cudaStream_t st)
+{
+    ScArgs A;
+    memset(&A, 0, sizeof(A));
+    A.q = q; A.qa = qa; A.out = out; A.dq_out = dq_out;
+    A.mstride = p->mstride; A.pitch = p->pitch;
+    A.mx = p->mx; A.my = p->my; A.mbc = p->mbc;
+    A.dtdx = dt / p->dx;
+    A.dtdy = (p->ndim > 1) ? dt / p->dy : 0.0;
+    for (int i = 0; i < 8; i++) A.rp.p[i] = p->rp_params[i];
+    weno_constants(A, p->weno_variant);
+    A.mode = mode; A.ca = ca; A.cb = cb; A.div = div;
+    A.cfl_bits = (unsigned long long *)cfl_dev;
+    const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
+    if (p->ndim == 1) {
+        switch (p->rp_id) {
+        case CLAWB200_RP_ACOUSTICS:
+            return old ? sc_launch1<RpAcoustics<1, 1>, true>(A, st) : sc_launch1<RpAcoustics<1, 1>, false>(A, st);
+        case CLAWB200_RP_ADVECTION:
+            return old ? sc_launch1<RpAdvection<1, 1>, true>(A, st) : sc_launch1<RpAdvection<1, 1>, false>(A, st);
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
+        }
+    }
+    A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+#define SC2(RPT)                                                                         \
+    return old ? sc_launch2<RPT, true>(A, st) : sc_launch2<RPT, false>(A, st)
+    switch (p->rp_id) {
+    case CLAWB200_RP_ACOUSTICS: return old ? sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, true>(A, st)
+                                           : sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, false>(A, st);
+    case CLAWB200_RP_ADVECTION: return old ? sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, true>(A, st)
+                                           : sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, false>(A, st);
+    case CLAWB200_RP_EULER5: return old ? sc_launch2<RpEuler5<1>, RpEuler5<2>, true>(A, st)
+                                        : sc_launch2<RpEuler5<1>, RpEuler5<2>, false>(A, st);
+    case CLAWB200_RP_SHALLOW: return old ? sc_launch2<RpShallow<1>, RpShallow<2>, true>(A, st)
+                                         : sc_launch2<RpShallow<1>, RpShallow<2>, false>(A, st);
+    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
+    }
+#undef SC2
+}
+
+extern "C" int clawb200_sharpclaw_stage(const clawb200_problem *p, const double *q, const double *qa,
+                                        double *out, double *dq_out, const double *aux, double dt,
+                                        int mode, double ca, double cb, double div,
+                                        double *cfl_dev, void *stream)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    int rc = check_problem(p, p->ndim);
+    if (rc) return rc;
+    if ((rc = check_rp_shape(p))) return rc;
+    if (p->mbc < 3) return fail(CLAWB200_ERR_INVALID, "WENO5 needs mbc >= 3");
+    if (mode < 0 || mode > 3) return fail(CLAWB200_ERR_INVALID, "bad stage mode");
+    if ((mode == 1 || mode == 2) && !qa) return fail(CLAWB200_ERR_INVALID, "this stage mode needs qa");
+    if (out == q) return fail(CLAWB200_ERR_INVALID, "out must not alias q");
+    (void)aux;
+    return sharpclaw_launch(p, q, qa, out, dq_out, dt, mode, ca, cb, div, cfl_dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// Host-pointer entry points: same kernels behind the reference's f2py signatures.
+// ---------------------------------------------------------------------------
+struct HostScratch {
+    double *d_aos = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_cfl = nullptr;
+    double *h_cfl = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+    int ensure(size_t n)
+    {
+        if (!st) {
+            CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            CUDA_OK(cudaMalloc(&d_cfl, 16 * sizeof(double)));
+            CUDA_OK(cudaMallocHost(&h_cfl, 16 * sizeof(double)));
+        }
+        if (n > cap) {
+            cudaFree(d_aos); cudaFree(d_a); cudaFree(d_b); cudaFree(d_c);
+            d_aos = d_a = d_b = d_c = nullptr; cap = 0;
+            CUDA_OK(cudaMalloc(&d_aos, n * sizeof(double)));
+            CUDA_OK(cudaMalloc(&d_a, n * sizeof(double)));
+            CUDA_OK(cudaMalloc(&d_b, n * sizeof(double)));
+            CUDA_OK(cudaMalloc(&d_c, n * sizeof(double)));
+            cap = n;
+        }
+        return 0;
+    }
+};
+static thread_local HostScratch g_hs;
+
+static clawb200_problem host_layout(const clawb200_problem *p)
+{
+    clawb200_problem P = *p;
+    int nx = p->mx + 2 * p->mbc;
+    int ny = (p->ndim > 1) ? p->my + 2 * p->mbc : 1;
+    P.pitch = nx;
+    P.mstride = (long long)nx * ny;
+    if (p->ndim == 1) P.my = 1;
+    return P;
+}
+
+static int host_upload(const clawb200_problem &P, const double *h, double *d_soa)
+{
+    int nx = P.pitch, ny = (int)(P.mstride / P.pitch);
+    size_t n = (size_t)P.meqn * nx * ny;
+    CUDA_OK(cudaMemcpyAsync(g_hs.d_aos, h, n * sizeof(double), cudaMemcpyHostToDevice, g_hs.st));
+    return clawb200_aos_to_soa(g_hs.d_aos, d_soa, P.meqn, nx, ny, P.mstride, P.pitch, g_hs.st);
+}
+static int host_download(const clawb200_problem &P, const double *d_soa, double *h)
+{
+    int nx = P.pitch, ny = (int)(P.mstride / P.pitch);
+    size_t n = (size_t)P.meqn * nx * ny;
+    int rc = clawb200_soa_to_aos(d_soa, g_hs.d_aos, P.meqn, nx, ny, P.mstride, P.pitch, g_hs.st);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(h, g_hs.d_aos, n * sizeof(double), cudaMemcpyDeviceToHost, g_hs.st));
+    return 0;
+}
+static int host_finish(double *cfl, int slot = 0)
+{
+    CUDA_OK(cudaMemcpyAsync(g_hs.h_cfl, g_hs.d_cfl, 16 * sizeof(double), cudaMemcpyDeviceToHost, g_hs.st));
+    CUDA_OK(cudaStreamSynchronize(g_hs.st));
+    if (cfl) *cfl = g_hs.h_cfl[slot];
+    return 0;
+}
+
+extern "C" int clawb200_step1_host(const clawb200_problem *p, double *q, const double *aux,
+                                   double dt, double *cfl)
+{
+    if (!p || !q) return fail(CLAWB200_ERR_INVALID, "null argument");
+    clawb200_problem P = host_layout(p);
+    size_t n = (size_t)P.meqn * P.mstride;
+    int rc = g_hs.ensure(n);
+    if (rc) return rc;
+    if ((rc = host_upload(P, q, g_hs.d_a))) return rc;
+    // cells outside 1..mx keep their input values (the Fortran also updates cells 0 and
+    // mx+1, which no caller reads: clawpack.py:406 keeps q[:, mbc:-mbc] only)
+    CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
+    if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = clawb200_step1(&P, g_hs.d_a, g_hs.d_b, aux, dt, g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = host_download(P, g_hs.d_b, q))) return rc;
+    return host_finish(cfl);
+}
+
+extern "C" int clawb200_step2ds_host(const clawb200_problem *p, const double *qold, double *qnew,
+                                     const double *aux, double dt, int ids, double *cfl)
+{
+    if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
+    clawb200_problem P = host_layout(p);
+    size_t n = (size_t)P.meqn * P.mstride;
+    int rc = g_hs.ensure(n);
+    if (rc) return rc;
+    if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
+    // qnew starts as the caller's qnew (== qold in the reference's usage): cells the sweep
+    // does not touch keep those values
+    if (qnew == qold) {
+        CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
+    } else if ((rc = host_upload(P, qnew, g_hs.d_b)))
+        return rc;
+    if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = clawb200_step2ds(&P, g_hs.d_a, g_hs.d_b, aux, dt, ids, g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = host_download(P, g_hs.d_b, qnew))) return rc;
+    return host_finish(cfl);
+}
+
+extern "C" int clawb200_step2_host(const clawb200_problem *p, const double *qold, double *qnew,
+                                   const double *aux, double dt, double *cfl)
+{
+    if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
+    clawb200_problem P = host_layout(p);
+    size_t n = (size_t)P.meqn * P.mstride;
+    int rc = g_hs.ensure(n);
+    if (rc) return rc;
+    if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
+    CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
+    if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = clawb200_step2(&P, g_hs.d_a, g_hs.d_b, aux, dt, g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = host_download(P, g_hs.d_b, qnew))) return rc;
+    return host_finish(cfl);
+}
+
+extern "C" int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const double *q, double *dq,
+                                          const double *aux, double dt, double *cfl)
+{
+    if (!p || !q || !dq) return fail(CLAWB200_ERR_INVALID, "null argument");
+    clawb200_problem P = host_layout(p);
+    size_t n = (size_t)P.meqn * P.mstride;
+    int rc = g_hs.ensure(n);
+    if (rc) return rc;
+    if ((rc = host_upload(P, q, g_hs.d_a))) return rc;
+    CUDA_OK(cudaMemsetAsync(g_hs.d_b, 0, n * sizeof(double), g_hs.st));
+    if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = clawb200_sharpclaw_stage(&P, g_hs.d_a, nullptr, nullptr, g_hs.d_b, aux, dt,
+                                       CLAWB200_STAGE_DQ_ONLY, 0.0, 0.0, 1.0, g_hs.d_cfl, g_hs.st)))
+        return rc;
+    if ((rc = host_download(P, g_hs.d_b, dq))) return rc;
+    return host_finish(cfl);
+}

@@ -1,0 +1,451 @@
+// rp.cuh -- pointwise Riemann solvers as inlined device functions (sm_100a).
+//
+// One struct per (equation set, sweep direction).  The sweeps in classic.cuh /
+// sharpclaw.cuh instantiate them as template parameters, so the normal solve
+// (rpn2 / rp1) and the transverse solve (rpt2) are inlined into the fused sweep
+// kernels; what the reference passes through the `comroe` common block
+// (development/rp_approaches/rpn2_euler_5wave.f:49-52) travels in registers as
+// the `roe[]` array instead.
+//
+// Arithmetic follows the reference statement by statement, left to right, and the
+// translation unit is compiled with -fmad=false, so results are bit-identical to
+// the strict-IEEE CPU oracle (oracle/claw_oracle.c), which is itself pinned to the
+// reference's golden files.
+//
+// Interface convention (rpn2_euler_5wave.f:24-25): the Riemann problem at interface i
+// has left state qr(:,i-1) and right state ql(:,i); here simply `l[]` and `r[]`.
+#pragma once
+
+#define CLAW_RP_ACOUSTICS 1
+#define CLAW_RP_ADVECTION 2
+#define CLAW_RP_EULER5 3
+#define CLAW_RP_SHALLOW 4
+
+struct RpParams {
+    double p[8];
+};
+
+__device__ __forceinline__ double dmax2(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double dmin2(double a, double b) { return (a < b) ? a : b; }
+
+// ---------------------------------------------------------------------------
+// Acoustics.  clawpack/riemann rp1_acoustics.f, rpn2_acoustics.f, rpt2_acoustics.f
+// (external repository).  cparam{rho,bulk,cc,zz}.
+// NDIM = 1: meqn 2 (p,u); NDIM = 2: meqn 3 (p,u,v).
+// ---------------------------------------------------------------------------
+template <int NDIM, int IXY>
+struct RpAcoustics {
+    static constexpr int ID = CLAW_RP_ACOUSTICS;
+    static constexpr int MEQN = NDIM + 1, MWAVES = 2, NROE = 1;
+    static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
+    __host__ __device__ static constexpr bool nz(int m, int mw) { return m == 0 || m == MU; }
+
+    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[MEQN],
+                                                 const double (&r)[MEQN], double (&wave)[MEQN][MWAVES],
+                                                 double (&s)[MWAVES], double (&amdq)[MEQN],
+                                                 double (&apdq)[MEQN], double (&roe)[NROE])
+    {
+        const double cc = P.p[2], zz = P.p[3];
+        double delta1 = r[0] - l[0];
+        double delta2 = r[MU] - l[MU];
+        double a1 = (-delta1 + zz * delta2) / (2.0 * zz);
+        double a2 = (delta1 + zz * delta2) / (2.0 * zz);
+        wave[0][0] = -a1 * zz;
+        wave[MU][0] = a1;
+        s[0] = -cc;
+        wave[0][1] = a2 * zz;
+        wave[MU][1] = a2;
+        s[1] = cc;
+        if (NDIM == 2) {
+            wave[NDIM == 2 ? MV : 0][0] = 0.0;
+            wave[NDIM == 2 ? MV : 0][1] = 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            amdq[m] = s[0] * wave[m][0];
+            apdq[m] = s[1] * wave[m][1];
+        }
+        roe[0] = 0.0;
+    }
+
+    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&asdq)[MEQN],
+                                                      double (&bm)[MEQN], double (&bp)[MEQN])
+    {
+        const double cc = P.p[2], zz = P.p[3];
+        constexpr int mv = (NDIM == 2) ? MV : 0, mu = (NDIM == 2) ? MU : 0;
+        double a1 = (-asdq[0] + zz * asdq[mv]) / (2.0 * zz);
+        double a2 = (asdq[0] + zz * asdq[mv]) / (2.0 * zz);
+        bm[0] = cc * a1 * zz;
+        bm[mu] = 0.0;
+        bm[mv] = -cc * a1;
+        bp[0] = cc * a2 * zz;
+        bp[mu] = 0.0;
+        bp[mv] = cc * a2;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Scalar advection.  clawpack/riemann rp1_advection.f, rpn2_advection.f,
+// rpt2_advection.f (external).  cparam{u} / {u,v}.
+// ---------------------------------------------------------------------------
+template <int NDIM, int IXY>
+struct RpAdvection {
+    static constexpr int ID = CLAW_RP_ADVECTION;
+    static constexpr int MEQN = 1, MWAVES = 1, NROE = 1;
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+
+    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[1],
+                                                 const double (&r)[1], double (&wave)[1][1],
+                                                 double (&s)[1], double (&amdq)[1],
+                                                 double (&apdq)[1], double (&roe)[NROE])
+    {
+        wave[0][0] = r[0] - l[0];
+        s[0] = (IXY == 2) ? P.p[1] : P.p[0];
+        amdq[0] = dmin2(s[0], 0.0) * wave[0][0];
+        apdq[0] = dmax2(s[0], 0.0) * wave[0][0];
+        roe[0] = 0.0;
+    }
+
+    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&asdq)[1], double (&bm)[1],
+                                                      double (&bp)[1])
+    {
+        double stran = (IXY == 2) ? P.p[0] : P.p[1];
+        double stranm = dmin2(stran, 0.0), stranp = dmax2(stran, 0.0);
+        bm[0] = stranm * asdq[0];
+        bp[0] = stranp * asdq[0];
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Euler, Roe solver, 4 acoustic/shear/entropy waves + tracer wave, entropy fix.
+// development/rp_approaches/rpn2_euler_5wave.f:5-302, rpt2_euler_5wave.f:4-98.
+// cparam{gamma,gamma1}.  roe[] = {u2v2,u,v,enth,a,g1a2,euv} (common /comroe/).
+// ---------------------------------------------------------------------------
+template <int IXY>
+struct RpEuler5 {
+    static constexpr int ID = CLAW_RP_EULER5;
+    static constexpr int MEQN = 5, MWAVES = 5, NROE = 7;
+    static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
+    // sparsity of wave(m,mw) as written at rpn2_euler_5wave.f:124-163
+    __host__ __device__ static constexpr bool nz(int m, int mw)
+    {
+        return (mw == 4) ? (m == 4) : (mw == 1) ? (m == MV || m == 3) : (m != 4);
+    }
+
+    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[5],
+                                                 const double (&r)[5], double (&wave)[5][5],
+                                                 double (&s)[5], double (&amdq)[5],
+                                                 double (&apdq)[5], double (&roe)[NROE])
+    {
+        const double gamma = P.p[0], gamma1 = P.p[1];
+        // :87-104
+        double rhsqrtl = sqrt(l[0]);
+        double rhsqrtr = sqrt(r[0]);
+        double pl = gamma1 * (l[3] - 0.5 * (l[1] * l[1] + l[2] * l[2]) / l[0]);
+        double pr = gamma1 * (r[3] - 0.5 * (r[1] * r[1] + r[2] * r[2]) / r[0]);
+        double rhsq2 = rhsqrtl + rhsqrtr;
+        double u = (l[MU] / rhsqrtl + r[MU] / rhsqrtr) / rhsq2;
+        double v = (l[MV] / rhsqrtl + r[MV] / rhsqrtr) / rhsq2;
+        double enth = (((l[3] + pl) / rhsqrtl + (r[3] + pr) / rhsqrtr)) / rhsq2;
+        double u2v2 = u * u + v * v;
+        double a2r = gamma1 * (enth - .5 * u2v2);
+        double a = sqrt(a2r);
+        double g1a2 = gamma1 / a2r;
+        double euv = enth - u2v2;
+        roe[0] = u2v2; roe[1] = u; roe[2] = v; roe[3] = enth; roe[4] = a; roe[5] = g1a2; roe[6] = euv;
+        // :110-119
+        double d1 = r[0] - l[0];
+        double d2 = r[MU] - l[MU];
+        double d3 = r[MV] - l[MV];
+        double d4 = r[3] - l[3];
+        double a3 = g1a2 * (euv * d1 + u * d2 + v * d3 - d4);
+        double a2 = d3 - v * d1;
+        double a4 = (d2 + (a - u) * d1 - a * a3) / (2.0 * a);
+        double a1 = d1 - a3 - a4;
+        // :124-163
+        wave[0][0] = a1;
+        wave[MU][0] = a1 * (u - a);
+        wave[MV][0] = a1 * v;
+        wave[3][0] = a1 * (enth - u * a);
+        wave[4][0] = 0.0;
+        s[0] = u - a;
+        wave[0][1] = 0.0;
+        wave[MU][1] = 0.0;
+        wave[MV][1] = a2;
+        wave[3][1] = a2 * v;
+        wave[4][1] = 0.0;
+        s[1] = u;
+        wave[0][2] = a3;
+        wave[MU][2] = a3 * u;
+        wave[MV][2] = a3 * v;
+        wave[3][2] = a3 * 0.5 * u2v2;
+        wave[4][2] = 0.0;
+        s[2] = u;
+        wave[0][3] = a4;
+        wave[MU][3] = a4 * (u + a);
+        wave[MV][3] = a4 * v;
+        wave[3][3] = a4 * (enth + u * a);
+        wave[4][3] = 0.0;
+        s[3] = u + a;
+        wave[0][4] = 0.0;
+        wave[MU][4] = 0.0;
+        wave[MV][4] = 0.0;
+        wave[3][4] = 0.0;
+        wave[4][4] = r[4] - l[4];
+        s[4] = u;
+        // :205-286 entropy fix
+        bool done = false;
+        {
+            double rhoim1 = l[0];
+            double pim1 = gamma1 * (l[3] - 0.5 * (l[MU] * l[MU] + l[MV] * l[MV]) / rhoim1);
+            double cim1 = sqrt(gamma * pim1 / rhoim1);
+            double s0 = l[MU] / rhoim1 - cim1;
+            if (s0 >= 0.0 && s[0] > 0.0) {
+#pragma unroll
+                for (int m = 0; m < 5; m++) amdq[m] = 0.0;
+                done = true;
+            }
+            if (!done) {
+                double rho1 = l[0] + wave[0][0];
+                double rhou1 = l[MU] + wave[MU][0];
+                double rhov1 = l[MV] + wave[MV][0];
+                double en1 = l[3] + wave[3][0];
+                double p1 = gamma1 * (en1 - 0.5 * (rhou1 * rhou1 + rhov1 * rhov1) / rho1);
+                double c1 = sqrt(gamma * p1 / rho1);
+                double s1 = rhou1 / rho1 - c1;
+                double sfract;
+                if (s0 < 0.0 && s1 > 0.0)
+                    sfract = s0 * (s1 - s[0]) / (s1 - s0);
+                else if (s[0] < 0.0)
+                    sfract = s[0];
+                else
+                    sfract = 0.0;
+#pragma unroll
+                for (int m = 0; m < 5; m++) amdq[m] = sfract * wave[m][0];
+                if (s[1] >= 0.0) done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+                amdq[m] = amdq[m] + s[1] * wave[m][1];
+                amdq[m] = amdq[m] + s[2] * wave[m][2];
+                amdq[m] = amdq[m] + s[4] * wave[m][4];
+            }
+            double rhoi = r[0];
+            double pi = gamma1 * (r[3] - 0.5 * (r[MU] * r[MU] + r[MV] * r[MV]) / rhoi);
+            double ci = sqrt(gamma * pi / rhoi);
+            double s3 = r[MU] / rhoi + ci;
+            double rho2 = r[0] - wave[0][3];
+            double rhou2 = r[MU] - wave[MU][3];
+            double rhov2 = r[MV] - wave[MV][3];
+            double en2 = r[3] - wave[3][3];
+            double p2 = gamma1 * (en2 - 0.5 * (rhou2 * rhou2 + rhov2 * rhov2) / rho2);
+            double c2 = sqrt(gamma * p2 / rho2);
+            double s2 = rhou2 / rho2 + c2;
+            double sfract = 0.0;
+            bool add4 = true;
+            if (s2 < 0.0 && s3 > 0.0)
+                sfract = s2 * (s3 - s[3]) / (s3 - s2);
+            else if (s[3] < 0.0)
+                sfract = s[3];
+            else
+                add4 = false;
+            if (add4) {
+#pragma unroll
+                for (int m = 0; m < 5; m++) amdq[m] = amdq[m] + sfract * wave[m][3];
+            }
+        }
+        // :291-298
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            double df = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 5; mw++) df = df + s[mw] * wave[m][mw];
+            apdq[m] = df - amdq[m];
+        }
+    }
+
+    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&asdq)[5], double (&bm)[5],
+                                                      double (&bp)[5])
+    {
+        const double u2v2 = roe[0], u = roe[1], v = roe[2], enth = roe[3], a = roe[4],
+                     g1a2 = roe[5], euv = roe[6];
+        double a3 = g1a2 * (euv * asdq[0] + u * asdq[MU] + v * asdq[MV] - asdq[3]);
+        double a2 = asdq[MU] - u * asdq[0];
+        double a4 = (asdq[MV] + (a - v) * asdq[0] - a * a3) / (2.0 * a);
+        double a1 = asdq[0] - a3 - a4;
+        double waveb[5][4], sb[4];
+        waveb[0][0] = a1;
+        waveb[MU][0] = a1 * u;
+        waveb[MV][0] = a1 * (v - a);
+        waveb[3][0] = a1 * (enth - v * a);
+        waveb[4][0] = 0.0;
+        sb[0] = v - a;
+        waveb[0][1] = a3;
+        waveb[MU][1] = a3 * u + a2;
+        waveb[MV][1] = a3 * v;
+        waveb[3][1] = a3 * 0.5 * u2v2 + a2 * u;
+        waveb[4][1] = 0.0;
+        sb[1] = v;
+        waveb[0][2] = a4;
+        waveb[MU][2] = a4 * u;
+        waveb[MV][2] = a4 * (v + a);
+        waveb[3][2] = a4 * (enth + v * a);
+        waveb[4][2] = 0.0;
+        sb[2] = v + a;
+        waveb[0][3] = 0.0;
+        waveb[MU][3] = 0.0;
+        waveb[MV][3] = 0.0;
+        waveb[3][3] = 0.0;
+        waveb[4][3] = asdq[4];
+        sb[3] = v;
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            bm[m] = 0.0;
+            bp[m] = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 4; mw++) {
+                bm[m] = bm[m] + dmin2(sb[mw], 0.0) * waveb[m][mw];
+                bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Shallow water, Roe solver with entropy fix.
+// clawpack/riemann rpn2_shallow_roe_with_efix.f, rpt2_shallow_roe_with_efix.f
+// (external).  cparam{grav}.  roe[] = {u,v,a}.
+// ---------------------------------------------------------------------------
+template <int IXY>
+struct RpShallow {
+    static constexpr int ID = CLAW_RP_SHALLOW;
+    static constexpr int MEQN = 3, MWAVES = 3, NROE = 3;
+    static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
+    __host__ __device__ static constexpr bool nz(int m, int mw)
+    {
+        return (mw == 1) ? (m == MV) : true;
+    }
+
+    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[3],
+                                                 const double (&r)[3], double (&wave)[3][3],
+                                                 double (&s)[3], double (&amdq)[3],
+                                                 double (&apdq)[3], double (&roe)[NROE])
+    {
+        const double grav = P.p[0];
+        double h = (l[0] + r[0]) * 0.50;
+        double hsqrtl = sqrt(l[0]);
+        double hsqrtr = sqrt(r[0]);
+        double hsq2 = hsqrtl + hsqrtr;
+        double u = (l[MU] / hsqrtl + r[MU] / hsqrtr) / hsq2;
+        double v = (l[MV] / hsqrtl + r[MV] / hsqrtr) / hsq2;
+        double a = sqrt(grav * h);
+        roe[0] = u; roe[1] = v; roe[2] = a;
+        double d1 = r[0] - l[0];
+        double d2 = r[MU] - l[MU];
+        double d3 = r[MV] - l[MV];
+        double a1 = ((u + a) * d1 - d2) * (0.50 / a);
+        double a2 = -v * d1 + d3;
+        double a3 = (-(u - a) * d1 + d2) * (0.50 / a);
+        wave[0][0] = a1;
+        wave[MU][0] = a1 * (u - a);
+        wave[MV][0] = a1 * v;
+        s[0] = u - a;
+        wave[0][1] = 0.0;
+        wave[MU][1] = 0.0;
+        wave[MV][1] = a2;
+        s[1] = u;
+        wave[0][2] = a3;
+        wave[MU][2] = a3 * (u + a);
+        wave[MV][2] = a3 * v;
+        s[2] = u + a;
+        bool done = false;
+        double him1 = l[0];
+        double s0 = l[MU] / him1 - sqrt(grav * him1);
+        if (s0 > 0.0 && s[0] > 0.0) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) amdq[m] = 0.0;
+            done = true;
+        }
+        if (!done) {
+            double h1 = l[0] + wave[0][0];
+            double hu1 = l[MU] + wave[MU][0];
+            double s1 = hu1 / h1 - sqrt(grav * h1);
+            double sfract;
+            if (s0 < 0.0 && s1 > 0.0)
+                sfract = s0 * ((s1 - s[0]) / (s1 - s0));
+            else if (s[0] < 0.0)
+                sfract = s[0];
+            else
+                sfract = 0.0;
+#pragma unroll
+            for (int m = 0; m < 3; m++) amdq[m] = sfract * wave[m][0];
+            if (s[1] > 0.0) done = true;
+        }
+        if (!done) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) amdq[m] = amdq[m] + s[1] * wave[m][1];
+            double hi = r[0];
+            double s03 = r[MU] / hi + sqrt(grav * hi);
+            double h3 = r[0] - wave[0][2];
+            double hu3 = r[MU] - wave[MU][2];
+            double s3 = hu3 / h3 + sqrt(grav * h3);
+            double sfract = 0.0;
+            bool add3 = true;
+            if (s3 < 0.0 && s03 > 0.0)
+                sfract = s3 * ((s03 - s[2]) / (s03 - s3));
+            else if (s[2] < 0.0)
+                sfract = s[2];
+            else
+                add3 = false;
+            if (add3) {
+#pragma unroll
+                for (int m = 0; m < 3; m++) amdq[m] = amdq[m] + sfract * wave[m][2];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            double df = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 3; mw++) df = df + s[mw] * wave[m][mw];
+            apdq[m] = df - amdq[m];
+        }
+    }
+
+    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&asdq)[3], double (&bm)[3],
+                                                      double (&bp)[3])
+    {
+        const double u = roe[0], v = roe[1], a = roe[2];
+        double a1 = (0.50 / a) * ((v + a) * asdq[0] - asdq[MV]);
+        double a2 = asdq[MU] - u * asdq[0];
+        double a3 = (0.50 / a) * (-(v - a) * asdq[0] + asdq[MV]);
+        double waveb[3][3], sb[3];
+        waveb[0][0] = a1;
+        waveb[MU][0] = a1 * u;
+        waveb[MV][0] = a1 * (v - a);
+        sb[0] = v - a;
+        waveb[0][1] = 0.0;
+        waveb[MU][1] = a2;
+        waveb[MV][1] = 0.0;
+        sb[1] = v;
+        waveb[0][2] = a3;
+        waveb[MU][2] = a3 * u;
+        waveb[MV][2] = a3 * (v + a);
+        sb[2] = v + a;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            bm[m] = 0.0;
+            bp[m] = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 3; mw++) {
+                bm[m] = bm[m] + dmin2(sb[mw], 0.0) * waveb[m][mw];
+                bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
+            }
+        }
+    }
+};

@@ -1,0 +1,326 @@
+// sharpclaw.cuh -- SharpClaw: WENO5 reconstruction + interface / in-cell Riemann
+// solves + fluctuation sum, fused with the SSP Runge-Kutta stage update (sm_100a).
+//
+// Replaces  src/fortran/2d/sharpclaw/flux2.f90:2-96 -> src/fortran/1d/sharpclaw/flux1.f90:2-195
+//           -> reconstruct.f90:85-116 (weno_comp) -> weno.f90:5-102 (PyWENO weno5)
+//           or reconstruct.f90:120-185 (hand-written weno5, lim_type 3)
+// and the numpy stage arithmetic of src/pyclaw/sharpclaw.py:172-206.
+//
+// One thread per column i.  The x-direction of a row is done through shared memory
+// (neighbouring threads hold neighbouring cells), the y-direction is a rolling 5-row
+// window private to the thread, so q is read once and the stage result written once.
+// dq = (0 + dq_x) + dq_y exactly as flux2.f90 accumulates it.
+#pragma once
+#include "rp.cuh"
+
+struct ScArgs {
+    const double *q;  // stage state, ghost cells filled
+    const double *qa; // second register of the RK combination (or null)
+    double *out;
+    double *dq_out;
+    long long mstride;
+    int pitch;
+    int mx, my, mbc;
+    double dtdx, dtdy;
+    RpParams rp;
+    // PyWENO coefficients (weno.f90:35-90), already rounded the way the chosen
+    // variant reads the literals
+    double c333, c1033, c366, c833, c633, c133, c433, c166;
+    double d01, d06, d03, eps;
+    double r183, r116, r0333, r0833, r0166;
+    double epweno; // reconstruct.f90:7
+    int mode;
+    double ca, cb, div;
+    unsigned long long *cfl_bits;
+    int rows_per_cta;
+};
+
+// weno.f90:35-98 for one component of one cell: ql = value at the left edge, qr at the right
+__device__ __forceinline__ void weno5_pyweno(const ScArgs &A, double qm2, double qm1, double q0,
+                                             double qp1, double qp2, double &ql, double &qr)
+{
+    double sigma0 = ((A.c333) * q0) * q0 + ((-A.c1033) * q0) * qp1 + ((A.c366) * q0) * qp2 +
+                    ((A.c833) * qp1) * qp1 + ((-A.c633) * qp1) * qp2 + ((A.c133) * qp2) * qp2;
+    double sigma1 = ((A.c133) * qm1) * qm1 + ((-A.c433) * qm1) * q0 + ((A.c166) * qm1) * qp1 +
+                    ((A.c433) * q0) * q0 + ((-A.c433) * q0) * qp1 + ((A.c133) * qp1) * qp1;
+    double sigma2 = ((A.c133) * qm2) * qm2 + ((-A.c633) * qm2) * qm1 + ((A.c366) * qm2) * q0 +
+                    ((A.c833) * qm1) * qm1 + ((-A.c1033) * qm1) * q0 + ((A.c333) * q0) * q0;
+    double e0 = (sigma0 + A.eps) * (sigma0 + A.eps);
+    double e1 = (sigma1 + A.eps) * (sigma1 + A.eps);
+    double e2 = (sigma2 + A.eps) * (sigma2 + A.eps);
+    double acc = 0.0;
+    double omega0 = A.d01 / e0;
+    acc = acc + omega0;
+    double omega1 = A.d06 / e1;
+    acc = acc + omega1;
+    double omega2 = A.d03 / e2;
+    acc = acc + omega2;
+    omega0 = omega0 / acc;
+    omega1 = omega1 / acc;
+    omega2 = omega2 / acc;
+    acc = 0.0;
+    double omega3 = A.d03 / e0;
+    acc = acc + omega3;
+    double omega4 = A.d06 / e1;
+    acc = acc + omega4;
+    double omega5 = A.d01 / e2;
+    acc = acc + omega5;
+    omega3 = omega3 / acc;
+    omega4 = omega4 / acc;
+    omega5 = omega5 / acc;
+    double fr0 = (A.r183) * q0 + (-A.r116) * qp1 + (A.r0333) * qp2;
+    double fr1 = (A.r0333) * qm1 + (A.r0833) * q0 + (-A.r0166) * qp1;
+    double fr2 = (-A.r0166) * qm2 + (A.r0833) * qm1 + (A.r0333) * q0;
+    double fr3 = (A.r0333) * q0 + (A.r0833) * qp1 + (-A.r0166) * qp2;
+    double fr4 = (-A.r0166) * qm1 + (A.r0833) * q0 + (A.r0333) * qp1;
+    double fr5 = (A.r0333) * qm2 + (-A.r116) * qm1 + (A.r183) * q0;
+    ql = omega0 * fr0 + omega1 * fr1 + omega2 * fr2;
+    qr = omega3 * fr3 + omega4 * fr4 + omega5 * fr5;
+}
+
+// reconstruct.f90:136-181 for one side.  (t1,t2,t3,e1,e2,e3) are the side's differences.
+__device__ __forceinline__ double weno5_old_side(double epweno, double t1, double t2, double t3,
+                                                 double e1, double e2, double e3, double base)
+{
+    double tt1 = 13. * (t1 * t1) + 3. * (e1 * e1);
+    double tt2 = 13. * (t2 * t2) + 3. * (e2 * e2);
+    double tt3 = 13. * (t3 * t3) + 3. * (e3 * e3);
+    tt1 = (epweno + tt1) * (epweno + tt1);
+    tt2 = (epweno + tt2) * (epweno + tt2);
+    tt3 = (epweno + tt3) * (epweno + tt3);
+    double s1 = tt2 * tt3;
+    double s2 = 6. * tt1 * tt3;
+    double s3 = 3. * tt1 * tt2;
+    double t0 = 1. / (s1 + s2 + s3);
+    s1 = s1 * t0;
+    s3 = s3 * t0;
+    return (s1 * (t2 - t1) + (0.5 * s3 - 0.25) * (t3 - t2)) / 3. + base;
+}
+
+__device__ __forceinline__ void weno5_old(const ScArgs &A, double a, double b, double c, double d,
+                                          double e, double &ql, double &qr)
+{
+    double d1 = b - a, d2 = c - b, d3 = d - c, d4 = e - d; // dq1m(c-1), dq1m(c), dq1m(c+1), dq1m(c+2)
+    // ql(c): m1 = 2 (im = -1) evaluated at position c
+    ql = weno5_old_side(A.epweno, -(d4 - d3), -(d3 - d2), -(d2 - d1), d4 - 3. * d3, d3 + d2,
+                        3. * d2 - d1, (-a + 7. * (b + c) - d) / 12.);
+    // qr(c): m1 = 1 (im = +1) evaluated at position c+1
+    qr = weno5_old_side(A.epweno, (d1 - d2), (d2 - d3), (d3 - d4), d1 - 3. * d2, d2 + d3,
+                        3. * d3 - d4, (-b + 7. * (c + d) - e) / 12.);
+}
+
+template <bool OLD>
+__device__ __forceinline__ void weno5(const ScArgs &A, double a, double b, double c, double d,
+                                      double e, double &ql, double &qr)
+{
+    if (OLD) weno5_old(A, a, b, c, d, e, ql, qr);
+    else weno5_pyweno(A, a, b, c, d, e, ql, qr);
+}
+
+__device__ __forceinline__ void sc_cfl_commit(double cfl, unsigned long long *cfl_bits)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double other = __shfl_xor_sync(0xffffffffu, cfl, o);
+        cfl = dmax2(cfl, other);
+    }
+    if ((threadIdx.x & 31) == 0 && cfl > 0.0)
+        atomicMax(cfl_bits, (unsigned long long)__double_as_longlong(cfl));
+}
+
+template <int MEQN>
+__device__ __forceinline__ void stage_store(const ScArgs &A, long long idx, const double (&q)[MEQN],
+                                            const double (&dq)[MEQN])
+{
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        const long long o = m * A.mstride + idx;
+        if (A.dq_out) A.dq_out[o] = dq[m];
+        if (A.mode == 0) {
+            A.out[o] = q[m] + dq[m] / A.div;
+        } else if (A.mode == 1) {
+            A.out[o] = A.ca * A.qa[o] + A.cb * (q[m] + dq[m]);
+        } else if (A.mode == 2) {
+            A.out[o] = (A.qa[o] + A.ca * q[m]) + A.cb * dq[m];
+        }
+    }
+}
+
+// x-direction of one row, shared by the 1-D and 2-D kernels.  On entry qs holds the
+// staged row (index k <-> cell i0-3+k).  Returns dq_x for the thread's cell; full=false
+// computes only the interface solve (rows 0 and my+1 contribute to the CFL number only).
+template <class RP, bool OLD, int NT>
+__device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, double *x1, double *x2,
+                                        int t, bool iface_cfl, bool full, double &cfl,
+                                        double (&dqx)[RP::MEQN])
+{
+    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    constexpr int QS = NT + 4;
+    double ql[MEQN], qr[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        const double *row = qs + m * QS + t;
+        weno5<OLD>(A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m]);
+        x1[m * NT + t] = qr[m];
+    }
+    __syncthreads();
+    double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+    double left[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) left[m] = x1[m * NT + (t > 0 ? t - 1 : 0)];
+    RP::solve(A.rp, left, ql, wave, s, amdq, apdq, roe);
+    if (iface_cfl) {
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, A.dtdx * s[mw]), -A.dtdx * s[mw]);
+    }
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) x2[m * NT + t] = amdq[m];
+    __syncthreads();
+    if (full) {
+        double amdq2[MEQN], apdq2[MEQN];
+        RP::solve(A.rp, ql, qr, wave, s, amdq2, apdq2, roe);
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            double an = x2[m * NT + (t < NT - 1 ? t + 1 : t)];
+            dqx[m] = 0.0 - A.dtdx * (an + apdq[m] + amdq2[m] + apdq2[m]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 2-D: thread t <-> column ic = i0-1+t, output columns t = 1 .. NT-2.
+// ---------------------------------------------------------------------------
+template <class RPX, class RPY, bool OLD, int NT>
+__global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
+{
+    constexpr int MEQN = RPX::MEQN, MW = RPX::MWAVES, NROE = RPX::NROE;
+    constexpr int NC = NT - 2;
+    constexpr int QS = NT + 4;
+    extern __shared__ double sm[];
+    double *qs = sm;             // [MEQN][NT+4]
+    double *x1 = qs + MEQN * QS; // [MEQN][NT]
+    double *x2 = x1 + MEQN * NT; // [MEQN][NT]
+
+    const int t = threadIdx.x;
+    const int mbc = A.mbc;
+    const int i0 = 1 + blockIdx.x * NC;
+    const int ic = i0 - 1 + t;
+    const int imax = A.mx + mbc;
+    const int icl = min(ic, imax) + mbc - 1;
+    const int cstage = min(i0 - 3 + t, imax) + mbc - 1;
+    const int cstage2 = min(i0 - 3 + NT + t, imax) + mbc - 1; // threads 0..3
+    const bool col_out = (t >= 1) && (t <= NC) && (ic <= A.mx);
+    const bool xiface = (t >= 1) && (ic >= 1) && (ic <= A.mx + 1);
+    const bool ycol = (ic >= 0) && (ic <= A.mx + 1);
+    const int j0 = 1 + blockIdx.y * A.rows_per_cta;
+    const int j1 = min(j0 + A.rows_per_cta, A.my + 1);
+
+    double cfl = 0.0;
+    double w0[MEQN], w1[MEQN], w2[MEQN], w3[MEQN], w4[MEQN];
+    double dx1[MEQN], dx2[MEQN], dx3[MEQN], dx4[MEQN];
+    double qr_prev[MEQN], apdq_prev[MEQN], amdq2_prev[MEQN], apdq2_prev[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        w0[m] = w1[m] = w2[m] = w3[m] = w4[m] = 1.0;
+        dx1[m] = dx2[m] = dx3[m] = dx4[m] = 0.0;
+        qr_prev[m] = 1.0; apdq_prev[m] = amdq2_prev[m] = apdq2_prev[m] = 0.0;
+    }
+
+    for (int k = j0 - 3; k <= j1 + 2; k++) {
+        const long long rowoff = (long long)A.pitch * (k + mbc - 1);
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            w0[m] = w1[m]; w1[m] = w2[m]; w2[m] = w3[m]; w3[m] = w4[m];
+            w4[m] = A.q[m * A.mstride + rowoff + icl];
+            dx4[m] = dx3[m]; dx3[m] = dx2[m]; dx2[m] = dx1[m];
+        }
+        const bool xfull = (k >= j0) && (k < j1);
+        const bool xcfl_only = (k == 0 && j0 == 1) || (k == A.my + 1 && j1 == A.my + 1);
+        if (xfull || xcfl_only) {
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                qs[m * QS + t] = A.q[m * A.mstride + rowoff + cstage];
+                if (t < 4) qs[m * QS + NT + t] = A.q[m * A.mstride + rowoff + cstage2];
+            }
+            __syncthreads();
+            sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1);
+        }
+
+        // y-direction: reconstruct cell c = k-2 from rows k-4 .. k
+        const int c = k - 2;
+        if (c >= j0 - 1) {
+            double ql[MEQN], qr[MEQN];
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) weno5<OLD>(A, w0[m], w1[m], w2[m], w3[m], w4[m], ql[m], qr[m]);
+            double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+            double amdq2[MEQN], apdq2[MEQN];
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) { amdq[m] = apdq[m] = amdq2[m] = apdq2[m] = 0.0; }
+            if (c >= j0) {
+                RPY::solve(A.rp, qr_prev, ql, wave, s, amdq, apdq, roe);
+                if (ycol && c >= 1 && c <= A.my + 1) {
+#pragma unroll
+                    for (int mw = 0; mw < MW; mw++)
+                        cfl = dmax2(dmax2(cfl, A.dtdy * s[mw]), -A.dtdy * s[mw]);
+                }
+                if (c < j1) RPY::solve(A.rp, ql, qr, wave, s, amdq2, apdq2, roe);
+                // cell c-1 = k-3 is complete
+                const int jc = c - 1;
+                if (jc >= j0 && jc < j1 && col_out) {
+                    double dq[MEQN];
+#pragma unroll
+                    for (int m = 0; m < MEQN; m++) {
+                        double dqy = 0.0 - A.dtdy * (amdq[m] + apdq_prev[m] + amdq2_prev[m] + apdq2_prev[m]);
+                        dq[m] = (0.0 + dx4[m]) + dqy;
+                    }
+                    stage_store<MEQN>(A, (long long)A.pitch * (jc + mbc - 1) + icl, w1, dq);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                qr_prev[m] = qr[m]; apdq_prev[m] = apdq[m];
+                amdq2_prev[m] = amdq2[m]; apdq2_prev[m] = apdq2[m];
+            }
+        }
+    }
+    sc_cfl_commit(cfl, A.cfl_bits);
+}
+
+// ---------------------------------------------------------------------------
+// 1-D: one row, x-direction only.
+// ---------------------------------------------------------------------------
+template <class RP, bool OLD, int NT>
+__global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
+{
+    constexpr int MEQN = RP::MEQN;
+    constexpr int NC = NT - 2;
+    constexpr int QS = NT + 4;
+    extern __shared__ double sm[];
+    double *qs = sm;
+    double *x1 = qs + MEQN * QS;
+    double *x2 = x1 + MEQN * NT;
+    const int t = threadIdx.x;
+    const int mbc = A.mbc;
+    const int i0 = 1 + blockIdx.x * NC;
+    const int ic = i0 - 1 + t;
+    const int imax = A.mx + mbc;
+    const int icl = min(ic, imax) + mbc - 1;
+    const int cstage = min(i0 - 3 + t, imax) + mbc - 1;
+    const int cstage2 = min(i0 - 3 + NT + t, imax) + mbc - 1;
+    const bool col_out = (t >= 1) && (t <= NC) && (ic <= A.mx);
+    const bool xiface = (t >= 1) && (ic >= 1) && (ic <= A.mx + 1);
+    double cfl = 0.0;
+    double q0[MEQN], dqx[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        qs[m * QS + t] = A.q[m * A.mstride + cstage];
+        if (t < 4) qs[m * QS + NT + t] = A.q[m * A.mstride + cstage2];
+        q0[m] = A.q[m * A.mstride + icl];
+        dqx[m] = 0.0;
+    }
+    __syncthreads();
+    sc_xrow<RP, OLD, NT>(A, qs, x1, x2, t, xiface, true, cfl, dqx);
+    if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
+    sc_cfl_commit(cfl, A.cfl_bits);
+}
+

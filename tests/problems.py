@@ -134,3 +134,40 @@ def random_state(rp, shape, seed=0):
     else:
         raise ValueError(rp)
     return np.asfortranarray(q)
+
+
+def smooth_state(rp, shape, seed=0):
+    """Seeded smooth-plus-jump data (WENO reconstructions of white noise leave the
+    admissible set for Euler); still exercises every entropy-fix branch."""
+    rng = np.random.RandomState(seed)
+    grids = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")
+
+    def field(lo, hi):
+        f = np.zeros(shape)
+        for _ in range(3):
+            ph = rng.uniform(0, 2 * np.pi, len(shape))
+            k = rng.randint(1, 4, len(shape))
+            term = np.ones(shape)
+            for g, kk, p in zip(grids, k, ph):
+                term = term * np.sin(2 * np.pi * kk * g + p)
+            f += term / 3.0
+        cut = rng.uniform(0.3, 0.7)
+        f += 0.5 * (grids[0] > cut) - 0.25
+        f += 0.01 * rng.uniform(-1, 1, shape)
+        f = (f - f.min()) / (f.max() - f.min())
+        return lo + (hi - lo) * f
+
+    if rp == "acoustics":
+        meqn = 2 if len(shape) == 1 else 3
+        q = np.stack([field(-1, 1) for _ in range(meqn)])
+    elif rp == "advection":
+        q = np.stack([field(0, 1)])
+    elif rp == "euler":
+        rho, u, v, p = field(0.6, 1.6), field(-1.6, 1.6), field(-1.6, 1.6), field(0.6, 1.6)
+        q = np.stack([rho, rho * u, rho * v, p / GAMMA1 + 0.5 * rho * (u * u + v * v), field(0, 1)])
+    elif rp == "shallow":
+        h = field(0.6, 1.6)
+        q = np.stack([h, h * field(-1.6, 1.6), h * field(-1.6, 1.6)])
+    else:
+        raise ValueError(rp)
+    return np.asfortranarray(q)

@@ -1,0 +1,154 @@
+"""
+Kernel-level parity: the CUDA sweeps, called through the C ABI's host-pointer entry
+points (the f2py-shaped signatures of include/clawb200.h), against the CPU oracle on the
+same seeded inputs.  Everything here is float64 and must agree BIT FOR BIT.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import problems
+from oracle import pyclaw_oracle as po
+from pyclaw_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+RPS = {
+    # name: (rp_id, params, meqn(2d), mwaves, limiters)
+    "acoustics": (1, [1.0, 4.0, 2.0, 2.0], 3, 2, [4, 4]),
+    "advection": (2, [0.7, -0.4], 1, 1, [3]),
+    "euler": (3, [1.4, 0.4], 5, 5, [4, 4, 4, 4, 2]),
+    "shallow": (4, [1.0], 3, 3, [4, 1, 2]),
+}
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _random_padded(rp, mx, my, mbc, seed, smooth=False):
+    shape = (mx + 2 * mbc, my + 2 * mbc) if my else (mx + 2 * mbc,)
+    q = (problems.smooth_state if smooth else problems.random_state)(rp, shape, seed)
+    return q
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "euler", "shallow"])
+@pytest.mark.parametrize("shape", [(37, 29), (130, 70), (251, 9)])
+@pytest.mark.parametrize("order", [1, 2])
+def test_step2ds(rp, shape, order):
+    rp_id, params, meqn, mwaves, lim = RPS[rp]
+    mx, my = shape
+    mbc = 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    method = [1, order, -1, 0, 0, 0, 0]
+    q = _random_padded(rp, mx, my, mbc, seed=mx + order)
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    for ids in (1, 2):
+        qn_o = q.copy("F")
+        cfl_o = po.step2ds(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim, ids)
+        qn_g = q.copy("F")
+        cfl_g = ctypes.c_double()
+        _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt, ids,
+                  ctypes.byref(cfl_g))
+        # the GPU sweep updates exactly the cells the Fortran updates
+        assert np.array_equal(qn_g, qn_o), (rp, ids, np.abs(qn_g - qn_o).max())
+        assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "euler", "shallow"])
+@pytest.mark.parametrize("shape", [(37, 29), (130, 70), (9, 251)])
+@pytest.mark.parametrize("order,trans", [(2, 2), (2, 1), (1, 1), (2, 0)])
+def test_step2_unsplit(rp, shape, order, trans):
+    rp_id, params, meqn, mwaves, lim = RPS[rp]
+    mx, my = shape
+    mbc = 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    method = [1, order, trans, 0, 0, 0, 0]
+    q = _random_padded(rp, mx, my, mbc, seed=my + trans)
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    qn_o = q.copy("F")
+    cfl_o = po.step2(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim)
+    qn_g = q.copy("F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt,
+              ctypes.byref(cfl_g))
+    # only interior cells are defined output (clawpack.py:555 keeps qbc[:,mbc:-mbc,mbc:-mbc])
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    assert np.array_equal(qn_g[inner], qn_o[inner]), (rp, np.abs(qn_g[inner] - qn_o[inner]).max())
+    assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection"])
+@pytest.mark.parametrize("mx", [5, 100, 800, 1001])
+@pytest.mark.parametrize("order", [1, 2])
+def test_step1(rp, mx, order):
+    rp_id, params, _, mwaves, lim = RPS[rp]
+    meqn = 2 if rp == "acoustics" else 1
+    params = [1.0, 1.0, 1.0, 1.0] if rp == "acoustics" else params
+    mbc = 2
+    dx, dt = 1.0 / mx, 0.4 / mx
+    method = [1, order, 0, 0, 0, 0, 0]
+    q = _random_padded(rp, mx, 0, mbc, seed=mx)
+    P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, method, lim)
+    q_o = q.copy("F")
+    cfl_o = po.step1(rp_id, params, mbc, mx, q_o, None, dx, dt, method, lim)
+    q_g = q.copy("F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_step1_host", ctypes.byref(P), _ptr(q_g), None, dt, ctypes.byref(cfl_g))
+    assert np.array_equal(q_g[:, mbc:-mbc], q_o[:, mbc:-mbc])
+    assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "euler", "shallow"])
+@pytest.mark.parametrize("shape", [(37, 29), (130, 70), (9, 140)])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_sharpclaw_dq2(rp, shape, variant):
+    rp_id, params, meqn, mwaves, _ = RPS[rp]
+    mx, my = shape
+    mbc = 3
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    q = _random_padded(rp, mx, my, mbc, seed=mx + variant, smooth=True)
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, weno_variant=variant)
+    dq_o, cfl_o = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, variant)
+    dq_g = np.zeros_like(q, order="F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt,
+              ctypes.byref(cfl_g))
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    assert not np.isnan(dq_o).any()
+    assert np.array_equal(dq_g[inner], dq_o[inner]), (rp, np.abs(dq_g[inner] - dq_o[inner]).max())
+    assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection"])
+@pytest.mark.parametrize("mx", [7, 100, 1001])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_sharpclaw_dq1(rp, mx, variant):
+    rp_id, params, _, mwaves, _ = RPS[rp]
+    meqn = 2 if rp == "acoustics" else 1
+    params = [1.0, 1.0, 1.0, 1.0] if rp == "acoustics" else params
+    mbc = 3
+    dx, dt = 1.0 / mx, 0.4 / mx
+    q = _random_padded(rp, mx, 0, mbc, seed=mx)
+    P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, weno_variant=variant)
+    dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, variant)
+    dq_g = np.zeros_like(q, order="F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt,
+              ctypes.byref(cfl_g))
+    assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc])
+    assert cfl_g.value == cfl_o
+
+
+def test_errors_are_reported_not_fatal():
+    P = _lib.make_problem(2, 5, 5, 2, 16, 16, 0.1, 0.1, 3, [1.4, 0.4], [1, 2, 2, 0, 0, 1, 1], [4] * 5)
+    q = np.zeros((5, 20, 20), order="F")
+    cfl = ctypes.c_double()
+    with pytest.raises(_lib.ClawB200Error):
+        _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(q.copy("F")), None, 0.1,
+                  ctypes.byref(cfl))
+    P2 = _lib.make_problem(2, 4, 5, 2, 16, 16, 0.1, 0.1, 3, [1.4, 0.4], None, [4] * 5)
+    with pytest.raises(_lib.ClawB200Error):
+        _lib.call("clawb200_step2_host", ctypes.byref(P2), _ptr(q), _ptr(q.copy("F")), None, 0.1,
+                  ctypes.byref(cfl))
