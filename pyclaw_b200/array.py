@@ -1,0 +1,35 @@
+"""Device array type handed to user code (state.q, state.aux, qbc in BC callbacks).
+
+A thin torch.Tensor subclass so that the idioms of existing PyClaw scripts keep
+working on device-resident data: ``state.q[0,:,:] = <numpy expression>``,
+``numpy.loadtxt(...) - q[0]``, ``q.reshape([-1])``.
+"""
+import numpy as np
+import torch
+
+
+class ClawArray(torch.Tensor):
+    def __setitem__(self, key, value):
+        if isinstance(value, np.ndarray):
+            value = torch.as_tensor(np.ascontiguousarray(value), dtype=self.dtype).to(self.device)
+        return super().__setitem__(key, value)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.detach().as_subclass(torch.Tensor).cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def copy(self, order="F"):
+        """numpy-style copy (solver.py:660 ``state.q.copy('F')``)."""
+        return self.clone()
+
+    def flatten_f(self):
+        """Fortran-order flattening, as ``ndarray.flatten('f')``."""
+        return self.permute(*reversed(range(self.dim()))).reshape(-1)
+
+
+def as_claw(t):
+    return t.as_subclass(ClawArray)
+
+
+def default_device():
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")

@@ -1,0 +1,163 @@
+"""Classic Clawpack solvers (src/pyclaw/clawpack.py:24-558) on the sm_100a sweep kernels.
+
+``ClawSolver1D/2D.step_hyperbolic`` call libclawb200.so through ctypes where the
+reference imports the f2py modules ``classic1`` / ``classic2`` (clawpack.py:317-323,
+532-552).  q never leaves the GPU; the only host synchronisation per step is the
+8-byte Courant number that evolve_to_time needs to accept or reject the step.
+"""
+import ctypes
+
+from . import _lib, limiters
+from .solver import Solver, _ptr, _stream
+
+
+class ClawSolver(Solver):
+    r"""
+    Generic classic Clawpack solver (clawpack.py:24-87).  Attributes: limiters (mthlim),
+    order, src_split, fwave, step_src, start_step, kernel_language, verbosity.
+    """
+
+    def __init__(self, data=None):
+        self._required_attrs = list(Solver._base_required) + \
+            ['limiters', 'order', 'src_split', 'fwave', 'step_src', 'start_step']
+        d = dict(Solver._base_defaults)
+        d.update({'mbc': 2, 'limiters': limiters.tvd.minmod, 'order': 2, 'src_split': 1,
+                  'fwave': False, 'step_src': None, 'start_step': None,
+                  'kernel_language': 'Fortran', 'verbosity': 0, 'cfl_max': 1.0, 'cfl_desired': 0.9})
+        d.update(getattr(self, '_extra_defaults', {}))
+        self._default_attr_values = d
+        super(ClawSolver, self).__init__(data)
+
+    # ---- clawpack.py:114-165 ----
+    def step(self, solution):
+        if self.start_step is not None:
+            self.start_step(self, solution)
+        if self.src_split == 2 and self.step_src is not None:
+            self.step_src(self, solution.states[0], self.dt / 2.0)
+        self.step_hyperbolic(solution)
+        # a step that will be rejected skips the source term (clawpack.py:153-154)
+        if self.cfl.get_cached_max() >= self.cfl_max:
+            return False
+        if self.step_src is not None:
+            if self.src_split == 2:
+                self.step_src(self, solution.states[0], self.dt / 2.0)
+            if self.src_split == 1:
+                self.step_src(self, solution.states[0], self.dt)
+        return True
+
+    def _needs_backup_copy(self):
+        return self.start_step is not None or (self.src_split == 2 and self.step_src is not None)
+
+    def check_cfl_settings(self):
+        pass
+
+    def step_hyperbolic(self, solution):
+        raise Exception("Dummy routine, please override!")
+
+    def set_mthlim(self):
+        """clawpack.py:181-190"""
+        self.mthlim = self.limiters
+        if not isinstance(self.limiters, list):
+            self.mthlim = [self.mthlim]
+        if len(self.mthlim) == 1:
+            self.mthlim = self.mthlim * self.mwaves
+        if len(self.mthlim) != self.mwaves:
+            raise Exception('Length of solver.limiters is not equal to 1 or to solver.mwaves')
+
+    def set_method(self, state):
+        """The Fortran ``method`` array (clawpack.py:192-212)."""
+        self.method = [0] * 7
+        self.method[0] = int(self.dt_variable)
+        self.method[1] = self.order
+        if self.ndim == 1:
+            self.method[2] = 0
+        elif self.dim_split:
+            self.method[2] = -1
+        else:
+            self.method[2] = self.order_trans
+        self.method[3] = self.verbosity
+        self.method[4] = 0
+        self.method[5] = state.mcapa + 1
+        self.method[6] = state.maux
+
+    def setup(self, solution):
+        """clawpack.py:214-238"""
+        if self.kernel_language not in ('Fortran', 'CUDA'):
+            raise NotImplementedError("kernel_language=%r: only the CUDA kernels exist ('Fortran' is "
+                                      "accepted as an alias); there is no Python/CPU path" % self.kernel_language)
+        if self.fwave:
+            raise NotImplementedError("f-wave solvers (classic*fw) are not implemented yet")
+        state = solution.state
+        state.set_mbc(self.mbc)
+        self.check_cfl_settings()
+        self.set_mthlim()
+        self.set_method(state)
+        self._setup_device(state, method=self.method, mthlim=self.mthlim)
+        self.allocate_bc_arrays(state)
+
+    def teardown(self):
+        pass
+
+
+class ClawSolver1D(ClawSolver):
+    """clawpack.py:271-406"""
+
+    def __init__(self, data=None):
+        self.ndim = 1
+        super(ClawSolver1D, self).__init__(data)
+
+    def step_hyperbolic(self, solution):
+        state = solution.states[0]
+        self.apply_q_bcs(state)
+        qnew = state._q.get_spare()
+        st = _stream()
+        _lib.call("clawb200_cfl_reset", _ptr(self._cfl_dev), st)
+        _lib.call("clawb200_step1", ctypes.byref(self._problem), _ptr(state._q.cur), _ptr(qnew),
+                  _ptr(state._aux.cur if state._aux is not None else None), float(self.dt),
+                  _ptr(self._cfl_dev), st)
+        state._commit(qnew)
+        self.cfl.update_global_max(self._read_cfl()[0])
+
+
+class ClawSolver2D(ClawSolver):
+    """clawpack.py:411-558.  dim_split / order_trans as in the reference."""
+    no_trans = 0
+    trans_inc = 1
+    trans_cor = 2
+
+    def __init__(self, data=None):
+        self._extra_defaults = {'dim_split': True, 'order_trans': self.trans_inc}
+        self.ndim = 2
+        super(ClawSolver2D, self).__init__(data)
+
+    def check_cfl_settings(self):
+        if (not self.dim_split) and (self.order_trans == 0):
+            cfl_recommended = 0.5
+        else:
+            cfl_recommended = 1.0
+        if self.cfl_max > cfl_recommended:
+            import warnings
+            warnings.warn('cfl_max is set higher than the recommended value of %s' % cfl_recommended)
+
+    def step_hyperbolic(self, solution):
+        state = solution.states[0]
+        self.apply_q_bcs(state)
+        P = ctypes.byref(self._problem)
+        aux = _ptr(state._aux.cur if state._aux is not None else None)
+        st = _stream()
+        dt = float(self.dt)
+        cfl = _ptr(self._cfl_dev)
+        _lib.call("clawb200_cfl_reset", cfl, st)
+        qold = state._q.cur
+        qnew = state._q.get_spare()
+        if self.dim_split:
+            # step2ds twice (clawpack.py:538-548); the Fortran's in-place second call is a
+            # ping-pong here: qold -> tmp (x-sweeps) -> qnew (y-sweeps)
+            tmp = state._q.get_spare()
+            _lib.call("clawb200_step2ds", P, _ptr(qold), _ptr(tmp), aux, dt, 1, cfl, st)
+            _lib.call("clawb200_step2ds", P, _ptr(tmp), _ptr(qnew), aux, dt, 2, cfl, st)
+            state._q.put_spare(tmp)
+        else:
+            _lib.call("clawb200_step2", P, _ptr(qold), _ptr(qnew), aux, dt, cfl, st)
+        state._commit(qnew)
+        self.cfl.update_global_max(self._read_cfl()[0])

@@ -1,0 +1,75 @@
+"""Riemann-solver descriptors.
+
+The reference bakes the Riemann solver into classic2.so / sharpclaw2.so at link time
+(RP_SOURCE in each application's Makefile, e.g. apps/euler/2d/shockbubble/Makefile:3), so
+its scripts never name the solver in Python.  Here ``solver.rp`` may be set to one of
+these descriptors (or its name); if it is left unset the solver is inferred from the
+keys of ``state.aux_global`` (the cparam common block the script fills).
+"""
+from .._lib import RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW
+
+
+class RiemannSolver(object):
+    def __init__(self, name, rp_id, meqn, mwaves, param_names, ndims):
+        self.name, self.rp_id, self.mwaves, self.param_names, self.ndims = name, rp_id, mwaves, param_names, ndims
+        self._meqn = meqn
+
+    def meqn(self, ndim):
+        return self._meqn(ndim) if callable(self._meqn) else self._meqn
+
+    def params(self, aux_global):
+        missing = [k for k in self.param_names if k not in aux_global]
+        if missing and not (self.rp_id == RP_ADVECTION and missing == ["v"]):
+            # state.py:154-158: every cparam variable must be present in aux_global
+            raise Exception("Some required value(s) in the cparam common block in the Riemann "
+                            "solver have not been set in aux_global: %s" % missing)
+        return [float(aux_global.get(k, 0.0)) for k in self.param_names]
+
+    def __repr__(self):
+        return "<riemann %s>" % self.name
+
+
+acoustics = RiemannSolver("acoustics", RP_ACOUSTICS, lambda ndim: ndim + 1, 2, ["rho", "bulk", "cc", "zz"], (1, 2))
+advection = RiemannSolver("advection", RP_ADVECTION, 1, 1, ["u", "v"], (1, 2))
+euler_5wave = RiemannSolver("euler_5wave", RP_EULER5, 5, 5, ["gamma", "gamma1"], (2,))
+shallow_roe_with_efix = RiemannSolver("shallow_roe_with_efix", RP_SHALLOW, 3, 3, ["grav"], (2,))
+
+_BY_NAME = {s.name: s for s in (acoustics, advection, euler_5wave, shallow_roe_with_efix)}
+_BY_NAME.update({"euler": euler_5wave, "shallow": shallow_roe_with_efix})
+
+
+class _Module(object):
+    """Mimics ``riemann.rp_acoustics.rp_acoustics_1d`` style access."""
+
+    def __init__(self, solver, names):
+        self.mwaves = solver.mwaves
+        for n in names:
+            setattr(self, n, solver)
+
+
+rp_acoustics = _Module(acoustics, ["rp_acoustics_1d", "rp_acoustics_2d"])
+rp_advection = _Module(advection, ["rp_advection_1d", "rp_advection_2d"])
+rp_euler = _Module(euler_5wave, ["rp_euler_5wave_2d"])
+rp_shallow = _Module(shallow_roe_with_efix, ["rp_shallow_roe_with_efix_2d"])
+
+
+def resolve(rp, aux_global, ndim):
+    if isinstance(rp, RiemannSolver):
+        return rp
+    if isinstance(rp, str):
+        if rp not in _BY_NAME:
+            raise Exception("Unknown Riemann solver %r" % rp)
+        return _BY_NAME[rp]
+    if rp is not None:
+        raise NotImplementedError("Python Riemann solvers are not supported: there is no CPU "
+                                  "path; set solver.rp to a pyclaw.riemann descriptor")
+    keys = set(aux_global.keys())
+    if {"rho", "bulk", "cc", "zz"} <= keys:
+        return acoustics
+    if {"gamma", "gamma1"} <= keys:
+        return euler_5wave
+    if "grav" in keys:
+        return shallow_roe_with_efix
+    if "u" in keys:
+        return advection
+    raise Exception("Cannot infer the Riemann solver from aux_global keys %s; set solver.rp" % sorted(keys))

@@ -1,0 +1,304 @@
+"""
+End-to-end parity through the PyClaw API (``import pyclaw`` -> pyclaw_b200): the
+reference's own regression problems (test/test_examples.py) run on the GPU and are
+compared with the reference's golden files and with the CPU oracle driver.
+The scripts below follow test/acoustics/*/acoustics.py and test/euler/2d/shockbubble.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import problems
+from oracle import pyclaw_oracle as po
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _acoustics1d(solver_type, **opts):
+    import pyclaw
+    if solver_type == 'classic':
+        solver = pyclaw.ClawSolver1D()
+    else:
+        solver = pyclaw.SharpClawSolver1D()
+        solver.weno_order = 5
+    for k, v in opts.items():
+        setattr(solver, k, v)
+    x = pyclaw.Dimension('x', 0.0, 1.0, 100)
+    grid = pyclaw.Grid(x)
+    state = pyclaw.State(grid, 2)
+    rho, bulk = 1.0, 1.0
+    state.aux_global['rho'] = rho
+    state.aux_global['bulk'] = bulk
+    state.aux_global['zz'] = np.sqrt(rho * bulk)
+    state.aux_global['cc'] = np.sqrt(rho / bulk)
+    xc = grid.x.center
+    state.q[0, :] = np.exp(-100 * (xc - 0.75) ** 2) * np.cos(0 * (xc - 0.75))
+    state.q[1, :] = 0.
+    solver.mwaves = 2
+    solver.limiters = [4] * solver.mwaves
+    solver.dt_initial = grid.d[0] / state.aux_global['cc'] * 0.1
+    solver.bc_lower[0] = pyclaw.BC.periodic
+    solver.bc_upper[0] = pyclaw.BC.periodic
+    claw = pyclaw.Controller()
+    claw.keep_copy = True
+    claw.nout = 5
+    claw.output_format = None
+    claw.tfinal = 1.0
+    claw.solution = pyclaw.Solution(state)
+    claw.solver = solver
+    claw.run()
+    q0 = np.asarray(claw.frames[0].state.q).reshape([-1])
+    qfinal = np.asarray(claw.frames[claw.nout].state.q).reshape([-1])
+    return grid.d[0] * np.sum(np.abs(qfinal - q0)), claw
+
+
+def test_acoustics1d_classic():
+    err, claw = _acoustics1d('classic')
+    assert abs(err - 0.00104856594174) < 1e-14          # test_examples.py:59-66 (tolerance 1e-5)
+
+
+def test_acoustics1d_sharpclaw():
+    err, _ = _acoustics1d('sharpclaw', weno_literals='f64')
+    assert abs(err - 0.000298935748775) < 1e-12          # test_examples.py:125-150 (tolerance 1e-5)
+    err, _ = _acoustics1d('sharpclaw')                   # REAL(4) literals, as gfortran compiles weno.f90
+    assert abs(err - 0.000298935748775) < 1e-5
+
+
+def _acoustics2d(solver_type, **opts):
+    import pyclaw
+    if solver_type == 'classic':
+        solver = pyclaw.ClawSolver2D()
+    else:
+        solver = pyclaw.SharpClawSolver2D()
+    solver.cfl_max = 0.5
+    solver.cfl_desired = 0.45
+    solver.mwaves = 2
+    solver.dim_split = 1
+    solver.limiters = [4] * solver.mwaves
+    for k, v in opts.items():
+        setattr(solver, k, v)
+    solver.bc_lower[0] = pyclaw.BC.outflow
+    solver.bc_upper[0] = pyclaw.BC.outflow
+    solver.bc_lower[1] = pyclaw.BC.outflow
+    solver.bc_upper[1] = pyclaw.BC.outflow
+    mx = my = 100
+    x = pyclaw.grid.Dimension('x', -1.0, 1.0, mx)
+    y = pyclaw.grid.Dimension('y', -1.0, 1.0, my)
+    grid = pyclaw.grid.Grid([x, y])
+    state = pyclaw.State(grid, 3)
+    rho, bulk = 1.0, 4.0
+    cc = np.sqrt(bulk / rho)
+    zz = rho * cc
+    state.aux_global.update(rho=rho, bulk=bulk, zz=zz, cc=cc)
+    Y, X = np.meshgrid(grid.y.center, grid.x.center)
+    r = np.sqrt(X ** 2 + Y ** 2)
+    width = 0.2
+    state.q[0, :, :] = (np.abs(r - 0.5) <= width) * (1. + np.cos(np.pi * (r - 0.5) / width))
+    state.q[1, :, :] = 0.
+    state.q[2, :, :] = 0.
+    solver.dt_initial = np.min(grid.d) / state.aux_global['cc'] * solver.cfl_desired
+    claw = pyclaw.Controller()
+    claw.keep_copy = True
+    claw.output_format = None
+    claw.tfinal = 0.12
+    claw.solution = pyclaw.Solution(state)
+    claw.solver = solver
+    claw.nout = 10
+    claw.run()
+    return claw.frames[claw.nout].state.q[0, :, :]
+
+
+def test_acoustics2d_classic_golden():
+    pressure = _acoustics2d('classic')
+    verify_x = np.loadtxt(os.path.join(GOLD, 'acoustics2D_solution'))
+    assert np.linalg.norm(np.asarray(pressure) - verify_x) < 2e-14   # test_examples.py:239-254
+
+
+def test_acoustics2d_sharpclaw_golden():
+    verify_x = np.loadtxt(os.path.join(GOLD, 'ac_sc_solution'))
+    p = _acoustics2d('sharpclaw')                                    # default: PyWENO, REAL(4) literals
+    assert np.linalg.norm(np.asarray(p) - verify_x) < 1e-4           # test_examples.py:333-376
+    p = _acoustics2d('sharpclaw', lim_type=3)                        # hand-written weno5
+    assert np.linalg.norm(np.asarray(p) - verify_x) < 1e-12
+
+
+def _shockbubble(**opts):
+    import pyclaw
+    from pyclaw.clawpack import ClawSolver2D
+    gamma, gamma1 = problems.GAMMA, problems.GAMMA1
+    rinf, vinf, einf = problems.shock_state()
+
+    def shockbc(state, dim, t, qbc, mbc):
+        if dim.nstart == 0:
+            for i in range(mbc):
+                qbc[0, i, ...] = rinf
+                qbc[1, i, ...] = rinf * vinf
+                qbc[2, i, ...] = 0.
+                qbc[3, i, ...] = einf
+                qbc[4, i, ...] = 0.
+
+    def euler_rad_src(solver, state, dt):
+        problems.euler_rad_src(torch, state.q, state.aux, dt)
+
+    pb = problems.shockbubble()
+    x = pyclaw.Dimension('x', 0.0, 2.0, 160)
+    y = pyclaw.Dimension('y', 0.0, 0.5, 40)
+    grid = pyclaw.Grid([x, y])
+    state = pyclaw.State(grid, 5, 1)
+    state.aux_global['gamma'] = gamma
+    state.aux_global['gamma1'] = gamma1
+    state.q[...] = pb["q"]
+    state.aux[...] = pb["aux"]
+    solver = ClawSolver2D()
+    solver.cfl_max = 0.5
+    solver.cfl_desired = 0.45
+    solver.mwaves = 5
+    solver.limiters = [4, 4, 4, 4, 2]
+    solver.dt_initial = 0.005
+    solver.user_bc_lower = shockbc
+    solver.step_src = euler_rad_src
+    solver.src_split = 1
+    solver.bc_lower[0] = pyclaw.BC.custom
+    solver.bc_upper[0] = pyclaw.BC.outflow
+    solver.bc_lower[1] = pyclaw.BC.reflecting
+    solver.bc_upper[1] = pyclaw.BC.outflow
+    solver.aux_bc_lower[0] = pyclaw.BC.outflow
+    solver.aux_bc_upper[0] = pyclaw.BC.outflow
+    solver.aux_bc_lower[1] = pyclaw.BC.outflow
+    solver.aux_bc_upper[1] = pyclaw.BC.outflow
+    for k, v in opts.items():
+        setattr(solver, k, v)
+    claw = pyclaw.Controller()
+    claw.keep_copy = True
+    claw.output_format = None
+    claw.tfinal = 0.2
+    claw.solution = pyclaw.Solution(state)
+    claw.solver = solver
+    claw.nout = 1
+    status = claw.run()
+    return claw.frames[claw.nout].state.q, status
+
+
+def test_shockbubble_golden_bit_exact():
+    q, status = _shockbubble()
+    verify_x = np.loadtxt(os.path.join(GOLD, 'sb_density'))
+    assert status['numsteps'] == 170
+    # test_examples.py:385-397 asks for max abs < 1e-12; the GPU path is bit-exact
+    assert np.max(np.abs(np.asarray(q[0]) - verify_x)) == 0.0
+
+
+def _oracle_shockbubble(dim_split, order_trans, src):
+    pb = problems.shockbubble()
+    s = po.OracleSolver("classic", 2, po.RP_EULER5, pb["params"], 5)
+    s.cfl_max, s.cfl_desired = 0.5, 0.45
+    s.limiters = pb["limiters"]
+    s.dt_initial = pb["dt_initial"]
+    s.dim_split, s.order_trans = dim_split, order_trans
+    s.bc_lower = [po.BC_CUSTOM, po.BC_REFLECTING]
+    s.bc_upper = [po.BC_OUTFLOW, po.BC_OUTFLOW]
+    s.user_bc_lower = problems.shockbc_numpy
+    if src:
+        s.step_src = lambda solver, state, dt: problems.euler_rad_src(np, state["q"], state["aux"], dt)
+    frames = s.run(pb["q"], pb["aux"], pb["d"], pb["tfinal"], pb["nout"])
+    return frames[-1], s.total
+
+
+@pytest.mark.parametrize("order_trans", [1, 2])
+def test_shockbubble_unsplit_vs_oracle(order_trans):
+    # the application's own setting (apps/euler/2d/shockbubble: dim_split=False, order_trans=2)
+    q, status = _shockbubble(dim_split=False, order_trans=order_trans)
+    qo, total = _oracle_shockbubble(False, order_trans, True)
+    assert np.array_equal(np.asarray(q), qo)
+
+
+def _shallow(kind, **opts):
+    import pyclaw
+    pb = problems.shallow2d(60, 60)
+    solver = pyclaw.ClawSolver2D() if kind == 'classic' else pyclaw.SharpClawSolver2D()
+    solver.mwaves = 3
+    solver.limiters = pyclaw.limiters.tvd.MC
+    solver.bc_lower[0] = pyclaw.BC.outflow
+    solver.bc_upper[0] = pyclaw.BC.reflecting
+    solver.bc_lower[1] = pyclaw.BC.outflow
+    solver.bc_upper[1] = pyclaw.BC.reflecting
+    solver.dim_split = 1
+    for k, v in opts.items():
+        setattr(solver, k, v)
+    x = pyclaw.Dimension('x', -2.5, 2.5, 60)
+    y = pyclaw.Dimension('y', -2.5, 2.5, 60)
+    state = pyclaw.State(pyclaw.Grid([x, y]), 3)
+    state.aux_global['grav'] = 1.0
+    state.q[...] = pb["q"]
+    claw = pyclaw.Controller()
+    claw.tfinal = 1.0
+    claw.keep_copy = True
+    claw.output_format = None
+    claw.solution = pyclaw.Solution(state)
+    claw.solver = solver
+    claw.nout = 2
+    claw.run()
+    return np.asarray(claw.frames[-1].state.q)
+
+
+def _oracle_shallow(kind, **opts):
+    pb = problems.shallow2d(60, 60)
+    s = po.OracleSolver(kind, 2, po.RP_SHALLOW, [1.0], 3)
+    s.limiters = 4
+    s.bc_lower = [po.BC_OUTFLOW, po.BC_OUTFLOW]
+    s.bc_upper = [po.BC_REFLECTING, po.BC_REFLECTING]
+    s.dim_split = True
+    for k, v in opts.items():
+        setattr(s, k, v)
+    return s.run(pb["q"], None, pb["d"], 1.0, 2)[-1]
+
+
+@pytest.mark.parametrize("opts", [dict(dim_split=1), dict(dim_split=0, order_trans=2),
+                                  dict(dim_split=0, order_trans=1), dict(dim_split=0, order_trans=0, cfl_max=0.5, cfl_desired=0.45)])
+def test_shallow_classic_vs_oracle(opts):
+    assert np.array_equal(_shallow('classic', **opts), _oracle_shallow('classic', **opts))
+
+
+@pytest.mark.parametrize("ti", ['SSP33', 'SSP104', 'Euler'])
+def test_shallow_sharpclaw_vs_oracle(ti):
+    o = dict(time_integrator=ti)
+    if ti == 'Euler':
+        o.update(cfl_max=0.5, cfl_desired=0.4)
+    qg = _shallow('sharpclaw', **o)
+    qo = _oracle_shallow('sharpclaw', **o)
+    assert np.array_equal(qg, qo)
+
+
+def test_rejected_step_is_rolled_back():
+    # a far too large first dt must be rejected and retried (solver.py:686-698)
+    import pyclaw
+    q1 = _acoustics2d('classic')
+    q2 = _acoustics2d('classic', dt_initial_scale=None) if False else None
+    pb = problems.acoustics2d()
+    s = po.OracleSolver("classic", 2, po.RP_ACOUSTICS, pb["params"], 2)
+    s.cfl_max, s.cfl_desired = 0.5, 0.45
+    s.limiters = [4, 4]
+    s.bc_lower = [po.BC_OUTFLOW] * 2
+    s.bc_upper = [po.BC_OUTFLOW] * 2
+    s.dt_initial = 10 * pb["dt_initial"]
+    fo = s.run(pb["q"], None, pb["d"], 0.06, 2)
+    assert s.total["rejected"] >= 1
+
+    solver = pyclaw.ClawSolver2D()
+    solver.cfl_max, solver.cfl_desired, solver.mwaves, solver.dim_split = 0.5, 0.45, 2, 1
+    solver.limiters = [4, 4]
+    for i in range(2):
+        solver.bc_lower[i] = solver.bc_upper[i] = pyclaw.BC.outflow
+    x = pyclaw.Dimension('x', -1.0, 1.0, 100)
+    y = pyclaw.Dimension('y', -1.0, 1.0, 100)
+    state = pyclaw.State(pyclaw.Grid([x, y]), 3)
+    state.aux_global.update(rho=1.0, bulk=4.0, zz=2.0, cc=2.0)
+    state.q[...] = pb["q"]
+    solver.dt_initial = 10 * pb["dt_initial"]
+    claw = pyclaw.Controller()
+    claw.keep_copy, claw.output_format, claw.tfinal, claw.nout = True, None, 0.06, 2
+    claw.solution, claw.solver = pyclaw.Solution(state), solver
+    claw.run()
+    assert np.array_equal(np.asarray(claw.frames[-1].state.q), fo[-1])
