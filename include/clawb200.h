@@ -120,6 +120,11 @@ int clawb200_sharpclaw_stage(const clawb200_problem *p, const double *q, const d
                              int mode, double ca, double cb, double div, double *cfl_dev,
                              void *stream);
 
+/* The stage-free combination in the middle of SSP104 (sharpclaw.py:195-196), fused:
+ *     s2 = q/25. + (9./25)*s1 ;  s1 = 15.*s2 - 5.*s1
+ * over n contiguous doubles (whole padded buffers). */
+int clawb200_ssp104_combine(const double *q, double *s1, double *s2, long long n, void *stream);
+
 /* Solver.qbc_lower / qbc_upper (src/pyclaw/solver.py:384-452) for one side of one
  * dimension.  narr = number of components of the array (meqn or maux); `negate` is the
  * component whose sign flips for a reflecting wall (idim+1), or -1 for none (aux). */

@@ -505,6 +505,29 @@ extern "C" int clawb200_sharpclaw_stage(const clawb200_problem *p, const double 
     return sharpclaw_launch(p, q, qa, out, dq_out, dt, mode, ca, cb, div, cfl_dev, (cudaStream_t)stream);
 }
 
+__global__ void ssp104_combine_kernel(const double *__restrict__ q, double *__restrict__ s1,
+                                      double *__restrict__ s2, long long n, double c925)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double a = s1[i];
+        double b = q[i] / 25. + c925 * a;
+        s2[i] = b;
+        s1[i] = 15. * b - 5. * a;
+    }
+}
+
+extern "C" int clawb200_ssp104_combine(const double *q, double *s1, double *s2, long long n, void *stream)
+{
+    if (!q || !s1 || !s2 || n < 0) return fail(CLAWB200_ERR_INVALID, "bad argument");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    ssp104_combine_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(q, s1, s2, n, 9. / 25);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // Host-pointer entry points: same kernels behind the reference's f2py signatures.
 // ---------------------------------------------------------------------------

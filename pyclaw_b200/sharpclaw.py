@@ -13,6 +13,12 @@ from . import _lib
 from .solver import Solver, CFLError, _ptr, _stream
 
 
+def _div(t, c):
+    """t / c with one IEEE division per element (torch evaluates ``tensor / python_float``
+    as a multiplication by the reciprocal on CUDA, which is not what numpy does)."""
+    return torch.div(t, torch.full((), float(c), dtype=t.dtype, device=t.device))
+
+
 def start_step(solver, solution):
     """Dummy routine called before each step (sharpclaw.py:19-25)."""
     pass
@@ -105,8 +111,8 @@ class SharpClawSolver(Solver):
                 ts = ts + self.dt / 6.
             # s2 = q/25 + 9/25 s1 ; s1 = 15 s2 - 5 s1   (sharpclaw.py:195-196)
             s2 = s2f.cur
-            s2.copy_(q0 / 25. + 9. / 25 * a)
-            a.copy_(15. * s2 - 5. * a)
+            _lib.call("clawb200_ssp104_combine", _ptr(q0), _ptr(a), _ptr(s2),
+                      ctypes.c_longlong(q0.numel()), _stream())
             ts = state.t + self.dt / 3.
             for i in range(4):
                 self._bcs_on(state, a, ts)
@@ -166,16 +172,16 @@ class SharpClawSolver(Solver):
                 new = 1. / 3. * state.q + 2. / 3. * (s.q + self.dq(s))
             elif self.time_integrator == 'SSP104':
                 s1, s2 = self._rk_stages[0], self._rk_stages[1]
-                s1.q = state.q + self.dq(state) / 6.
+                s1.q = state.q + _div(self.dq(state), 6.)
                 s1.t = state.t + self.dt / 6.
                 for i in range(4):
-                    s1.q = s1.q + self.dq(s1) / 6.
+                    s1.q = s1.q + _div(self.dq(s1), 6.)
                     s1.t = s1.t + self.dt / 6.
-                s2.q = state.q / 25. + 9. / 25 * s1.q
+                s2.q = _div(state.q, 25.) + 9. / 25 * s1.q
                 s1.q = 15. * s2.q - 5. * s1.q
                 s1.t = state.t + self.dt / 3.
                 for i in range(4):
-                    s1.q = s1.q + self.dq(s1) / 6.
+                    s1.q = s1.q + _div(self.dq(s1), 6.)
                     s1.t = s1.t + self.dt / 6.
                 new = s2.q + 0.6 * s1.q + 0.1 * self.dq(s1)
             else:

@@ -76,6 +76,14 @@ def shockbc_numpy(idim, t, qbc, mbc):
         qbc[4, i, ...] = 0.
 
 
+def _sdiv(xp, c, arr):
+    """scalar / array with one IEEE division per element.  (torch evaluates
+    ``python_float / tensor`` as ``tensor.reciprocal() * python_float``, which rounds twice.)"""
+    if xp is np:
+        return c / arr
+    return xp.div(xp.full_like(arr, c), arr)
+
+
 def euler_rad_src(xp, q, aux, dt):
     """test/euler/2d/shockbubble.py:59-94; ``xp`` is numpy or torch (same op order)."""
     dt2 = dt / 2.
@@ -84,20 +92,22 @@ def euler_rad_src(xp, q, aux, dt):
     rho = q[0]
     u = q[1] / rho
     v = q[2] / rho
-    press = GAMMA1 * (q[3] - 0.5 * rho * (u ** 2 + v ** 2))
+    press = GAMMA1 * (q[3] - 0.5 * rho * (u * u + v * v))
     qstar = xp.empty_like(q)
-    qstar[0] = q[0] - dt2 * (ndim - 1) / rad * q[2]
-    qstar[1] = q[1] - dt2 * (ndim - 1) / rad * rho * u * v
-    qstar[2] = q[2] - dt2 * (ndim - 1) / rad * rho * v * v
-    qstar[3] = q[3] - dt2 * (ndim - 1) / rad * v * (q[3] + press)
+    c2 = _sdiv(xp, dt2 * (ndim - 1), rad)
+    qstar[0] = q[0] - c2 * q[2]
+    qstar[1] = q[1] - c2 * rho * u * v
+    qstar[2] = q[2] - c2 * rho * v * v
+    qstar[3] = q[3] - c2 * v * (q[3] + press)
     rho = qstar[0]
     u = qstar[1] / rho
     v = qstar[2] / rho
-    press = GAMMA1 * (qstar[3] - 0.5 * rho * (u ** 2 + v ** 2))
-    q[0] = q[0] - dt * (ndim - 1) / rad * qstar[2]
-    q[1] = q[1] - dt * (ndim - 1) / rad * rho * u * v
-    q[2] = q[2] - dt * (ndim - 1) / rad * rho * v * v
-    q[3] = q[3] - dt * (ndim - 1) / rad * v * (qstar[3] + press)
+    press = GAMMA1 * (qstar[3] - 0.5 * rho * (u * u + v * v))
+    c1 = _sdiv(xp, dt * (ndim - 1), rad)
+    q[0] = q[0] - c1 * qstar[2]
+    q[1] = q[1] - c1 * rho * u * v
+    q[2] = q[2] - c1 * rho * v * v
+    q[3] = q[3] - c1 * v * (qstar[3] + press)
 
 
 def shallow2d(mx=150, my=150, rad=0.5, hl=2., hr=1.):

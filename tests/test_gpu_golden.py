@@ -263,11 +263,13 @@ def test_shallow_classic_vs_oracle(opts):
 
 @pytest.mark.parametrize("ti", ['SSP33', 'SSP104', 'Euler'])
 def test_shallow_sharpclaw_vs_oracle(ti):
-    o = dict(time_integrator=ti)
-    if ti == 'Euler':
-        o.update(cfl_max=0.5, cfl_desired=0.4)
+    # the reference's default cfl 2.45/2.5 is tuned for SSP104 in 1-D; use values that are
+    # stable for each integrator on this 2-D problem so that the comparison is NaN free
+    cfl = {'Euler': (0.5, 0.4), 'SSP33': (0.6, 0.5), 'SSP104': (1.3, 1.2)}[ti]
+    o = dict(time_integrator=ti, cfl_max=cfl[0], cfl_desired=cfl[1])
     qg = _shallow('sharpclaw', **o)
     qo = _oracle_shallow('sharpclaw', **o)
+    assert not np.isnan(qo).any()
     assert np.array_equal(qg, qo)
 
 
