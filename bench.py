@@ -1,0 +1,491 @@
+#!/usr/bin/env python
+"""
+bench.py -- cell-updates/s (float64) of the finite-volume time step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+N > 1 is launched by the driver with torch.distributed.run (one rank per GPU); the grid
+is then N y-slabs of the per-GPU size (weak scaling) with NCCL halo exchange and an
+all-reduce(MAX) of the Courant number.  Rank 0 prints ONE JSON line.
+
+Workloads (BASELINE.json `configs`):
+  euler      (default) 2-D Euler 5-wave Roe, ClawSolver2D unsplit + transverse, 8192^2 per GPU
+  acoustics  2-D acoustics, ClawSolver2D unsplit + transverse rpt2, 4096^2
+  shallow    2-D shallow water, SharpClawSolver2D WENO5 + SSP33, 8192^2 per GPU
+A "step" is one full time step through the public API (solver.evolve_to_time(solution)):
+boundary conditions, sweeps, Courant-number reduction and the 8-byte read-back that the
+dt controller needs.  `value` counts accepted steps only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GAMMA, GAMMA1 = 1.4, 0.4
+
+WORKLOADS = {
+    # name: per-GPU grid, meqn, algorithmic bytes per cell-step
+    "euler": dict(n=8192, meqn=5, mwaves=5, balg=80, label="euler5_roe_unsplit_8192x8192_per_gpu"),
+    "acoustics": dict(n=4096, meqn=3, mwaves=2, balg=48, label="acoustics_unsplit_rpt2_4096x4096_per_gpu"),
+    "shallow": dict(n=8192, meqn=3, mwaves=3, balg=192, label="shallow_sharpclaw_weno5_ssp33_8192x8192_per_gpu"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------
+# problem set-up through the PyClaw API
+# --------------------------------------------------------------------------------------
+def shock_state(pinf=5.):
+    rinf = (GAMMA1 + pinf * (GAMMA + 1.)) / ((GAMMA + 1.) + GAMMA1 * pinf)
+    vinf = 1. / np.sqrt(GAMMA) * (pinf - 1.) / np.sqrt(0.5 * ((GAMMA + 1.) / GAMMA) * pinf + 0.5 * GAMMA1 / GAMMA)
+    einf = 0.5 * rinf * vinf ** 2 + pinf / GAMMA1
+    return rinf, vinf, einf
+
+
+def build_problem(pyclaw, workload, n, nranks, torch):
+    """Synthetic data of the BASELINE shapes: analytic initial conditions evaluated on the
+    device (no RNG), n x n cells per GPU, n x (n*nranks) globally."""
+    if workload == "euler":
+        # test/euler/2d/shockbubble.py scaled up: bubble of light gas, shock entering from
+        # the left ghost cells; source term off (kernel metric)
+        x = pyclaw.Dimension('x', 0.0, 2.0, n)
+        y = pyclaw.Dimension('y', 0.0, 2.0 * nranks, n * nranks)
+        state = pyclaw.State(pyclaw.Grid([x, y]), 5)
+        state.aux_global['gamma'] = GAMMA
+        state.aux_global['gamma1'] = GAMMA1
+        xc = torch.as_tensor(state.grid.x.center, device=state.device)
+        yc = torch.as_tensor(state.grid.y.center, device=state.device)
+        r = torch.sqrt((xc[:, None] - 0.5) ** 2 + (yc[None, :] - 0.0) ** 2)
+        inside = (r <= 0.2).to(torch.float64)
+        q = state.q
+        q[0] = 0.1 * inside + 1.0 * (1.0 - inside)
+        q[1] = 0.
+        q[2] = 0.
+        q[3] = 1.0 / GAMMA1
+        q[4] = inside
+        solver = pyclaw.ClawSolver2D()
+        solver.mwaves = 5
+        solver.limiters = [4, 4, 4, 4, 2]
+        solver.dim_split = False
+        solver.order_trans = 2
+        solver.cfl_max, solver.cfl_desired = 0.5, 0.45
+        rinf, vinf, einf = shock_state()
+
+        def shockbc(state, dim, t, qbc, mbc):
+            if dim.nstart == 0:
+                qbc[0, :mbc] = rinf
+                qbc[1, :mbc] = rinf * vinf
+                qbc[2, :mbc] = 0.
+                qbc[3, :mbc] = einf
+                qbc[4, :mbc] = 0.
+        solver.user_bc_lower = shockbc
+        solver.bc_lower[0] = pyclaw.BC.custom
+        solver.bc_upper[0] = pyclaw.BC.outflow
+        solver.bc_lower[1] = pyclaw.BC.reflecting
+        solver.bc_upper[1] = pyclaw.BC.outflow
+        solver.dt_initial = 0.1 * state.grid.d[0]
+    elif workload == "acoustics":
+        x = pyclaw.Dimension('x', -1.0, 1.0, n)
+        y = pyclaw.Dimension('y', -1.0, -1.0 + 2.0 * nranks, n * nranks)
+        state = pyclaw.State(pyclaw.Grid([x, y]), 3)
+        rho, bulk = 1.0, 4.0
+        cc = np.sqrt(bulk / rho)
+        state.aux_global.update(rho=rho, bulk=bulk, zz=rho * cc, cc=cc)
+        xc = torch.as_tensor(state.grid.x.center, device=state.device)
+        yc = torch.as_tensor(state.grid.y.center, device=state.device)
+        r = torch.sqrt(xc[:, None] ** 2 + yc[None, :] ** 2)
+        width = 0.2
+        q = state.q
+        q[0] = (torch.abs(r - 0.5) <= width) * (1. + torch.cos(np.pi * (r - 0.5) / width))
+        q[1] = 0.
+        q[2] = 0.
+        solver = pyclaw.ClawSolver2D()
+        solver.mwaves = 2
+        solver.limiters = [4, 4]
+        solver.dim_split = False
+        solver.order_trans = 2
+        for i in range(2):
+            solver.bc_lower[i] = solver.bc_upper[i] = pyclaw.BC.outflow
+        solver.dt_initial = 0.5 * state.grid.d[0] / cc
+    elif workload == "shallow":
+        x = pyclaw.Dimension('x', -2.5, 2.5, n)
+        y = pyclaw.Dimension('y', -2.5, -2.5 + 5.0 * nranks, n * nranks)
+        state = pyclaw.State(pyclaw.Grid([x, y]), 3)
+        state.aux_global['grav'] = 1.0
+        xc = torch.as_tensor(state.grid.x.center, device=state.device)
+        yc = torch.as_tensor(state.grid.y.center, device=state.device)
+        r = torch.sqrt(xc[:, None] ** 2 + yc[None, :] ** 2)
+        inside = (r <= 0.5).to(torch.float64)
+        q = state.q
+        q[0] = 2.0 * inside + 1.0 * (1.0 - inside)
+        q[1] = 0.
+        q[2] = 0.
+        solver = pyclaw.SharpClawSolver2D()
+        solver.mwaves = 3
+        solver.time_integrator = 'SSP33'
+        solver.cfl_max, solver.cfl_desired = 0.6, 0.5
+        solver.bc_lower[0] = solver.bc_lower[1] = pyclaw.BC.outflow
+        solver.bc_upper[0] = solver.bc_upper[1] = pyclaw.BC.reflecting
+        solver.dt_initial = 0.2 * state.grid.d[0]
+    else:
+        raise SystemExit("unknown workload %s" % workload)
+    return state, solver
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace('.', '').isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nme, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        smax = int(float(self.samples[0][1])) if self.samples else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU legs: the oracle (strict-IEEE C restatement of the reference's Fortran path) on the
+# host cores.  This is the only place bench.py touches oracle/.
+# --------------------------------------------------------------------------------------
+def cpu_problem(workload, n):
+    import problems
+    if workload == "euler":
+        pb = problems.shockbubble(n, n, xupper=2.0, yupper=2.0)
+        rp, params, lim = 3, [GAMMA, GAMMA1], [4, 4, 4, 4, 2]
+    elif workload == "acoustics":
+        pb = problems.acoustics2d(n, n)
+        rp, params, lim = 1, pb["params"], [4, 4]
+    else:
+        pb = problems.shallow2d(n, n)
+        rp, params, lim = 4, [1.0], [4, 4, 4]
+    return pb, rp, params, lim
+
+
+def cpu_step_fn(workload, n, nthreads):
+    """Returns (fn, cells) where fn() advances one full time step on an n x n sample."""
+    from oracle import pyclaw_oracle as po
+    pb, rp, params, lim = cpu_problem(workload, n)
+    q = pb["q"]
+    dx, dy = pb["d"]
+    if workload == "shallow":
+        mbc = 3
+        s = po.OracleSolver("sharpclaw", 2, rp, params, 3)
+        s.time_integrator = "SSP33"
+        s.bc_lower = [po.BC_OUTFLOW] * 2
+        s.bc_upper = [po.BC_REFLECTING] * 2
+        s.nthreads = nthreads
+        s.setup(q, None, [dx, dy])
+        s.dt = 0.2 * dx
+        st = {"q": q.copy("F"), "t": 0.0}
+
+        def fn():
+            s.step(st)
+    else:
+        s = po.OracleSolver("classic", 2, rp, params, len(lim))
+        s.limiters = lim
+        s.dim_split = False
+        s.order_trans = 2
+        s.bc_lower = [po.BC_OUTFLOW] * 2
+        s.bc_upper = [po.BC_OUTFLOW] * 2
+        s.nthreads = max(nthreads, 2)  # slab driver (nthreads=1 would take the serial path; same result)
+        if nthreads == 1:
+            s.nthreads = 1
+        s.setup(q, None, [dx, dy])
+        s.dt = 0.1 * dx
+        st = {"q": q.copy("F"), "t": 0.0}
+
+        def fn():
+            s._hyperbolic_classic(st)
+    return fn, n * n
+
+
+def time_cpu(workload, n, nthreads, budget_s):
+    fn, cells = cpu_step_fn(workload, n, nthreads)
+    fn()  # warm
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        fn()
+        k += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or k >= 50:
+            break
+    return cells * k / el, k, el
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    wl = WORKLOADS[args.workload]
+    n = 2048 if args.workload != "shallow" else 1024
+    fn, cells = cpu_step_fn(args.workload, n, ncores)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    el = time.perf_counter() - t0
+    value = cells * args.steps / el
+    sample = "%dx%d sample of the workload, %d host threads (y-slabs), oracle C port of step2/flux2/rpn2/rpt2" % (n, n, ncores)
+    line = {
+        "impl": "reference", "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": ncores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="euler", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override the per-GPU grid size (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import petclaw as pyclaw
+        pyclaw.init("nccl")
+    else:
+        import pyclaw
+    from pyclaw_b200 import _lib
+
+    wl = WORKLOADS[args.workload]
+    n = args.n or wl["n"]
+    state, solver = build_problem(pyclaw, args.workload, n, world, torch)
+    solution = pyclaw.Solution(state)
+    solver.setup(solution)
+    solver.dt = solver.dt_initial
+    solver.max_steps = 10 ** 9
+    cells_per_rank = n * n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: lets dt settle at cfl_desired -------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        solver.evolve_to_time(solution)
+
+    # ---- timed region ---------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    accepted = 0
+    ev0.record()
+    for _ in range(args.steps):
+        st = solver.evolve_to_time(solution)
+        accepted += st['numsteps']
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        acc = torch.tensor([accepted], dtype=torch.float64, device="cuda")
+        dist.all_reduce(acc, op=dist.ReduceOp.MIN)
+        accepted = int(acc.item())
+    value = cells_per_rank * world * accepted / (ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    peak, peak_kind = peaks()
+    # ---- per-kernel timing of the dominant kernel (CUDA events on the launch stream) ----
+    roofline = None
+    P = ctypes.byref(solver._problem)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    F = state._q
+    solver.apply_q_bcs(state)
+    scratch = F.get_spare()
+    kern = {}
+    if args.workload in ("euler", "acoustics"):
+        scratch.copy_(F.cur)
+        launches_per_step = 2
+        for name, part, bytes_per_cell in (("xsweep_kernel<TRANS>", 1, 2 * wl["meqn"] * 8),
+                                           ("ysweep_kernel<TRANS>", 2, 3 * wl["meqn"] * 8)):
+            for rep in range(2):
+                _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), None, float(solver.dt), part,
+                          ptr(solver._cfl_dev), stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for rep in range(reps):
+                _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), None, float(solver.dt), part,
+                          ptr(solver._cfl_dev), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            kern[name] = (e0.elapsed_time(e1) / reps, bytes_per_cell)
+    else:
+        launches_per_step = 3
+        for rep in range(2):
+            solver._stage(F.cur, None, scratch, 0, 0, 0, 1.0, 0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for rep in range(reps):
+            solver._stage(F.cur, None, scratch, 0, 0, 0, 1.0, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        kern["sc2d_kernel"] = (e0.elapsed_time(e1) / reps, 2 * wl["meqn"] * 8)
+    F.put_spare(scratch)
+    dom = max(kern, key=lambda k: kern[k][0])
+    kms, bpc = kern[dom]
+    achieved = bpc * cells_per_rank / (kms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "kernel_ms": kms, "algorithmic_bytes_per_cell_per_launch": bpc,
+                "all_kernels_ms": {k: v[0] for k, v in kern.items()},
+                "step_frac": value / world * wl["balg"] / 1e9 / peak,
+                "step_algorithmic_bytes_per_cell": wl["balg"]}
+
+    # ---- e2e: the f2py-shaped C ABI call with HOST buffers (H2D + kernels + D2H timed) ----
+    e2e = None
+    if not args.no_e2e and args.workload in ("euler", "acoustics"):
+        mbc = solver.mbc
+        nx = n + 2 * mbc
+        host_in = torch.empty((nx, nx, wl["meqn"]), dtype=torch.float64).pin_memory()
+        host_out = torch.empty((nx, nx, wl["meqn"]), dtype=torch.float64).pin_memory()
+        # Fortran-ordered q(m,i,j) == C-ordered [j][i][m]
+        host_in.copy_(F.cur.permute(1, 2, 0))
+        from pyclaw_b200._lib import make_problem
+        Ph = make_problem(2, wl["meqn"], wl["mwaves"], mbc, n, n, state.grid.d[0], state.grid.d[1],
+                          solver._rp.rp_id, solver._rp.params(state.aux_global), solver.method, solver.mthlim)
+        cflv = ctypes.c_double()
+        hp = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.call("clawb200_step2_host", ctypes.byref(Ph), hp(host_in), hp(host_out), None, float(solver.dt),
+                  ctypes.byref(cflv))
+        k = 3
+        t0 = time.perf_counter()
+        for _ in range(k):
+            _lib.call("clawb200_step2_host", ctypes.byref(Ph), hp(host_in), hp(host_out), None, float(solver.dt),
+                      ctypes.byref(cflv))
+        el = time.perf_counter() - t0
+        nbytes = host_in.numel() * 8
+        e2e = {"value": cells_per_rank * k / el, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes + 8, "steps": k,
+               "what": "clawb200_step2_host: pinned host qold -> H2D -> layout kernel -> sweeps -> D2H qnew, per step",
+               "resident_api": {"value": value, "unit": "cell-updates/s",
+                                "what": "solver.evolve_to_time through the pyclaw API, q resident in HBM, "
+                                        "8-byte CFL read back per step"}}
+        del host_in, host_out
+    elif not args.no_e2e:
+        e2e = {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * 3,
+               "what": "solver.evolve_to_time through the pyclaw API (q resident in HBM; dt in, per-stage CFL out)"}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------
+    cpu = None
+    if not args.no_cpu and world == 1:
+        ncores = os.cpu_count() or 1
+        ncpu = 1024
+        v, k, el = time_cpu(args.workload, ncpu, ncores, 12.0)
+        cpu = {"value": v, "unit": "cell-updates/s", "cores": ncores, "kind": "port",
+               "sample": "%d steps on a %dx%d sample of the workload in %.1f s, y-slab threads over the oracle C port" % (k, ncpu, ncpu, el)}
+
+    bc_launches = sum(1 for b in solver.bc_lower + solver.bc_upper if b in (1, 2, 3))
+    # kernels of libclawb200.so per accepted step: boundary fills + sweeps (classic), or
+    # per Runge-Kutta stage: boundary fills + one fused stage kernel (SharpClaw SSP33)
+    if args.workload == "shallow":
+        per_step_launches = 3 * (bc_launches + 1)
+    else:
+        per_step_launches = bc_launches + launches_per_step
+    line = {
+        "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl["label"], "cells_per_gpu": cells_per_rank, "accepted_steps": accepted,
+                   "l2": "inputs larger than L2 (%.1f GB per field)" % (cells_per_rank * wl["meqn"] * 8 / 1e9),
+                   "parallelism": "y-slabs x%d" % world, "arithmetic": "strict IEEE, -fmad=false (bit-exact vs oracle)"},
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": args.steps * per_step_launches,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+
+
+if __name__ == "__main__":
+    main()

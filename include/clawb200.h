@@ -101,6 +101,12 @@ int clawb200_step2ds(const clawb200_problem *p, const double *q_in, double *q_ou
 int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
                    const double *aux, double dt, double *cfl_dev, void *stream);
 
+/* The same step restricted to one family of sweeps, for per-kernel timing (bench.py):
+ * parts = 1 x-sweeps only (qnew <- qold + x contributions), 2 y-sweeps only (qnew updated
+ * in place), 3 both (= clawb200_step2). */
+int clawb200_step2_parts(const clawb200_problem *p, const double *qold, double *qnew,
+                         const double *aux, double dt, int parts, double *cfl_dev, void *stream);
+
 /* sharpclaw1.flux1 / sharpclaw2.flux2 (src/fortran/1d/sharpclaw/flux1.f90:2-195,
  * src/fortran/2d/sharpclaw/flux2.f90:2-96; sharpclaw.py:385,558) fused with the
  * Runge-Kutta stage update that sharpclaw.py:172-206 performs in numpy.  q is the

@@ -217,8 +217,9 @@ extern "C" int clawb200_step2ds(const clawb200_problem *p, const double *q_in, d
     return 0;
 }
 
-extern "C" int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
-                              const double *aux, double dt, double *cfl_dev, void *stream)
+extern "C" int clawb200_step2_parts(const clawb200_problem *p, const double *qold, double *qnew,
+                                    const double *aux, double dt, int parts, double *cfl_dev,
+                                    void *stream)
 {
     int rc = check_problem(p, 2);
     if (rc) return rc;
@@ -226,14 +227,26 @@ extern "C" int clawb200_step2(const clawb200_problem *p, const double *qold, dou
     if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
     if (qold == qnew) return fail(CLAWB200_ERR_INVALID, "qold and qnew must differ");
     if (p->method[2] < 0) return fail(CLAWB200_ERR_INVALID, "method[2] < 0 means dimensional splitting: call step2ds");
+    if (parts < 1 || parts > 3) return fail(CLAWB200_ERR_INVALID, "parts must be 1, 2 or 3");
     (void)aux;
     cudaStream_t st = (cudaStream_t)stream;
     SweepArgs A = make_args(p, qold, qnew, dt, cfl_dev);
     A.ilo = 1; A.ihi = p->mx; A.jlo = 1; A.jhi = p->my;
-    A.rows_per_cta = pick_rows(p->my, (p->mx + XNT - 4) / (XNT - 3));
-    if ((rc = dispatch_x<true>(p->rp_id, A, st))) return rc;
-    A.rows_per_cta = pick_rows(p->my, (p->mx + YNT - 3) / (YNT - 2));
-    return dispatch_y<true>(p->rp_id, A, st);
+    if (parts & 1) {
+        A.rows_per_cta = pick_rows(p->my, (p->mx + XNT - 4) / (XNT - 3));
+        if ((rc = dispatch_x<true>(p->rp_id, A, st))) return rc;
+    }
+    if (parts & 2) {
+        A.rows_per_cta = pick_rows(p->my, (p->mx + YNT - 3) / (YNT - 2));
+        if ((rc = dispatch_y<true>(p->rp_id, A, st))) return rc;
+    }
+    return 0;
+}
+
+extern "C" int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
+                              const double *aux, double dt, double *cfl_dev, void *stream)
+{
+    return clawb200_step2_parts(p, qold, qnew, aux, dt, 3, cfl_dev, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -140,6 +140,7 @@ class Solver(object):
             d[0], d[1] if grid.ndim > 1 else 1.0, self._rp.rp_id, self._rp.params(state.aux_global),
             method=method, mthlim=mthlim, maux=state.maux, pitch=state._q.pitch,
             mstride=state._q.mstride, weno_variant=weno_variant)
+        self._halo = state._partition
         self._cfl_dev = torch.zeros(16, dtype=torch.float64, device=state.device)
         self._cfl_host = torch.zeros(16, dtype=torch.float64).pin_memory()
 

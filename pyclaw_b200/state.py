@@ -80,6 +80,7 @@ class State(object):
             raise Exception("A PyClaw State object must be initialized with a PyClaw Grid object.")
         self.grid = grid
         self.device = torch.device(device) if device is not None else default_device()
+        self._partition = self._make_partition(grid)
         self.p = None
         self.F = None
         self.aux_global = {}
@@ -89,6 +90,10 @@ class State(object):
         self._aux = _Field(maux, grid.ng, 0, self.device) if maux > 0 else None
         self._backup = None
         self._explicit = None
+
+    def _make_partition(self, grid):
+        """Single-GPU State: no partition.  petclaw.State overrides this."""
+        return getattr(grid, '_partition', None)
 
     # ---- q / aux as interior views ----
     @property
@@ -221,7 +226,11 @@ class State(object):
         self._release_backup()
 
     def __deepcopy__(self, memo={}):
-        result = self.__class__(copy.deepcopy(self.grid), self.meqn, self.maux, device=self.device)
+        g = copy.deepcopy(self.grid)
+        g._partition = self._partition
+        for d_new, d_old in zip(g.dimensions, self.grid.dimensions):
+            d_new._set_range(d_old.nstart, d_old.nend)
+        result = self.__class__(g, self.meqn, self.maux, device=self.device)
         result.t = copy.deepcopy(self.t)
         result.set_mbc(0)
         result.q = self.q
