@@ -18,6 +18,26 @@ class ClawArray(torch.Tensor):
         a = self.detach().as_subclass(torch.Tensor).cpu().numpy()
         return a if dtype is None else a.astype(dtype)
 
+    # mixed numpy / device arithmetic (``numpy.loadtxt(...) - q[0]`` in the reference's tests)
+    def _co(self, other):
+        if isinstance(other, np.ndarray):
+            return torch.as_tensor(np.ascontiguousarray(other), dtype=self.dtype).to(self.device)
+        return other
+
+    def __add__(self, o): return super().__add__(self._co(o))
+    def __radd__(self, o): return super().__radd__(self._co(o))
+    def __sub__(self, o): return super().__sub__(self._co(o))
+    def __rsub__(self, o): return super().__rsub__(self._co(o))
+    def __mul__(self, o): return super().__mul__(self._co(o))
+    def __rmul__(self, o): return super().__rmul__(self._co(o))
+    def __truediv__(self, o): return super().__truediv__(self._co(o))
+
+    def __rtruediv__(self, o):
+        o = self._co(o)
+        if isinstance(o, torch.Tensor):
+            return torch.div(o, self)
+        return super().__rtruediv__(o)
+
     def copy(self, order="F"):
         """numpy-style copy (solver.py:660 ``state.q.copy('F')``)."""
         return self.clone()

@@ -74,14 +74,18 @@ class SlabPartition(object):
         lo = self.lower_nbr if self.lower_nbr >= 0 else (self.size - 1 if wrap else None)
         hi = self.upper_nbr if self.upper_nbr < self.size else (0 if wrap else None)
         b = self._buffers(field, mbc)
+        # Order matters when both neighbours are the same rank (2 ranks, periodic): NCCL
+        # matches the messages of a pair by posting order, so "my top rows" must pair with
+        # the peer's "lower ghost" receive: upward traffic first, downward traffic second.
         ops = []
-        if lo is not None:
-            b['send_lo'].copy_(t[:, mbc:2 * mbc])
-            ops.append(dist.P2POp(dist.isend, b['send_lo'], lo, self.group))
-            ops.append(dist.P2POp(dist.irecv, b['recv_lo'], lo, self.group))
         if hi is not None:
             b['send_hi'].copy_(t[:, nloc:nloc + mbc])
             ops.append(dist.P2POp(dist.isend, b['send_hi'], hi, self.group))
+        if lo is not None:
+            ops.append(dist.P2POp(dist.irecv, b['recv_lo'], lo, self.group))
+            b['send_lo'].copy_(t[:, mbc:2 * mbc])
+            ops.append(dist.P2POp(dist.isend, b['send_lo'], lo, self.group))
+        if hi is not None:
             ops.append(dist.P2POp(dist.irecv, b['recv_hi'], hi, self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):

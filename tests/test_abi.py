@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads without a GPU
+and exports every symbol that include/clawb200.h declares; no compute is attempted."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pyclaw_b200 import _lib, build as build_mod
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "clawb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(clawb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    build_mod.build()
+    L = _lib.load()
+    assert L.clawb200_version() >= 100
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "symbol %s declared in clawb200.h is not exported" % n
+
+
+def test_ctypes_signatures_cover_the_header():
+    declared = set(_declared_symbols()) - {"clawb200_version", "clawb200_last_error"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_problem_struct_matches_header_layout():
+    # offsets implied by the header's field order (natural alignment)
+    P = _lib.Problem
+    assert P.ndim.offset == 0 and P.mx.offset == 20 and P.dx.offset == 32
+    assert P.method.offset == 48 and P.mthlim.offset == 76 and P.rp_id.offset == 108
+    assert P.rp_params.offset == 112 and P.mstride.offset == 176 and P.pitch.offset == 184
+    assert ctypes.sizeof(P) == 192
+
+
+def test_invalid_arguments_return_errors_without_a_gpu():
+    # argument validation happens before any CUDA call, so it can be exercised on CPU
+    P = _lib.make_problem(2, 5, 5, 2, 16, 16, 0.1, 0.1, _lib.RP_EULER5, [1.4, 0.4], None, [4] * 5)
+    with pytest.raises(_lib.ClawB200Error, match="differ"):
+        _lib.call("clawb200_step2", ctypes.byref(P), ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0.1,
+                  ctypes.c_void_p(8), None)
+    P.method[5] = 1
+    with pytest.raises(_lib.ClawB200Error, match="capacity"):
+        _lib.call("clawb200_step2", ctypes.byref(P), ctypes.c_void_p(8), ctypes.c_void_p(16), None, 0.1,
+                  ctypes.c_void_p(8), None)
+    P2 = _lib.make_problem(2, 4, 5, 2, 16, 16, 0.1, 0.1, _lib.RP_EULER5, [1.4, 0.4], None, [4] * 5)
+    with pytest.raises(_lib.ClawB200Error, match="meqn"):
+        _lib.call("clawb200_step2ds", ctypes.byref(P2), ctypes.c_void_p(8), ctypes.c_void_p(16), None, 0.1, 1,
+                  ctypes.c_void_p(8), None)
+
+
+def test_no_cpu_fallback():
+    """On a host without CUDA the solvers must refuse to run rather than fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import pyclaw
+    x = pyclaw.Dimension('x', 0., 1., 16)
+    y = pyclaw.Dimension('y', 0., 1., 16)
+    state = pyclaw.State(pyclaw.Grid([x, y]), 3)
+    state.aux_global.update(rho=1., bulk=4., cc=2., zz=2.)
+    solver = pyclaw.ClawSolver2D()
+    solver.mwaves = 2
+    for i in range(2):
+        solver.bc_lower[i] = solver.bc_upper[i] = pyclaw.BC.outflow
+    with pytest.raises(_lib.ClawB200Error, match="no CPU fallback"):
+        solver.setup(pyclaw.Solution(state))
