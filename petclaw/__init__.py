@@ -24,7 +24,11 @@ def init(backend=None):
         return world()
     if torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
-    dist.init_process_group(backend or ('nccl' if torch.cuda.is_available() else 'gloo'))
+    # a short collective timeout turns a mismatched exchange into a quick error instead of
+    # a ten-minute hang
+    import datetime
+    dist.init_process_group(backend or ('nccl' if torch.cuda.is_available() else 'gloo'),
+                            timeout=datetime.timedelta(seconds=int(os.environ.get('CLAWB200_DIST_TIMEOUT', 180))))
     return world()
 
 
