@@ -293,6 +293,8 @@ def main():
     ap.add_argument("--workload", default="euler", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override the per-GPU grid size (debug)")
+    ap.add_argument("--perturb", action="store_true",
+                    help="add a smooth non-zero velocity field (SURVEY 8(d): branch behaviour differs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
     args = ap.parse_args()
@@ -319,6 +321,15 @@ def main():
     wl = WORKLOADS[args.workload]
     n = args.n or wl["n"]
     state, solver = build_problem(pyclaw, args.workload, n, world, torch)
+    if args.perturb and args.workload in ("euler", "shallow"):
+        xc = torch.as_tensor(state.grid.x.center, device=state.device)
+        yc = torch.as_tensor(state.grid.y.center, device=state.device)
+        bump = torch.sin(2 * np.pi * xc)[:, None] * torch.sin(2 * np.pi * yc)[None, :]
+        rho = state.q[0].clone()
+        state.q[1] = rho * 0.3 * bump
+        state.q[2] = -rho * 0.2 * bump
+        if args.workload == "euler":
+            state.q[3] = state.q[3] + 0.5 * (state.q[1] ** 2 + state.q[2] ** 2) / rho
     solution = pyclaw.Solution(state)
     solver.setup(solution)
     solver.dt = solver.dt_initial

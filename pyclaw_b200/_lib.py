@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libclawb200.so")
+# CLAWB200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("CLAWB200_LIB") or os.path.join(_HERE, "csrc", "libclawb200.so")
 
 MAXWAVES = 8
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW = 1, 2, 3, 4

@@ -46,13 +46,14 @@ struct SweepArgs {
 };
 
 // philim.f:4-58
-__device__ __forceinline__ double philim(double a, double b, int meth)
+template <class AR>
+__device__ __forceinline__ double philim(AR &ar, double a, double b, int meth)
 {
-    double r = b / a;
+    double r = ar.div(b, a);
     switch (meth) {
     case 1: return dmax2(0.0, dmin2(1.0, r));
     case 2: return dmax2(dmax2(0.0, dmin2(1.0, 2.0 * r)), dmin2(2.0, r));
-    case 3: return (r + fabs(r)) / (1.0 + fabs(r));
+    case 3: return ar.div(r + fabs(r), 1.0 + fabs(r));
     case 4: {
         double c = (1.0 + r) / 2.0;
         return dmax2(0.0, dmin2(dmin2(c, 2.0), 2.0 * r));
@@ -64,8 +65,8 @@ __device__ __forceinline__ double philim(double a, double b, int meth)
 // limiter.f:29-55 for one interface, given the (unlimited) dot products with the
 // neighbouring interfaces.  Entries with RP::nz == false are structurally zero and
 // skipped: adding +0 to a running sum that started at +0 never changes it.
-template <class RP>
-__device__ __forceinline__ void limit_waves(double (&wave)[RP::MEQN][RP::MWAVES],
+template <class RP, class AR>
+__device__ __forceinline__ void limit_waves(AR &ar, double (&wave)[RP::MEQN][RP::MWAVES],
                                             const double (&s)[RP::MWAVES],
                                             const double (&wnorm2)[RP::MWAVES],
                                             const double (&dotl)[RP::MWAVES],
@@ -75,7 +76,7 @@ __device__ __forceinline__ void limit_waves(double (&wave)[RP::MEQN][RP::MWAVES]
     for (int mw = 0; mw < RP::MWAVES; mw++) {
         if (mthlim[mw] == 0) continue;
         if (wnorm2[mw] == 0.0) continue;
-        double wlimitr = philim(wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], mthlim[mw]);
+        double wlimitr = philim(ar, wnorm2[mw], (s[mw] > 0.0) ? dotl[mw] : dotr[mw], mthlim[mw]);
 #pragma unroll
         for (int m = 0; m < RP::MEQN; m++)
             if (RP::nz(m, mw)) wave[m][mw] = wlimitr * wave[m][mw];
@@ -117,7 +118,7 @@ __device__ __forceinline__ void cfl_commit(double cfl, unsigned long long *cfl_b
 //              rows j0 .. j1-1, contributions applied in the order of SURVEY.md A.3.
 // ---------------------------------------------------------------------------
 template <class RP, bool TRANS, int NT>
-__global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
+__global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs A)
 {
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
     constexpr int NC = NT - 3;
@@ -150,12 +151,31 @@ __global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
 
     const int rbeg = TRANS ? j0 - 1 : j0;
     const int rend = TRANS ? j1 : j1 - 1;
+    // software prefetch: the row for iteration r+1 is requested before the arithmetic of
+    // row r starts, so its HBM latency is hidden behind a full row of Riemann solves
+    double qn[MEQN], qn2[MEQN];
+    {
+        const long long ro = (long long)A.pitch * (rbeg + mbc - 1);
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            qn[m] = A.qin[m * A.mstride + ro + cload];
+            qn2[m] = (t == 0) ? A.qin[m * A.mstride + ro + cload2] : 0.0;
+        }
+    }
     for (int r = rbeg; r <= rend; r++) {
         const long long rowoff = (long long)A.pitch * (r + mbc - 1);
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
-            qs[m * QS + t] = A.qin[m * A.mstride + rowoff + cload];
-            if (t == 0) qs[m * QS + NT] = A.qin[m * A.mstride + rowoff + cload2];
+            qs[m * QS + t] = qn[m];
+            if (t == 0) qs[m * QS + NT] = qn2[m];
+        }
+        if (r < rend) {
+            const long long ro = rowoff + A.pitch;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                qn[m] = A.qin[m * A.mstride + ro + cload];
+                if (t == 0) qn2[m] = A.qin[m * A.mstride + ro + cload2];
+            }
         }
         __syncthreads();
         double l[MEQN], rr[MEQN];
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
         for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
 
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
-        RP::solve(A.rp, l, rr, wave, s, amdq, apdq, roe);
+        with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, wave, s, amdq, apdq, roe); });
         if (iface_ok) {
 #pragma unroll
             for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
@@ -180,8 +200,9 @@ __global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
         double cqxx[MEQN];
 #pragma unroll
         for (int m = 0; m < MEQN; m++) cqxx[m] = 0.0;
+        double bmp[MEQN], bpp[MEQN], bmm[MEQN], bpm[MEQN];
+        double wnorm2[MW], dotl[MW], dotr[MW];
         if (order2 && t >= 1 && t <= NT - 2) {
-            double wnorm2[MW], dotl[MW], dotr[MW];
 #pragma unroll
             for (int mw = 0; mw < MW; mw++) {
                 double n2 = 0.0, dl = 0.0, dr = 0.0;
@@ -196,28 +217,45 @@ __global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
                 }
                 wnorm2[mw] = n2; dotl[mw] = dl; dotr[mw] = dr;
             }
-            limit_waves<RP>(wave, s, wnorm2, dotl, dotr, A.mthlim);
-            double dtdxave = 0.5 * (dtdx + dtdx);
-            second_order<RP>(wave, s, dtdxave, cqxx);
+        }
+        // limiter, second-order correction and the two transverse solves: one block of
+        // branch-free arithmetic (the exact re-run restores the unlimited waves first)
+        {
+            const bool lim = order2 && t >= 1 && t <= NT - 2;
+            with_arith([&](auto &ar) {
+                if (!ar.FAST && lim) { // re-run: the unlimited waves are still in shared memory
+#pragma unroll
+                    for (int m = 0; m < MEQN; m++)
+#pragma unroll
+                        for (int mw = 0; mw < MW; mw++)
+                            if (RP::nz(m, mw)) wave[m][mw] = ws[(m * MW + mw) * NT + t];
+                }
+                if (lim) {
+                    limit_waves<RP>(ar, wave, s, wnorm2, dotl, dotr, A.mthlim);
+                    double dtdxave = 0.5 * (dtdx + dtdx);
+                    second_order<RP>(wave, s, dtdxave, cqxx);
+                }
+                if (TRANS) {
+                    double asdq[MEQN];
+                    if (A.trans > 0) {
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq[m] + cqxx[m]) : amdq[m];
+                        RP::transverse(ar, A.rp, roe, asdq, bmm, bpm);
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq[m] - cqxx[m]) : apdq[m];
+                        RP::transverse(ar, A.rp, roe, asdq, bmp, bpp);
+                    } else { // flux2.f:151 -- gadd stays zero
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp[m] = bpp[m] = 0.0;
+                    }
+                }
+            });
         }
         double F[MEQN];
 #pragma unroll
         for (int m = 0; m < MEQN; m++) F[m] = 0.5 * cqxx[m];
 
-        double bmp[MEQN], bpp[MEQN];
         if (TRANS) {
-            double asdq[MEQN], bmm[MEQN], bpm[MEQN];
-            if (A.trans > 0) {
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq[m] + cqxx[m]) : amdq[m];
-                RP::transverse(A.rp, roe, asdq, bmm, bpm);
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq[m] - cqxx[m]) : apdq[m];
-                RP::transverse(A.rp, roe, asdq, bmp, bpp);
-            } else { // flux2.f:151 -- gadd stays zero
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp[m] = bpp[m] = 0.0;
-            }
 #pragma unroll
             for (int m = 0; m < MEQN; m++) {
                 xs[(2 * MEQN + m) * NT + t] = bmm[m];
@@ -284,16 +322,39 @@ __global__ void __launch_bounds__(NT) xsweep_kernel(const SweepArgs A)
 // at step k.  TRANS=false: step2ds.f ids=2.  TRANS=true: step2.f y-sweeps; qout is
 // updated in place (it already holds the x-sweep result), transverse increments to
 // the neighbouring columns go through shared memory.
+//
+// The rolling window (waves, Roe averages and fluctuations of interface k-1, the
+// "goes to the upper cell" parts of interface k-2) lives in thread-private shared-memory
+// slots laid out [slot][thread], not in registers: the Riemann solve needs ~100 live
+// registers on its own, and keeping ~50 more doubles of window across it either spills
+// or halves the occupancy.
 // ---------------------------------------------------------------------------
+template <class RP, bool TRANS>
+struct YSlots {
+    static constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    static constexpr int W = 0;                       // wave(m,mw) of interface k-1 (unlimited)
+    static constexpr int AM1 = W + MEQN * MW;         // amdq of interface k-1
+    static constexpr int AP1 = AM1 + MEQN;            // apdq of interface k-1
+    static constexpr int AP2 = AP1 + MEQN;            // apdq of interface k-2
+    static constexpr int F2 = AP2 + MEQN;             // correction flux of interface k-2
+    static constexpr int ROE = F2 + MEQN;             // Roe data of interface k-1   (TRANS)
+    static constexpr int BMP2 = ROE + NROE;           // B^- A^+ dq of interface k-2 (TRANS)
+    static constexpr int BPP2 = BMP2 + MEQN;          // B^+ A^+ dq of interface k-2 (TRANS)
+    static constexpr int COUNT = TRANS ? BPP2 + MEQN : ROE;
+};
+
 template <class RP, bool TRANS, int NT>
-__global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
+__global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs A)
 {
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
     constexpr int NC = TRANS ? NT - 2 : NT;
+    using SL = YSlots<RP, TRANS>;
     extern __shared__ double sm[];
-    double *gs = sm; // [2][2*MEQN][NT]  G1', G2' of the cells in the current row (double buffered)
+    double *gs = sm;                                   // [2][2*MEQN][NT] G1', G2' exchange (TRANS)
+    double *ys = sm + (TRANS ? 4 * MEQN * NT : 0);     // [SL::COUNT][NT] rolling window
 
     const int t = threadIdx.x;
+#define YS(slot) ys[(slot) * NT + t]
     const int mbc = A.mbc;
     const int i0 = A.ilo + blockIdx.x * NC;
     const int ic = TRANS ? i0 - 1 + t : i0 + t;      // this thread's column (Fortran index)
@@ -308,47 +369,45 @@ __global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
     const double hdtdy = 0.5 * dtdy;
 
     double cfl = 0.0;
-    double qm1[MEQN], qm2[MEQN];
-    double wm1[MEQN][MW], sm1[MW], amdq1[MEQN], apdq1[MEQN], roe1[NROE];
-    double norm1[MW], dot1[MW];
-    double apdq2[MEQN], F2[MEQN], bmp2[MEQN], bpp2[MEQN];
+    double qm1[MEQN], qm2[MEQN], sm1[MW], norm1[MW], dot1[MW];
 #pragma unroll
-    for (int m = 0; m < MEQN; m++) {
-        qm1[m] = qm2[m] = 0.0; amdq1[m] = apdq1[m] = apdq2[m] = F2[m] = bmp2[m] = bpp2[m] = 0.0;
-#pragma unroll
-        for (int mw = 0; mw < MW; mw++) wm1[m][mw] = 0.0;
-    }
+    for (int m = 0; m < MEQN; m++) { qm1[m] = 1.0; qm2[m] = 1.0; }
 #pragma unroll
     for (int mw = 0; mw < MW; mw++) { sm1[mw] = 0.0; norm1[mw] = 0.0; dot1[mw] = 0.0; }
-#pragma unroll
-    for (int n = 0; n < NROE; n++) roe1[n] = 1.0;
+    for (int sl = 0; sl < SL::COUNT; sl++) YS(sl) = (TRANS && sl >= SL::ROE && sl < SL::ROE + NROE) ? 1.0 : 0.0;
 
     int buf = 0;
+    double qnext[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++)
+        qnext[m] = A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl];
     for (int k = j0 - 2; k <= j1 + 1; k++) {
         const long long rowoff = (long long)A.pitch * (k + mbc - 1);
         double qk[MEQN];
 #pragma unroll
-        for (int m = 0; m < MEQN; m++) qk[m] = A.qin[m * A.mstride + rowoff + icl];
+        for (int m = 0; m < MEQN; m++) qk[m] = qnext[m];
+        if (k <= j1) { // prefetch row k+1 while row k is being processed
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) qnext[m] = A.qin[m * A.mstride + rowoff + A.pitch + icl];
+        }
+        // TRANS: the x-sweep result of the cell completed in this iteration (row k-2) is
+        // requested now, a full Riemann solve before it is needed
+        double qx[MEQN];
+        if (TRANS) {
+            const bool need = (k - 2 >= j0) && (k - 2 < j1) && col_out;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++)
+                qx[m] = need ? A.qout[m * A.mstride + (long long)A.pitch * (k - 2 + mbc - 1) + icl] : 0.0;
+        }
 
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
         double normk[MW], dotk[MW];
+        double wl[MEQN][MW]; // unlimited waves of interface k-1
         if (k >= j0 - 1) {
-            RP::solve(A.rp, qm1, qk, wave, s, amdq, apdq, roe);
+            with_arith([&](auto &ar) { RP::solve(ar, A.rp, qm1, qk, wave, s, amdq, apdq, roe); });
             if (col_cfl && k >= 1 && k <= A.my + 1) {
 #pragma unroll
                 for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdy * s[mw]), -dtdy * s[mw]);
-            }
-#pragma unroll
-            for (int mw = 0; mw < MW; mw++) {
-                double n2 = 0.0, d = 0.0;
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) {
-                    if (RP::nz(m, mw)) {
-                        n2 = n2 + wave[m][mw] * wave[m][mw];
-                        d = d + wm1[m][mw] * wave[m][mw];
-                    }
-                }
-                normk[mw] = n2; dotk[mw] = d;
             }
         } else {
 #pragma unroll
@@ -358,38 +417,69 @@ __global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
                 for (int mw = 0; mw < MW; mw++) wave[m][mw] = 0.0;
             }
 #pragma unroll
-            for (int mw = 0; mw < MW; mw++) { s[mw] = 0.0; normk[mw] = 0.0; dotk[mw] = 0.0; }
+            for (int mw = 0; mw < MW; mw++) s[mw] = 0.0;
 #pragma unroll
             for (int n = 0; n < NROE; n++) roe[n] = 1.0;
         }
-
-        // limit interface k-1 and form its correction flux
-        double cqxx[MEQN], F1[MEQN];
 #pragma unroll
-        for (int m = 0; m < MEQN; m++) cqxx[m] = 0.0;
-        if (order2 && k >= j0 + 1) {
-            limit_waves<RP>(wm1, sm1, norm1, dot1, dotk, A.mthlim);
-            double dtdxave = 0.5 * (dtdy + dtdy);
-            second_order<RP>(wm1, sm1, dtdxave, cqxx);
+        for (int mw = 0; mw < MW; mw++) {
+            double n2 = 0.0, d = 0.0;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                if (RP::nz(m, mw)) {
+                    wl[m][mw] = YS(SL::W + m * MW + mw);
+                    n2 = n2 + wave[m][mw] * wave[m][mw];
+                    d = d + wl[m][mw] * wave[m][mw];
+                } else {
+                    wl[m][mw] = 0.0;
+                }
+            }
+            normk[mw] = n2; dotk[mw] = d;
+        }
+
+        // limit interface k-1, form its correction flux and split it transversely
+        double cqxx[MEQN], F1[MEQN], amdq1[MEQN], apdq1[MEQN];
+        double bmm[MEQN], bpm[MEQN], bmp1[MEQN], bpp1[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) { amdq1[m] = YS(SL::AM1 + m); apdq1[m] = YS(SL::AP1 + m); }
+        {
+            const bool lim = order2 && k >= j0 + 1;
+            double roe1[NROE];
+            if (TRANS) {
+#pragma unroll
+                for (int n = 0; n < NROE; n++) roe1[n] = YS(SL::ROE + n);
+            }
+            with_arith([&](auto &ar) {
+                double wlim[MEQN][MW];
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    cqxx[m] = 0.0;
+#pragma unroll
+                    for (int mw = 0; mw < MW; mw++) wlim[m][mw] = wl[m][mw];
+                }
+                if (lim) {
+                    limit_waves<RP>(ar, wlim, sm1, norm1, dot1, dotk, A.mthlim);
+                    double dtdxave = 0.5 * (dtdy + dtdy);
+                    second_order<RP>(wlim, sm1, dtdxave, cqxx);
+                }
+                if (TRANS) {
+                    if (A.trans > 0) {
+                        double asdq[MEQN];
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq1[m] + cqxx[m]) : amdq1[m];
+                        RP::transverse(ar, A.rp, roe1, asdq, bmm, bpm);
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq1[m] - cqxx[m]) : apdq1[m];
+                        RP::transverse(ar, A.rp, roe1, asdq, bmp1, bpp1);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp1[m] = bpp1[m] = 0.0;
+                    }
+                }
+            });
         }
 #pragma unroll
         for (int m = 0; m < MEQN; m++) F1[m] = 0.5 * cqxx[m];
-
-        double bmm[MEQN], bpm[MEQN], bmp1[MEQN], bpp1[MEQN];
-        if (TRANS) {
-            if (A.trans > 0) {
-                double asdq[MEQN];
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq1[m] + cqxx[m]) : amdq1[m];
-                RP::transverse(A.rp, roe1, asdq, bmm, bpm);
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq1[m] - cqxx[m]) : apdq1[m];
-                RP::transverse(A.rp, roe1, asdq, bmp1, bpp1);
-            } else {
-#pragma unroll
-                for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp1[m] = bpp1[m] = 0.0;
-            }
-        }
 
         // complete cell k-2
         const int jc = k - 2;
@@ -399,8 +489,8 @@ __global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
             if (row_out && col_out) {
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {
-                    double qaddv = (0.0 - dtdy * apdq2[m]) - dtdy * amdq1[m];
-                    double dF = F1[m] - F2[m];
+                    double qaddv = (0.0 - dtdy * YS(SL::AP2 + m)) - dtdy * amdq1[m];
+                    double dF = F1[m] - YS(SL::F2 + m);
                     A.qout[m * A.mstride + oidx] = (qm2[m] + qaddv) - dtdy * dF;
                 }
             }
@@ -409,10 +499,10 @@ __global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
             if (row_out) {
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {
-                    double qaddv = (0.0 - dtdy * apdq2[m]) - dtdy * amdq1[m];
-                    double dF = F1[m] - F2[m];
-                    double G1 = (0.0 - hdtdy * bmm[m]) - hdtdy * bmp2[m];
-                    double G2 = (0.0 - hdtdy * bpm[m]) - hdtdy * bpp2[m];
+                    double qaddv = (0.0 - dtdy * YS(SL::AP2 + m)) - dtdy * amdq1[m];
+                    double dF = F1[m] - YS(SL::F2 + m);
+                    double G1 = (0.0 - hdtdy * bmm[m]) - hdtdy * YS(SL::BMP2 + m);
+                    double G2 = (0.0 - hdtdy * bpm[m]) - hdtdy * YS(SL::BPP2 + m);
                     mainE[m] = (qaddv - dtdy * dF - dtdx * (G2 - G1));
                     gs[(buf * 2 * MEQN + m) * NT + t] = G1;
                     gs[(buf * 2 * MEQN + MEQN + m) * NT + t] = G2;
@@ -424,7 +514,7 @@ __global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
                 for (int m = 0; m < MEQN; m++) {
                     double G2l = gs[(buf * 2 * MEQN + MEQN + m) * NT + t - 1];
                     double G1r = gs[(buf * 2 * MEQN + m) * NT + t + 1];
-                    double q = A.qout[m * A.mstride + oidx];
+                    double q = qx[m];
                     q = q + dtdx * G2l;
                     q = q + mainE[m];
                     q = q - dtdx * G1r;
@@ -438,17 +528,23 @@ __global__ void __launch_bounds__(NT) ysweep_kernel(const SweepArgs A)
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             qm2[m] = qm1[m]; qm1[m] = qk[m];
-            apdq2[m] = apdq1[m]; F2[m] = F1[m];
-            amdq1[m] = amdq[m]; apdq1[m] = apdq[m];
-            if (TRANS) { bmp2[m] = bmp1[m]; bpp2[m] = bpp1[m]; }
+            YS(SL::AP2 + m) = apdq1[m];
+            YS(SL::F2 + m) = F1[m];
+            YS(SL::AM1 + m) = amdq[m];
+            YS(SL::AP1 + m) = apdq[m];
+            if (TRANS) { YS(SL::BMP2 + m) = bmp1[m]; YS(SL::BPP2 + m) = bpp1[m]; }
 #pragma unroll
-            for (int mw = 0; mw < MW; mw++) wm1[m][mw] = wave[m][mw];
+            for (int mw = 0; mw < MW; mw++)
+                if (RP::nz(m, mw)) YS(SL::W + m * MW + mw) = wave[m][mw];
         }
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) { sm1[mw] = s[mw]; norm1[mw] = normk[mw]; dot1[mw] = dotk[mw]; }
+        if (TRANS) {
 #pragma unroll
-        for (int n = 0; n < NROE; n++) roe1[n] = roe[n];
+            for (int n = 0; n < NROE; n++) YS(SL::ROE + n) = roe[n];
+        }
     }
+#undef YS
     cfl_commit(cfl, A.cfl_bits);
 }
 
@@ -489,7 +585,7 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
 #pragma unroll
     for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
     double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
-    RP::solve(A.rp, l, rr, wave, s, amdq, apdq, roe);
+    with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, wave, s, amdq, apdq, roe); });
     double cfl = 0.0;
     if (iface_ok) {
 #pragma unroll
@@ -522,7 +618,16 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
             }
             wnorm2[mw] = n2; dotl[mw] = dl; dotr[mw] = dr;
         }
-        limit_waves<RP>(wave, s, wnorm2, dotl, dotr, A.mthlim);
+        with_arith([&](auto &ar) {
+            if (!ar.FAST) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++)
+#pragma unroll
+                    for (int mw = 0; mw < MW; mw++)
+                        if (RP::nz(m, mw)) wave[m][mw] = ws[(m * MW + mw) * NT + t];
+            }
+            limit_waves<RP>(ar, wave, s, wnorm2, dotl, dotr, A.mthlim);
+        });
         // step1.f:121-128
         double dtdxave = 0.5 * (dtdx + dtdx);
 #pragma unroll

@@ -99,7 +99,7 @@ template <class RP, bool TRANS>
 static int launch_y(SweepArgs A, cudaStream_t st)
 {
     constexpr int NC = TRANS ? YNT - 2 : YNT;
-    size_t smem = TRANS ? sizeof(double) * (2 * 2 * RP::MEQN * YNT) : 0;
+    size_t smem = sizeof(double) * YNT * ((TRANS ? 4 * RP::MEQN : 0) + YSlots<RP, TRANS>::COUNT);
     auto k = ysweep_kernel<RP, TRANS, YNT>;
     CUDA_OK(set_smem(k, smem));
     int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;

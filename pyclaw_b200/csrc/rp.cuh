@@ -14,7 +14,12 @@
 //
 // Interface convention (rpn2_euler_5wave.f:24-25): the Riemann problem at interface i
 // has left state qr(:,i-1) and right state ql(:,i); here simply `l[]` and `r[]`.
+//
+// Every division and square root goes through an arithmetic policy `AR` (arith.cuh):
+// same correctly-rounded results, but divisions by a common denominator share one
+// refined reciprocal and no operation carries its own slow-path branch.
 #pragma once
+#include "arith.cuh"
 
 #define CLAW_RP_ACOUSTICS 1
 #define CLAW_RP_ADVECTION 2
@@ -37,19 +42,26 @@ template <int NDIM, int IXY>
 struct RpAcoustics {
     static constexpr int ID = CLAW_RP_ACOUSTICS;
     static constexpr int MEQN = NDIM + 1, MWAVES = 2, NROE = 1;
+#ifndef CLAW_AC_X_MINB
+#define CLAW_AC_X_MINB 5
+#define CLAW_AC_Y_MINB 4
+#endif
+    static constexpr int X_MINB = CLAW_AC_X_MINB, Y_MINB = CLAW_AC_Y_MINB; // CTAs/SM the sweeps are compiled for
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
     __host__ __device__ static constexpr bool nz(int m, int mw) { return m == 0 || m == MU; }
 
-    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[MEQN],
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[MEQN],
                                                  const double (&r)[MEQN], double (&wave)[MEQN][MWAVES],
                                                  double (&s)[MWAVES], double (&amdq)[MEQN],
                                                  double (&apdq)[MEQN], double (&roe)[NROE])
     {
         const double cc = P.p[2], zz = P.p[3];
+        const Recip r2z = ar.rcp(2.0 * zz);
         double delta1 = r[0] - l[0];
         double delta2 = r[MU] - l[MU];
-        double a1 = (-delta1 + zz * delta2) / (2.0 * zz);
-        double a2 = (delta1 + zz * delta2) / (2.0 * zz);
+        double a1 = ar.div(-delta1 + zz * delta2, r2z);
+        double a2 = ar.div(delta1 + zz * delta2, r2z);
         wave[0][0] = -a1 * zz;
         wave[MU][0] = a1;
         s[0] = -cc;
@@ -68,14 +80,16 @@ struct RpAcoustics {
         roe[0] = 0.0;
     }
 
-    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
                                                       const double (&asdq)[MEQN],
                                                       double (&bm)[MEQN], double (&bp)[MEQN])
     {
         const double cc = P.p[2], zz = P.p[3];
         constexpr int mv = (NDIM == 2) ? MV : 0, mu = (NDIM == 2) ? MU : 0;
-        double a1 = (-asdq[0] + zz * asdq[mv]) / (2.0 * zz);
-        double a2 = (asdq[0] + zz * asdq[mv]) / (2.0 * zz);
+        const Recip r2z = ar.rcp(2.0 * zz);
+        double a1 = ar.div(-asdq[0] + zz * asdq[mv], r2z);
+        double a2 = ar.div(asdq[0] + zz * asdq[mv], r2z);
         bm[0] = cc * a1 * zz;
         bm[mu] = 0.0;
         bm[mv] = -cc * a1;
@@ -93,9 +107,11 @@ template <int NDIM, int IXY>
 struct RpAdvection {
     static constexpr int ID = CLAW_RP_ADVECTION;
     static constexpr int MEQN = 1, MWAVES = 1, NROE = 1;
+    static constexpr int X_MINB = 6, Y_MINB = 6;
     __host__ __device__ static constexpr bool nz(int, int) { return true; }
 
-    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[1],
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[1],
                                                  const double (&r)[1], double (&wave)[1][1],
                                                  double (&s)[1], double (&amdq)[1],
                                                  double (&apdq)[1], double (&roe)[NROE])
@@ -107,7 +123,8 @@ struct RpAdvection {
         roe[0] = 0.0;
     }
 
-    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
                                                       const double (&asdq)[1], double (&bm)[1],
                                                       double (&bp)[1])
     {
@@ -126,7 +143,12 @@ struct RpAdvection {
 template <int IXY>
 struct RpEuler5 {
     static constexpr int ID = CLAW_RP_EULER5;
-    static constexpr int MEQN = 5, MWAVES = 5, NROE = 7;
+    static constexpr int MEQN = 5, MWAVES = 5, NROE = 8; // 7 Roe quantities + 1/(2a)
+#ifndef CLAW_EU_X_MINB
+#define CLAW_EU_X_MINB 2
+#define CLAW_EU_Y_MINB 2
+#endif
+    static constexpr int X_MINB = CLAW_EU_X_MINB, Y_MINB = CLAW_EU_Y_MINB;
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
     // sparsity of wave(m,mw) as written at rpn2_euler_5wave.f:124-163
     __host__ __device__ static constexpr bool nz(int m, int mw)
@@ -134,27 +156,32 @@ struct RpEuler5 {
         return (mw == 4) ? (m == 4) : (mw == 1) ? (m == MV || m == 3) : (m != 4);
     }
 
-    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[5],
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[5],
                                                  const double (&r)[5], double (&wave)[5][5],
                                                  double (&s)[5], double (&amdq)[5],
                                                  double (&apdq)[5], double (&roe)[NROE])
     {
         const double gamma = P.p[0], gamma1 = P.p[1];
         // :87-104
-        double rhsqrtl = sqrt(l[0]);
-        double rhsqrtr = sqrt(r[0]);
-        double pl = gamma1 * (l[3] - 0.5 * (l[1] * l[1] + l[2] * l[2]) / l[0]);
-        double pr = gamma1 * (r[3] - 0.5 * (r[1] * r[1] + r[2] * r[2]) / r[0]);
+        double rhsqrtl = ar.sqrt(l[0]);
+        double rhsqrtr = ar.sqrt(r[0]);
+        const Recip rl0 = ar.rcp(l[0]), rr0 = ar.rcp(r[0]);
+        double pl = gamma1 * (l[3] - ar.div(0.5 * (l[1] * l[1] + l[2] * l[2]), rl0));
+        double pr = gamma1 * (r[3] - ar.div(0.5 * (r[1] * r[1] + r[2] * r[2]), rr0));
         double rhsq2 = rhsqrtl + rhsqrtr;
-        double u = (l[MU] / rhsqrtl + r[MU] / rhsqrtr) / rhsq2;
-        double v = (l[MV] / rhsqrtl + r[MV] / rhsqrtr) / rhsq2;
-        double enth = (((l[3] + pl) / rhsqrtl + (r[3] + pr) / rhsqrtr)) / rhsq2;
+        const Recip rsl = ar.rcp(rhsqrtl), rsr = ar.rcp(rhsqrtr), rs2 = ar.rcp(rhsq2);
+        double u = ar.div(ar.div(l[MU], rsl) + ar.div(r[MU], rsr), rs2);
+        double v = ar.div(ar.div(l[MV], rsl) + ar.div(r[MV], rsr), rs2);
+        double enth = ar.div((ar.div(l[3] + pl, rsl) + ar.div(r[3] + pr, rsr)), rs2);
         double u2v2 = u * u + v * v;
         double a2r = gamma1 * (enth - .5 * u2v2);
-        double a = sqrt(a2r);
-        double g1a2 = gamma1 / a2r;
+        double a = ar.sqrt(a2r);
+        double g1a2 = ar.div(gamma1, a2r);
         double euv = enth - u2v2;
+        const Recip r2a = ar.rcp(2.0 * a);
         roe[0] = u2v2; roe[1] = u; roe[2] = v; roe[3] = enth; roe[4] = a; roe[5] = g1a2; roe[6] = euv;
+        roe[7] = r2a.r;
         // :110-119
         double d1 = r[0] - l[0];
         double d2 = r[MU] - l[MU];
@@ -162,7 +189,7 @@ struct RpEuler5 {
         double d4 = r[3] - l[3];
         double a3 = g1a2 * (euv * d1 + u * d2 + v * d3 - d4);
         double a2 = d3 - v * d1;
-        double a4 = (d2 + (a - u) * d1 - a * a3) / (2.0 * a);
+        double a4 = ar.div(d2 + (a - u) * d1 - a * a3, r2a);
         double a1 = d1 - a3 - a4;
         // :124-163
         wave[0][0] = a1;
@@ -195,13 +222,14 @@ struct RpEuler5 {
         wave[3][4] = 0.0;
         wave[4][4] = r[4] - l[4];
         s[4] = u;
-        // :205-286 entropy fix
+        // :205-286 entropy fix.  pim1 / pi below are bitwise equal to pl / pr above (the
+        // sums of squares differ only in the order of a commutative addition), so they and
+        // the divisions by rho(i-1), rho(i) are not repeated.
         bool done = false;
         {
-            double rhoim1 = l[0];
-            double pim1 = gamma1 * (l[3] - 0.5 * (l[MU] * l[MU] + l[MV] * l[MV]) / rhoim1);
-            double cim1 = sqrt(gamma * pim1 / rhoim1);
-            double s0 = l[MU] / rhoim1 - cim1;
+            double pim1 = pl;
+            double cim1 = ar.sqrt(ar.div(gamma * pim1, rl0));
+            double s0 = ar.div(l[MU], rl0) - cim1;
             if (s0 >= 0.0 && s[0] > 0.0) {
 #pragma unroll
                 for (int m = 0; m < 5; m++) amdq[m] = 0.0;
@@ -212,12 +240,13 @@ struct RpEuler5 {
                 double rhou1 = l[MU] + wave[MU][0];
                 double rhov1 = l[MV] + wave[MV][0];
                 double en1 = l[3] + wave[3][0];
-                double p1 = gamma1 * (en1 - 0.5 * (rhou1 * rhou1 + rhov1 * rhov1) / rho1);
-                double c1 = sqrt(gamma * p1 / rho1);
-                double s1 = rhou1 / rho1 - c1;
+                const Recip rr1 = ar.rcp(rho1);
+                double p1 = gamma1 * (en1 - ar.div(0.5 * (rhou1 * rhou1 + rhov1 * rhov1), rr1));
+                double c1 = ar.sqrt(ar.div(gamma * p1, rr1));
+                double s1 = ar.div(rhou1, rr1) - c1;
                 double sfract;
                 if (s0 < 0.0 && s1 > 0.0)
-                    sfract = s0 * (s1 - s[0]) / (s1 - s0);
+                    sfract = ar.div(s0 * (s1 - s[0]), s1 - s0);
                 else if (s[0] < 0.0)
                     sfract = s[0];
                 else
@@ -234,21 +263,21 @@ struct RpEuler5 {
                 amdq[m] = amdq[m] + s[2] * wave[m][2];
                 amdq[m] = amdq[m] + s[4] * wave[m][4];
             }
-            double rhoi = r[0];
-            double pi = gamma1 * (r[3] - 0.5 * (r[MU] * r[MU] + r[MV] * r[MV]) / rhoi);
-            double ci = sqrt(gamma * pi / rhoi);
-            double s3 = r[MU] / rhoi + ci;
+            double pi = pr;
+            double ci = ar.sqrt(ar.div(gamma * pi, rr0));
+            double s3 = ar.div(r[MU], rr0) + ci;
             double rho2 = r[0] - wave[0][3];
             double rhou2 = r[MU] - wave[MU][3];
             double rhov2 = r[MV] - wave[MV][3];
             double en2 = r[3] - wave[3][3];
-            double p2 = gamma1 * (en2 - 0.5 * (rhou2 * rhou2 + rhov2 * rhov2) / rho2);
-            double c2 = sqrt(gamma * p2 / rho2);
-            double s2 = rhou2 / rho2 + c2;
+            const Recip rr2 = ar.rcp(rho2);
+            double p2 = gamma1 * (en2 - ar.div(0.5 * (rhou2 * rhou2 + rhov2 * rhov2), rr2));
+            double c2 = ar.sqrt(ar.div(gamma * p2, rr2));
+            double s2 = ar.div(rhou2, rr2) + c2;
             double sfract = 0.0;
             bool add4 = true;
             if (s2 < 0.0 && s3 > 0.0)
-                sfract = s2 * (s3 - s[3]) / (s3 - s2);
+                sfract = ar.div(s2 * (s3 - s[3]), s3 - s2);
             else if (s[3] < 0.0)
                 sfract = s[3];
             else
@@ -268,15 +297,17 @@ struct RpEuler5 {
         }
     }
 
-    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
                                                       const double (&asdq)[5], double (&bm)[5],
                                                       double (&bp)[5])
     {
         const double u2v2 = roe[0], u = roe[1], v = roe[2], enth = roe[3], a = roe[4],
                      g1a2 = roe[5], euv = roe[6];
+        const Recip r2a{2.0 * a, roe[7]}; // refined in solve() (already validated there)
         double a3 = g1a2 * (euv * asdq[0] + u * asdq[MU] + v * asdq[MV] - asdq[3]);
         double a2 = asdq[MU] - u * asdq[0];
-        double a4 = (asdq[MV] + (a - v) * asdq[0] - a * a3) / (2.0 * a);
+        double a4 = ar.div(asdq[MV] + (a - v) * asdq[0] - a * a3, r2a);
         double a1 = asdq[0] - a3 - a4;
         double waveb[5][4], sb[4];
         waveb[0][0] = a1;
@@ -324,33 +355,41 @@ struct RpEuler5 {
 template <int IXY>
 struct RpShallow {
     static constexpr int ID = CLAW_RP_SHALLOW;
-    static constexpr int MEQN = 3, MWAVES = 3, NROE = 3;
+    static constexpr int MEQN = 3, MWAVES = 3, NROE = 4; // u, v, a, 0.5/a
+#ifndef CLAW_SW_X_MINB
+#define CLAW_SW_X_MINB 4
+#define CLAW_SW_Y_MINB 3
+#endif
+    static constexpr int X_MINB = CLAW_SW_X_MINB, Y_MINB = CLAW_SW_Y_MINB;
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
     __host__ __device__ static constexpr bool nz(int m, int mw)
     {
         return (mw == 1) ? (m == MV) : true;
     }
 
-    __device__ __forceinline__ static void solve(const RpParams &P, const double (&l)[3],
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[3],
                                                  const double (&r)[3], double (&wave)[3][3],
                                                  double (&s)[3], double (&amdq)[3],
                                                  double (&apdq)[3], double (&roe)[NROE])
     {
         const double grav = P.p[0];
         double h = (l[0] + r[0]) * 0.50;
-        double hsqrtl = sqrt(l[0]);
-        double hsqrtr = sqrt(r[0]);
+        double hsqrtl = ar.sqrt(l[0]);
+        double hsqrtr = ar.sqrt(r[0]);
         double hsq2 = hsqrtl + hsqrtr;
-        double u = (l[MU] / hsqrtl + r[MU] / hsqrtr) / hsq2;
-        double v = (l[MV] / hsqrtl + r[MV] / hsqrtr) / hsq2;
-        double a = sqrt(grav * h);
-        roe[0] = u; roe[1] = v; roe[2] = a;
+        const Recip rsl = ar.rcp(hsqrtl), rsr = ar.rcp(hsqrtr), rs2 = ar.rcp(hsq2);
+        double u = ar.div(ar.div(l[MU], rsl) + ar.div(r[MU], rsr), rs2);
+        double v = ar.div(ar.div(l[MV], rsl) + ar.div(r[MV], rsr), rs2);
+        double a = ar.sqrt(grav * h);
+        double hoa = ar.div(0.50, a);
+        roe[0] = u; roe[1] = v; roe[2] = a; roe[3] = hoa;
         double d1 = r[0] - l[0];
         double d2 = r[MU] - l[MU];
         double d3 = r[MV] - l[MV];
-        double a1 = ((u + a) * d1 - d2) * (0.50 / a);
+        double a1 = ((u + a) * d1 - d2) * hoa;
         double a2 = -v * d1 + d3;
-        double a3 = (-(u - a) * d1 + d2) * (0.50 / a);
+        double a3 = (-(u - a) * d1 + d2) * hoa;
         wave[0][0] = a1;
         wave[MU][0] = a1 * (u - a);
         wave[MV][0] = a1 * v;
@@ -365,7 +404,7 @@ struct RpShallow {
         s[2] = u + a;
         bool done = false;
         double him1 = l[0];
-        double s0 = l[MU] / him1 - sqrt(grav * him1);
+        double s0 = ar.div(l[MU], him1) - ar.sqrt(grav * him1);
         if (s0 > 0.0 && s[0] > 0.0) {
 #pragma unroll
             for (int m = 0; m < 3; m++) amdq[m] = 0.0;
@@ -374,10 +413,10 @@ struct RpShallow {
         if (!done) {
             double h1 = l[0] + wave[0][0];
             double hu1 = l[MU] + wave[MU][0];
-            double s1 = hu1 / h1 - sqrt(grav * h1);
+            double s1 = ar.div(hu1, h1) - ar.sqrt(grav * h1);
             double sfract;
             if (s0 < 0.0 && s1 > 0.0)
-                sfract = s0 * ((s1 - s[0]) / (s1 - s0));
+                sfract = s0 * ar.div(s1 - s[0], s1 - s0);
             else if (s[0] < 0.0)
                 sfract = s[0];
             else
@@ -390,14 +429,14 @@ struct RpShallow {
 #pragma unroll
             for (int m = 0; m < 3; m++) amdq[m] = amdq[m] + s[1] * wave[m][1];
             double hi = r[0];
-            double s03 = r[MU] / hi + sqrt(grav * hi);
+            double s03 = ar.div(r[MU], hi) + ar.sqrt(grav * hi);
             double h3 = r[0] - wave[0][2];
             double hu3 = r[MU] - wave[MU][2];
-            double s3 = hu3 / h3 + sqrt(grav * h3);
+            double s3 = ar.div(hu3, h3) + ar.sqrt(grav * h3);
             double sfract = 0.0;
             bool add3 = true;
             if (s3 < 0.0 && s03 > 0.0)
-                sfract = s3 * ((s03 - s[2]) / (s03 - s3));
+                sfract = s3 * ar.div(s03 - s[2], s03 - s3);
             else if (s[2] < 0.0)
                 sfract = s[2];
             else
@@ -416,14 +455,15 @@ struct RpShallow {
         }
     }
 
-    __device__ __forceinline__ static void transverse(const RpParams &P, const double (&roe)[NROE],
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
                                                       const double (&asdq)[3], double (&bm)[3],
                                                       double (&bp)[3])
     {
-        const double u = roe[0], v = roe[1], a = roe[2];
-        double a1 = (0.50 / a) * ((v + a) * asdq[0] - asdq[MV]);
+        const double u = roe[0], v = roe[1], a = roe[2], hoa = roe[3]; // hoa = 0.5/a from solve()
+        double a1 = hoa * ((v + a) * asdq[0] - asdq[MV]);
         double a2 = asdq[MU] - u * asdq[0];
-        double a3 = (0.50 / a) * (-(v - a) * asdq[0] + asdq[MV]);
+        double a3 = hoa * (-(v - a) * asdq[0] + asdq[MV]);
         double waveb[3][3], sb[3];
         waveb[0][0] = a1;
         waveb[MU][0] = a1 * u;

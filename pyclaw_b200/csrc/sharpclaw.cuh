@@ -35,8 +35,11 @@ struct ScArgs {
     int rows_per_cta;
 };
 
-// weno.f90:35-98 for one component of one cell: ql = value at the left edge, qr at the right
-__device__ __forceinline__ void weno5_pyweno(const ScArgs &A, double qm2, double qm1, double q0,
+// weno.f90:35-98 for one component of one cell: ql = value at the left edge, qr at the right.
+// The six weights are quotients over three denominators and two normalisations, i.e. five
+// reciprocals for twelve divisions.
+template <class AR>
+__device__ __forceinline__ void weno5_pyweno(AR &ar, const ScArgs &A, double qm2, double qm1, double q0,
                                              double qp1, double qp2, double &ql, double &qr)
 {
     double sigma0 = ((A.c333) * q0) * q0 + ((-A.c1033) * q0) * qp1 + ((A.c366) * q0) * qp2 +
@@ -45,29 +48,31 @@ __device__ __forceinline__ void weno5_pyweno(const ScArgs &A, double qm2, double
                     ((A.c433) * q0) * q0 + ((-A.c433) * q0) * qp1 + ((A.c133) * qp1) * qp1;
     double sigma2 = ((A.c133) * qm2) * qm2 + ((-A.c633) * qm2) * qm1 + ((A.c366) * qm2) * q0 +
                     ((A.c833) * qm1) * qm1 + ((-A.c1033) * qm1) * q0 + ((A.c333) * q0) * q0;
-    double e0 = (sigma0 + A.eps) * (sigma0 + A.eps);
-    double e1 = (sigma1 + A.eps) * (sigma1 + A.eps);
-    double e2 = (sigma2 + A.eps) * (sigma2 + A.eps);
+    const Recip e0 = ar.rcp((sigma0 + A.eps) * (sigma0 + A.eps));
+    const Recip e1 = ar.rcp((sigma1 + A.eps) * (sigma1 + A.eps));
+    const Recip e2 = ar.rcp((sigma2 + A.eps) * (sigma2 + A.eps));
     double acc = 0.0;
-    double omega0 = A.d01 / e0;
+    double omega0 = ar.div(A.d01, e0);
     acc = acc + omega0;
-    double omega1 = A.d06 / e1;
+    double omega1 = ar.div(A.d06, e1);
     acc = acc + omega1;
-    double omega2 = A.d03 / e2;
+    double omega2 = ar.div(A.d03, e2);
     acc = acc + omega2;
-    omega0 = omega0 / acc;
-    omega1 = omega1 / acc;
-    omega2 = omega2 / acc;
+    const Recip ra = ar.rcp(acc);
+    omega0 = ar.div(omega0, ra);
+    omega1 = ar.div(omega1, ra);
+    omega2 = ar.div(omega2, ra);
     acc = 0.0;
-    double omega3 = A.d03 / e0;
+    double omega3 = ar.div(A.d03, e0);
     acc = acc + omega3;
-    double omega4 = A.d06 / e1;
+    double omega4 = ar.div(A.d06, e1);
     acc = acc + omega4;
-    double omega5 = A.d01 / e2;
+    double omega5 = ar.div(A.d01, e2);
     acc = acc + omega5;
-    omega3 = omega3 / acc;
-    omega4 = omega4 / acc;
-    omega5 = omega5 / acc;
+    const Recip rb = ar.rcp(acc);
+    omega3 = ar.div(omega3, rb);
+    omega4 = ar.div(omega4, rb);
+    omega5 = ar.div(omega5, rb);
     double fr0 = (A.r183) * q0 + (-A.r116) * qp1 + (A.r0333) * qp2;
     double fr1 = (A.r0333) * qm1 + (A.r0833) * q0 + (-A.r0166) * qp1;
     double fr2 = (-A.r0166) * qm2 + (A.r0833) * qm1 + (A.r0333) * q0;
@@ -79,8 +84,10 @@ __device__ __forceinline__ void weno5_pyweno(const ScArgs &A, double qm2, double
 }
 
 // reconstruct.f90:136-181 for one side.  (t1,t2,t3,e1,e2,e3) are the side's differences.
-__device__ __forceinline__ double weno5_old_side(double epweno, double t1, double t2, double t3,
-                                                 double e1, double e2, double e3, double base)
+template <class AR>
+__device__ __forceinline__ double weno5_old_side(AR &ar, double epweno, double t1, double t2, double t3,
+                                                 double e1, double e2, double e3, double qa, double qb,
+                                                 double qc, double qd)
 {
     double tt1 = 13. * (t1 * t1) + 3. * (e1 * e1);
     double tt2 = 13. * (t2 * t2) + 3. * (e2 * e2);
@@ -91,30 +98,33 @@ __device__ __forceinline__ double weno5_old_side(double epweno, double t1, doubl
     double s1 = tt2 * tt3;
     double s2 = 6. * tt1 * tt3;
     double s3 = 3. * tt1 * tt2;
-    double t0 = 1. / (s1 + s2 + s3);
+    double t0 = ar.div(1., s1 + s2 + s3);
     s1 = s1 * t0;
     s3 = s3 * t0;
-    return (s1 * (t2 - t1) + (0.5 * s3 - 0.25) * (t3 - t2)) / 3. + base;
+    // (-q(i-2) + 7 (q(i-1) + q(i)) - q(i+1)) / 12
+    return ar.div(s1 * (t2 - t1) + (0.5 * s3 - 0.25) * (t3 - t2), 3.) +
+           ar.div(-qa + 7. * (qb + qc) - qd, 12.);
 }
 
-__device__ __forceinline__ void weno5_old(const ScArgs &A, double a, double b, double c, double d,
+template <class AR>
+__device__ __forceinline__ void weno5_old(AR &ar, const ScArgs &A, double a, double b, double c, double d,
                                           double e, double &ql, double &qr)
 {
     double d1 = b - a, d2 = c - b, d3 = d - c, d4 = e - d; // dq1m(c-1), dq1m(c), dq1m(c+1), dq1m(c+2)
     // ql(c): m1 = 2 (im = -1) evaluated at position c
-    ql = weno5_old_side(A.epweno, -(d4 - d3), -(d3 - d2), -(d2 - d1), d4 - 3. * d3, d3 + d2,
-                        3. * d2 - d1, (-a + 7. * (b + c) - d) / 12.);
+    ql = weno5_old_side(ar, A.epweno, -(d4 - d3), -(d3 - d2), -(d2 - d1), d4 - 3. * d3, d3 + d2,
+                        3. * d2 - d1, a, b, c, d);
     // qr(c): m1 = 1 (im = +1) evaluated at position c+1
-    qr = weno5_old_side(A.epweno, (d1 - d2), (d2 - d3), (d3 - d4), d1 - 3. * d2, d2 + d3,
-                        3. * d3 - d4, (-b + 7. * (c + d) - e) / 12.);
+    qr = weno5_old_side(ar, A.epweno, (d1 - d2), (d2 - d3), (d3 - d4), d1 - 3. * d2, d2 + d3,
+                        3. * d3 - d4, b, c, d, e);
 }
 
-template <bool OLD>
-__device__ __forceinline__ void weno5(const ScArgs &A, double a, double b, double c, double d,
+template <bool OLD, class AR>
+__device__ __forceinline__ void weno5(AR &ar, const ScArgs &A, double a, double b, double c, double d,
                                       double e, double &ql, double &qr)
 {
-    if (OLD) weno5_old(A, a, b, c, d, e, ql, qr);
-    else weno5_pyweno(A, a, b, c, d, e, ql, qr);
+    if (OLD) weno5_old(ar, A, a, b, c, d, e, ql, qr);
+    else weno5_pyweno(ar, A, a, b, c, d, e, ql, qr);
 }
 
 __device__ __forceinline__ void sc_cfl_commit(double cfl, unsigned long long *cfl_bits)
@@ -137,7 +147,7 @@ __device__ __forceinline__ void stage_store(const ScArgs &A, long long idx, cons
         const long long o = m * A.mstride + idx;
         if (A.dq_out) A.dq_out[o] = dq[m];
         if (A.mode == 0) {
-            A.out[o] = q[m] + dq[m] / A.div;
+            A.out[o] = q[m] + ((A.div == 1.0) ? dq[m] : dq[m] / A.div);
         } else if (A.mode == 1) {
             A.out[o] = A.ca * A.qa[o] + A.cb * (q[m] + dq[m]);
         } else if (A.mode == 2) {
@@ -157,18 +167,21 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
     constexpr int QS = NT + 4;
     double ql[MEQN], qr[MEQN];
+    with_arith([&](auto &ar) {
 #pragma unroll
-    for (int m = 0; m < MEQN; m++) {
-        const double *row = qs + m * QS + t;
-        weno5<OLD>(A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m]);
-        x1[m * NT + t] = qr[m];
-    }
+        for (int m = 0; m < MEQN; m++) {
+            const double *row = qs + m * QS + t;
+            weno5<OLD>(ar, A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m]);
+        }
+    });
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) x1[m * NT + t] = qr[m];
     __syncthreads();
     double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
     double left[MEQN];
 #pragma unroll
     for (int m = 0; m < MEQN; m++) left[m] = x1[m * NT + (t > 0 ? t - 1 : 0)];
-    RP::solve(A.rp, left, ql, wave, s, amdq, apdq, roe);
+    with_arith([&](auto &ar) { RP::solve(ar, A.rp, left, ql, wave, s, amdq, apdq, roe); });
     if (iface_cfl) {
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, A.dtdx * s[mw]), -A.dtdx * s[mw]);
@@ -178,7 +191,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
     __syncthreads();
     if (full) {
         double amdq2[MEQN], apdq2[MEQN];
-        RP::solve(A.rp, ql, qr, wave, s, amdq2, apdq2, roe);
+        with_arith([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, wave, s, amdq2, apdq2, roe); });
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             double an = x2[m * NT + (t < NT - 1 ? t + 1 : t)];
@@ -226,12 +239,23 @@ __global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
         qr_prev[m] = 1.0; apdq_prev[m] = amdq2_prev[m] = apdq2_prev[m] = 0.0;
     }
 
+    // software prefetch of the next row (own column, staging column, 4 extra columns)
+    double pn[MEQN], ps[MEQN], ps2[MEQN];
+    {
+        const long long ro = (long long)A.pitch * (j0 - 3 + mbc - 1);
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            pn[m] = A.q[m * A.mstride + ro + icl];
+            ps[m] = A.q[m * A.mstride + ro + cstage];
+            ps2[m] = (t < 4) ? A.q[m * A.mstride + ro + cstage2] : 0.0;
+        }
+    }
     for (int k = j0 - 3; k <= j1 + 2; k++) {
         const long long rowoff = (long long)A.pitch * (k + mbc - 1);
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             w0[m] = w1[m]; w1[m] = w2[m]; w2[m] = w3[m]; w3[m] = w4[m];
-            w4[m] = A.q[m * A.mstride + rowoff + icl];
+            w4[m] = pn[m];
             dx4[m] = dx3[m]; dx3[m] = dx2[m]; dx2[m] = dx1[m];
         }
         const bool xfull = (k >= j0) && (k < j1);
@@ -239,9 +263,20 @@ __global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
         if (xfull || xcfl_only) {
 #pragma unroll
             for (int m = 0; m < MEQN; m++) {
-                qs[m * QS + t] = A.q[m * A.mstride + rowoff + cstage];
-                if (t < 4) qs[m * QS + NT + t] = A.q[m * A.mstride + rowoff + cstage2];
+                qs[m * QS + t] = ps[m];
+                if (t < 4) qs[m * QS + NT + t] = ps2[m];
             }
+        }
+        if (k < j1 + 2) {
+            const long long ro = rowoff + A.pitch;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                pn[m] = A.q[m * A.mstride + ro + icl];
+                ps[m] = A.q[m * A.mstride + ro + cstage];
+                if (t < 4) ps2[m] = A.q[m * A.mstride + ro + cstage2];
+            }
+        }
+        if (xfull || xcfl_only) {
             __syncthreads();
             sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1);
         }
@@ -250,20 +285,24 @@ __global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
         const int c = k - 2;
         if (c >= j0 - 1) {
             double ql[MEQN], qr[MEQN];
+            with_arith([&](auto &ar) {
 #pragma unroll
-            for (int m = 0; m < MEQN; m++) weno5<OLD>(A, w0[m], w1[m], w2[m], w3[m], w4[m], ql[m], qr[m]);
+                for (int m = 0; m < MEQN; m++)
+                    weno5<OLD>(ar, A, w0[m], w1[m], w2[m], w3[m], w4[m], ql[m], qr[m]);
+            });
             double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
             double amdq2[MEQN], apdq2[MEQN];
 #pragma unroll
             for (int m = 0; m < MEQN; m++) { amdq[m] = apdq[m] = amdq2[m] = apdq2[m] = 0.0; }
             if (c >= j0) {
-                RPY::solve(A.rp, qr_prev, ql, wave, s, amdq, apdq, roe);
+                with_arith([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, wave, s, amdq, apdq, roe); });
                 if (ycol && c >= 1 && c <= A.my + 1) {
 #pragma unroll
                     for (int mw = 0; mw < MW; mw++)
                         cfl = dmax2(dmax2(cfl, A.dtdy * s[mw]), -A.dtdy * s[mw]);
                 }
-                if (c < j1) RPY::solve(A.rp, ql, qr, wave, s, amdq2, apdq2, roe);
+                if (c < j1)
+                    with_arith([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, wave, s, amdq2, apdq2, roe); });
                 // cell c-1 = k-3 is complete
                 const int jc = c - 1;
                 if (jc >= j0 && jc < j1 && col_out) {
