@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
     constexpr int NC = NT - 3;
     constexpr int QS = NT + 1;
     extern __shared__ double sm[];
-    double *qs = sm;                 // [MEQN][NT+1]   staged q row
-    double *ws = qs + MEQN * QS;     // [MEQN*MW][NT]  unlimited waves
+    double *qs0 = sm;                // [2][MEQN][NT+1] staged q rows (double buffered)
+    double *qs = qs0;
+    double *ws = qs0 + 2 * MEQN * QS; // [MEQN*MW][NT]  unlimited waves
     double *xs = ws + MEQN * MW * NT; // [4*MEQN][NT]   amdq, F, bm(A-), bp(A-) of each interface
 
     const int t = threadIdx.x;
@@ -151,33 +152,35 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
 
     const int rbeg = TRANS ? j0 - 1 : j0;
     const int rend = TRANS ? j1 : j1 - 1;
-    // software prefetch: the row for iteration r+1 is requested before the arithmetic of
-    // row r starts, so its HBM latency is hidden behind a full row of Riemann solves
-    double qn[MEQN], qn2[MEQN];
+    // Asynchronous staging (cp.async): the row for iteration r+1 is requested before the
+    // arithmetic of row r starts, straight into the other half of a double-buffered
+    // shared-memory row, so its HBM latency hides behind a full row of Riemann solves.
     {
         const long long ro = (long long)A.pitch * (rbeg + mbc - 1);
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
-            qn[m] = A.qin[m * A.mstride + ro + cload];
-            qn2[m] = (t == 0) ? A.qin[m * A.mstride + ro + cload2] : 0.0;
+            cp_async8(&qs[m * QS + t], &A.qin[m * A.mstride + ro + cload]);
+            if (t == 0) cp_async8(&qs[m * QS + NT], &A.qin[m * A.mstride + ro + cload2]);
         }
+        cp_async_commit();
     }
+    int qb = 0;
     for (int r = rbeg; r <= rend; r++) {
         const long long rowoff = (long long)A.pitch * (r + mbc - 1);
-#pragma unroll
-        for (int m = 0; m < MEQN; m++) {
-            qs[m * QS + t] = qn[m];
-            if (t == 0) qs[m * QS + NT] = qn2[m];
-        }
+        cp_async_wait_all();
+        __syncthreads();
+        double *qs = qs0 + qb * (MEQN * QS);
         if (r < rend) {
+            double *qsn = qs0 + (qb ^ 1) * (MEQN * QS);
             const long long ro = rowoff + A.pitch;
 #pragma unroll
             for (int m = 0; m < MEQN; m++) {
-                qn[m] = A.qin[m * A.mstride + ro + cload];
-                if (t == 0) qn2[m] = A.qin[m * A.mstride + ro + cload2];
+                cp_async8(&qsn[m * QS + t], &A.qin[m * A.mstride + ro + cload]);
+                if (t == 0) cp_async8(&qsn[m * QS + NT], &A.qin[m * A.mstride + ro + cload2]);
             }
+            cp_async_commit();
         }
-        __syncthreads();
+        qb ^= 1;
         double l[MEQN], rr[MEQN];
 #pragma unroll
         for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
@@ -340,7 +343,10 @@ struct YSlots {
     static constexpr int ROE = F2 + MEQN;             // Roe data of interface k-1   (TRANS)
     static constexpr int BMP2 = ROE + NROE;           // B^- A^+ dq of interface k-2 (TRANS)
     static constexpr int BPP2 = BMP2 + MEQN;          // B^+ A^+ dq of interface k-2 (TRANS)
-    static constexpr int COUNT = TRANS ? BPP2 + MEQN : ROE;
+    static constexpr int STATE_END = TRANS ? BPP2 + MEQN : ROE;
+    static constexpr int QN = STATE_END;              // [2][MEQN] cp.async landing slots: next row of qin
+    static constexpr int QX = QN + 2 * MEQN;          // [2][MEQN] cp.async landing slots: x-sweep result (TRANS)
+    static constexpr int COUNT = TRANS ? QX + 2 * MEQN : QX;
 };
 
 template <class RP, bool TRANS, int NT>
@@ -374,32 +380,39 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     for (int m = 0; m < MEQN; m++) { qm1[m] = 1.0; qm2[m] = 1.0; }
 #pragma unroll
     for (int mw = 0; mw < MW; mw++) { sm1[mw] = 0.0; norm1[mw] = 0.0; dot1[mw] = 0.0; }
-    for (int sl = 0; sl < SL::COUNT; sl++) YS(sl) = (TRANS && sl >= SL::ROE && sl < SL::ROE + NROE) ? 1.0 : 0.0;
+    for (int sl = 0; sl < SL::STATE_END; sl++) YS(sl) = (TRANS && sl >= SL::ROE && sl < SL::ROE + NROE) ? 1.0 : 0.0;
 
     int buf = 0;
-    double qnext[MEQN];
+    // cp.async staging of row k+1 (and, TRANS, of the x-sweep result of row k-1) into
+    // thread-private slots, double buffered on the parity of k
 #pragma unroll
     for (int m = 0; m < MEQN; m++)
-        qnext[m] = A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl];
+        cp_async8(&YS(SL::QN + m), &A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl]);
+    cp_async_commit();
+    int par = 0;
     for (int k = j0 - 2; k <= j1 + 1; k++) {
         const long long rowoff = (long long)A.pitch * (k + mbc - 1);
+        cp_async_wait_all();
         double qk[MEQN];
 #pragma unroll
-        for (int m = 0; m < MEQN; m++) qk[m] = qnext[m];
-        if (k <= j1) { // prefetch row k+1 while row k is being processed
-#pragma unroll
-            for (int m = 0; m < MEQN; m++) qnext[m] = A.qin[m * A.mstride + rowoff + A.pitch + icl];
-        }
-        // TRANS: the x-sweep result of the cell completed in this iteration (row k-2) is
-        // requested now, a full Riemann solve before it is needed
-        double qx[MEQN];
-        if (TRANS) {
-            const bool need = (k - 2 >= j0) && (k - 2 < j1) && col_out;
+        for (int m = 0; m < MEQN; m++) qk[m] = YS(SL::QN + par * MEQN + m);
+        const int qxslot = SL::QX + par * MEQN; // x-sweep result of row k-2, requested last iteration
+        if (k <= j1) {
 #pragma unroll
             for (int m = 0; m < MEQN; m++)
-                qx[m] = need ? A.qout[m * A.mstride + (long long)A.pitch * (k - 2 + mbc - 1) + icl] : 0.0;
+                cp_async8(&YS(SL::QN + (par ^ 1) * MEQN + m), &A.qin[m * A.mstride + rowoff + A.pitch + icl]);
         }
-
+        if (TRANS) {
+            const bool need = (k - 1 >= j0) && (k - 1 < j1) && col_out;
+            if (need) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++)
+                    cp_async8(&YS(SL::QX + (par ^ 1) * MEQN + m),
+                              &A.qout[m * A.mstride + (long long)A.pitch * (k - 1 + mbc - 1) + icl]);
+            }
+        }
+        cp_async_commit();
+        par ^= 1;
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
         double normk[MW], dotk[MW];
         double wl[MEQN][MW]; // unlimited waves of interface k-1
@@ -514,7 +527,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
                 for (int m = 0; m < MEQN; m++) {
                     double G2l = gs[(buf * 2 * MEQN + MEQN + m) * NT + t - 1];
                     double G1r = gs[(buf * 2 * MEQN + m) * NT + t + 1];
-                    double q = qx[m];
+                    double q = YS(qxslot + m);
                     q = q + dtdx * G2l;
                     q = q + mainE[m];
                     q = q - dtdx * G1r;

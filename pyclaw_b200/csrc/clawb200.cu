@@ -85,7 +85,7 @@ template <class RP, bool TRANS>
 static int launch_x(SweepArgs A, cudaStream_t st)
 {
     constexpr int NC = XNT - 3;
-    size_t smem = sizeof(double) * (RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
+    size_t smem = sizeof(double) * (2 * RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
     auto k = xsweep_kernel<RP, TRANS, XNT>;
     CUDA_OK(set_smem(k, smem));
     int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
@@ -440,7 +440,7 @@ template <class RPX, class RPY, bool OLD>
 static int sc_launch2(const ScArgs &A, cudaStream_t st)
 {
     constexpr int NC = SNT - 2;
-    size_t smem = sizeof(double) * (RPX::MEQN * (SNT + 4) + 2 * RPX::MEQN * SNT);
+    size_t smem = sizeof(double) * (2 * RPX::MEQN * (SNT + 4) + 2 * RPX::MEQN * SNT);
     auto k = sc2d_kernel<RPX, RPY, OLD, SNT>;
     CUDA_OK(set_smem(k, smem));
     dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);

@@ -147,7 +147,13 @@ __device__ __forceinline__ void stage_store(const ScArgs &A, long long idx, cons
         const long long o = m * A.mstride + idx;
         if (A.dq_out) A.dq_out[o] = dq[m];
         if (A.mode == 0) {
-            A.out[o] = q[m] + ((A.div == 1.0) ? dq[m] : dq[m] / A.div);
+            double v = dq[m];
+            if (A.div != 1.0) { // dq/6 of SSP104: zero increments are common, keep them off the slow path
+                FastArith fa;
+                v = fa.div(dq[m], A.div);
+                if (fa.bad()) v = dq[m] / A.div;
+            }
+            A.out[o] = q[m] + v;
         } else if (A.mode == 1) {
             A.out[o] = A.ca * A.qa[o] + A.cb * (q[m] + dq[m]);
         } else if (A.mode == 2) {
@@ -210,9 +216,9 @@ __global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
     constexpr int NC = NT - 2;
     constexpr int QS = NT + 4;
     extern __shared__ double sm[];
-    double *qs = sm;             // [MEQN][NT+4]
-    double *x1 = qs + MEQN * QS; // [MEQN][NT]
-    double *x2 = x1 + MEQN * NT; // [MEQN][NT]
+    double *qs0 = sm;                 // [2][MEQN][NT+4] staged rows (double buffered)
+    double *x1 = qs0 + 2 * MEQN * QS; // [MEQN][NT]
+    double *x2 = x1 + MEQN * NT;      // [MEQN][NT]
 
     const int t = threadIdx.x;
     const int mbc = A.mbc;
@@ -239,45 +245,43 @@ __global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
         qr_prev[m] = 1.0; apdq_prev[m] = amdq2_prev[m] = apdq2_prev[m] = 0.0;
     }
 
-    // software prefetch of the next row (own column, staging column, 4 extra columns)
-    double pn[MEQN], ps[MEQN], ps2[MEQN];
+    // cp.async staging: row k+1 is requested into the other half of a double-buffered
+    // shared-memory row before row k is processed (index kk <-> cell i0-3+kk)
     {
         const long long ro = (long long)A.pitch * (j0 - 3 + mbc - 1);
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
-            pn[m] = A.q[m * A.mstride + ro + icl];
-            ps[m] = A.q[m * A.mstride + ro + cstage];
-            ps2[m] = (t < 4) ? A.q[m * A.mstride + ro + cstage2] : 0.0;
+            cp_async8(&qs0[m * QS + t], &A.q[m * A.mstride + ro + cstage]);
+            if (t < 4) cp_async8(&qs0[m * QS + NT + t], &A.q[m * A.mstride + ro + cstage2]);
         }
+        cp_async_commit();
     }
+    int qb = 0;
     for (int k = j0 - 3; k <= j1 + 2; k++) {
         const long long rowoff = (long long)A.pitch * (k + mbc - 1);
+        cp_async_wait_all();
+        __syncthreads();
+        const double *qs = qs0 + qb * (MEQN * QS);
+        if (k < j1 + 2) {
+            double *qsn = qs0 + (qb ^ 1) * (MEQN * QS);
+            const long long ro = rowoff + A.pitch;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                cp_async8(&qsn[m * QS + t], &A.q[m * A.mstride + ro + cstage]);
+                if (t < 4) cp_async8(&qsn[m * QS + NT + t], &A.q[m * A.mstride + ro + cstage2]);
+            }
+            cp_async_commit();
+        }
+        qb ^= 1;
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             w0[m] = w1[m]; w1[m] = w2[m]; w2[m] = w3[m]; w3[m] = w4[m];
-            w4[m] = pn[m];
+            w4[m] = qs[m * QS + t + 2]; // this thread's own column
             dx4[m] = dx3[m]; dx3[m] = dx2[m]; dx2[m] = dx1[m];
         }
         const bool xfull = (k >= j0) && (k < j1);
         const bool xcfl_only = (k == 0 && j0 == 1) || (k == A.my + 1 && j1 == A.my + 1);
         if (xfull || xcfl_only) {
-#pragma unroll
-            for (int m = 0; m < MEQN; m++) {
-                qs[m * QS + t] = ps[m];
-                if (t < 4) qs[m * QS + NT + t] = ps2[m];
-            }
-        }
-        if (k < j1 + 2) {
-            const long long ro = rowoff + A.pitch;
-#pragma unroll
-            for (int m = 0; m < MEQN; m++) {
-                pn[m] = A.q[m * A.mstride + ro + icl];
-                ps[m] = A.q[m * A.mstride + ro + cstage];
-                if (t < 4) ps2[m] = A.q[m * A.mstride + ro + cstage2];
-            }
-        }
-        if (xfull || xcfl_only) {
-            __syncthreads();
             sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1);
         }
 
