@@ -152,3 +152,37 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(_lib.ClawB200Error):
         _lib.call("clawb200_step2_host", ctypes.byref(P2), _ptr(q), _ptr(q.copy("F")), None, 0.1,
                   ctypes.byref(cfl))
+
+
+def test_f2py_shaped_modules():
+    """INTEGRATION.md path B: the f2py call signatures of classic2 / sharpclaw2."""
+    from pyclaw_b200 import f2py_shim
+    mx, my, mbc = 50, 41, 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    q = _random_padded("euler", mx, my, mbc, seed=11)
+    method, lim = [1, 2, 2, 0, 0, 0, 0], [4, 4, 4, 4, 2]
+    classic2 = f2py_shim.classic2('euler_5wave')
+    classic2.cparam.gamma, classic2.cparam.gamma1 = 1.4, 0.4
+    qnew = q.copy('F')
+    out, cfl = classic2.step2(max(mx, my), mbc, mx, my, q, qnew, None, dx, dy, dt, method, lim)
+    assert out is qnew
+    qo = q.copy('F')
+    cfl_o = po.step2(3, [1.4, 0.4], mbc, mx, my, q, qo, None, dx, dy, dt, method, lim)
+    assert np.array_equal(qnew[:, mbc:-mbc, mbc:-mbc], qo[:, mbc:-mbc, mbc:-mbc]) and cfl == cfl_o
+    # dimensional splitting exactly as clawpack.py:538-548 calls it (second call aliased)
+    method[2] = -1
+    qnew = q.copy('F')
+    qq, cx = classic2.step2ds(max(mx, my), mbc, mx, my, q, qnew, None, dx, dy, dt, method, lim, None, None, None, None, 1)
+    qq, cy = classic2.step2ds(max(mx, my), mbc, mx, my, qq, qq, None, dx, dy, dt, method, lim, None, None, None, None, 2)
+    qo = q.copy('F')
+    ox = po.step2ds(3, [1.4, 0.4], mbc, mx, my, q, qo, None, dx, dy, dt, method, lim, 1)
+    oy = po.step2ds(3, [1.4, 0.4], mbc, mx, my, qo, qo, None, dx, dy, dt, method, lim, 2)
+    assert np.array_equal(qq, qo) and max(cx, cy) == max(ox, oy)
+    q3 = _random_padded("shallow", mx, my, 3, seed=2, smooth=True)
+    sharpclaw2 = f2py_shim.sharpclaw2('shallow_roe_with_efix')
+    sharpclaw2.cparam.grav = 1.0
+    dq, cfl = sharpclaw2.flux2(q3, None, dt, 0.0, 3, max(mx, my), mx, my, dx=dx, dy=dy)
+    dqo, cflo = po.sc_flux2(4, [1.0], 3, 3, mx, my, q3, dx, dy, dt, 0)
+    assert np.array_equal(dq[:, 3:-3, 3:-3], dqo[:, 3:-3, 3:-3]) and cfl == cflo
+    with pytest.raises(ValueError):
+        classic2.step2(max(mx, my), mbc, mx, my, np.ascontiguousarray(q), qnew, None, dx, dy, dt, method, lim)
