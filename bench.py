@@ -424,7 +424,9 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+            tr = json.load(f).get(args.workload, {}).get(dom)
+            if tr:  # measured DRAM bytes per cell per launch (ncu), scaled to this launch's cells
+                traffic = tr["bytes_per_cell"] * cells_per_rank
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "kernel_ms": kms, "algorithmic_bytes_per_cell_per_launch": bpc,
