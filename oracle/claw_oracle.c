@@ -23,7 +23,9 @@
  *   development/rp_approaches/rpn2_euler_5wave.f:5-302, rpt2_euler_5wave.f:4-98
  * Riemann solvers that live in the external clawpack/riemann repository (un-vendored,
  * un-pinned) are restated from their published algorithm:
- *   rp1/rpn2/rpt2 acoustics, rp1/rpn2/rpt2 advection, rpn2/rpt2 shallow Roe + efix.
+ *   rp1/rpn2/rpt2 acoustics, rp1/rpn2/rpt2 advection, rpn2/rpt2 shallow Roe + efix,
+ *   rpn2/rpt2 shallow water on the sphere (with apps/shallow-sphere/{step2qcor,qcor,src2,
+ *   setaux,qinit,mapc2p}.f, which ARE in the reference tree).
  */
 #include <math.h>
 #include <pthread.h>
@@ -34,6 +36,7 @@
 #define RP_ADVECTION 2
 #define RP_EULER5 3
 #define RP_SHALLOW 4
+#define RP_SPHERE 5 /* shallow water on the sphere: params g, dxcom, dycom ; 16 aux ; step2qcor */
 
 #define WENO_PYWENO_F32 0 /* weno.f90 literals read as REAL(4), as gfortran does */
 #define WENO_PYWENO_F64 1 /* same formulas, literals read as doubles            */
@@ -46,6 +49,7 @@ typedef struct {
     /* acoustics: p[0]=rho p[1]=bulk p[2]=cc p[3]=zz ; advection: p[0]=u p[1]=v ;
        euler: p[0]=gamma p[1]=gamma1 ; shallow: p[0]=grav */
     /* common /comroe/ twin: filled by rpn2, read by rpt2 on the same slice */
+    double dxcom, dycom; /* common /comxyt/ */
     int nroe;
     double *u2v2, *u, *v, *enth, *a, *g1a2, *euv, *h;
 } rp_ctx;
@@ -346,11 +350,19 @@ static void rpn_shallow(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int m
         }
 }
 
+static void rpn_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                       const double *ql, const double *qr, const double *auxl, const double *auxr,
+                       double *wave, double *s, double *amdq, double *apdq);
+static void rpt_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx, const double *ql,
+                       const double *aux1, const double *aux2, const double *aux3, int imp,
+                       const double *asdq, double *bmasdq, double *bpasdq);
+
 static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
-                const double *ql, const double *qr,
+                const double *ql, const double *qr, const double *auxl, const double *auxr,
                 double *wave, double *s, double *amdq, double *apdq)
 {
     switch (c->rp_id) {
+    case RP_SPHERE: rpn_sphere(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
     case RP_ACOUSTICS: rpn_acoustics(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_ADVECTION: rpn_advection(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_EULER5: rpn_euler5(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
@@ -361,10 +373,15 @@ static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
 /* ------------------------------------------------------------------------- */
 /* Transverse Riemann solvers                                                */
 /* ------------------------------------------------------------------------- */
-static void rpt(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+static void rpt(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx, const double *ql,
+                const double *aux1, const double *aux2, const double *aux3, int imp,
                 const double *asdq, double *bmasdq, double *bpasdq)
 {
     int mu, mv;
+    if (c->rp_id == RP_SPHERE) {
+        rpt_sphere(c, ixy, meqn, mwaves, mbc, mx, ql, aux1, aux2, aux3, imp, asdq, bmasdq, bpasdq);
+        return;
+    }
     if (ixy == 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
     (void)mwaves;
     if (c->rp_id == RP_ACOUSTICS) {
@@ -466,6 +483,218 @@ static void rpt(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
     }
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* Shallow water on the sphere.                                              */
+/* clawpack/riemann rpn2_shallow_sphere.f, rpt2_shallow_sphere.f (external,  */
+/* un-vendored; restated from the published algorithm): the   */
+/* 3-D momentum is rotated into the edge-normal / edge-tangent frame stored  */
+/* in aux(2:7) (ixy=1) or aux(8:13) (ixy=2), a 1-D shallow water Roe solve   */
+/* with entropy fix is done there, speeds are scaled by the edge length      */
+/* ratio gamma/dy, waves are rotated back and the fluctuations are projected */
+/* onto the tangent plane with aux(14:16).  Pinned only by                   */
+/* test/swsphere_height (1e-4): PARITY OTHERWISE UNPINNED.                   */
+/* common /sw/ g = p[0]; common /comxyt/ dxcom, dycom = c->dxcom, c->dycom.  */
+/* ------------------------------------------------------------------------- */
+#define AX(arr, ma, i) arr[(ma) + 16 * IX(i)]
+static void rpn_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                       const double *ql, const double *qr, const double *auxl, const double *auxr,
+                       double *wave, double *s, double *amdq, double *apdq)
+{
+    const double g = c->p[0];
+    const double dy = (ixy == 1) ? c->dycom : c->dxcom;
+    const int ioff = (ixy == 1) ? 1 : 7;
+    double *u = c->u, *v = c->v, *a = c->a, *h = c->h;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int k = IX(i);
+        double enx = AX(auxl, ioff + 0, i), eny = AX(auxl, ioff + 1, i), enz = AX(auxl, ioff + 2, i);
+        double etx = AX(auxl, ioff + 3, i), ety = AX(auxl, ioff + 4, i), etz = AX(auxl, ioff + 5, i);
+        double gamma = sqrt(etx * etx + ety * ety + etz * etz);
+        etx = etx / gamma; ety = ety / gamma; etz = etz / gamma;
+        double hunl = enx * Q2(ql, 1, i) + eny * Q2(ql, 2, i) + enz * Q2(ql, 3, i);
+        double hunr = enx * Q2(qr, 1, i - 1) + eny * Q2(qr, 2, i - 1) + enz * Q2(qr, 3, i - 1);
+        double hutl = etx * Q2(ql, 1, i) + ety * Q2(ql, 2, i) + etz * Q2(ql, 3, i);
+        double hutr = etx * Q2(qr, 1, i - 1) + ety * Q2(qr, 2, i - 1) + etz * Q2(qr, 3, i - 1);
+        double hl = Q2(ql, 0, i), hr = Q2(qr, 0, i - 1);
+        h[k] = (hl + hr) * 0.50;
+        double hsqr = sqrt(hr), hsql = sqrt(hl), hsq = hsqr + hsql;
+        u[k] = (hunr / hsqr + hunl / hsql) / hsq;
+        v[k] = (hutr / hsqr + hutl / hsql) / hsq;
+        a[k] = sqrt(g * h[k]);
+        double d1 = hl - hr, d2 = hunl - hunr, d3 = hutl - hutr;
+        double a1 = ((u[k] + a[k]) * d1 - d2) * (0.50 / a[k]);
+        double a2 = -v[k] * d1 + d3;
+        double a3 = (-(u[k] - a[k]) * d1 + d2) * (0.50 / a[k]);
+        WV(0, 0, i) = a1;
+        WV(1, 0, i) = a1 * (u[k] - a[k]) * enx + a1 * v[k] * etx;
+        WV(2, 0, i) = a1 * (u[k] - a[k]) * eny + a1 * v[k] * ety;
+        WV(3, 0, i) = a1 * (u[k] - a[k]) * enz + a1 * v[k] * etz;
+        SP(0, i) = (u[k] - a[k]) * gamma / dy;
+        WV(0, 1, i) = 0.0;
+        WV(1, 1, i) = a2 * etx;
+        WV(2, 1, i) = a2 * ety;
+        WV(3, 1, i) = a2 * etz;
+        SP(1, i) = u[k] * gamma / dy;
+        WV(0, 2, i) = a3;
+        WV(1, 2, i) = a3 * (u[k] + a[k]) * enx + a3 * v[k] * etx;
+        WV(2, 2, i) = a3 * (u[k] + a[k]) * eny + a3 * v[k] * ety;
+        WV(3, 2, i) = a3 * (u[k] + a[k]) * enz + a3 * v[k] * etz;
+        SP(2, i) = (u[k] + a[k]) * gamma / dy;
+    }
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double enx = AX(auxl, ioff + 0, i), eny = AX(auxl, ioff + 1, i), enz = AX(auxl, ioff + 2, i);
+        double etx = AX(auxl, ioff + 3, i), ety = AX(auxl, ioff + 4, i), etz = AX(auxl, ioff + 5, i);
+        double gamma = sqrt(etx * etx + ety * ety + etz * etz);
+        double hunl = enx * Q2(ql, 1, i) + eny * Q2(ql, 2, i) + enz * Q2(ql, 3, i);
+        double hunr = enx * Q2(qr, 1, i - 1) + eny * Q2(qr, 2, i - 1) + enz * Q2(qr, 3, i - 1);
+        double him1 = Q2(qr, 0, i - 1);
+        double s0 = (hunr / him1 - sqrt(g * him1)) * gamma / dy;
+        if (s0 > 0.0 && SP(0, i) > 0.0) {
+            for (int m = 0; m < 4; m++) Q2(amdq, m, i) = 0.0;
+            continue;
+        }
+        double h1 = Q2(qr, 0, i - 1) + WV(0, 0, i);
+        double hu1 = hunr + (enx * WV(1, 0, i) + eny * WV(2, 0, i) + enz * WV(3, 0, i));
+        double s1 = (hu1 / h1 - sqrt(g * h1)) * gamma / dy;
+        double sfract;
+        if (s0 < 0.0 && s1 > 0.0)
+            sfract = s0 * ((s1 - SP(0, i)) / (s1 - s0));
+        else if (SP(0, i) < 0.0)
+            sfract = SP(0, i);
+        else
+            sfract = 0.0;
+        for (int m = 0; m < 4; m++) Q2(amdq, m, i) = sfract * WV(m, 0, i);
+        if (SP(1, i) > 0.0) continue;
+        for (int m = 0; m < 4; m++) Q2(amdq, m, i) = Q2(amdq, m, i) + SP(1, i) * WV(m, 1, i);
+        double hi = Q2(ql, 0, i);
+        double s03 = (hunl / hi + sqrt(g * hi)) * gamma / dy;
+        double h3 = Q2(ql, 0, i) - WV(0, 2, i);
+        double hu3 = hunl - (enx * WV(1, 2, i) + eny * WV(2, 2, i) + enz * WV(3, 2, i));
+        double s3 = (hu3 / h3 + sqrt(g * h3)) * gamma / dy;
+        if (s3 < 0.0 && s03 > 0.0)
+            sfract = s3 * ((s03 - SP(2, i)) / (s03 - s3));
+        else if (SP(2, i) < 0.0)
+            sfract = SP(2, i);
+        else
+            continue;
+        for (int m = 0; m < 4; m++) Q2(amdq, m, i) = Q2(amdq, m, i) + sfract * WV(m, 2, i);
+    }
+    for (int m = 0; m < 4; m++)
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            double df = 0.0;
+            for (int mw = 0; mw < mwaves; mw++) df = df + SP(mw, i) * WV(m, mw, i);
+            Q2(apdq, m, i) = df - Q2(amdq, m, i);
+        }
+    /* project the momentum components of amdq / apdq onto the tangent plane */
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double erx = AX(auxr, 13, i - 1), ery = AX(auxr, 14, i - 1), erz = AX(auxr, 15, i - 1);
+        double amn = erx * Q2(amdq, 1, i) + ery * Q2(amdq, 2, i) + erz * Q2(amdq, 3, i);
+        Q2(amdq, 1, i) = Q2(amdq, 1, i) - amn * erx;
+        Q2(amdq, 2, i) = Q2(amdq, 2, i) - amn * ery;
+        Q2(amdq, 3, i) = Q2(amdq, 3, i) - amn * erz;
+        erx = AX(auxl, 13, i); ery = AX(auxl, 14, i); erz = AX(auxl, 15, i);
+        double apn = erx * Q2(apdq, 1, i) + ery * Q2(apdq, 2, i) + erz * Q2(apdq, 3, i);
+        Q2(apdq, 1, i) = Q2(apdq, 1, i) - apn * erx;
+        Q2(apdq, 2, i) = Q2(apdq, 2, i) - apn * ery;
+        Q2(apdq, 3, i) = Q2(apdq, 3, i) - apn * erz;
+    }
+}
+
+/* one side (up- or down-going) of rpt2_shallow_sphere: edge data from `auxe`, state of
+   cell i1 of the current slice, projection with the radial vector of `auxp` */
+static void rpt_sphere_side(double g, double dx, int ioff, int meqn, int mbc, int i, int i1,
+                            const double *ql, const double *auxe, const double *auxp,
+                            const double *asdq, double *bout, int up)
+{
+    double enx = AX(auxe, ioff + 0, i1), eny = AX(auxe, ioff + 1, i1), enz = AX(auxe, ioff + 2, i1);
+    double etx = AX(auxe, ioff + 3, i1), ety = AX(auxe, ioff + 4, i1), etz = AX(auxe, ioff + 5, i1);
+    double gamma = sqrt(etx * etx + ety * ety + etz * etz);
+    etx = etx / gamma; ety = ety / gamma; etz = etz / gamma;
+    double h = Q2(ql, 0, i1);
+    double u = (enx * Q2(ql, 1, i1) + eny * Q2(ql, 2, i1) + enz * Q2(ql, 3, i1)) / h;
+    double v = (etx * Q2(ql, 1, i1) + ety * Q2(ql, 2, i1) + etz * Q2(ql, 3, i1)) / h;
+    double a = sqrt(g * h);
+    double a1 = enx * Q2(asdq, 1, i) + eny * Q2(asdq, 2, i) + enz * Q2(asdq, 3, i);
+    double a2 = etx * Q2(asdq, 1, i) + ety * Q2(asdq, 2, i) + etz * Q2(asdq, 3, i);
+    double d1 = Q2(asdq, 0, i), d2 = a1, d3 = a2;
+    a1 = ((u + a) * d1 - d2) * (0.50 / a);
+    a2 = -v * d1 + d3;
+    double a3 = (-(u - a) * d1 + d2) * (0.50 / a);
+    double waveb[4][3], sb[3];
+    waveb[0][0] = a1;
+    waveb[1][0] = a1 * (u - a) * enx + a1 * v * etx;
+    waveb[2][0] = a1 * (u - a) * eny + a1 * v * ety;
+    waveb[3][0] = a1 * (u - a) * enz + a1 * v * etz;
+    sb[0] = (u - a) * gamma / dx;
+    waveb[0][1] = 0.0;
+    waveb[1][1] = a2 * etx;
+    waveb[2][1] = a2 * ety;
+    waveb[3][1] = a2 * etz;
+    sb[1] = u * gamma / dx;
+    waveb[0][2] = a3;
+    waveb[1][2] = a3 * (u + a) * enx + a3 * v * etx;
+    waveb[2][2] = a3 * (u + a) * eny + a3 * v * ety;
+    waveb[3][2] = a3 * (u + a) * enz + a3 * v * etz;
+    sb[2] = (u + a) * gamma / dx;
+    for (int m = 0; m < 4; m++) {
+        Q2(bout, m, i) = 0.0;
+        for (int mw = 0; mw < 3; mw++)
+            Q2(bout, m, i) = Q2(bout, m, i) +
+                             (up ? dmax2(sb[mw], 0.0) : dmin2(sb[mw], 0.0)) * waveb[m][mw];
+    }
+    double erx = AX(auxp, 13, i1), ery = AX(auxp, 14, i1), erz = AX(auxp, 15, i1);
+    double bn = erx * Q2(bout, 1, i) + ery * Q2(bout, 2, i) + erz * Q2(bout, 3, i);
+    Q2(bout, 1, i) = Q2(bout, 1, i) - bn * erx;
+    Q2(bout, 2, i) = Q2(bout, 2, i) - bn * ery;
+    Q2(bout, 3, i) = Q2(bout, 3, i) - bn * erz;
+}
+
+static void rpt_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx, const double *ql,
+                       const double *aux1, const double *aux2, const double *aux3, int imp,
+                       const double *asdq, double *bmasdq, double *bpasdq)
+{
+    const double g = c->p[0];
+    const double dx = (ixy == 1) ? c->dxcom : c->dycom;
+    const int ioff = (ixy == 1) ? 7 : 1;
+    (void)mwaves;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int i1 = (imp == 1) ? i - 1 : i; /* the cell the fluctuation moves into */
+        /* up-going: the edge between this slice and the next one is the bottom edge of
+           the cell in aux3; down-going: the bottom edge of the cell in aux2 */
+        rpt_sphere_side(g, dx, ioff, meqn, mbc, i, i1, ql, aux3, aux3, asdq, bpasdq, 1);
+        rpt_sphere_side(g, dx, ioff, meqn, mbc, i, i1, ql, aux2, aux1, asdq, bmasdq, 0);
+    }
+}
+
+/* apps/shallow-sphere/qcor.f:2-72 */
+static void oracle_qcor(rp_ctx *c, int ixy, int i, const double *aux, const double *q, int meqn,
+                        int mbc, double *qc)
+{
+    const double g = c->p[0];
+    int in;
+    double dy;
+    if (ixy == 1) { in = 1; dy = c->dycom; } else { in = 7; dy = c->dxcom; }
+    double etxl = AX(aux, in + 3, i), etyl = AX(aux, in + 4, i), etzl = AX(aux, in + 5, i);
+    double gammal = sqrt(etxl * etxl + etyl * etyl + etzl * etzl) / dy;
+    double enxl = AX(aux, in, i) * gammal, enyl = AX(aux, in + 1, i) * gammal, enzl = AX(aux, in + 2, i) * gammal;
+    double etxr = AX(aux, in + 3, i + 1), etyr = AX(aux, in + 4, i + 1), etzr = AX(aux, in + 5, i + 1);
+    double gammar = sqrt(etxr * etxr + etyr * etyr + etzr * etzr) / dy;
+    double enxr = AX(aux, in, i + 1) * gammar, enyr = AX(aux, in + 1, i + 1) * gammar, enzr = AX(aux, in + 2, i + 1) * gammar;
+    double q1 = Q2(q, 0, i), q2 = Q2(q, 1, i), q3 = Q2(q, 2, i), q4 = Q2(q, 3, i);
+    qc[0] = (enxr - enxl) * q2 + (enyr - enyl) * q3 + (enzr - enzl) * q4;
+    qc[1] = (enxr - enxl) * (q2 * q2 / q1 + 0.5 * g * (q1 * q1)) + (enyr - enyl) * (q2 * q3 / q1) +
+            (enzr - enzl) * (q2 * q4 / q1);
+    qc[2] = (enxr - enxl) * (q2 * q3 / q1) + (enyr - enyl) * (q3 * q3 / q1 + 0.5 * g * (q1 * q1)) +
+            (enzr - enzl) * (q3 * q4 / q1);
+    qc[3] = (enxr - enxl) * (q2 * q4 / q1) + (enyr - enyl) * (q3 * q4 / q1) +
+            (enzr - enzl) * (q4 * q4 / q1 + 0.5 * g * (q1 * q1));
+    double erx = AX(aux, 13, i), ery = AX(aux, 14, i), erz = AX(aux, 15, i);
+    double qcn = erx * qc[1] + ery * qc[2] + erz * qc[3];
+    qc[1] = qc[1] - qcn * erx;
+    qc[2] = qc[2] - qcn * ery;
+    qc[3] = qc[3] - qcn * erz;
+}
+
 /* ------------------------------------------------------------------------- */
 /* philim.f:4-58 and limiter.f:4-60                                          */
 /* ------------------------------------------------------------------------- */
@@ -538,7 +767,7 @@ double oracle_step1(int rp_id, const double *rp_params, int meqn, int mwaves, in
         if (mcapa > 0) dtdx[IX(i)] = dt / (dx * aux[(mcapa - 1) + maux * IX(i)]);
         else dtdx[IX(i)] = dt / dx;
     }
-    rpn(&c, 0, meqn, mwaves, mbc, mx, q, q, wave, s, amdq, apdq);
+    rpn(&c, 0, meqn, mwaves, mbc, mx, q, q, aux, aux, wave, s, amdq, apdq);
     /* forall: first statement for all (i,m), then the second (:93-96) */
     for (int i = 1; i <= mx + 1; i++)
         for (int m = 0; m < meqn; m++)
@@ -576,8 +805,18 @@ double oracle_step1(int rp_id, const double *rp_params, int meqn, int mwaves, in
 typedef struct {
     double *wave, *s, *amdq, *apdq, *cqxx, *bmasdq, *bpasdq;
     double *q1d, *qadd, *fadd, *gadd, *dtdx1d, *dtdy1d;
+    double *aux1, *aux2, *aux3;
+    int maux;
 } work2;
 
+static void work2_alloc_aux(work2 *w, int n, int maux)
+{
+    int ma = maux > 0 ? maux : 1;
+    w->maux = maux;
+    w->aux1 = (double *)calloc((size_t)n * ma, sizeof(double));
+    w->aux2 = (double *)calloc((size_t)n * ma, sizeof(double));
+    w->aux3 = (double *)calloc((size_t)n * ma, sizeof(double));
+}
 static void work2_alloc(work2 *w, int n, int meqn, int mwaves)
 {
     w->wave = (double *)calloc((size_t)n * meqn * mwaves, sizeof(double));
@@ -599,6 +838,7 @@ static void work2_free(work2 *w)
     free(w->wave); free(w->s); free(w->amdq); free(w->apdq); free(w->cqxx);
     free(w->bmasdq); free(w->bpasdq); free(w->q1d); free(w->qadd); free(w->fadd);
     free(w->gadd); free(w->dtdx1d); free(w->dtdy1d);
+    free(w->aux1); free(w->aux2); free(w->aux3);
 }
 
 #define GADD(m, k, i) gadd[(m) + meqn * ((k) + 2 * IX(i))]
@@ -620,7 +860,7 @@ static double flux2(rp_ctx *c, int ixy, int maxm, int meqn, int mwaves, int mbc,
             GADD(m, 0, i) = 0.0;
             GADD(m, 1, i) = 0.0;
         }
-    rpn(c, ixy, meqn, mwaves, mbc, mx, q1d, q1d, wave, s, amdq, apdq);
+    rpn(c, ixy, meqn, mwaves, mbc, mx, q1d, q1d, w->aux2, w->aux2, wave, s, amdq, apdq);
     /* :103-106 forall with two statements */
     for (int i = 1; i <= mx + 1; i++)
         for (int m = 0; m < meqn; m++)
@@ -653,13 +893,13 @@ static double flux2(rp_ctx *c, int ixy, int maxm, int meqn, int mwaves, int mbc,
                 Q2(apdq, m, i) = Q2(apdq, m, i) - Q2(cqxx, m, i);
             }
     }
-    rpt(c, ixy, meqn, mwaves, mbc, mx, amdq, bmasdq, bpasdq);
+    rpt(c, ixy, meqn, mwaves, mbc, mx, q1d, w->aux1, w->aux2, w->aux3, 1, amdq, bmasdq, bpasdq);
     for (int i = 1; i <= mx + 1; i++)
         for (int m = 0; m < meqn; m++) {
             GADD(m, 0, i - 1) = GADD(m, 0, i - 1) - 0.5 * dtdx1d[IX(i - 1)] * Q2(bmasdq, m, i);
             GADD(m, 1, i - 1) = GADD(m, 1, i - 1) - 0.5 * dtdx1d[IX(i - 1)] * Q2(bpasdq, m, i);
         }
-    rpt(c, ixy, meqn, mwaves, mbc, mx, apdq, bmasdq, bpasdq);
+    rpt(c, ixy, meqn, mwaves, mbc, mx, q1d, w->aux1, w->aux2, w->aux3, 2, apdq, bmasdq, bpasdq);
     for (int i = 1; i <= mx + 1; i++)
         for (int m = 0; m < meqn; m++) {
             GADD(m, 0, i) = GADD(m, 0, i) - 0.5 * dtdx1d[IX(i)] * Q2(bmasdq, m, i);
@@ -694,12 +934,15 @@ double oracle_step2ds(int rp_id, const double *rp_params, int maxm, int meqn, in
     rp_ctx_init(&c, rp_id, rp_params, n);
     work2 w;
     work2_alloc(&w, n, meqn, mwaves);
+    work2_alloc_aux(&w, n, maux);
+    c.dxcom = dx; c.dycom = dy;
     int mcapa = method[5];
     double cfl = 0.0;
     double dtdx = dt / dx, dtdy = dt / dy;
     if (mcapa == 0)
         for (int k = 0; k < n; k++) { w.dtdx1d[k] = dtdx; w.dtdy1d[k] = dtdy; }
     double *q1d = w.q1d, *qadd = w.qadd, *fadd = w.fadd;
+#define AUXS(arr, ma, i) arr[(ma) + maux * IX(i)]
     if (ids == 1) {
         for (int j = 1 - mbc; j <= my + mbc; j++) {
             for (int i = 1 - mbc; i <= mx + mbc; i++)
@@ -707,6 +950,12 @@ double oracle_step2ds(int rp_id, const double *rp_params, int maxm, int meqn, in
             if (mcapa > 0)
                 for (int i = 1 - mbc; i <= mx + mbc; i++)
                     w.dtdx1d[IX(i)] = dtdx / AUX3(mcapa - 1, i, j);
+            for (int ma = 0; ma < maux; ma++)
+                for (int i = 1 - mbc; i <= mx + mbc; i++) {
+                    AUXS(w.aux2, ma, i) = AUX3(ma, i, j);
+                    if (j != 1 - mbc) AUXS(w.aux1, ma, i) = AUX3(ma, i, j - 1);
+                    if (j != my + mbc) AUXS(w.aux3, ma, i) = AUX3(ma, i, j + 1);
+                }
             double cfl1d = flux2(&c, 1, maxm, meqn, mwaves, mbc, mx, q1d, w.dtdx1d, method, mthlim, &w);
             cfl = dmax2(cfl, cfl1d);
             if (mcapa == 0) {
@@ -730,6 +979,12 @@ double oracle_step2ds(int rp_id, const double *rp_params, int maxm, int meqn, in
             if (mcapa > 0)
                 for (int j = 1 - mbc; j <= my + mbc; j++)
                     w.dtdy1d[IX(j)] = dtdy / AUX3(mcapa - 1, i, j);
+            for (int ma = 0; ma < maux; ma++)
+                for (int j = 1 - mbc; j <= my + mbc; j++) {
+                    AUXS(w.aux2, ma, j) = AUX3(ma, i, j);
+                    if (i != 1 - mbc) AUXS(w.aux1, ma, j) = AUX3(ma, i - 1, j);
+                    if (i != mx + mbc) AUXS(w.aux3, ma, j) = AUX3(ma, i + 1, j);
+                }
             double cfl1d = flux2(&c, 2, maxm, meqn, mwaves, mbc, my, q1d, w.dtdy1d, method, mthlim, &w);
             cfl = dmax2(cfl, cfl1d);
             if (mcapa == 0) {
@@ -764,6 +1019,10 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
     rp_ctx_init(&c, rp_id, rp_params, n);
     work2 w;
     work2_alloc(&w, n, meqn, mwaves);
+    work2_alloc_aux(&w, n, maux);
+    c.dxcom = dx; c.dycom = dy;
+    const int use_qcor = (rp_id == RP_SPHERE); /* apps/shallow-sphere/step2qcor.f replaces step2.f */
+    double qc[4];
     int mcapa = method[5];
     double cfl = 0.0;
     double dtdx = dt / dx, dtdy = dt / dy;
@@ -776,6 +1035,12 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
         if (mcapa > 0)
             for (int i = 1 - mbc; i <= mx + mbc; i++)
                 w.dtdx1d[IX(i)] = dtdx / AUX3(mcapa - 1, i, j);
+        for (int ma = 0; ma < maux; ma++)
+            for (int i = 1 - mbc; i <= mx + mbc; i++) {
+                AUXS(w.aux1, ma, i) = AUX3(ma, i, j - 1);
+                AUXS(w.aux2, ma, i) = AUX3(ma, i, j);
+                AUXS(w.aux3, ma, i) = AUX3(ma, i, j + 1);
+            }
         double cfl1d = flux2(&c, 1, maxm, meqn, mwaves, mbc, mx, q1d, w.dtdx1d, method, mthlim, &w);
         cfl = dmax2(cfl, cfl1d);
         if (mcapa == 0) {
@@ -788,8 +1053,9 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
                     Q3(qnew, m, i, j + 1) = Q3(qnew, m, i, j + 1) + dtdy * GADD(m, 1, i);
                 }
         } else {
-            for (int m = 0; m < meqn; m++)
-                for (int i = 1; i <= mx; i++) {
+            for (int i = 1; i <= mx; i++) {
+                if (use_qcor) oracle_qcor(&c, 1, i, w.aux2, q1d, meqn, mbc, qc);
+                for (int m = 0; m < meqn; m++) {
                     Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, i) -
                                         (dtdx * (Q2(fadd, m, i + 1) - Q2(fadd, m, i)) +
                                          dtdy * (GADD(m, 1, i) - GADD(m, 0, i))) /
@@ -798,7 +1064,11 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
                                             dtdy * GADD(m, 0, i) / AUX3(mcapa - 1, i, j - 1);
                     Q3(qnew, m, i, j + 1) = Q3(qnew, m, i, j + 1) +
                                             dtdy * GADD(m, 1, i) / AUX3(mcapa - 1, i, j + 1);
+                    /* step2qcor.f:158-159 */
+                    if (use_qcor)
+                        Q3(qnew, m, i, j) = Q3(qnew, m, i, j) - dtdx * qc[m] / AUX3(mcapa - 1, i, j);
                 }
+            }
         }
     }
     for (int i = 0; i <= mx + 1; i++) {
@@ -807,6 +1077,12 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
         if (mcapa > 0)
             for (int j = 1 - mbc; j <= my + mbc; j++)
                 w.dtdy1d[IX(j)] = dtdy / AUX3(mcapa - 1, i, j);
+        for (int ma = 0; ma < maux; ma++)
+            for (int j = 1 - mbc; j <= my + mbc; j++) {
+                AUXS(w.aux1, ma, j) = AUX3(ma, i - 1, j);
+                AUXS(w.aux2, ma, j) = AUX3(ma, i, j);
+                AUXS(w.aux3, ma, j) = AUX3(ma, i + 1, j);
+            }
         double cfl1d = flux2(&c, 2, maxm, meqn, mwaves, mbc, my, q1d, w.dtdy1d, method, mthlim, &w);
         cfl = dmax2(cfl, cfl1d);
         if (mcapa == 0) {
@@ -820,8 +1096,9 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
                     Q3(qnew, m, i + 1, j) = Q3(qnew, m, i + 1, j) + dtdx * GADD(m, 1, j);
                 }
         } else {
-            for (int m = 0; m < meqn; m++)
-                for (int j = 1; j <= my; j++) {
+            for (int j = 1; j <= my; j++) {
+                if (use_qcor) oracle_qcor(&c, 2, j, w.aux2, q1d, meqn, mbc, qc);
+                for (int m = 0; m < meqn; m++) {
                     Q3(qnew, m, i, j) = Q3(qnew, m, i, j) + Q2(qadd, m, j) -
                                         (dtdy * (Q2(fadd, m, j + 1) - Q2(fadd, m, j)) +
                                          dtdx * (GADD(m, 1, j) - GADD(m, 0, j))) /
@@ -830,7 +1107,11 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
                                             dtdx * GADD(m, 0, j) / AUX3(mcapa - 1, i - 1, j);
                     Q3(qnew, m, i + 1, j) = Q3(qnew, m, i + 1, j) +
                                             dtdx * GADD(m, 1, j) / AUX3(mcapa - 1, i + 1, j);
+                    /* step2qcor.f:244-245 */
+                    if (use_qcor)
+                        Q3(qnew, m, i, j) = Q3(qnew, m, i, j) - dtdy * qc[m] / AUX3(mcapa - 1, i, j);
                 }
+            }
         }
     }
     work2_free(&w);
@@ -990,7 +1271,7 @@ static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, do
     memcpy(qr, q1d, sizeof(double) * n * meqn);
     if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
     else weno5_pyweno(q1d, ql, qr, meqn, mx, mbc, weno_variant == WENO_PYWENO_F32);
-    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq);
+    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, NULL, NULL, wave, s, amdq, apdq);
     double cfl = 0.0;
     for (int mw = 0; mw < mwaves; mw++)
         for (int i = 1; i <= mx + 1; i++)
@@ -1001,7 +1282,7 @@ static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, do
             Q2(qr, m, i - 1) = Q2(ql, m, i);
             Q2(ql, m, i) = Q2(qr, m, i);
         }
-    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq2, apdq2);
+    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, NULL, NULL, wave, s, amdq2, apdq2);
     for (int i = 1; i <= mx; i++)
         for (int m = 0; m < meqn; m++)
             Q2(dq1d, m, i) = Q2(dq1d, m, i) -

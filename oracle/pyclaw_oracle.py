@@ -22,7 +22,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW = 1, 2, 3, 4
+RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 
@@ -57,6 +57,12 @@ def lib():
         L.oracle_step2_slabs.argtypes = [i, _dp, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, _ip, _ip, i, i]
         L.oracle_sc_flux2_slabs.restype = d
         L.oracle_sc_flux2_slabs.argtypes = [i, _dp, i, i, i, i, i, _dp, _dp, d, d, d, i, i]
+        L.oracle_sphere_setaux.restype = None
+        L.oracle_sphere_setaux.argtypes = [i, i, i, d, d, d, d, _dp, d]
+        L.oracle_sphere_qinit.restype = None
+        L.oracle_sphere_qinit.argtypes = [i, i, i, d, d, d, d, _dp, d]
+        L.oracle_sphere_src2.restype = None
+        L.oracle_sphere_src2.argtypes = [i, i, d, d, d, d, _dp, _dp, d, d]
         _LIB = L
     return _LIB
 
@@ -146,6 +152,27 @@ def sc_flux2(rp_id, rp_params, mwaves, mbc, mx, my, q, dx, dy, dt, weno_variant,
 
 
 # ---------------------------------------------------------------------------
+# shallow water on the sphere: application helpers (apps/shallow-sphere/*.f)
+# ---------------------------------------------------------------------------
+def sphere_setaux(mbc, mx, my, xlower, ylower, dx, dy, Rsphere=1.0):
+    aux = np.zeros((16, mx + 2 * mbc, my + 2 * mbc), order="F")
+    lib().oracle_sphere_setaux(mbc, mx, my, xlower, ylower, dx, dy, _p(aux), Rsphere)
+    return aux
+
+
+def sphere_qinit(mbc, mx, my, xlower, ylower, dx, dy, Rsphere=1.0):
+    q = np.zeros((4, mx + 2 * mbc, my + 2 * mbc), order="F")
+    lib().oracle_sphere_qinit(mbc, mx, my, xlower, ylower, dx, dy, _p(q), Rsphere)
+    return q
+
+
+def sphere_src2(q, aux, xlower, ylower, dx, dy, dt, Rsphere=1.0):
+    """src2.f on interior arrays; q is updated in place (must be F-contiguous)."""
+    assert q.flags["F_CONTIGUOUS"] and aux.flags["F_CONTIGUOUS"]
+    lib().oracle_sphere_src2(q.shape[1], q.shape[2], xlower, ylower, dx, dy, _p(q), _p(aux), dt, Rsphere)
+
+
+# ---------------------------------------------------------------------------
 # boundary conditions (solver.py:354-452)
 # ---------------------------------------------------------------------------
 def fill_bcs(qbc, mbc, bc_lower, bc_upper, user_lower=None, user_upper=None, t=0.0, negate=True):
@@ -197,6 +224,7 @@ class OracleSolver(object):
         self.bc_lower, self.bc_upper = [None] * ndim, [None] * ndim
         self.aux_bc_lower, self.aux_bc_upper = [BC_OUTFLOW] * ndim, [BC_OUTFLOW] * ndim
         self.user_bc_lower = self.user_bc_upper = None
+        self.user_aux_bc_lower = self.user_aux_bc_upper = None
         self.step_src = None
         self.src_split = 1
         if kind == "classic":
@@ -219,7 +247,8 @@ class OracleSolver(object):
         if aux is not None:
             self.auxbc = np.zeros([aux.shape[0]] + [n + 2 * mbc for n in self.n], order="F")
             _interior(self.auxbc, mbc)[...] = aux
-            fill_bcs(self.auxbc, mbc, self.aux_bc_lower, self.aux_bc_upper, negate=False)
+            fill_bcs(self.auxbc, mbc, self.aux_bc_lower, self.aux_bc_upper, self.user_aux_bc_lower,
+                     self.user_aux_bc_upper, negate=False)
         else:
             self.auxbc = None
         if self.kind == "classic":
@@ -371,6 +400,7 @@ class OracleSolver(object):
     # ---- controller.py:195-303, outstyle 1 ----
     def run(self, q0, aux, d, tfinal, nout, t0=0.0):
         state = {"q": np.array(q0, order="F", copy=True), "aux": aux, "t": t0}
+        self.dt = self.dt_initial
         self.setup(state["q"], aux, d)
         frames = [state["q"].copy("F")]
         total = {"numsteps": 0, "rejected": 0}

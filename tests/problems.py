@@ -181,3 +181,34 @@ def smooth_state(rp, shape, seed=0):
     else:
         raise ValueError(rp)
     return np.asfortranarray(q)
+
+
+# ---------------------------------------------------------------------------
+# shallow water on the sphere (test/shallow_sphere/shallow_4_Rossby_Haurwitz_wave.py)
+# ---------------------------------------------------------------------------
+SPHERE_G = 11489.57219
+
+
+def sphere_problem(mx=40, my=20, mbc=2):
+    """Initial data through the oracle's restatement of setaux.f / qinit.f (host, init time)."""
+    from oracle import pyclaw_oracle as po
+    xlower, xupper, ylower, yupper = -3.0, 1.0, -1.0, 1.0
+    dx, dy = (xupper - xlower) / mx, (yupper - ylower) / my
+    auxtmp = po.sphere_setaux(mbc, mx, my, xlower, ylower, dx, dy)
+    qtmp = po.sphere_qinit(mbc, mx, my, xlower, ylower, dx, dy)
+    return dict(q=np.asfortranarray(qtmp[:, mbc:-mbc, mbc:-mbc]), aux=np.asfortranarray(auxtmp[:, mbc:-mbc, mbc:-mbc]),
+                auxbc_full=auxtmp, d=[dx, dy], lower=[xlower, ylower], params=[SPHERE_G], tfinal=10.0, nout=10)
+
+
+def sphere_qbc_lower_y(idim, t, qbc, mbc):
+    """shallow_4_Rossby_Haurwitz_wave.py:292-300 (idim is 1 here)"""
+    for j in range(mbc):
+        qbc1D = qbc[:, :, 2 * mbc - 1 - j].copy()
+        qbc[:, :, j] = qbc1D[:, ::-1]
+
+
+def sphere_qbc_upper_y(idim, t, qbc, mbc):
+    my = qbc.shape[2] - 2 * mbc
+    for j in range(mbc):
+        qbc1D = qbc[:, :, my + mbc - 1 - j].copy()
+        qbc[:, :, my + mbc + j] = qbc1D[:, ::-1]
