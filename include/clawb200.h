@@ -42,6 +42,8 @@ extern "C" {
 #define CLAWB200_RP_ADVECTION 2 /* rp1/rpn2/rpt2_advection ; params {u,v}              */
 #define CLAWB200_RP_EULER5 3    /* rpn2/rpt2_euler_5wave   ; params {gamma,gamma1}     */
 #define CLAWB200_RP_SHALLOW 4   /* rpn2/rpt2_shallow_roe_with_efix ; params {grav}     */
+#define CLAWB200_RP_SPHERE 5    /* rpn2/rpt2_shallow_sphere + step2qcor/qcor (apps/shallow-sphere);
+                                   params {g, dxcom, dycom} (0 = take dx, dy); 16 aux, mcapa = 1 */
 
 /* Boundary condition ids = pyclaw.BC (src/pyclaw/solver.py:17-23) */
 #define CLAWB200_BC_CUSTOM 0

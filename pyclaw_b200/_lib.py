@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLAWB200_LIB") or os.path.join(_HERE, "csrc", "libclawb200.so")
 
 MAXWAVES = 8
-RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW = 1, 2, 3, 4
+RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
 STAGE_AXPY, STAGE_CONVEX, STAGE_FINAL104, STAGE_DQ_ONLY = 0, 1, 2, 3
 

@@ -43,7 +43,28 @@ struct SweepArgs {
     int rows_per_cta;
     int jlo, jhi; // first / last output row (Fortran index)
     int ilo, ihi; // first / last output column
+    const double *aux;      // aux[ma][j][i], same pitch as q (or null)
+    long long amstride;     // component stride of aux
+    int mcapa;              // method(6): 0 = none, else 1-based aux component of the capacity
 };
+
+// aux of Fortran cell (i, j), clamped into the padded array (threads outside the strip
+// compute throw-away values from valid memory)
+__device__ __forceinline__ AuxCell aux_cell(const SweepArgs &A, int i, int j)
+{
+    int ic = min(max(i, 1 - A.mbc), A.mx + A.mbc) + A.mbc - 1;
+    int jc = min(max(j, 1 - A.mbc), A.my + A.mbc) + A.mbc - 1;
+    return AuxCell{A.aux + (long long)A.pitch * jc + ic, A.amstride};
+}
+
+// a / b with one correctly rounded division, fast path first (arith.cuh)
+__device__ __forceinline__ double div1(double a, double b)
+{
+    FastArith fa;
+    double v = fa.div(a, b);
+    if (fa.bad()) v = a / b;
+    return v;
+}
 
 // philim.f:4-58
 template <class AR>
@@ -117,9 +138,10 @@ __device__ __forceinline__ void cfl_commit(double cfl, unsigned long long *cfl_b
 // TRANS=true : unsplit (step2.f x-sweeps): slices j0-1 .. j1 are processed for output
 //              rows j0 .. j1-1, contributions applied in the order of SURVEY.md A.3.
 // ---------------------------------------------------------------------------
-template <class RP, bool TRANS, int NT>
+template <class RP, bool TRANS, bool CAPA, int NT>
 __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs A)
 {
+    constexpr bool AUXRP = (RP::MAUX > 0);
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
     constexpr int NC = NT - 3;
     constexpr int QS = NT + 1;
@@ -143,7 +165,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
     const bool order2 = (A.order != 1);
     const bool trans2 = order2 && (A.trans == 2);
     const double dtdx = A.dtdx, dtdy = A.dtdy;
-    const double hdtdx = 0.5 * dtdx;
+    const AuxCell nocell{nullptr, 0};
 
     double cfl = 0.0;
     double accPrev[MEQN], pendA[MEQN];
@@ -185,11 +207,26 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
 #pragma unroll
         for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
 
+        // capacity function: dtdx1d(i) = dtdx / capa(i,j)  (step2.f:91-95)
+        double dtdx_c = dtdx, dtdx_l = dtdx, capa_c = 1.0, capa_m = 1.0, capa_p = 1.0;
+        if (CAPA) {
+            capa_c = aux_cell(A, ii, r)(A.mcapa - 1);
+            dtdx_c = div1(dtdx, capa_c);
+            dtdx_l = div1(dtdx, aux_cell(A, ii - 1, r)(A.mcapa - 1));
+            if (TRANS) {
+                capa_m = aux_cell(A, ii, r - 1)(A.mcapa - 1);
+                capa_p = aux_cell(A, ii, r + 1)(A.mcapa - 1);
+            }
+        }
+        const double hdtdx = 0.5 * dtdx_c;
+        const AuxCell axl = AUXRP ? aux_cell(A, ii - 1, r) : nocell;
+        const AuxCell axr = AUXRP ? aux_cell(A, ii, r) : nocell;
+
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
-        with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, wave, s, amdq, apdq, roe); });
+        with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, axl, axr, wave, s, amdq, apdq, roe); });
         if (iface_ok) {
 #pragma unroll
-            for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+            for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx_c * s[mw]), -dtdx_l * s[mw]);
         }
         if (order2) {
 #pragma unroll
@@ -235,18 +272,22 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                 }
                 if (lim) {
                     limit_waves<RP>(ar, wave, s, wnorm2, dotl, dotr, A.mthlim);
-                    double dtdxave = 0.5 * (dtdx + dtdx);
+                    double dtdxave = 0.5 * (dtdx_l + dtdx_c);
                     second_order<RP>(wave, s, dtdxave, cqxx);
                 }
                 if (TRANS) {
                     double asdq[MEQN];
                     if (A.trans > 0) {
+                        // rpt2 sees the cell the fluctuation moves into, in the rows below /
+                        // at / above this one (aux1, aux2, aux3 of step2.f:99-107)
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq[m] + cqxx[m]) : amdq[m];
-                        RP::transverse(ar, A.rp, roe, asdq, bmm, bpm);
+                        RP::transverse(ar, A.rp, roe, l, AUXRP ? aux_cell(A, ii - 1, r - 1) : nocell, axl,
+                                       AUXRP ? aux_cell(A, ii - 1, r + 1) : nocell, asdq, bmm, bpm);
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq[m] - cqxx[m]) : apdq[m];
-                        RP::transverse(ar, A.rp, roe, asdq, bmp, bpp);
+                        RP::transverse(ar, A.rp, roe, rr, AUXRP ? aux_cell(A, ii, r - 1) : nocell, axr,
+                                       AUXRP ? aux_cell(A, ii, r + 1) : nocell, asdq, bmp, bpp);
                     } else { // flux2.f:151 -- gadd stays zero
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp[m] = bpp[m] = 0.0;
@@ -293,26 +334,41 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                 if (cell_ok) {
 #pragma unroll
                     for (int m = 0; m < MEQN; m++) {
-                        double qaddv = (0.0 - dtdx * apdq[m]) - dtdx * xs[m * NT + tn];
+                        double qaddv = (0.0 - dtdx_c * apdq[m]) - dtdx_c * xs[m * NT + tn];
                         double dF = xs[(MEQN + m) * NT + tn] - F[m];
-                        A.qout[m * A.mstride + oidx] = (rr[m] + qaddv) - dtdx * dF;
+                        if (!CAPA)
+                            A.qout[m * A.mstride + oidx] = (rr[m] + qaddv) - dtdx * dF;
+                        else // step2ds.f:152-156: the division binds to the flux difference only
+                            A.qout[m * A.mstride + oidx] = (rr[m] + qaddv) - div1(dtdx * dF, capa_c);
                     }
                 }
             } else {
+                double qcv[MEQN];
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) qcv[m] = 0.0;
+                if constexpr (RP::QCOR) { // apps/shallow-sphere/step2qcor.f:147
+                    with_arith([&](auto &ar) { RP::qcor(ar, A.rp, rr, axr, aux_cell(A, ii + 1, r), qcv); });
+                }
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {
-                    double qaddv = (0.0 - dtdx * apdq[m]) - dtdx * xs[m * NT + tn];
+                    double qaddv = (0.0 - dtdx_c * apdq[m]) - dtdx_c * xs[m * NT + tn];
                     double dF = xs[(MEQN + m) * NT + tn] - F[m];
                     double G1 = (0.0 - hdtdx * xs[(2 * MEQN + m) * NT + tn]) - hdtdx * bmp[m];
                     double G2 = (0.0 - hdtdx * xs[(3 * MEQN + m) * NT + tn]) - hdtdx * bpp[m];
                     // row r-1 receives its last x-sweep contribution and is complete
-                    double done = accPrev[m] - dtdy * G1;
+                    double done = CAPA ? accPrev[m] - div1(dtdy * G1, capa_m) : accPrev[m] - dtdy * G1;
                     if (cell_ok && r - 1 >= j0 && r - 1 < j1)
                         A.qout[m * A.mstride + oidx - A.pitch] = done;
                     double acc = rr[m] + pendA[m];
-                    acc = acc + qaddv - dtdx * dF - dtdy * (G2 - G1);
+                    if (!CAPA) {
+                        acc = acc + qaddv - dtdx * dF - dtdy * (G2 - G1);
+                        pendA[m] = dtdy * G2;
+                    } else { // step2.f:145-152
+                        acc = acc + qaddv - div1(dtdx * dF + dtdy * (G2 - G1), capa_c);
+                        if (RP::QCOR) acc = acc - div1(dtdx * qcv[m], capa_c);
+                        pendA[m] = div1(dtdy * G2, capa_p);
+                    }
                     accPrev[m] = acc;
-                    pendA[m] = dtdy * G2;
                 }
             }
         }
@@ -349,9 +405,10 @@ struct YSlots {
     static constexpr int COUNT = TRANS ? QX + 2 * MEQN : QX;
 };
 
-template <class RP, bool TRANS, int NT>
+template <class RP, bool TRANS, bool CAPA, int NT>
 __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs A)
 {
+    constexpr bool AUXRP = (RP::MAUX > 0);
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
     constexpr int NC = TRANS ? NT - 2 : NT;
     using SL = YSlots<RP, TRANS>;
@@ -372,7 +429,9 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     const bool order2 = (A.order != 1);
     const bool trans2 = order2 && (A.trans == 2);
     const double dtdx = A.dtdx, dtdy = A.dtdy;
-    const double hdtdy = 0.5 * dtdy;
+    const AuxCell nocell{nullptr, 0};
+    // capacity function: dtdy1d(j) = dtdy / capa(i,j), rolling along the column
+    double dy_k = dtdy, dy_1 = dtdy, dy_2 = dtdy, cap_1 = 1.0, cap_2 = 1.0;
 
     double cfl = 0.0;
     double qm1[MEQN], qm2[MEQN], sm1[MW], norm1[MW], dot1[MW];
@@ -416,11 +475,19 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
         double normk[MW], dotk[MW];
         double wl[MEQN][MW]; // unlimited waves of interface k-1
+        double cap_k = 1.0;
+        if (CAPA) {
+            cap_k = aux_cell(A, ic, k)(A.mcapa - 1);
+            dy_k = div1(dtdy, cap_k);
+        }
         if (k >= j0 - 1) {
-            with_arith([&](auto &ar) { RP::solve(ar, A.rp, qm1, qk, wave, s, amdq, apdq, roe); });
+            with_arith([&](auto &ar) {
+                RP::solve(ar, A.rp, qm1, qk, AUXRP ? aux_cell(A, ic, k - 1) : nocell,
+                          AUXRP ? aux_cell(A, ic, k) : nocell, wave, s, amdq, apdq, roe);
+            });
             if (col_cfl && k >= 1 && k <= A.my + 1) {
 #pragma unroll
-                for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdy * s[mw]), -dtdy * s[mw]);
+                for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dy_k * s[mw]), -dy_1 * s[mw]);
             }
         } else {
 #pragma unroll
@@ -472,18 +539,24 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
                 }
                 if (lim) {
                     limit_waves<RP>(ar, wlim, sm1, norm1, dot1, dotk, A.mthlim);
-                    double dtdxave = 0.5 * (dtdy + dtdy);
+                    double dtdxave = 0.5 * (dy_2 + dy_1);
                     second_order<RP>(wlim, sm1, dtdxave, cqxx);
                 }
                 if (TRANS) {
                     if (A.trans > 0) {
+                        // interface k-1: A- dq moves into cell k-2, A+ dq into cell k-1; the
+                        // transverse slices are the columns i-1, i, i+1 (step2.f:178-186)
                         double asdq[MEQN];
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq1[m] + cqxx[m]) : amdq1[m];
-                        RP::transverse(ar, A.rp, roe1, asdq, bmm, bpm);
+                        RP::transverse(ar, A.rp, roe1, qm2, AUXRP ? aux_cell(A, ic - 1, k - 2) : nocell,
+                                       AUXRP ? aux_cell(A, ic, k - 2) : nocell,
+                                       AUXRP ? aux_cell(A, ic + 1, k - 2) : nocell, asdq, bmm, bpm);
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq1[m] - cqxx[m]) : apdq1[m];
-                        RP::transverse(ar, A.rp, roe1, asdq, bmp1, bpp1);
+                        RP::transverse(ar, A.rp, roe1, qm1, AUXRP ? aux_cell(A, ic - 1, k - 1) : nocell,
+                                       AUXRP ? aux_cell(A, ic, k - 1) : nocell,
+                                       AUXRP ? aux_cell(A, ic + 1, k - 1) : nocell, asdq, bmp1, bpp1);
                     } else {
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp1[m] = bpp1[m] = 0.0;
@@ -498,25 +571,38 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
         const int jc = k - 2;
         const bool row_out = (jc >= j0) && (jc < j1);
         const long long oidx = (long long)A.pitch * (jc + mbc - 1) + icl;
+        const double hdtdy = 0.5 * dy_2;
         if (!TRANS) {
             if (row_out && col_out) {
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {
-                    double qaddv = (0.0 - dtdy * YS(SL::AP2 + m)) - dtdy * amdq1[m];
+                    double qaddv = (0.0 - dy_2 * YS(SL::AP2 + m)) - dy_2 * amdq1[m];
                     double dF = F1[m] - YS(SL::F2 + m);
-                    A.qout[m * A.mstride + oidx] = (qm2[m] + qaddv) - dtdy * dF;
+                    if (!CAPA)
+                        A.qout[m * A.mstride + oidx] = (qm2[m] + qaddv) - dtdy * dF;
+                    else
+                        A.qout[m * A.mstride + oidx] = (qm2[m] + qaddv) - div1(dtdy * dF, cap_2);
                 }
             }
         } else {
-            double mainE[MEQN];
+            double mainE[MEQN], qaddk[MEQN], qcv[MEQN];
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) qcv[m] = 0.0;
             if (row_out) {
+                if constexpr (RP::QCOR) { // apps/shallow-sphere/step2qcor.f:233
+                    with_arith([&](auto &ar) {
+                        RP::qcor(ar, A.rp, qm2, aux_cell(A, ic, k - 2), aux_cell(A, ic, k - 1), qcv);
+                    });
+                }
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {
-                    double qaddv = (0.0 - dtdy * YS(SL::AP2 + m)) - dtdy * amdq1[m];
+                    double qaddv = (0.0 - dy_2 * YS(SL::AP2 + m)) - dy_2 * amdq1[m];
                     double dF = F1[m] - YS(SL::F2 + m);
                     double G1 = (0.0 - hdtdy * bmm[m]) - hdtdy * YS(SL::BMP2 + m);
                     double G2 = (0.0 - hdtdy * bpm[m]) - hdtdy * YS(SL::BPP2 + m);
-                    mainE[m] = (qaddv - dtdy * dF - dtdx * (G2 - G1));
+                    if (!CAPA) mainE[m] = (qaddv - dtdy * dF - dtdx * (G2 - G1));
+                    else mainE[m] = div1(dtdy * dF + dtdx * (G2 - G1), cap_2);
+                    qaddk[m] = qaddv;
                     gs[(buf * 2 * MEQN + m) * NT + t] = G1;
                     gs[(buf * 2 * MEQN + MEQN + m) * NT + t] = G2;
                 }
@@ -528,9 +614,16 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
                     double G2l = gs[(buf * 2 * MEQN + MEQN + m) * NT + t - 1];
                     double G1r = gs[(buf * 2 * MEQN + m) * NT + t + 1];
                     double q = YS(qxslot + m);
-                    q = q + dtdx * G2l;
-                    q = q + mainE[m];
-                    q = q - dtdx * G1r;
+                    if (!CAPA) {
+                        q = q + dtdx * G2l;
+                        q = q + mainE[m];
+                        q = q - dtdx * G1r;
+                    } else { // step2.f:227-234 (+ step2qcor.f:244-245)
+                        q = q + div1(dtdx * G2l, cap_2);
+                        q = q + qaddk[m] - mainE[m];
+                        if (RP::QCOR) q = q - div1(dtdy * qcv[m], cap_2);
+                        q = q - div1(dtdx * G1r, cap_2);
+                    }
                     A.qout[m * A.mstride + oidx] = q;
                 }
             }
@@ -538,6 +631,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
         }
 
         // shift the window
+        dy_2 = dy_1; dy_1 = dy_k; cap_2 = cap_1; cap_1 = cap_k;
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             qm2[m] = qm1[m]; qm1[m] = qk[m];
@@ -598,7 +692,8 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
 #pragma unroll
     for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
     double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
-    with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, wave, s, amdq, apdq, roe); });
+    const AuxCell nocell{nullptr, 0};
+    with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, nocell, nocell, wave, s, amdq, apdq, roe); });
     double cfl = 0.0;
     if (iface_ok) {
 #pragma unroll

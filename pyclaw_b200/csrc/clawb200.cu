@@ -47,16 +47,37 @@ static int check_problem(const clawb200_problem *p, int ndim)
     if (p->mx < 1 || p->my < 1) return fail(CLAWB200_ERR_INVALID, "mx, my must be positive");
     if (p->mwaves < 1 || p->mwaves > CLAWB200_MAXWAVES) return fail(CLAWB200_ERR_INVALID, "bad mwaves");
     if (p->pitch < p->mx + 2 * p->mbc) return fail(CLAWB200_ERR_INVALID, "pitch smaller than padded row");
-    if (p->method[5] != 0)
-        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function (mcapa) not supported by this build");
+    if (p->method[5] < 0 || p->method[5] > p->maux)
+        return fail(CLAWB200_ERR_INVALID, "method[5] (mcapa+1) must index an aux component");
+    return 0;
+}
+
+// capacity functions / aux arrays are compiled for the 2-D classic sweeps of these solvers
+static int check_aux(const clawb200_problem *p, const double *aux, bool classic2d)
+{
+    const bool capa = p->method[5] > 0;
+    const bool need_aux = capa || p->rp_id == CLAWB200_RP_SPHERE;
+    if (!need_aux) return 0;
+    if (!classic2d)
+        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function / aux-dependent solvers: 2-D classic sweeps only");
+    if (!aux) return fail(CLAWB200_ERR_INVALID, "aux array required (mcapa > 0 or aux-dependent Riemann solver)");
+    if (p->rp_id == CLAWB200_RP_SPHERE && (p->maux < 16 || !capa))
+        return fail(CLAWB200_ERR_INVALID, "the sphere solver needs its 16 aux components and mcapa");
+    if (capa && !(p->rp_id == CLAWB200_RP_ACOUSTICS || p->rp_id == CLAWB200_RP_ADVECTION ||
+                  p->rp_id == CLAWB200_RP_SPHERE))
+        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function (mcapa) is compiled for the acoustics, "
+                                              "advection and sphere solvers only");
     return 0;
 }
 
 static SweepArgs make_args(const clawb200_problem *p, const double *qin, double *qout, double dt,
-                           double *cfl_dev)
+                           double *cfl_dev, const double *aux = nullptr)
 {
     SweepArgs A;
     memset(&A, 0, sizeof(A));
+    A.aux = aux;
+    A.amstride = p->mstride; // aux shares the padded shape (and pitch) of q
+    A.mcapa = p->method[5];
     A.qin = qin; A.qbase = qin; A.qout = qout;
     A.mstride = p->mstride; A.pitch = p->pitch;
     A.mx = p->mx; A.my = p->my; A.mbc = p->mbc;
@@ -66,6 +87,10 @@ static SweepArgs make_args(const clawb200_problem *p, const double *qin, double 
     A.trans = p->method[2];
     for (int i = 0; i < CLAW_MAXWAVES; i++) A.mthlim[i] = (i < p->mwaves) ? p->mthlim[i] : 0;
     for (int i = 0; i < 8; i++) A.rp.p[i] = p->rp_params[i];
+    if (p->rp_id == CLAWB200_RP_SPHERE) { // common /comxyt/ dxcom, dycom
+        if (A.rp.p[1] == 0.0) A.rp.p[1] = p->dx;
+        if (A.rp.p[2] == 0.0) A.rp.p[2] = p->dy;
+    }
     A.cfl_bits = (unsigned long long *)cfl_dev;
     return A;
 }
@@ -81,12 +106,12 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 constexpr int XNT = 128; // threads per CTA of the x-engine
 constexpr int YNT = 128; // threads per CTA of the y-engine
 
-template <class RP, bool TRANS>
+template <class RP, bool TRANS, bool CAPA = false>
 static int launch_x(SweepArgs A, cudaStream_t st)
 {
     constexpr int NC = XNT - 3;
     size_t smem = sizeof(double) * (2 * RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
-    auto k = xsweep_kernel<RP, TRANS, XNT>;
+    auto k = xsweep_kernel<RP, TRANS, CAPA, XNT>;
     CUDA_OK(set_smem(k, smem));
     int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
     dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
@@ -95,12 +120,12 @@ static int launch_x(SweepArgs A, cudaStream_t st)
     return 0;
 }
 
-template <class RP, bool TRANS>
+template <class RP, bool TRANS, bool CAPA = false>
 static int launch_y(SweepArgs A, cudaStream_t st)
 {
     constexpr int NC = TRANS ? YNT - 2 : YNT;
     size_t smem = sizeof(double) * YNT * ((TRANS ? 4 * RP::MEQN : 0) + YSlots<RP, TRANS>::COUNT);
-    auto k = ysweep_kernel<RP, TRANS, YNT>;
+    auto k = ysweep_kernel<RP, TRANS, CAPA, YNT>;
     CUDA_OK(set_smem(k, smem));
     int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
     dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
@@ -122,6 +147,14 @@ static int pick_rows(int nrows, int ncol_ctas)
 template <bool TRANS>
 static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
 {
+    if (A.mcapa > 0) {
+        switch (rp_id) {
+        case CLAWB200_RP_ACOUSTICS: return launch_x<RpAcoustics<2, 1>, TRANS, true>(A, st);
+        case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS, true>(A, st);
+        case CLAWB200_RP_SPHERE: return launch_x<RpSphere<1>, TRANS, true>(A, st);
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
+        }
+    }
     switch (rp_id) {
     case CLAWB200_RP_ACOUSTICS: return launch_x<RpAcoustics<2, 1>, TRANS>(A, st);
     case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS>(A, st);
@@ -133,6 +166,14 @@ static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
 template <bool TRANS>
 static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
 {
+    if (A.mcapa > 0) {
+        switch (rp_id) {
+        case CLAWB200_RP_ACOUSTICS: return launch_y<RpAcoustics<2, 2>, TRANS, true>(A, st);
+        case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS, true>(A, st);
+        case CLAWB200_RP_SPHERE: return launch_y<RpSphere<2>, TRANS, true>(A, st);
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
+        }
+    }
     switch (rp_id) {
     case CLAWB200_RP_ACOUSTICS: return launch_y<RpAcoustics<2, 2>, TRANS>(A, st);
     case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS>(A, st);
@@ -150,11 +191,12 @@ static int check_rp_shape(const clawb200_problem *p)
     case CLAWB200_RP_ADVECTION: meqn = 1; mwaves = 1; break;
     case CLAWB200_RP_EULER5: meqn = 5; mwaves = 5; break;
     case CLAWB200_RP_SHALLOW: meqn = 3; mwaves = 3; break;
+    case CLAWB200_RP_SPHERE: meqn = 4; mwaves = 3; break;
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
     if (p->meqn != meqn || p->mwaves != mwaves)
         return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
-    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SHALLOW) && p->ndim != 2)
+    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SHALLOW || p->rp_id == CLAWB200_RP_SPHERE) && p->ndim != 2)
         return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 2-D only");
     return 0;
 }
@@ -167,7 +209,7 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
     if ((rc = check_rp_shape(p))) return rc;
     if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
     if (q_in == q_out) return fail(CLAWB200_ERR_INVALID, "q_in and q_out must differ");
-    (void)aux;
+    if ((rc = check_aux(p, aux, false))) return rc;
     SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev);
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int NT = 128, NC = NT - 3;
@@ -198,8 +240,8 @@ extern "C" int clawb200_step2ds(const clawb200_problem *p, const double *q_in, d
     if ((rc = check_rp_shape(p))) return rc;
     if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
     if (q_in == q_out) return fail(CLAWB200_ERR_INVALID, "q_in and q_out must differ");
-    (void)aux;
-    SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev);
+    if ((rc = check_aux(p, aux, true))) return rc;
+    SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev, aux);
     A.trans = -1;
     cudaStream_t st = (cudaStream_t)stream;
     if (ids == 1) {
@@ -228,9 +270,9 @@ extern "C" int clawb200_step2_parts(const clawb200_problem *p, const double *qol
     if (qold == qnew) return fail(CLAWB200_ERR_INVALID, "qold and qnew must differ");
     if (p->method[2] < 0) return fail(CLAWB200_ERR_INVALID, "method[2] < 0 means dimensional splitting: call step2ds");
     if (parts < 1 || parts > 3) return fail(CLAWB200_ERR_INVALID, "parts must be 1, 2 or 3");
-    (void)aux;
+    if ((rc = check_aux(p, aux, true))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    SweepArgs A = make_args(p, qold, qnew, dt, cfl_dev);
+    SweepArgs A = make_args(p, qold, qnew, dt, cfl_dev, aux);
     A.ilo = 1; A.ihi = p->mx; A.jlo = 1; A.jhi = p->my;
     if (parts & 1) {
         A.rows_per_cta = pick_rows(p->my, (p->mx + XNT - 4) / (XNT - 3));
@@ -514,7 +556,7 @@ extern "C" int clawb200_sharpclaw_stage(const clawb200_problem *p, const double 
     if (mode < 0 || mode > 3) return fail(CLAWB200_ERR_INVALID, "bad stage mode");
     if ((mode == 1 || mode == 2) && !qa) return fail(CLAWB200_ERR_INVALID, "this stage mode needs qa");
     if (out == q) return fail(CLAWB200_ERR_INVALID, "out must not alias q");
-    (void)aux;
+    if ((rc = check_aux(p, aux, false))) return rc;
     return sharpclaw_launch(p, q, qa, out, dq_out, dt, mode, ca, cb, div, cfl_dev, (cudaStream_t)stream);
 }
 
@@ -546,6 +588,18 @@ extern "C" int clawb200_ssp104_combine(const double *q, double *s1, double *s2, 
 // ---------------------------------------------------------------------------
 struct HostScratch {
     double *d_aos = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_cfl = nullptr;
+    double *d_aux = nullptr;
+    size_t aux_cap = 0;
+    int ensure_aux(size_t n)
+    {
+        if (n > aux_cap) {
+            cudaFree(d_aux);
+            d_aux = nullptr; aux_cap = 0;
+            CUDA_OK(cudaMalloc(&d_aux, n * sizeof(double)));
+            aux_cap = n;
+        }
+        return 0;
+    }
     double *h_cfl = nullptr;
     size_t cap = 0;
     cudaStream_t st = nullptr;
@@ -588,6 +642,22 @@ static int host_upload(const clawb200_problem &P, const double *h, double *d_soa
     CUDA_OK(cudaMemcpyAsync(g_hs.d_aos, h, n * sizeof(double), cudaMemcpyHostToDevice, g_hs.st));
     return clawb200_aos_to_soa(g_hs.d_aos, d_soa, P.meqn, nx, ny, P.mstride, P.pitch, g_hs.st);
 }
+// aux(maux, nx, ny) host array -> device SoA with the component stride of q
+static int host_upload_aux(const clawb200_problem &P, const double *h_aux, const double **d_aux)
+{
+    *d_aux = nullptr;
+    if (!h_aux || P.maux <= 0) return 0;
+    int nx = P.pitch, ny = (int)(P.mstride / P.pitch);
+    size_t n = (size_t)P.maux * nx * ny;
+    if (n > g_hs.cap) return fail(CLAWB200_ERR_INVALID, "internal: scratch not sized for aux");
+    int rc;
+    if ((rc = g_hs.ensure_aux(n))) return rc;
+    CUDA_OK(cudaMemcpyAsync(g_hs.d_aos, h_aux, n * sizeof(double), cudaMemcpyHostToDevice, g_hs.st));
+    if ((rc = clawb200_aos_to_soa(g_hs.d_aos, g_hs.d_aux, P.maux, nx, ny, P.mstride, P.pitch, g_hs.st))) return rc;
+    *d_aux = g_hs.d_aux;
+    return 0;
+}
+
 static int host_download(const clawb200_problem &P, const double *d_soa, double *h)
 {
     int nx = P.pitch, ny = (int)(P.mstride / P.pitch);
@@ -629,7 +699,7 @@ extern "C" int clawb200_step2ds_host(const clawb200_problem *p, const double *qo
     if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
     clawb200_problem P = host_layout(p);
     size_t n = (size_t)P.meqn * P.mstride;
-    int rc = g_hs.ensure(n);
+    int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
     if (rc) return rc;
     if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
     // qnew starts as the caller's qnew (== qold in the reference's usage): cells the sweep
@@ -639,7 +709,9 @@ extern "C" int clawb200_step2ds_host(const clawb200_problem *p, const double *qo
     } else if ((rc = host_upload(P, qnew, g_hs.d_b)))
         return rc;
     if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
-    if ((rc = clawb200_step2ds(&P, g_hs.d_a, g_hs.d_b, aux, dt, ids, g_hs.d_cfl, g_hs.st))) return rc;
+    const double *d_aux;
+    if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
+    if ((rc = clawb200_step2ds(&P, g_hs.d_a, g_hs.d_b, d_aux, dt, ids, g_hs.d_cfl, g_hs.st))) return rc;
     if ((rc = host_download(P, g_hs.d_b, qnew))) return rc;
     return host_finish(cfl);
 }
@@ -650,12 +722,14 @@ extern "C" int clawb200_step2_host(const clawb200_problem *p, const double *qold
     if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
     clawb200_problem P = host_layout(p);
     size_t n = (size_t)P.meqn * P.mstride;
-    int rc = g_hs.ensure(n);
+    int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
     if (rc) return rc;
     if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
     CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
     if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
-    if ((rc = clawb200_step2(&P, g_hs.d_a, g_hs.d_b, aux, dt, g_hs.d_cfl, g_hs.st))) return rc;
+    const double *d_aux;
+    if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
+    if ((rc = clawb200_step2(&P, g_hs.d_a, g_hs.d_b, d_aux, dt, g_hs.d_cfl, g_hs.st))) return rc;
     if ((rc = host_download(P, g_hs.d_b, qnew))) return rc;
     return host_finish(cfl);
 }

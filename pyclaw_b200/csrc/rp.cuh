@@ -26,8 +26,18 @@
 #define CLAW_RP_EULER5 3
 #define CLAW_RP_SHALLOW 4
 
+#define CLAW_RP_SPHERE 5
+
 struct RpParams {
     double p[8];
+};
+
+// One cell of the aux array (structure of arrays, component stride `ms`); read through
+// the read-only path.  A null cell is passed to solvers that use no aux data.
+struct AuxCell {
+    const double *p;
+    long long ms;
+    __device__ __forceinline__ double operator()(int ma) const { return __ldg(p + ma * ms); }
 };
 
 __device__ __forceinline__ double dmax2(double a, double b) { return (a > b) ? a : b; }
@@ -46,13 +56,16 @@ struct RpAcoustics {
 #define CLAW_AC_X_MINB 5
 #define CLAW_AC_Y_MINB 4
 #endif
-    static constexpr int X_MINB = CLAW_AC_X_MINB, Y_MINB = CLAW_AC_Y_MINB; // CTAs/SM the sweeps are compiled for
+    static constexpr int X_MINB = CLAW_AC_X_MINB, Y_MINB = CLAW_AC_Y_MINB;
+    static constexpr int MAUX = 0; // aux components read by the solver
+    static constexpr bool QCOR = false; // CTAs/SM the sweeps are compiled for
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
     __host__ __device__ static constexpr bool nz(int m, int mw) { return m == 0 || m == MU; }
 
     template <class AR>
     __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[MEQN],
-                                                 const double (&r)[MEQN], double (&wave)[MEQN][MWAVES],
+                                                 const double (&r)[MEQN], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[MEQN][MWAVES],
                                                  double (&s)[MWAVES], double (&amdq)[MEQN],
                                                  double (&apdq)[MEQN], double (&roe)[NROE])
     {
@@ -82,6 +95,8 @@ struct RpAcoustics {
 
     template <class AR>
     __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[MEQN], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
                                                       const double (&asdq)[MEQN],
                                                       double (&bm)[MEQN], double (&bp)[MEQN])
     {
@@ -108,11 +123,14 @@ struct RpAdvection {
     static constexpr int ID = CLAW_RP_ADVECTION;
     static constexpr int MEQN = 1, MWAVES = 1, NROE = 1;
     static constexpr int X_MINB = 6, Y_MINB = 6;
+    static constexpr int MAUX = 0;
+    static constexpr bool QCOR = false;
     __host__ __device__ static constexpr bool nz(int, int) { return true; }
 
     template <class AR>
     __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[1],
-                                                 const double (&r)[1], double (&wave)[1][1],
+                                                 const double (&r)[1], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[1][1],
                                                  double (&s)[1], double (&amdq)[1],
                                                  double (&apdq)[1], double (&roe)[NROE])
     {
@@ -125,6 +143,8 @@ struct RpAdvection {
 
     template <class AR>
     __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[1], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
                                                       const double (&asdq)[1], double (&bm)[1],
                                                       double (&bp)[1])
     {
@@ -149,6 +169,8 @@ struct RpEuler5 {
 #define CLAW_EU_Y_MINB 2
 #endif
     static constexpr int X_MINB = CLAW_EU_X_MINB, Y_MINB = CLAW_EU_Y_MINB;
+    static constexpr int MAUX = 0;
+    static constexpr bool QCOR = false;
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
     // sparsity of wave(m,mw) as written at rpn2_euler_5wave.f:124-163
     __host__ __device__ static constexpr bool nz(int m, int mw)
@@ -158,7 +180,8 @@ struct RpEuler5 {
 
     template <class AR>
     __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[5],
-                                                 const double (&r)[5], double (&wave)[5][5],
+                                                 const double (&r)[5], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[5][5],
                                                  double (&s)[5], double (&amdq)[5],
                                                  double (&apdq)[5], double (&roe)[NROE])
     {
@@ -299,6 +322,8 @@ struct RpEuler5 {
 
     template <class AR>
     __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[5], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
                                                       const double (&asdq)[5], double (&bm)[5],
                                                       double (&bp)[5])
     {
@@ -361,6 +386,8 @@ struct RpShallow {
 #define CLAW_SW_Y_MINB 3
 #endif
     static constexpr int X_MINB = CLAW_SW_X_MINB, Y_MINB = CLAW_SW_Y_MINB;
+    static constexpr int MAUX = 0;
+    static constexpr bool QCOR = false;
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
     __host__ __device__ static constexpr bool nz(int m, int mw)
     {
@@ -369,7 +396,8 @@ struct RpShallow {
 
     template <class AR>
     __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[3],
-                                                 const double (&r)[3], double (&wave)[3][3],
+                                                 const double (&r)[3], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[3][3],
                                                  double (&s)[3], double (&amdq)[3],
                                                  double (&apdq)[3], double (&roe)[NROE])
     {
@@ -457,6 +485,8 @@ struct RpShallow {
 
     template <class AR>
     __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[3], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
                                                       const double (&asdq)[3], double (&bm)[3],
                                                       double (&bp)[3])
     {
@@ -487,5 +517,242 @@ struct RpShallow {
                 bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
             }
         }
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// Shallow water on the sphere (3-D Cartesian momentum, 16 aux components).
+// clawpack/riemann rpn2_shallow_sphere.f, rpt2_shallow_sphere.f (external)
+// with apps/shallow-sphere/qcor.f:2-72 for the step2qcor correction.
+// params: p[0] = g (common /sw/), p[1] = dxcom, p[2] = dycom (common /comxyt/).
+// aux (0-based): 0 kappa | 1-3 normal, 4-6 tangent of the LEFT edge | 7-9 normal,
+// 10-12 tangent of the BOTTOM edge | 13-15 radial unit vector at the cell centre
+// (apps/shallow-sphere/setaux.f:9-25).  The oracle restatement of this solver reproduces
+// test/swsphere_height to 2e-17.
+// ---------------------------------------------------------------------------
+template <int IXY>
+struct RpSphere {
+    static constexpr int ID = CLAW_RP_SPHERE;
+    static constexpr int MEQN = 4, MWAVES = 3, NROE = 1;
+    static constexpr int X_MINB = 2, Y_MINB = 2;
+    static constexpr int MAUX = 16;
+    static constexpr bool QCOR = true;
+    static constexpr int IOFF = (IXY == 2) ? 7 : 1;   // edge data of the sweep direction
+    static constexpr int IOFFT = (IXY == 2) ? 1 : 7;  // edge data of the transverse direction
+    __host__ __device__ static constexpr bool nz(int m, int mw) { return !(m == 0 && mw == 1); }
+
+    // axl = cell i-1 (its radial vector projects amdq), axr = cell i (owns the edge)
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[4],
+                                                 const double (&r)[4], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[4][3], double (&s)[3], double (&amdq)[4],
+                                                 double (&apdq)[4], double (&roe)[NROE])
+    {
+        const double g = P.p[0];
+        const double dy = (IXY == 2) ? P.p[1] : P.p[2];
+        const double enx = axr(IOFF + 0), eny = axr(IOFF + 1), enz = axr(IOFF + 2);
+        double etx = axr(IOFF + 3), ety = axr(IOFF + 4), etz = axr(IOFF + 5);
+        const double gamma = ar.sqrt(etx * etx + ety * ety + etz * etz);
+        const Recip rg = ar.rcp(gamma);
+        etx = ar.div(etx, rg); ety = ar.div(ety, rg); etz = ar.div(etz, rg);
+        // "ql" of the Fortran is the right cell, "qr" the left cell
+        double hunl = enx * r[1] + eny * r[2] + enz * r[3];
+        double hunr = enx * l[1] + eny * l[2] + enz * l[3];
+        double hutl = etx * r[1] + ety * r[2] + etz * r[3];
+        double hutr = etx * l[1] + ety * l[2] + etz * l[3];
+        double hl = r[0], hr = l[0];
+        double h = (hl + hr) * 0.50;
+        double hsqr = ar.sqrt(hr), hsql = ar.sqrt(hl), hsq = hsqr + hsql;
+        const Recip rsr = ar.rcp(hsqr), rsl = ar.rcp(hsql), rsq = ar.rcp(hsq);
+        double u = ar.div(ar.div(hunr, rsr) + ar.div(hunl, rsl), rsq);
+        double v = ar.div(ar.div(hutr, rsr) + ar.div(hutl, rsl), rsq);
+        double a = ar.sqrt(g * h);
+        double hoa = ar.div(0.50, a);
+        double d1 = hl - hr, d2 = hunl - hunr, d3 = hutl - hutr;
+        double a1 = ((u + a) * d1 - d2) * hoa;
+        double a2 = -v * d1 + d3;
+        double a3 = (-(u - a) * d1 + d2) * hoa;
+        const Recip rdy = ar.rcp(dy);
+        wave[0][0] = a1;
+        wave[1][0] = a1 * (u - a) * enx + a1 * v * etx;
+        wave[2][0] = a1 * (u - a) * eny + a1 * v * ety;
+        wave[3][0] = a1 * (u - a) * enz + a1 * v * etz;
+        s[0] = ar.div((u - a) * gamma, rdy);
+        wave[0][1] = 0.0;
+        wave[1][1] = a2 * etx;
+        wave[2][1] = a2 * ety;
+        wave[3][1] = a2 * etz;
+        s[1] = ar.div(u * gamma, rdy);
+        wave[0][2] = a3;
+        wave[1][2] = a3 * (u + a) * enx + a3 * v * etx;
+        wave[2][2] = a3 * (u + a) * eny + a3 * v * ety;
+        wave[3][2] = a3 * (u + a) * enz + a3 * v * etz;
+        s[2] = ar.div((u + a) * gamma, rdy);
+        // entropy fix
+        bool done = false;
+        double him1 = l[0];
+        double s0 = ar.div((ar.div(hunr, him1) - ar.sqrt(g * him1)) * gamma, rdy);
+        if (s0 > 0.0 && s[0] > 0.0) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) amdq[m] = 0.0;
+            done = true;
+        }
+        if (!done) {
+            double h1 = l[0] + wave[0][0];
+            double hu1 = hunr + (enx * wave[1][0] + eny * wave[2][0] + enz * wave[3][0]);
+            double s1 = ar.div((ar.div(hu1, h1) - ar.sqrt(g * h1)) * gamma, rdy);
+            double sfract;
+            if (s0 < 0.0 && s1 > 0.0)
+                sfract = s0 * ar.div(s1 - s[0], s1 - s0);
+            else if (s[0] < 0.0)
+                sfract = s[0];
+            else
+                sfract = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; m++) amdq[m] = sfract * wave[m][0];
+            if (s[1] > 0.0) done = true;
+        }
+        if (!done) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) amdq[m] = amdq[m] + s[1] * wave[m][1];
+            double hi = r[0];
+            double s03 = ar.div((ar.div(hunl, hi) + ar.sqrt(g * hi)) * gamma, rdy);
+            double h3 = r[0] - wave[0][2];
+            double hu3 = hunl - (enx * wave[1][2] + eny * wave[2][2] + enz * wave[3][2]);
+            double s3 = ar.div((ar.div(hu3, h3) + ar.sqrt(g * h3)) * gamma, rdy);
+            double sfract = 0.0;
+            bool add3 = true;
+            if (s3 < 0.0 && s03 > 0.0)
+                sfract = s3 * ar.div(s03 - s[2], s03 - s3);
+            else if (s[2] < 0.0)
+                sfract = s[2];
+            else
+                add3 = false;
+            if (add3) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) amdq[m] = amdq[m] + sfract * wave[m][2];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            double df = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 3; mw++) df = df + s[mw] * wave[m][mw];
+            apdq[m] = df - amdq[m];
+        }
+        // project the momentum components onto the tangent plane
+        {
+            double erx = axl(13), ery = axl(14), erz = axl(15);
+            double amn = erx * amdq[1] + ery * amdq[2] + erz * amdq[3];
+            amdq[1] = amdq[1] - amn * erx;
+            amdq[2] = amdq[2] - amn * ery;
+            amdq[3] = amdq[3] - amn * erz;
+            erx = axr(13); ery = axr(14); erz = axr(15);
+            double apn = erx * apdq[1] + ery * apdq[2] + erz * apdq[3];
+            apdq[1] = apdq[1] - apn * erx;
+            apdq[2] = apdq[2] - apn * ery;
+            apdq[3] = apdq[3] - apn * erz;
+        }
+        roe[0] = 0.0;
+    }
+
+    // one side of rpt2: edge data from `axe`, radial vector from `axp`, state of the cell
+    template <class AR, bool UP>
+    __device__ __forceinline__ static void side(AR &ar, double g, double dx, const double (&qc)[4],
+                                                const AuxCell &axe, const AuxCell &axp,
+                                                const double (&asdq)[4], double (&b)[4])
+    {
+        const double enx = axe(IOFFT + 0), eny = axe(IOFFT + 1), enz = axe(IOFFT + 2);
+        double etx = axe(IOFFT + 3), ety = axe(IOFFT + 4), etz = axe(IOFFT + 5);
+        const double gamma = ar.sqrt(etx * etx + ety * ety + etz * etz);
+        const Recip rg = ar.rcp(gamma);
+        etx = ar.div(etx, rg); ety = ar.div(ety, rg); etz = ar.div(etz, rg);
+        const double h = qc[0];
+        const Recip rh = ar.rcp(h);
+        double u = ar.div(enx * qc[1] + eny * qc[2] + enz * qc[3], rh);
+        double v = ar.div(etx * qc[1] + ety * qc[2] + etz * qc[3], rh);
+        double a = ar.sqrt(g * h);
+        double hoa = ar.div(0.50, a);
+        double d2 = enx * asdq[1] + eny * asdq[2] + enz * asdq[3];
+        double d3 = etx * asdq[1] + ety * asdq[2] + etz * asdq[3];
+        double d1 = asdq[0];
+        double a1 = ((u + a) * d1 - d2) * hoa;
+        double a2 = -v * d1 + d3;
+        double a3 = (-(u - a) * d1 + d2) * hoa;
+        double waveb[4][3], sb[3];
+        const Recip rdx = ar.rcp(dx);
+        waveb[0][0] = a1;
+        waveb[1][0] = a1 * (u - a) * enx + a1 * v * etx;
+        waveb[2][0] = a1 * (u - a) * eny + a1 * v * ety;
+        waveb[3][0] = a1 * (u - a) * enz + a1 * v * etz;
+        sb[0] = ar.div((u - a) * gamma, rdx);
+        waveb[0][1] = 0.0;
+        waveb[1][1] = a2 * etx;
+        waveb[2][1] = a2 * ety;
+        waveb[3][1] = a2 * etz;
+        sb[1] = ar.div(u * gamma, rdx);
+        waveb[0][2] = a3;
+        waveb[1][2] = a3 * (u + a) * enx + a3 * v * etx;
+        waveb[2][2] = a3 * (u + a) * eny + a3 * v * ety;
+        waveb[3][2] = a3 * (u + a) * enz + a3 * v * etz;
+        sb[2] = ar.div((u + a) * gamma, rdx);
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            b[m] = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 3; mw++)
+                b[m] = b[m] + (UP ? dmax2(sb[mw], 0.0) : dmin2(sb[mw], 0.0)) * waveb[m][mw];
+        }
+        double erx = axp(13), ery = axp(14), erz = axp(15);
+        double bn = erx * b[1] + ery * b[2] + erz * b[3];
+        b[1] = b[1] - bn * erx;
+        b[2] = b[2] - bn * ery;
+        b[3] = b[3] - bn * erz;
+    }
+
+    // qc = state of the cell the fluctuation moves into; ax1/ax2/ax3 = that cell in the
+    // previous / current / next slice
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[4], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
+                                                      const double (&asdq)[4], double (&bm)[4], double (&bp)[4])
+    {
+        const double g = P.p[0];
+        const double dx = (IXY == 2) ? P.p[2] : P.p[1];
+        side<AR, true>(ar, g, dx, qc, ax3, ax3, asdq, bp);
+        side<AR, false>(ar, g, dx, qc, ax2, ax1, asdq, bm);
+    }
+
+    // apps/shallow-sphere/qcor.f:2-72: axi = this cell, axn = the next cell along the sweep
+    template <class AR>
+    __device__ __forceinline__ static void qcor(AR &ar, const RpParams &P, const double (&q)[4],
+                                                const AuxCell &axi, const AuxCell &axn, double (&qcv)[4])
+    {
+        const double g = P.p[0];
+        const double dy = (IXY == 2) ? P.p[1] : P.p[2];
+        const Recip rdy = ar.rcp(dy);
+        double etxl = axi(IOFF + 3), etyl = axi(IOFF + 4), etzl = axi(IOFF + 5);
+        double gammal = ar.div(ar.sqrt(etxl * etxl + etyl * etyl + etzl * etzl), rdy);
+        double enxl = axi(IOFF + 0) * gammal, enyl = axi(IOFF + 1) * gammal, enzl = axi(IOFF + 2) * gammal;
+        double etxr = axn(IOFF + 3), etyr = axn(IOFF + 4), etzr = axn(IOFF + 5);
+        double gammar = ar.div(ar.sqrt(etxr * etxr + etyr * etyr + etzr * etzr), rdy);
+        double enxr = axn(IOFF + 0) * gammar, enyr = axn(IOFF + 1) * gammar, enzr = axn(IOFF + 2) * gammar;
+        const double q1 = q[0], q2 = q[1], q3 = q[2], q4 = q[3];
+        const Recip r1 = ar.rcp(q1);
+        const double hg = 0.5 * g * (q1 * q1);
+        qcv[0] = (enxr - enxl) * q2 + (enyr - enyl) * q3 + (enzr - enzl) * q4;
+        qcv[1] = (enxr - enxl) * (ar.div(q2 * q2, r1) + hg) + (enyr - enyl) * ar.div(q2 * q3, r1) +
+                 (enzr - enzl) * ar.div(q2 * q4, r1);
+        qcv[2] = (enxr - enxl) * ar.div(q2 * q3, r1) + (enyr - enyl) * (ar.div(q3 * q3, r1) + hg) +
+                 (enzr - enzl) * ar.div(q3 * q4, r1);
+        qcv[3] = (enxr - enxl) * ar.div(q2 * q4, r1) + (enyr - enyl) * ar.div(q3 * q4, r1) +
+                 (enzr - enzl) * (ar.div(q4 * q4, r1) + hg);
+        double erx = axi(13), ery = axi(14), erz = axi(15);
+        double qcn = erx * qcv[1] + ery * qcv[2] + erz * qcv[3];
+        qcv[1] = qcv[1] - qcn * erx;
+        qcv[2] = qcv[2] - qcn * ery;
+        qcv[3] = qcv[3] - qcn * erz;
     }
 };

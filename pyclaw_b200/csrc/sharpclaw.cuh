@@ -187,7 +187,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
     double left[MEQN];
 #pragma unroll
     for (int m = 0; m < MEQN; m++) left[m] = x1[m * NT + (t > 0 ? t - 1 : 0)];
-    with_arith([&](auto &ar) { RP::solve(ar, A.rp, left, ql, wave, s, amdq, apdq, roe); });
+    with_arith([&](auto &ar) { RP::solve(ar, A.rp, left, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
     if (iface_cfl) {
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, A.dtdx * s[mw]), -A.dtdx * s[mw]);
@@ -197,7 +197,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
     __syncthreads();
     if (full) {
         double amdq2[MEQN], apdq2[MEQN];
-        with_arith([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, wave, s, amdq2, apdq2, roe); });
+        with_arith([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             double an = x2[m * NT + (t < NT - 1 ? t + 1 : t)];
@@ -299,14 +299,14 @@ __global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
 #pragma unroll
             for (int m = 0; m < MEQN; m++) { amdq[m] = apdq[m] = amdq2[m] = apdq2[m] = 0.0; }
             if (c >= j0) {
-                with_arith([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, wave, s, amdq, apdq, roe); });
+                with_arith([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
                 if (ycol && c >= 1 && c <= A.my + 1) {
 #pragma unroll
                     for (int mw = 0; mw < MW; mw++)
                         cfl = dmax2(dmax2(cfl, A.dtdy * s[mw]), -A.dtdy * s[mw]);
                 }
                 if (c < j1)
-                    with_arith([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, wave, s, amdq2, apdq2, roe); });
+                    with_arith([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
                 // cell c-1 = k-3 is complete
                 const int jc = c - 1;
                 if (jc >= j0 && jc < j1 && col_out) {

@@ -6,20 +6,21 @@ its scripts never name the solver in Python.  Here ``solver.rp`` may be set to o
 these descriptors (or its name); if it is left unset the solver is inferred from the
 keys of ``state.aux_global`` (the cparam common block the script fills).
 """
-from .._lib import RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW
+from .._lib import RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE
 
 
 class RiemannSolver(object):
-    def __init__(self, name, rp_id, meqn, mwaves, param_names, ndims):
+    def __init__(self, name, rp_id, meqn, mwaves, param_names, ndims, optional=()):
         self.name, self.rp_id, self.mwaves, self.param_names, self.ndims = name, rp_id, mwaves, param_names, ndims
         self._meqn = meqn
+        self.optional = set(optional)
 
     def meqn(self, ndim):
         return self._meqn(ndim) if callable(self._meqn) else self._meqn
 
     def params(self, aux_global):
-        missing = [k for k in self.param_names if k not in aux_global]
-        if missing and not (self.rp_id == RP_ADVECTION and missing == ["v"]):
+        missing = [k for k in self.param_names if k not in aux_global and k not in self.optional]
+        if missing:
             # state.py:154-158: every cparam variable must be present in aux_global
             raise Exception("Some required value(s) in the cparam common block in the Riemann "
                             "solver have not been set in aux_global: %s" % missing)
@@ -30,11 +31,16 @@ class RiemannSolver(object):
 
 
 acoustics = RiemannSolver("acoustics", RP_ACOUSTICS, lambda ndim: ndim + 1, 2, ["rho", "bulk", "cc", "zz"], (1, 2))
-advection = RiemannSolver("advection", RP_ADVECTION, 1, 1, ["u", "v"], (1, 2))
+advection = RiemannSolver("advection", RP_ADVECTION, 1, 1, ["u", "v"], (1, 2), optional=["v"])
 euler_5wave = RiemannSolver("euler_5wave", RP_EULER5, 5, 5, ["gamma", "gamma1"], (2,))
 shallow_roe_with_efix = RiemannSolver("shallow_roe_with_efix", RP_SHALLOW, 3, 3, ["grav"], (2,))
 
-_BY_NAME = {s.name: s for s in (acoustics, advection, euler_5wave, shallow_roe_with_efix)}
+# shallow water on the sphere (apps/shallow-sphere): `g` is the reference's common /sw/ g;
+# dxcom / dycom (common /comxyt/) default to the grid spacing
+shallow_sphere = RiemannSolver("shallow_sphere", RP_SPHERE, 4, 3, ["g", "dxcom", "dycom"], (2,),
+                               optional=["dxcom", "dycom"])
+
+_BY_NAME = {s.name: s for s in (acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere)}
 _BY_NAME.update({"euler": euler_5wave, "shallow": shallow_roe_with_efix})
 
 

@@ -304,3 +304,112 @@ def test_rejected_step_is_rolled_back():
     claw.solution, claw.solver = pyclaw.Solution(state), solver
     claw.run()
     assert np.array_equal(np.asarray(claw.frames[-1].state.q), fo[-1])
+
+
+def _sphere_api(mx=40, my=20, tfinal=10.0, nout=10):
+    """test/shallow_sphere/shallow_4_Rossby_Haurwitz_wave.py on the GPU.  setaux.f / qinit.f
+    are init-time helpers of the application (f2py `problem` module in the reference); here
+    their restatement supplies the initial arrays.  src2.f (Coriolis, 4-stage RK + tangent
+    plane projection) is the per-step source term and runs on the device."""
+    import pyclaw
+    pb = problems.sphere_problem(mx, my)
+    full = pb["auxbc_full"]
+    mbc = 2
+
+    def qbc_lower_y(state, dim, t, qbc, mbc):
+        for j in range(mbc):
+            qbc[:, :, j] = torch.flip(qbc[:, :, 2 * mbc - 1 - j], dims=[1])
+
+    def qbc_upper_y(state, dim, t, qbc, mbc):
+        my_ = state.grid.ng[1]
+        for j in range(mbc):
+            qbc[:, :, my_ + mbc + j] = torch.flip(qbc[:, :, my_ + mbc - 1 - j], dims=[1])
+
+    def auxbc_lower_y(state, dim, t, auxbc, mbc):
+        auxbc[:, :, :mbc] = full[:, :, :mbc]
+
+    def auxbc_upper_y(state, dim, t, auxbc, mbc):
+        auxbc[:, :, -mbc:] = full[:, :, -mbc:]
+
+    df = float(np.float32(12.600576))          # "12.600576e0" is a REAL(4) literal in src2.f:38
+    six = None
+
+    def src2(solver, state, dt):
+        nonlocal six
+        q, aux = state.q, state.aux
+        er = [aux[13], aux[14], aux[15]]       # = mapc2p(cell centre), what src2.f recomputes
+        if six is None:
+            six = torch.full((), 6.0, dtype=q.dtype, device=q.device)
+
+        def project():
+            qn = er[0] * q[1] + er[1] * q[2] + er[2] * q[3]
+            q[1] = q[1] - qn * er[0]
+            q[2] = q[2] - qn * er[1]
+            q[3] = q[3] - qn * er[2]
+        project()
+        fcor = df * er[2]
+        RK = []
+        hu, hv, hw = q[1], q[2], q[3]
+        for st in range(4):
+            if st > 0:
+                hu = q[1] + 0.5 * RK[st - 1][0]
+                hv = q[2] + 0.5 * RK[st - 1][1]
+                hw = q[3] + 0.5 * RK[st - 1][2]
+            RK.append((fcor * dt * (er[2] * hv - er[1] * hw),
+                       dt * fcor * (er[0] * hw - er[2] * hu),
+                       dt * fcor * (er[1] * hu - er[0] * hv)))
+        for m in range(3):
+            q[m + 1] = q[m + 1] + torch.div(RK[0][m] + 2.0 * RK[1][m] + 2.0 * RK[2][m] + RK[3][m], six)
+        project()
+
+    solver = pyclaw.ClawSolver2D()
+    solver.rp = pyclaw.riemann.shallow_sphere
+    solver.bc_lower[0] = pyclaw.BC.periodic
+    solver.bc_upper[0] = pyclaw.BC.periodic
+    solver.bc_lower[1] = pyclaw.BC.custom
+    solver.bc_upper[1] = pyclaw.BC.custom
+    solver.user_bc_lower = qbc_lower_y
+    solver.user_bc_upper = qbc_upper_y
+    solver.aux_bc_lower[0] = pyclaw.BC.periodic
+    solver.aux_bc_upper[0] = pyclaw.BC.periodic
+    solver.aux_bc_lower[1] = pyclaw.BC.custom
+    solver.aux_bc_upper[1] = pyclaw.BC.custom
+    solver.user_aux_bc_lower = auxbc_lower_y
+    solver.user_aux_bc_upper = auxbc_upper_y
+    solver.dim_split = 0
+    solver.order_trans = 2
+    solver.mwaves = 3
+    solver.src_split = 2
+    solver.step_src = src2
+    solver.limiters = pyclaw.limiters.tvd.MC
+    x = pyclaw.Dimension('x', -3.0, 1.0, mx)
+    y = pyclaw.Dimension('y', -1.0, 1.0, my)
+    state = pyclaw.State(pyclaw.Grid([x, y]), 4, 16)
+    state.aux_global['g'] = problems.SPHERE_G
+    state.aux[:, :, :] = pb["aux"]
+    state.mcapa = 0
+    state.q[:, :, :] = pb["q"]
+    claw = pyclaw.Controller()
+    claw.keep_copy = True
+    claw.output_format = None
+    claw.outstyle = 1
+    claw.nout = nout
+    claw.tfinal = tfinal
+    claw.solution = pyclaw.Solution(state)
+    claw.solver = solver
+    claw.run()
+    return np.asarray(claw.frames[claw.nout].state.q)
+
+
+def test_shallow_sphere_golden():
+    # test_examples.py:456-472 asks for a Frobenius norm < 1e-4 against test/swsphere_height
+    q = _sphere_api()
+    gold = np.loadtxt(os.path.join(GOLD, 'swsphere_height'))
+    assert np.linalg.norm(q[0] - gold) < 1e-15
+
+
+def test_shallow_sphere_vs_oracle():
+    import test_oracle_golden as tog
+    frames, s = tog._oracle_sphere(tfinal=2.0)
+    q = _sphere_api(tfinal=2.0)
+    assert np.array_equal(q, frames[-1])

@@ -186,3 +186,65 @@ def test_f2py_shaped_modules():
     assert np.array_equal(dq[:, 3:-3, 3:-3], dqo[:, 3:-3, 3:-3]) and cfl == cflo
     with pytest.raises(ValueError):
         classic2.step2(max(mx, my), mbc, mx, my, np.ascontiguousarray(q), qnew, None, dx, dy, dt, method, lim)
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection"])
+@pytest.mark.parametrize("shape", [(37, 29), (130, 70)])
+@pytest.mark.parametrize("trans", [-1, 0, 1, 2])
+def test_capacity_function(rp, shape, trans):
+    """mcapa > 0: dtdx1d = dtdx/capa and the /capa update forms of step2.f:145-152,227-234
+    and step2ds.f:152-156,228-232."""
+    rp_id, params, meqn, mwaves, lim = RPS[rp]
+    mx, my = shape
+    mbc = 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    method = [1, 2, trans, 0, 0, 1, 1]
+    q = _random_padded(rp, mx, my, mbc, seed=mx + trans)
+    rng = np.random.RandomState(7)
+    aux = np.asfortranarray(rng.uniform(0.5, 1.5, (1, mx + 2 * mbc, my + 2 * mbc)))
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim, maux=1)
+    cfl_g = ctypes.c_double()
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    if trans < 0:
+        for ids in (1, 2):
+            qn_o = q.copy("F")
+            cfl_o = po.step2ds(rp_id, params, mbc, mx, my, q, qn_o, aux, dx, dy, dt, method, lim, ids)
+            qn_g = q.copy("F")
+            _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), _ptr(aux), dt, ids,
+                      ctypes.byref(cfl_g))
+            assert np.array_equal(qn_g, qn_o), (ids, np.abs(qn_g - qn_o).max())
+            assert cfl_g.value == cfl_o
+    else:
+        qn_o = q.copy("F")
+        cfl_o = po.step2(rp_id, params, mbc, mx, my, q, qn_o, aux, dx, dy, dt, method, lim)
+        qn_g = q.copy("F")
+        _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), _ptr(aux), dt,
+                  ctypes.byref(cfl_g))
+        assert np.array_equal(qn_g[inner], qn_o[inner]), np.abs(qn_g[inner] - qn_o[inner]).max()
+        assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("shape", [(40, 20), (128, 64)])
+def test_shallow_sphere_step(shape):
+    """rpn2/rpt2_shallow_sphere + step2qcor on the Rossby-Haurwitz data (16 aux, capa)."""
+    mx, my = shape
+    mbc = 2
+    pb = problems.sphere_problem(mx, my)
+    dx, dy = pb["d"]
+    aux = pb["auxbc_full"]
+    qbc = np.zeros((4, mx + 2 * mbc, my + 2 * mbc), order="F")
+    qbc[:, mbc:-mbc, mbc:-mbc] = pb["q"]
+    po.fill_bcs(qbc, mbc, [po.BC_PERIODIC, po.BC_CUSTOM], [po.BC_PERIODIC, po.BC_CUSTOM],
+                problems.sphere_qbc_lower_y, problems.sphere_qbc_upper_y)
+    method, lim = [1, 2, 2, 0, 0, 1, 16], [4, 4, 4]
+    dt = 0.4 * dx / 4.0
+    qn_o = qbc.copy("F")
+    cfl_o = po.step2(po.RP_SPHERE, pb["params"], mbc, mx, my, qbc, qn_o, aux, dx, dy, dt, method, lim)
+    P = _lib.make_problem(2, 4, 3, mbc, mx, my, dx, dy, _lib.RP_SPHERE, pb["params"], method, lim, maux=16)
+    qn_g = qbc.copy("F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(qbc), _ptr(qn_g), _ptr(aux), dt, ctypes.byref(cfl_g))
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    assert not np.isnan(qn_o).any() and cfl_o > 0
+    assert np.array_equal(qn_g[inner], qn_o[inner]), np.abs(qn_g[inner] - qn_o[inner]).max()
+    assert cfl_g.value == cfl_o
