@@ -315,7 +315,8 @@ struct RpEuler5 {
         for (int m = 0; m < 5; m++) {
             double df = 0.0;
 #pragma unroll
-            for (int mw = 0; mw < 5; mw++) df = df + s[mw] * wave[m][mw];
+            for (int mw = 0; mw < 5; mw++)
+                if (nz(m, mw)) df = df + s[mw] * wave[m][mw]; // zero entries add +-0 to a sum that starts at +0
             apdq[m] = df - amdq[m];
         }
     }
@@ -359,14 +360,18 @@ struct RpEuler5 {
         waveb[3][3] = 0.0;
         waveb[4][3] = asdq[4];
         sb[3] = v;
+        // waveb(5,1:3) and waveb(1:4,4) are literal zeros (rpt2_euler_5wave.f:57-80): adding
+        // their +-0 products to sums that start at +0 changes nothing, so they are skipped
 #pragma unroll
         for (int m = 0; m < 5; m++) {
             bm[m] = 0.0;
             bp[m] = 0.0;
 #pragma unroll
             for (int mw = 0; mw < 4; mw++) {
-                bm[m] = bm[m] + dmin2(sb[mw], 0.0) * waveb[m][mw];
-                bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
+                if ((mw == 3) == (m == 4)) {
+                    bm[m] = bm[m] + dmin2(sb[mw], 0.0) * waveb[m][mw];
+                    bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
+                }
             }
         }
     }
@@ -478,7 +483,8 @@ struct RpShallow {
         for (int m = 0; m < 3; m++) {
             double df = 0.0;
 #pragma unroll
-            for (int mw = 0; mw < 3; mw++) df = df + s[mw] * wave[m][mw];
+            for (int mw = 0; mw < 3; mw++)
+                if (nz(m, mw)) df = df + s[mw] * wave[m][mw];
             apdq[m] = df - amdq[m];
         }
     }
@@ -507,14 +513,17 @@ struct RpShallow {
         waveb[MU][2] = a3 * u;
         waveb[MV][2] = a3 * (v + a);
         sb[2] = v + a;
+        // waveb(1,2) and waveb(mv,2) are literal zeros: skipped (sums start at +0)
 #pragma unroll
         for (int m = 0; m < 3; m++) {
             bm[m] = 0.0;
             bp[m] = 0.0;
 #pragma unroll
             for (int mw = 0; mw < 3; mw++) {
-                bm[m] = bm[m] + dmin2(sb[mw], 0.0) * waveb[m][mw];
-                bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
+                if (mw != 1 || m == MU) {
+                    bm[m] = bm[m] + dmin2(sb[mw], 0.0) * waveb[m][mw];
+                    bp[m] = bp[m] + dmax2(sb[mw], 0.0) * waveb[m][mw];
+                }
             }
         }
     }
