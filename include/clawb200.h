@@ -76,6 +76,10 @@ typedef struct clawb200_problem {
     long long mstride;
     int pitch;
     int weno_variant;              /* SharpClaw only */
+    /* Optional: device address of a double holding dt.  When non-NULL the classic sweeps read
+       the time step from there and ignore their `dt` argument, so that the launch sequence of
+       a step does not depend on dt and can be replayed as a CUDA graph. */
+    const double *dt_dev;
 } clawb200_problem;
 
 int clawb200_version(void);

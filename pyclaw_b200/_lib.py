@@ -34,6 +34,7 @@ class Problem(ctypes.Structure):
         ("mstride", ctypes.c_longlong),
         ("pitch", ctypes.c_int),
         ("weno_variant", ctypes.c_int),
+        ("dt_dev", ctypes.c_void_p),
     ]
 
 
@@ -57,6 +58,7 @@ def make_problem(ndim, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, rp_params, meth
     p.pitch = nx if pitch is None else pitch
     p.mstride = p.pitch * ny if mstride is None else mstride
     p.weno_variant = weno_variant
+    p.dt_dev = None
     return p
 
 

@@ -48,6 +48,61 @@ class ClawSolver(Solver):
     def _needs_backup_copy(self):
         return self.start_step is not None or (self.src_split == 2 and self.step_src is not None)
 
+    # ---- CUDA-graph replay of the hyperbolic step -------------------------------------
+    # A step is a fixed sequence of launches (ghost-cell fills, Courant-number reset, sweeps,
+    # Courant-number read-back); only dt and the buffer addresses change.  dt is read by the
+    # kernels from a device scalar (clawb200_problem.dt_dev), so the sequence is captured once
+    # per buffer rotation and replayed: one graph launch per step instead of ~10 Python/ctypes
+    # round trips.  Not used with custom (Python) boundary conditions or a slab partition.
+    use_cuda_graph = True
+
+    def _graph_ok(self, state):
+        from .solver import BC
+        return (self.use_cuda_graph and self._halo is None and
+                BC.custom not in list(self.bc_lower) + list(self.bc_upper))
+
+    def _hyperbolic_sequence(self, state, launch):
+        """bc fill + cfl reset + sweeps + cfl read-back, eagerly or through a cached graph.
+        ``launch(problem_ref, cfl_ptr, stream_ptr)`` issues the sweep kernels."""
+        import torch
+        if not self._graph_ok(state):
+            self.apply_q_bcs(state)
+            st = _stream()
+            _lib.call("clawb200_cfl_reset", _ptr(self._cfl_dev), st)
+            launch(ctypes.byref(self._problem), _ptr(self._cfl_dev), st)
+            return self._read_cfl()[0]
+        if getattr(self, '_dt_dev', None) is None:
+            self._dt_dev = torch.zeros(1, dtype=torch.float64, device=state.device)
+            self._dt_pin = torch.zeros(1, dtype=torch.float64).pin_memory()
+            self._gproblem = type(self._problem).from_buffer_copy(self._problem)
+            self._gproblem.dt_dev = self._dt_dev.data_ptr()
+            self._graphs = {}
+
+        def sequence():
+            self._dt_dev.copy_(self._dt_pin, non_blocking=True)
+            self.apply_q_bcs(state)
+            st = _stream()
+            _lib.call("clawb200_cfl_reset", _ptr(self._cfl_dev), st)
+            launch(ctypes.byref(self._gproblem), _ptr(self._cfl_dev), st)
+            self._cfl_host.copy_(self._cfl_dev, non_blocking=True)
+
+        self._dt_pin[0] = float(self.dt)
+        key = self._graph_key
+        g = self._graphs.get(key)
+        if g is None:
+            sequence()                               # this step, eagerly
+            torch.cuda.current_stream().synchronize()
+            cfl = float(self._cfl_host[0])
+            if len(self._graphs) < 16:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):            # record the same sequence for next time
+                    sequence()
+                self._graphs[key] = g
+            return cfl
+        g.replay()
+        torch.cuda.current_stream().synchronize()
+        return float(self._cfl_host[0])
+
     def check_cfl_settings(self):
         pass
 
@@ -108,15 +163,17 @@ class ClawSolver1D(ClawSolver):
 
     def step_hyperbolic(self, solution):
         state = solution.states[0]
-        self.apply_q_bcs(state)
+        qold = state._q.cur
         qnew = state._q.get_spare()
-        st = _stream()
-        _lib.call("clawb200_cfl_reset", _ptr(self._cfl_dev), st)
-        _lib.call("clawb200_step1", ctypes.byref(self._problem), _ptr(state._q.cur), _ptr(qnew),
-                  _ptr(state._aux.cur if state._aux is not None else None), float(self.dt),
-                  _ptr(self._cfl_dev), st)
+        aux = _ptr(state._aux.cur if state._aux is not None else None)
+        dt = float(self.dt)
+
+        def launch(P, cfl, st):
+            _lib.call("clawb200_step1", P, _ptr(qold), _ptr(qnew), aux, dt, cfl, st)
+        self._graph_key = (qold.data_ptr(), qnew.data_ptr())
+        cfl = self._hyperbolic_sequence(state, launch)
         state._commit(qnew)
-        self.cfl.update_global_max(self._read_cfl()[0])
+        self.cfl.update_global_max(cfl)
 
 
 class ClawSolver2D(ClawSolver):
@@ -141,23 +198,23 @@ class ClawSolver2D(ClawSolver):
 
     def step_hyperbolic(self, solution):
         state = solution.states[0]
-        self.apply_q_bcs(state)
-        P = ctypes.byref(self._problem)
         aux = _ptr(state._aux.cur if state._aux is not None else None)
-        st = _stream()
         dt = float(self.dt)
-        cfl = _ptr(self._cfl_dev)
-        _lib.call("clawb200_cfl_reset", cfl, st)
         qold = state._q.cur
         qnew = state._q.get_spare()
-        if self.dim_split:
-            # step2ds twice (clawpack.py:538-548); the Fortran's in-place second call is a
-            # ping-pong here: qold -> tmp (x-sweeps) -> qnew (y-sweeps)
-            tmp = state._q.get_spare()
-            _lib.call("clawb200_step2ds", P, _ptr(qold), _ptr(tmp), aux, dt, 1, cfl, st)
-            _lib.call("clawb200_step2ds", P, _ptr(tmp), _ptr(qnew), aux, dt, 2, cfl, st)
+        tmp = state._q.get_spare() if self.dim_split else None
+
+        def launch(P, cfl, st):
+            if self.dim_split:
+                # step2ds twice (clawpack.py:538-548); the Fortran's in-place second call is a
+                # ping-pong here: qold -> tmp (x-sweeps) -> qnew (y-sweeps)
+                _lib.call("clawb200_step2ds", P, _ptr(qold), _ptr(tmp), aux, dt, 1, cfl, st)
+                _lib.call("clawb200_step2ds", P, _ptr(tmp), _ptr(qnew), aux, dt, 2, cfl, st)
+            else:
+                _lib.call("clawb200_step2", P, _ptr(qold), _ptr(qnew), aux, dt, cfl, st)
+        self._graph_key = (qold.data_ptr(), qnew.data_ptr(), tmp.data_ptr() if tmp is not None else 0)
+        cfl = self._hyperbolic_sequence(state, launch)
+        if tmp is not None:
             state._q.put_spare(tmp)
-        else:
-            _lib.call("clawb200_step2", P, _ptr(qold), _ptr(qnew), aux, dt, cfl, st)
         state._commit(qnew)
-        self.cfl.update_global_max(self._read_cfl()[0])
+        self.cfl.update_global_max(cfl)

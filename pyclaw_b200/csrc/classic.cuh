@@ -34,7 +34,10 @@ struct SweepArgs {
     long long mstride;
     int pitch;
     int mx, my, mbc;
-    double dtdx, dtdy; // dt/dx, dt/dy
+    double dtdx, dtdy; // dt/dx, dt/dy (used when dt_dev is null)
+    double dx, dy;
+    const double *dt_dev; // if set, the time step is read from device memory: the launch
+                          // sequence of a step is then independent of dt (CUDA-graph replay)
     int order;         // method(2)
     int trans;         // method(3): -1 dim-split, 0 none, 1 increment, 2 increment+correction
     int mthlim[CLAW_MAXWAVES];
@@ -55,6 +58,19 @@ __device__ __forceinline__ AuxCell aux_cell(const SweepArgs &A, int i, int j)
     int ic = min(max(i, 1 - A.mbc), A.mx + A.mbc) + A.mbc - 1;
     int jc = min(max(j, 1 - A.mbc), A.my + A.mbc) + A.mbc - 1;
     return AuxCell{A.aux + (long long)A.pitch * jc + ic, A.amstride};
+}
+
+// dt/dx, dt/dy: from the host-computed values or, for graph replay, from the device scalar
+// (one IEEE division, the same bits as the host's `dt / dx`)
+__device__ __forceinline__ void load_dt(const SweepArgs &A, double &dtdx, double &dtdy)
+{
+    dtdx = A.dtdx;
+    dtdy = A.dtdy;
+    if (A.dt_dev) {
+        const double dt = __ldg(A.dt_dev);
+        dtdx = dt / A.dx;
+        dtdy = dt / A.dy;
+    }
 }
 
 // a / b with one correctly rounded division, fast path first (arith.cuh)
@@ -164,7 +180,8 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
     const bool iface_ok = (ii >= 1) && (ii <= A.mx + 1) && (t >= 1) && (t <= NT - 2);
     const bool order2 = (A.order != 1);
     const bool trans2 = order2 && (A.trans == 2);
-    const double dtdx = A.dtdx, dtdy = A.dtdy;
+    double dtdx, dtdy;
+    load_dt(A, dtdx, dtdy);
     const AuxCell nocell{nullptr, 0};
 
     double cfl = 0.0;
@@ -428,7 +445,8 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     const int j1 = min(j0 + A.rows_per_cta, A.jhi + 1);
     const bool order2 = (A.order != 1);
     const bool trans2 = order2 && (A.trans == 2);
-    const double dtdx = A.dtdx, dtdy = A.dtdy;
+    double dtdx, dtdy;
+    load_dt(A, dtdx, dtdy);
     const AuxCell nocell{nullptr, 0};
     // capacity function: dtdy1d(j) = dtdy / capa(i,j), rolling along the column
     double dy_k = dtdy, dy_1 = dtdy, dy_2 = dtdy, cap_1 = 1.0, cap_2 = 1.0;
@@ -680,7 +698,8 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
     const bool cell_ok = (t >= 1) && (t <= NC) && (ii <= A.mx);
     const bool iface_ok = (ii >= 1) && (ii <= A.mx + 1) && (t >= 1) && (t <= NT - 2);
     const bool order2 = (A.order != 1);
-    const double dtdx = A.dtdx;
+    double dtdx, dtdy_unused;
+    load_dt(A, dtdx, dtdy_unused);
 
 #pragma unroll
     for (int m = 0; m < MEQN; m++) {

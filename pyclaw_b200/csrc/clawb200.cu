@@ -6,7 +6,9 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/clawb200.h"
 #include "classic.cuh"
@@ -83,6 +85,9 @@ static SweepArgs make_args(const clawb200_problem *p, const double *qin, double 
     A.mx = p->mx; A.my = p->my; A.mbc = p->mbc;
     A.dtdx = dt / p->dx;
     A.dtdy = (p->ndim > 1) ? dt / p->dy : 0.0;
+    A.dx = p->dx;
+    A.dy = (p->ndim > 1) ? p->dy : 1.0;
+    A.dt_dev = p->dt_dev;
     A.order = p->method[1];
     A.trans = p->method[2];
     for (int i = 0; i < CLAW_MAXWAVES; i++) A.mthlim[i] = (i < p->mwaves) ? p->mthlim[i] : 0;
@@ -95,11 +100,20 @@ static SweepArgs make_args(const clawb200_problem *p, const double *qin, double 
     return A;
 }
 
+// opt in to > 48 KB of dynamic shared memory, once per kernel
 template <class K>
 static cudaError_t set_smem(K kernel, size_t bytes)
 {
-    if (bytes > 48 * 1024)
-        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static std::mutex mu;
+    static std::unordered_map<const void *, size_t> granted;
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &g = granted[(const void *)kernel];
+    if (bytes > g) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        g = bytes;
+    }
     return cudaSuccess;
 }
 
@@ -627,6 +641,7 @@ static thread_local HostScratch g_hs;
 static clawb200_problem host_layout(const clawb200_problem *p)
 {
     clawb200_problem P = *p;
+    P.dt_dev = nullptr;
     int nx = p->mx + 2 * p->mbc;
     int ny = (p->ndim > 1) ? p->my + 2 * p->mbc : 1;
     P.pitch = nx;

@@ -42,7 +42,7 @@ def test_problem_struct_matches_header_layout():
     assert P.ndim.offset == 0 and P.mx.offset == 20 and P.dx.offset == 32
     assert P.method.offset == 48 and P.mthlim.offset == 76 and P.rp_id.offset == 108
     assert P.rp_params.offset == 112 and P.mstride.offset == 176 and P.pitch.offset == 184
-    assert ctypes.sizeof(P) == 192
+    assert P.dt_dev.offset == 192 and ctypes.sizeof(P) == 200
 
 
 def test_invalid_arguments_return_errors_without_a_gpu():
@@ -51,8 +51,8 @@ def test_invalid_arguments_return_errors_without_a_gpu():
     with pytest.raises(_lib.ClawB200Error, match="differ"):
         _lib.call("clawb200_step2", ctypes.byref(P), ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0.1,
                   ctypes.c_void_p(8), None)
-    P.method[5] = 1
-    with pytest.raises(_lib.ClawB200Error, match="capacity"):
+    P.method[5] = 1                      # mcapa without an aux array
+    with pytest.raises(_lib.ClawB200Error, match="aux"):
         _lib.call("clawb200_step2", ctypes.byref(P), ctypes.c_void_p(8), ctypes.c_void_p(16), None, 0.1,
                   ctypes.c_void_p(8), None)
     P2 = _lib.make_problem(2, 4, 5, 2, 16, 16, 0.1, 0.1, _lib.RP_EULER5, [1.4, 0.4], None, [4] * 5)

@@ -413,3 +413,34 @@ def test_shallow_sphere_vs_oracle():
     frames, s = tog._oracle_sphere(tfinal=2.0)
     q = _sphere_api(tfinal=2.0)
     assert np.array_equal(q, frames[-1])
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """The captured-and-replayed step (clawpack.py `_hyperbolic_sequence`) against eager launches."""
+    import pyclaw
+    outs = []
+    for use_graph in (True, False):
+        saved = pyclaw.ClawSolver2D.use_cuda_graph
+        pyclaw.ClawSolver2D.use_cuda_graph = use_graph
+        try:
+            outs.append(np.asarray(_acoustics2d('classic', dim_split=0, order_trans=2)))
+            outs.append(np.asarray(_acoustics2d('classic')))
+        finally:
+            pyclaw.ClawSolver2D.use_cuda_graph = saved
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+    # and the graphs were really used
+    solver = pyclaw.ClawSolver2D()
+    solver.mwaves = 2
+    for i in range(2):
+        solver.bc_lower[i] = solver.bc_upper[i] = pyclaw.BC.outflow
+    x = pyclaw.Dimension('x', -1.0, 1.0, 64)
+    y = pyclaw.Dimension('y', -1.0, 1.0, 64)
+    state = pyclaw.State(pyclaw.Grid([x, y]), 3)
+    state.aux_global.update(rho=1.0, bulk=4.0, zz=2.0, cc=2.0)
+    state.q[...] = problems.acoustics2d(64, 64)["q"]
+    sol = pyclaw.Solution(state)
+    solver.setup(sol)
+    solver.dt = 0.001
+    for _ in range(8):
+        solver.evolve_to_time(sol)
+    assert 1 <= len(solver._graphs) <= 6
