@@ -158,7 +158,11 @@ int clawb200_halo_pack(const clawb200_problem *p, const double *q, int narr, int
 int clawb200_halo_unpack(const clawb200_problem *p, double *q, int narr, int row0,
                          int nrows, const double *buf, void *stream);
 
-/* ---- host-pointer entry points (the f2py signatures) ----------------------------- */
+/* ---- host-pointer entry points (the f2py signatures) -----------------------------
+ * As the Fortran documents (step2.f:8-9), qold and qnew are taken to be identical on entry:
+ * only qold is uploaded, qnew receives the result (untouched cells = qold).  Large 2-D
+ * problems are processed as a pipeline of row slabs so that the upload of one slab, the
+ * sweeps of the previous one and the download of the one before overlap. */
 
 /* (q, cfl) = classic1.step1(mbc, mx, qbc, auxbc, dx, dt, method, mthlim); q updated in place */
 int clawb200_step1_host(const clawb200_problem *p, double *q, const double *aux, double dt,

@@ -650,6 +650,14 @@ static clawb200_problem host_layout(const clawb200_problem *p)
     return P;
 }
 
+static int check_problem_host(const clawb200_problem *p)
+{
+    clawb200_problem P = host_layout(p);
+    int rc = check_problem(&P, 2);
+    if (rc) return rc;
+    return check_rp_shape(&P);
+}
+
 static int host_upload(const clawb200_problem &P, const double *h, double *d_soa)
 {
     int nx = P.pitch, ny = (int)(P.mstride / P.pitch);
@@ -690,6 +698,145 @@ static int host_finish(double *cfl, int slot = 0)
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Slab pipeline for the host-pointer entry points.  A full-field H2D copy, the sweeps and a
+// full-field D2H copy in sequence leave both PCIe directions idle two thirds of the time.
+// The grid is cut into row slabs (the reference's arrays have j slowest, so a slab of rows
+// is one contiguous chunk of the host array); slab k is uploaded while slab k-1 is computed
+// and slab k-2 is downloaded, on three streams.  Each slab is an independent sub-problem
+// with its own mbc ghost rows taken from the caller's qold -- exactly the slab partition of
+// the multi-GPU path, so results are bit-identical to the single-pass call.
+// ---------------------------------------------------------------------------
+struct SlabPipe {
+    static constexpr int NBUF = 3;
+    double *d_in_aos[NBUF] = {}, *d_in[NBUF] = {}, *d_out[NBUF] = {}, *d_out_aos[NBUF] = {};
+    size_t cap = 0;
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[NBUF] = {}, e_cmp[NBUF] = {}, e_out[NBUF] = {};
+    int ensure(size_t n)
+    {
+        if (!s_in) {
+            CUDA_OK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            for (int b = 0; b < NBUF; b++) {
+                CUDA_OK(cudaEventCreateWithFlags(&e_in[b], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&e_cmp[b], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&e_out[b], cudaEventDisableTiming));
+            }
+        }
+        if (n > cap) {
+            for (int b = 0; b < NBUF; b++) {
+                cudaFree(d_in_aos[b]); cudaFree(d_in[b]); cudaFree(d_out[b]); cudaFree(d_out_aos[b]);
+                d_in_aos[b] = d_in[b] = d_out[b] = d_out_aos[b] = nullptr;
+            }
+            cap = 0;
+            for (int b = 0; b < NBUF; b++) {
+                CUDA_OK(cudaMalloc(&d_in_aos[b], n * sizeof(double)));
+                CUDA_OK(cudaMalloc(&d_in[b], n * sizeof(double)));
+                CUDA_OK(cudaMalloc(&d_out[b], n * sizeof(double)));
+                CUDA_OK(cudaMalloc(&d_out_aos[b], n * sizeof(double)));
+            }
+            cap = n;
+        }
+        return 0;
+    }
+};
+static thread_local SlabPipe g_pipe;
+
+// mode 0: unsplit step2 ; mode 1: step2ds x-sweeps (ids = 1) ; mode 2: step2ds y-sweeps (ids = 2).
+// `p` is the full problem (host layout).  qnew_init: the caller's qnew (cells the sweep does not
+// touch keep these values); it may alias qold.
+static int host_pipeline(const clawb200_problem *p, const double *qold, double *qnew, double dt,
+                         int mode, double *cfl)
+{
+    const int mbc = p->mbc, meqn = p->meqn;
+    const int nx = p->mx + 2 * mbc;
+    const int ny_tot = p->my + 2 * mbc;
+    const size_t rowd = (size_t)nx * meqn; // doubles per padded row of the host array
+    // rows this call produces, in padded (0-based) row numbers
+    const int out0 = (mode == 1) ? 0 : mbc;
+    const int out1 = (mode == 1) ? ny_tot : mbc + p->my;
+    const int halo = (mode == 1) ? 0 : mbc; // input rows needed beyond the output rows
+    int nslab = (out1 - out0 + 511) / 512;
+    if (nslab < 1) nslab = 1;
+    const int rows_per = (out1 - out0 + nslab - 1) / nslab;
+    const size_t nmax = rowd * (size_t)(rows_per + 2 * mbc);
+    int rc = g_hs.ensure(16);
+    if (rc) return rc;
+    if ((rc = g_pipe.ensure(nmax))) return rc;
+    SlabPipe &S = g_pipe;
+    CUDA_OK(cudaMemsetAsync(g_hs.d_cfl, 0, sizeof(double), S.s_cmp));
+    int prev_r0 = 0, prev_off = 0, prev_n = 0, last = -1;
+    for (int k = 0; k < nslab; k++) {
+        const int b = k % SlabPipe::NBUF;
+        const int r0 = out0 + k * rows_per;
+        const int r1 = (r0 + rows_per < out1) ? r0 + rows_per : out1;
+        if (r0 >= r1) break;
+        const int in0 = r0 - halo, in1 = r1 + halo; // input rows [in0, in1)
+        const int nrow_in = in1 - in0;
+        // the slab as a stand-alone problem in device layout
+        clawb200_problem P = *p;
+        P.dt_dev = nullptr;
+        P.pitch = nx;
+        P.my = (mode == 1) ? nrow_in - 2 * mbc : r1 - r0;
+        if (mode == 1 && P.my < 1) P.my = 1;
+        const int ny_s = (mode == 1) ? nrow_in : nrow_in;
+        P.mstride = (long long)nx * ny_s;
+        const size_t nd = rowd * (size_t)nrow_in;
+        // buffer b is free once the download of slab k-NBUF has completed
+        if (k >= SlabPipe::NBUF) {
+            CUDA_OK(cudaStreamWaitEvent(S.s_in, S.e_out[b], 0));
+            CUDA_OK(cudaStreamWaitEvent(S.s_cmp, S.e_out[b], 0));
+        }
+        CUDA_OK(cudaMemcpyAsync(S.d_in_aos[b], qold + rowd * (size_t)in0, nd * sizeof(double),
+                                cudaMemcpyHostToDevice, S.s_in));
+        CUDA_OK(cudaEventRecord(S.e_in[b], S.s_in));
+        CUDA_OK(cudaStreamWaitEvent(S.s_cmp, S.e_in[b], 0));
+        if ((rc = clawb200_aos_to_soa(S.d_in_aos[b], S.d_in[b], meqn, nx, nrow_in, P.mstride, nx, S.s_cmp))) return rc;
+        // step2.f:8-9 / step2ds.f: "on entry, qold and qnew should be identical": cells the
+        // sweep does not touch are taken from qold
+        CUDA_OK(cudaMemcpyAsync(S.d_out[b], S.d_in[b], nd * sizeof(double), cudaMemcpyDeviceToDevice, S.s_cmp));
+        if (mode == 0) {
+            rc = clawb200_step2(&P, S.d_in[b], S.d_out[b], nullptr, dt, g_hs.d_cfl, S.s_cmp);
+        } else if (mode == 2) {
+            rc = clawb200_step2ds(&P, S.d_in[b], S.d_out[b], nullptr, dt, 2, g_hs.d_cfl, S.s_cmp);
+        } else {
+            // x-sweeps over every row of the slab: present the rows as ghost + interior rows
+            // of a problem whose padded height is the slab height
+            rc = clawb200_step2ds(&P, S.d_in[b], S.d_out[b], nullptr, dt, 1, g_hs.d_cfl, S.s_cmp);
+        }
+        if (rc) return rc;
+        if ((rc = clawb200_soa_to_aos(S.d_out[b], S.d_out_aos[b], meqn, nx, nrow_in, P.mstride, nx, S.s_cmp))) return rc;
+        CUDA_OK(cudaEventRecord(S.e_cmp[b], S.s_cmp));
+        // Download the output rows of the PREVIOUS slab now, after this slab's upload has been
+        // issued: with qold == qnew (the reference's aliased step2ds call) the upload of slab
+        // k reads rows that the download of slab k-1 overwrites.
+        if (k > 0) {
+            const int pb = (k - 1) % SlabPipe::NBUF;
+            CUDA_OK(cudaStreamWaitEvent(S.s_out, S.e_in[b], 0));
+            CUDA_OK(cudaStreamWaitEvent(S.s_out, S.e_cmp[pb], 0));
+            CUDA_OK(cudaMemcpyAsync(qnew + rowd * (size_t)prev_r0, S.d_out_aos[pb] + rowd * (size_t)prev_off,
+                                    rowd * (size_t)prev_n * sizeof(double), cudaMemcpyDeviceToHost, S.s_out));
+            CUDA_OK(cudaEventRecord(S.e_out[pb], S.s_out));
+        }
+        prev_r0 = r0; prev_off = r0 - in0; prev_n = r1 - r0; last = k;
+    }
+    if (last >= 0) {
+        const int pb = last % SlabPipe::NBUF;
+        CUDA_OK(cudaStreamWaitEvent(S.s_out, S.e_cmp[pb], 0));
+        CUDA_OK(cudaMemcpyAsync(qnew + rowd * (size_t)prev_r0, S.d_out_aos[pb] + rowd * (size_t)prev_off,
+                                rowd * (size_t)prev_n * sizeof(double), cudaMemcpyDeviceToHost, S.s_out));
+        CUDA_OK(cudaEventRecord(S.e_out[pb], S.s_out));
+    }
+    CUDA_OK(cudaMemcpyAsync(g_hs.h_cfl, g_hs.d_cfl, sizeof(double), cudaMemcpyDeviceToHost, S.s_cmp));
+    CUDA_OK(cudaStreamSynchronize(S.s_cmp));
+    CUDA_OK(cudaStreamSynchronize(S.s_out));
+    CUDA_OK(cudaStreamSynchronize(S.s_in));
+    if (cfl) *cfl = g_hs.h_cfl[0];
+    return 0;
+}
+
 extern "C" int clawb200_step1_host(const clawb200_problem *p, double *q, const double *aux,
                                    double dt, double *cfl)
 {
@@ -712,17 +859,20 @@ extern "C" int clawb200_step2ds_host(const clawb200_problem *p, const double *qo
                                      const double *aux, double dt, int ids, double *cfl)
 {
     if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (!aux && p->ndim == 2 && p->method[5] == 0 && p->rp_id != CLAWB200_RP_SPHERE && p->my >= 1024 &&
+        (ids == 1 || ids == 2)) {
+        int rc0 = check_problem_host(p);
+        if (rc0) return rc0;
+        return host_pipeline(p, qold, qnew, dt, ids, cfl);
+    }
     clawb200_problem P = host_layout(p);
     size_t n = (size_t)P.meqn * P.mstride;
     int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
     if (rc) return rc;
     if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
-    // qnew starts as the caller's qnew (== qold in the reference's usage): cells the sweep
-    // does not touch keep those values
-    if (qnew == qold) {
-        CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
-    } else if ((rc = host_upload(P, qnew, g_hs.d_b)))
-        return rc;
+    // step2ds.f:9-10: "on entry, qold and qnew should be identical" -- cells the sweep does
+    // not touch are taken from qold (qnew is not uploaded)
+    CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
     if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
     const double *d_aux;
     if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
@@ -735,6 +885,11 @@ extern "C" int clawb200_step2_host(const clawb200_problem *p, const double *qold
                                    const double *aux, double dt, double *cfl)
 {
     if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (!aux && p->ndim == 2 && p->method[5] == 0 && p->rp_id != CLAWB200_RP_SPHERE && p->my >= 1024) {
+        int rc0 = check_problem_host(p);
+        if (rc0) return rc0;
+        return host_pipeline(p, qold, qnew, dt, 0, cfl);
+    }
     clawb200_problem P = host_layout(p);
     size_t n = (size_t)P.meqn * P.mstride;
     int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);

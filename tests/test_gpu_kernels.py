@@ -248,3 +248,35 @@ def test_shallow_sphere_step(shape):
     assert not np.isnan(qn_o).any() and cfl_o > 0
     assert np.array_equal(qn_g[inner], qn_o[inner]), np.abs(qn_g[inner] - qn_o[inner]).max()
     assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "euler"])
+def test_host_slab_pipeline(rp):
+    """Tall grids go through the slab pipeline of the host entry points (upload / sweeps /
+    download overlapped); results must equal the oracle's single pass bit for bit."""
+    rp_id, params, meqn, mwaves, lim = RPS[rp]
+    mx, my, mbc = 24, 1500, 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    q = _random_padded(rp, mx, my, mbc, seed=3)
+    cfl_g = ctypes.c_double()
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    # unsplit
+    method = [1, 2, 2, 0, 0, 0, 0]
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    qn_o = q.copy("F")
+    cfl_o = po.step2(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim)
+    qn_g = q.copy("F")
+    _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt, ctypes.byref(cfl_g))
+    assert np.array_equal(qn_g[inner], qn_o[inner]) and cfl_g.value == cfl_o
+    assert np.array_equal(qn_g[:, :, :mbc], q[:, :, :mbc])          # ghost rows untouched
+    # dimensional splitting, second call aliased as in clawpack.py:543-544
+    method = [1, 2, -1, 0, 0, 0, 0]
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    qo = q.copy("F")
+    ox = po.step2ds(rp_id, params, mbc, mx, my, q, qo, None, dx, dy, dt, method, lim, 1)
+    oy = po.step2ds(rp_id, params, mbc, mx, my, qo, qo, None, dx, dy, dt, method, lim, 2)
+    qg = q.copy("F")
+    cx, cy = ctypes.c_double(), ctypes.c_double()
+    _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(q), _ptr(qg), None, dt, 1, ctypes.byref(cx))
+    _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(qg), _ptr(qg), None, dt, 2, ctypes.byref(cy))
+    assert np.array_equal(qg, qo) and (cx.value, cy.value) == (ox, oy)
