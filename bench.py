@@ -489,6 +489,9 @@ def main():
     # per Runge-Kutta stage: boundary fills + one fused stage kernel (SharpClaw SSP33)
     if args.workload == "shallow":
         per_step_launches = 3 * (bc_launches + 1)
+    elif world > 1:
+        # overlapped halo path: x-BC fills run twice, the sweeps as interior + 2 boundary ranges
+        per_step_launches = 2 * bc_launches + 3 * launches_per_step
     else:
         per_step_launches = bc_launches + launches_per_step
     line = {

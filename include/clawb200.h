@@ -113,6 +113,15 @@ int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
 int clawb200_step2_parts(const clawb200_problem *p, const double *qold, double *qnew,
                          const double *aux, double dt, int parts, double *cfl_dev, void *stream);
 
+/* The same step for output rows jlo..jhi only (1-based interior rows, inclusive).  Lets the
+ * caller update the rows that do not depend on a neighbour's halo while the halo exchange is
+ * still in flight, and the `mbc` boundary rows afterwards; launching disjoint ranges that
+ * cover 1..my gives the same result as one clawb200_step2 call (the Courant number is
+ * max-accumulated). */
+int clawb200_step2_rows(const clawb200_problem *p, const double *qold, double *qnew,
+                        const double *aux, double dt, int jlo, int jhi, double *cfl_dev,
+                        void *stream);
+
 /* sharpclaw1.flux1 / sharpclaw2.flux2 (src/fortran/1d/sharpclaw/flux1.f90:2-195,
  * src/fortran/2d/sharpclaw/flux2.f90:2-96; sharpclaw.py:385,558) fused with the
  * Runge-Kutta stage update that sharpclaw.py:172-206 performs in numpy.  q is the

@@ -74,6 +74,7 @@ SIGNATURES = {
     "clawb200_step2ds": [_pp, _dp, _dp, _dp, _d, _i, _dp, _vp],
     "clawb200_step2": [_pp, _dp, _dp, _dp, _d, _dp, _vp],
     "clawb200_step2_parts": [_pp, _dp, _dp, _dp, _d, _i, _dp, _vp],
+    "clawb200_step2_rows": [_pp, _dp, _dp, _dp, _d, _i, _i, _dp, _vp],
     "clawb200_sharpclaw_stage": [_pp, _dp, _dp, _dp, _dp, _dp, _d, _i, _d, _d, _d, _dp, _vp],
     "clawb200_ssp104_combine": [_dp, _dp, _dp, ctypes.c_longlong, _vp],
     "clawb200_bc_fill": [_pp, _dp, _i, _i, _i, _i, _i, _vp],

@@ -196,8 +196,49 @@ class ClawSolver2D(ClawSolver):
             import warnings
             warnings.warn('cfl_max is set higher than the recommended value of %s' % cfl_recommended)
 
+    # Multi-GPU (slab partition), unsplit: the halo exchange runs on its own stream while
+    # the rows that do not depend on a neighbour's halo are updated; the mbc boundary rows
+    # per side follow once the halo has landed.
+    overlap_halo = True
+
+    def _step_overlapped(self, state):
+        import torch
+        from .solver import BC
+        part, F, mbc = self._halo, state._q, self.mbc
+        my = state.grid.ng[1]
+        qold, qnew = F.cur, F.get_spare()
+        aux = _ptr(state._aux.cur if state._aux is not None else None)
+        dt = float(self.dt)
+        P, cfl = ctypes.byref(self._problem), _ptr(self._cfl_dev)
+        cur = torch.cuda.current_stream()
+        if getattr(self, '_hstream', None) is None:
+            self._hstream = torch.cuda.Stream()
+            self._ev0, self._ev1 = torch.cuda.Event(), torch.cuda.Event()
+        self._ev0.record(cur)
+        with torch.cuda.stream(self._hstream):
+            self._hstream.wait_event(self._ev0)
+            part.exchange(F, F.ncomp, periodic=[b == BC.periodic for b in self.bc_lower])
+            self._ev1.record(self._hstream)
+        # x-direction boundary conditions and the interior rows, concurrently with the exchange
+        self.apply_q_bcs(state, exchange=False, dims=[0])
+        st = _stream()
+        _lib.call("clawb200_cfl_reset", cfl, st)
+        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1 + mbc, my - mbc, cfl, st)
+        # the halo has landed: ghost rows get their x-BCs, edge ranks their y-BCs, then the
+        # boundary rows are updated
+        cur.wait_event(self._ev1)
+        self.apply_q_bcs(state, exchange=False)
+        st = _stream()
+        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1, mbc, cfl, st)
+        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, my - mbc + 1, my, cfl, st)
+        state._commit(qnew)
+        self.cfl.update_global_max(self._read_cfl()[0])
+
     def step_hyperbolic(self, solution):
         state = solution.states[0]
+        if (self._halo is not None and self._halo.size > 1 and self.overlap_halo and not self.dim_split
+                and state.grid.ng[1] > 4 * self.mbc):
+            return self._step_overlapped(state)
         aux = _ptr(state._aux.cur if state._aux is not None else None)
         dt = float(self.dt)
         qold = state._q.cur

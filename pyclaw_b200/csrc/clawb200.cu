@@ -273,9 +273,8 @@ extern "C" int clawb200_step2ds(const clawb200_problem *p, const double *q_in, d
     return 0;
 }
 
-extern "C" int clawb200_step2_parts(const clawb200_problem *p, const double *qold, double *qnew,
-                                    const double *aux, double dt, int parts, double *cfl_dev,
-                                    void *stream)
+static int step2_impl(const clawb200_problem *p, const double *qold, double *qnew, const double *aux,
+                      double dt, int parts, int jlo, int jhi, double *cfl_dev, void *stream)
 {
     int rc = check_problem(p, 2);
     if (rc) return rc;
@@ -284,19 +283,38 @@ extern "C" int clawb200_step2_parts(const clawb200_problem *p, const double *qol
     if (qold == qnew) return fail(CLAWB200_ERR_INVALID, "qold and qnew must differ");
     if (p->method[2] < 0) return fail(CLAWB200_ERR_INVALID, "method[2] < 0 means dimensional splitting: call step2ds");
     if (parts < 1 || parts > 3) return fail(CLAWB200_ERR_INVALID, "parts must be 1, 2 or 3");
+    if (jlo < 1 || jhi > p->my) return fail(CLAWB200_ERR_INVALID, "row range outside 1..my");
+    if (jlo > jhi) return 0; // empty range
     if ((rc = check_aux(p, aux, true))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     SweepArgs A = make_args(p, qold, qnew, dt, cfl_dev, aux);
-    A.ilo = 1; A.ihi = p->mx; A.jlo = 1; A.jhi = p->my;
+    A.ilo = 1; A.ihi = p->mx; A.jlo = jlo; A.jhi = jhi;
+    const int nrows = jhi - jlo + 1;
     if (parts & 1) {
-        A.rows_per_cta = pick_rows(p->my, (p->mx + XNT - 4) / (XNT - 3));
+        A.rows_per_cta = pick_rows(nrows, (p->mx + XNT - 4) / (XNT - 3));
         if ((rc = dispatch_x<true>(p->rp_id, A, st))) return rc;
     }
     if (parts & 2) {
-        A.rows_per_cta = pick_rows(p->my, (p->mx + YNT - 3) / (YNT - 2));
+        A.rows_per_cta = pick_rows(nrows, (p->mx + YNT - 3) / (YNT - 2));
         if ((rc = dispatch_y<true>(p->rp_id, A, st))) return rc;
     }
     return 0;
+}
+
+extern "C" int clawb200_step2_parts(const clawb200_problem *p, const double *qold, double *qnew,
+                                    const double *aux, double dt, int parts, double *cfl_dev,
+                                    void *stream)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    return step2_impl(p, qold, qnew, aux, dt, parts, 1, p->my, cfl_dev, stream);
+}
+
+extern "C" int clawb200_step2_rows(const clawb200_problem *p, const double *qold, double *qnew,
+                                   const double *aux, double dt, int jlo, int jhi, double *cfl_dev,
+                                   void *stream)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    return step2_impl(p, qold, qnew, aux, dt, 3, jlo, jhi, cfl_dev, stream);
 }
 
 extern "C" int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,

@@ -161,12 +161,15 @@ class Solver(object):
         else:
             self.auxbc = None
 
-    def _fill(self, state, arr_field, arr_view, bc_lower, bc_upper, user_lower, user_upper, is_q):
+    def _fill(self, state, arr_field, arr_view, bc_lower, bc_upper, user_lower, user_upper, is_q,
+              exchange=True, dims=None):
         grid = state.grid
         P = self._problem
-        if self._halo is not None:
+        if exchange and self._halo is not None:
             self._halo.exchange(arr_field, arr_field.ncomp, periodic=[b == BC.periodic for b in bc_lower])
         for idim, dim in enumerate(grid.dimensions):
+            if dims is not None and idim not in dims:
+                continue
             for side, bcs, user in ((0, bc_lower, user_lower), (1, bc_upper, user_upper)):
                 on_boundary = (dim.nstart == 0) if side == 0 else (dim.nend == dim.n)
                 if not on_boundary:
@@ -185,12 +188,12 @@ class Solver(object):
                 else:
                     raise NotImplementedError("Boundary condition %s not implemented" % bc)
 
-    def apply_q_bcs(self, state):
+    def apply_q_bcs(self, state, exchange=True, dims=None):
         """Fill the ghost cells of the state's padded q (solver.py:315-381): dimension by
         dimension, lower then upper, so corner values come out as in the reference."""
         self.qbc = state._q.padded()
         self._fill(state, state._q, self.qbc, self.bc_lower, self.bc_upper,
-                   self.user_bc_lower, self.user_bc_upper, True)
+                   self.user_bc_lower, self.user_bc_upper, True, exchange=exchange, dims=dims)
 
     def apply_aux_bcs(self, state):
         """solver.py:456-506; done once in setup (aux is time independent by default)."""
