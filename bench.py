@@ -38,6 +38,8 @@ WORKLOADS = {
     "euler": dict(n=8192, meqn=5, mwaves=5, balg=80, label="euler5_roe_unsplit_8192x8192_per_gpu"),
     "acoustics": dict(n=4096, meqn=3, mwaves=2, balg=48, label="acoustics_unsplit_rpt2_4096x4096_per_gpu"),
     "shallow": dict(n=8192, meqn=3, mwaves=3, balg=192, label="shallow_sharpclaw_weno5_ssp33_8192x8192_per_gpu"),
+    # config 5: shallow water on the sphere, 4096 x 2048 per GPU (n = cells in y; x has 2n)
+    "sphere": dict(n=2048, meqn=4, mwaves=3, balg=192, label="shallow_sphere_rossby_haurwitz_4096x2048_per_gpu"),
 }
 
 
@@ -144,6 +146,11 @@ def build_problem(pyclaw, workload, n, nranks, torch):
         solver.bc_lower[0] = solver.bc_lower[1] = pyclaw.BC.outflow
         solver.bc_upper[0] = solver.bc_upper[1] = pyclaw.BC.reflecting
         solver.dt_initial = 0.2 * state.grid.d[0]
+    elif workload == "sphere":
+        # apps/shallow-sphere: 16 aux, capacity function, pole-fold custom BCs, Strang src2
+        from pyclaw_b200.apps import shallow_sphere as app
+        state, solver = app.setup(pyclaw, mx=2 * n, my=n * nranks)
+        solver.dt_initial = 0.1 * state.grid.d[0] / 4.0
     else:
         raise SystemExit("unknown workload %s" % workload)
     return state, solver
@@ -290,7 +297,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="euler", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="euler", choices=sorted(WORKLOADS))  # sphere: no --impl reference arm
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override the per-GPU grid size (debug)")
     ap.add_argument("--perturb", action="store_true",
@@ -334,7 +341,7 @@ def main():
     solver.setup(solution)
     solver.dt = solver.dt_initial
     solver.max_steps = 10 ** 9
-    cells_per_rank = n * n
+    cells_per_rank = n * n if args.workload != "sphere" else 2 * n * n
 
     def barrier():
         if world > 1:
@@ -387,19 +394,21 @@ def main():
     solver._halo = halo
     scratch = F.get_spare()
     kern = {}
-    if args.workload in ("euler", "acoustics"):
+    if args.workload in ("euler", "acoustics", "sphere"):
         scratch.copy_(F.cur)
+        auxp = ptr(state._aux.cur) if state._aux is not None else None
         launches_per_step = 2
-        for name, part, bytes_per_cell in (("xsweep_kernel<TRANS>", 1, 2 * wl["meqn"] * 8),
-                                           ("ysweep_kernel<TRANS>", 2, 3 * wl["meqn"] * 8)):
+        auxb = 16 * 8 if args.workload == "sphere" else 0   # each launch also streams the aux array once
+        for name, part, bytes_per_cell in (("xsweep_kernel<TRANS>", 1, 2 * wl["meqn"] * 8 + auxb),
+                                           ("ysweep_kernel<TRANS>", 2, 3 * wl["meqn"] * 8 + auxb)):
             for rep in range(2):
-                _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), None, float(solver.dt), part,
+                _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), auxp, float(solver.dt), part,
                           ptr(solver._cfl_dev), stream)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
             e0.record()
             for rep in range(reps):
-                _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), None, float(solver.dt), part,
+                _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), auxp, float(solver.dt), part,
                           ptr(solver._cfl_dev), stream)
             e1.record()
             torch.cuda.synchronize()
@@ -477,7 +486,7 @@ def main():
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and args.workload != "sphere":
         ncores = os.cpu_count() or 1
         ncpu = 1024
         v, k, el = time_cpu(args.workload, ncpu, ncores, 12.0)

@@ -146,6 +146,11 @@ int clawb200_sharpclaw_stage(const clawb200_problem *p, const double *q, const d
  * over n contiguous doubles (whole padded buffers). */
 int clawb200_ssp104_combine(const double *q, double *s1, double *s2, long long n, void *stream);
 
+/* apps/shallow-sphere/src2.f:2-147 (the f2py `problem.src2` the reference script wraps as
+ * solver.step_src): Coriolis source term with tangent-plane projection, in place on the
+ * interior cells of q; aux is the 16-component sphere array. */
+int clawb200_sphere_src2(const clawb200_problem *p, double *q, const double *aux, double dt, void *stream);
+
 /* Solver.qbc_lower / qbc_upper (src/pyclaw/solver.py:384-452) for one side of one
  * dimension.  narr = number of components of the array (meqn or maux); `negate` is the
  * component whose sign flips for a reflecting wall (idim+1), or -1 for none (aux). */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "clawb200_step2_rows": [_pp, _dp, _dp, _dp, _d, _i, _i, _dp, _vp],
     "clawb200_sharpclaw_stage": [_pp, _dp, _dp, _dp, _dp, _dp, _d, _i, _d, _d, _d, _dp, _vp],
     "clawb200_ssp104_combine": [_dp, _dp, _dp, ctypes.c_longlong, _vp],
+    "clawb200_sphere_src2": [_pp, _dp, _dp, _d, _vp],
     "clawb200_bc_fill": [_pp, _dp, _i, _i, _i, _i, _i, _vp],
     "clawb200_aos_to_soa": [_dp, _dp, _i, _i, _i, ctypes.c_longlong, _i, _vp],
     "clawb200_soa_to_aos": [_dp, _dp, _i, _i, _i, ctypes.c_longlong, _i, _vp],

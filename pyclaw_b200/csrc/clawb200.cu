@@ -592,6 +592,61 @@ extern "C" int clawb200_sharpclaw_stage(const clawb200_problem *p, const double 
     return sharpclaw_launch(p, q, qa, out, dq_out, dt, mode, ca, cb, div, cfl_dev, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------
+// apps/shallow-sphere/src2.f:2-147 as one pointwise kernel: tangent-plane projection,
+// 4-stage Runge-Kutta on the Coriolis term, projection again.  The radial unit vector that
+// src2.f recomputes with mapc2p at every call is aux(14:16) (same function of the same
+// arguments, bit for bit).  Interior cells only.
+// ---------------------------------------------------------------------------
+__global__ void sphere_src2_kernel(double *__restrict__ q, const double *__restrict__ aux,
+                                   long long mstride, int pitch, int mx, int my, int mbc, double dt, double df)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= mx || j >= my) return;
+    const long long o = (long long)(j + mbc) * pitch + (i + mbc);
+    const double erx = aux[13 * mstride + o], ery = aux[14 * mstride + o], erz = aux[15 * mstride + o];
+    double q2 = q[1 * mstride + o], q3 = q[2 * mstride + o], q4 = q[3 * mstride + o];
+    double qn = erx * q2 + ery * q3 + erz * q4;
+    q2 = q2 - qn * erx;
+    q3 = q3 - qn * ery;
+    q4 = q4 - qn * erz;
+    const double fcor = df * erz;
+    double RK[4][3];
+    double hu = q2, hv = q3, hw = q4;
+#pragma unroll
+    for (int st = 0; st < 4; st++) {
+        if (st > 0) {
+            hu = q2 + 0.5 * RK[st - 1][0];
+            hv = q3 + 0.5 * RK[st - 1][1];
+            hw = q4 + 0.5 * RK[st - 1][2];
+        }
+        RK[st][0] = fcor * dt * (erz * hv - ery * hw);
+        RK[st][1] = dt * fcor * (erx * hw - erz * hu);
+        RK[st][2] = dt * fcor * (ery * hu - erx * hv);
+    }
+    q2 = q2 + (RK[0][0] + 2.0 * RK[1][0] + 2.0 * RK[2][0] + RK[3][0]) / 6.0;
+    q3 = q3 + (RK[0][1] + 2.0 * RK[1][1] + 2.0 * RK[2][1] + RK[3][1]) / 6.0;
+    q4 = q4 + (RK[0][2] + 2.0 * RK[1][2] + 2.0 * RK[2][2] + RK[3][2]) / 6.0;
+    qn = erx * q2 + ery * q3 + erz * q4;
+    q[1 * mstride + o] = q2 - qn * erx;
+    q[2 * mstride + o] = q3 - qn * ery;
+    q[3 * mstride + o] = q4 - qn * erz;
+}
+
+extern "C" int clawb200_sphere_src2(const clawb200_problem *p, double *q, const double *aux, double dt,
+                                    void *stream)
+{
+    if (!p || !q || !aux) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (p->ndim != 2 || p->meqn != 4 || p->maux < 16)
+        return fail(CLAWB200_ERR_INVALID, "sphere_src2 needs the 4-equation, 16-aux sphere problem");
+    dim3 grid((p->mx + 127) / 128, p->my);
+    sphere_src2_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(q, aux, p->mstride, p->pitch, p->mx, p->my,
+                                                               p->mbc, dt, (double)12.600576e0f);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 __global__ void ssp104_combine_kernel(const double *__restrict__ q, double *__restrict__ s1,
                                       double *__restrict__ s2, long long n, double c925)
 {
