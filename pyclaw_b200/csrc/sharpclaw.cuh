@@ -209,8 +209,11 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
 // ---------------------------------------------------------------------------
 // 2-D: thread t <-> column ic = i0-1+t, output columns t = 1 .. NT-2.
 // ---------------------------------------------------------------------------
+#ifndef CLAW_SC_MINB
+#define CLAW_SC_MINB 2
+#endif
 template <class RPX, class RPY, bool OLD, int NT>
-__global__ void __launch_bounds__(NT) sc2d_kernel(const ScArgs A)
+__global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_kernel(const ScArgs A)
 {
     constexpr int MEQN = RPX::MEQN, MW = RPX::MWAVES, NROE = RPX::NROE;
     constexpr int NC = NT - 2;

@@ -280,3 +280,68 @@ def test_host_slab_pipeline(rp):
     _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(q), _ptr(qg), None, dt, 1, ctypes.byref(cx))
     _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(qg), _ptr(qg), None, dt, 2, ctypes.byref(cy))
     assert np.array_equal(qg, qo) and (cx.value, cy.value) == (ox, oy)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (4, 4), (125, 64), (126, 65), (124, 63), (250, 128),
+                                   (251, 129), (127, 1), (1, 130), (376, 5)])
+def test_tile_boundary_shapes(shape):
+    """Grid sizes at and around the CTA tile sizes (125 / 126 columns, 64-row strips) and
+    degenerate grids: classic unsplit + dim-split (Euler) and SharpClaw (shallow)."""
+    mx, my = shape
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    cfl_g = ctypes.c_double()
+    # classic
+    mbc = 2
+    rp_id, params, meqn, mwaves, lim = RPS["euler"]
+    q = _random_padded("euler", mx, my, mbc, seed=mx * 7 + my)
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    method = [1, 2, 2, 0, 0, 0, 0]
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    qn_o = q.copy("F")
+    cfl_o = po.step2(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim)
+    qn_g = q.copy("F")
+    _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt, ctypes.byref(cfl_g))
+    assert np.array_equal(qn_g[inner], qn_o[inner]) and cfl_g.value == cfl_o
+    method = [1, 2, -1, 0, 0, 0, 0]
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    for ids in (1, 2):
+        qn_o = q.copy("F")
+        cfl_o = po.step2ds(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim, ids)
+        qn_g = q.copy("F")
+        _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt, ids, ctypes.byref(cfl_g))
+        assert np.array_equal(qn_g, qn_o) and cfl_g.value == cfl_o
+    # sharpclaw
+    mbc = 3
+    rp_id, params, meqn, mwaves, _ = RPS["shallow"]
+    q = _random_padded("shallow", mx, my, mbc, seed=mx + my, smooth=(mx > 3 and my > 3))
+    if mx <= 3 or my <= 3:
+        q = np.asfortranarray(0.9 + 0.2 * q / np.abs(q).max())   # keep tiny grids admissible
+        q[1:] *= 0.1
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, weno_variant=0)
+    dq_o, cfl_o = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, 0)
+    dq_g = np.zeros_like(q, order="F")
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    assert not np.isnan(dq_o).any()
+    assert np.array_equal(dq_g[inner], dq_o[inner]) and cfl_g.value == cfl_o
+
+
+def test_extreme_magnitudes_take_the_exact_path():
+    """Values far outside the fast division / sqrt windows (arith.cuh) must fall back to the
+    IEEE operators and still agree bit for bit: acoustics scaled by 1e-290 and 1e+250."""
+    rp_id, params, meqn, mwaves, lim = RPS["acoustics"]
+    mx, my, mbc = 40, 33, 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    method = [1, 2, 2, 0, 0, 0, 0]
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    for scale in (1e-290, 1e-160, 1e250):
+        q = np.asfortranarray(_random_padded("acoustics", mx, my, mbc, seed=5) * scale)
+        q[:, 10:20, 10:20] = 0.0                      # exact zeros: zero numerators and 0/0 limiter skips
+        qn_o = q.copy("F")
+        cfl_o = po.step2(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim)
+        qn_g = q.copy("F")
+        cfl_g = ctypes.c_double()
+        _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt, ctypes.byref(cfl_g))
+        assert np.array_equal(qn_g[inner], qn_o[inner], equal_nan=True), scale
+        assert cfl_g.value == cfl_o
