@@ -44,6 +44,19 @@ class State(_state.State):
         return part
 
 
+class Solution(_impl.solution.Solution):
+    """Solution whose frames are read back onto the slab partition."""
+    _state_class = State
+
+
+class Controller(_impl.controller.Controller):
+    """src/petclaw/controller.py:8-17: identical except for the default output format."""
+
+    def __init__(self):
+        super(Controller, self).__init__()
+        self.output_format = 'petsc'
+
+
 for _name in ('limiters', 'riemann', 'grid', 'solution', 'solver', 'clawpack', 'sharpclaw',
               'controller', 'util'):
     _sys.modules['petclaw.' + _name] = getattr(_impl, _name)

@@ -1,6 +1,7 @@
 """Controller (src/pyclaw/controller.py:31-303): the output-time loop around
-``solver.evolve_to_time``.  File output and plotting are outside the hot-path scope:
-``output_format`` must be None (frames are kept in memory with ``keep_copy``)."""
+``solver.evolve_to_time``.  Frames are written through ``Solution.write`` in
+``output_format`` ('ascii', 'petsc', a list of those, or None) and/or kept in memory with
+``keep_copy``.  Plotting is outside the hot-path scope."""
 import copy
 import logging
 import os
@@ -26,10 +27,10 @@ class Controller(object):
         self.frames = []
         self.write_aux_init = False
         self.write_aux_always = False
-        # the reference defaults to 'ascii'; no writer exists here, so writing is skipped
-        # with a log message unless the script sets output_format = None itself
         self.output_format = 'ascii'
         self.output_file_prefix = None
+        self.outdir_p = './_output/_p'
+        self.file_prefix_p = 'claw_p'
         self.output_options = {}
         self.tfinal = 1.0
         self.outstyle = 1
@@ -42,7 +43,6 @@ class Controller(object):
         self.compute_F = None
         self.F_file_name = 'F'
         self.F_path = './_output/' + self.F_file_name + '.txt'
-        self._warned_output = False
 
     def __str__(self):
         output = "Controller attributes:\n"
@@ -60,14 +60,16 @@ class Controller(object):
         if not self.solution.is_valid():
             raise Exception("Initial solution is not valid.")
 
-    def _write(self, frame):
-        if self.output_format is not None and not self._warned_output:
-            logging.getLogger('io').info("output_format=%r: no file writers in pyclaw_b200 "
-                                         "(outside the hot-path scope); frames are not written"
-                                         % self.output_format)
-            self._warned_output = True
+    def _write(self, frame, write_aux):
+        """controller.py:242-259 / :277-291"""
+        if self.output_format is None:
+            return
         if self.compute_p is not None:
             self.compute_p(self.solution.state)
+            self.solution.write(frame, self.outdir_p, self.output_format, self.file_prefix_p,
+                                write_aux=False, options=self.output_options, write_p=True)
+        self.solution.write(frame, self.outdir, self.output_format, self.output_file_prefix,
+                            write_aux, self.output_options)
 
     def run(self):
         """controller.py:195-303"""
@@ -89,7 +91,10 @@ class Controller(object):
             raise Exception("Invalid output style %s" % self.outstyle)
         if self.keep_copy:
             self.frames.append(copy.deepcopy(self.solution))
-        self._write(frame)
+        if self.output_format is not None and os.path.exists(self.outdir) and self.overwrite == False:
+            raise Exception("Refusing to overwrite existing output data. \
+                 \nEither delete/move the directory or set controller.overwrite=True.")
+        self._write(frame, self.write_aux_init)
         self.write_F('w')
         status = self.solver.status
         for t in output_times[1:]:
@@ -101,7 +106,7 @@ class Controller(object):
             frame.increment()
             if self.keep_copy:
                 self.frames.append(copy.deepcopy(self.solution))
-            self._write(frame)
+            self._write(frame, self.write_aux_always)
             self.write_F()
             for f in self.solution.state.grid.gauge_files:
                 f.flush()
@@ -120,4 +125,5 @@ class Controller(object):
                     F_file.write(str(self.solution.t) + ' ' + ' '.join(str(j) for j in F) + '\n')
 
     def is_proc_0(self):
-        return True
+        from .parallel import world
+        return world()[0] == 0

@@ -1,5 +1,7 @@
-"""Solution (src/pyclaw/solution.py:35-456): a list of States with attribute forwarding.
-File input/output (solution.read/write, io/*.py) is outside the hot-path scope."""
+"""Solution (src/pyclaw/solution.py:35-456): a list of States with attribute forwarding,
+``write`` / ``read`` through the formats of ``pyclaw_b200.io``."""
+import os
+
 from .grid import Grid, Dimension
 from .state import State
 
@@ -29,7 +31,16 @@ class Solution(object):
             elif isinstance(arg[0], (Grid, Dimension)) or isinstance(arg[0], list):
                 raise Exception("Solution(grid) needs meqn in this snapshot's API: build a State first")
             elif isinstance(arg[0], int):
-                raise NotImplementedError("reading frames from disk is outside the hot-path scope")
+                # Solution(frame, path=..., format=..., file_prefix=..., read_aux=..., options=...)
+                # (solution.py:168-199)
+                frame = arg[0]
+                defaults = {'path': './', 'format': 'ascii', 'file_prefix': None,
+                            'read_aux': False, 'options': {}}
+                for k in kargs:
+                    if k not in defaults:
+                        raise Exception("Invalid keyword argument %r" % k)
+                defaults.update(kargs)
+                self.read(frame, **defaults)
             else:
                 raise Exception("Invalid argument list")
 
@@ -72,6 +83,29 @@ class Solution(object):
             if getattr(state, attr) is None or overwrite:
                 setattr(state, attr, value)
 
-    def write(self, *args, **kwargs):
-        raise NotImplementedError("file output is outside the hot-path scope; set "
-                                  "controller.output_format = None and use keep_copy")
+    def write(self, frame, path='./', format='ascii', file_prefix=None, write_aux=False,
+              options={}, write_p=False):
+        """solution.py:356-404.  ``format`` is a name or a list of names of ``io.write_<name>``."""
+        from . import io
+        path = os.path.expandvars(os.path.expanduser(path))
+        os.makedirs(path, exist_ok=True)
+        for form in ([format] if isinstance(format, str) else list(format)):
+            write_func = getattr(io, 'write_%s' % form, None)
+            if write_func is None:
+                raise IOError("unknown output format %r" % form)
+            kw = {} if file_prefix is None else {'file_prefix': file_prefix}
+            write_func(self, frame, path, write_aux=write_aux, options=options, write_p=write_p, **kw)
+
+    def read(self, frame, path='./', format='ascii', file_prefix=None, read_aux=False, options={}):
+        """solution.py:406-447"""
+        from . import io
+        path = os.path.expandvars(os.path.expanduser(path))
+        read_func = getattr(io, 'read_%s' % format, None)
+        if read_func is None:
+            raise IOError("unknown input format %r" % format)
+        opts = dict(options)
+        opts.setdefault('state_class', self._state_class)
+        kw = {} if file_prefix is None else {'file_prefix': file_prefix}
+        read_func(self, frame, path, read_aux=read_aux, options=opts, **kw)
+
+    _state_class = State

@@ -81,3 +81,49 @@ def test_slab_range_is_a_partition():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[k][1] == r[k + 1][0] for k in range(size - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def _io_worker(rank, world, port, path, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import petclaw as pyclaw
+        mx, my, meqn, maux = 6, 9, 2, 1
+        grid = pyclaw.Grid([pyclaw.Dimension('x', 0., 1., mx), pyclaw.Dimension('y', 0., 2., my)])
+        state = pyclaw.State(grid, meqn, maux, device='cpu')
+        j0, j1 = grid.y.nstart, grid.y.nend
+        f = lambda m, i, j: 100. * m + 10. * i + 0.125 * j
+        I, J = np.meshgrid(np.arange(mx), np.arange(j0, j1), indexing='ij')
+        for m in range(meqn):
+            state.q[m, :, :] = f(m, I, J)
+        state.aux[0, :, :] = f(7, I, J)
+        state.t = 1.5
+        sol = pyclaw.Solution(state)
+        ok = pyclaw.Controller().output_format == 'petsc'
+        for fmt in ('petsc', 'ascii'):
+            sol.write(2, path, fmt, write_aux=True)
+            dist.barrier()
+            # every rank reads the frame back onto its own slab
+            back = pyclaw.Solution(2, path=path, format=fmt, read_aux=True)
+            ok &= isinstance(back.state, pyclaw.State) and back.state.grid.y.nstart == j0
+            ok &= np.array_equal(np.asarray(back.q), np.asarray(state.q))
+            ok &= np.array_equal(np.asarray(back.aux), np.asarray(state.aux))
+            ok &= back.t == 1.5
+            dist.barrier()
+        if rank == 0:
+            # the files hold the global field, written once
+            import pyclaw as serial
+            glob = serial.Solution(2, path=path, format='petsc', options={'state_class': serial.State})
+            ok &= np.asarray(glob.q).shape == (meqn, mx, my) and float(np.asarray(glob.q)[1, 4, 8]) == f(1, 4, 8)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frames_written_and_restarted_on_two_ranks(tmp_path):
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_io_worker, args=(world, port, str(tmp_path), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
