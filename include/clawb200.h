@@ -44,6 +44,11 @@ extern "C" {
 #define CLAWB200_RP_SHALLOW 4   /* rpn2/rpt2_shallow_roe_with_efix ; params {grav}     */
 #define CLAWB200_RP_SPHERE 5    /* rpn2/rpt2_shallow_sphere + step2qcor/qcor (apps/shallow-sphere);
                                    params {g, dxcom, dycom} (0 = take dx, dy); 16 aux, mcapa = 1 */
+/* f-wave solvers: the sweeps use the second-order correction of step1fw.f:135-136 /
+ * flux2fw.f:151-152 (the reference's classic1fw / classic2fw modules, clawpack.py:222). */
+#define CLAWB200_RP_NEL_FWAVE 6 /* rp1_nonlinear_elasticity_fwave (apps/elasticity/1d/stegoton);
+                                   aux {rho, K}; params {stress law: 1 linear, 2 exponential} */
+#define CLAWB200_RP_PSYSTEM 7   /* rpn2/rpt2_psystem (test/psystem); aux {rho, E, law, eps} */
 
 /* Boundary condition ids = pyclaw.BC (src/pyclaw/solver.py:17-23) */
 #define CLAWB200_BC_CUSTOM 0

@@ -37,6 +37,9 @@
 #define RP_EULER5 3
 #define RP_SHALLOW 4
 #define RP_SPHERE 5 /* shallow water on the sphere: params g, dxcom, dycom ; 16 aux ; step2qcor */
+#define RP_NEL_FWAVE 6 /* 1-D nonlinear elasticity, f-waves: aux = rho, K ; params[0] = stress law */
+#define RP_PSYSTEM 7   /* 2-D p-system, f-waves: aux = rho, E, stress law, eps ; rpt2 */
+#define RP_IS_FWAVE(id) ((id) == RP_NEL_FWAVE || (id) == RP_PSYSTEM)
 
 #define WENO_PYWENO_F32 0 /* weno.f90 literals read as REAL(4), as gfortran does */
 #define WENO_PYWENO_F64 1 /* same formulas, literals read as doubles            */
@@ -50,6 +53,7 @@ typedef struct {
        euler: p[0]=gamma p[1]=gamma1 ; shallow: p[0]=grav */
     /* common /comroe/ twin: filled by rpn2, read by rpt2 on the same slice */
     double dxcom, dycom; /* common /comxyt/ */
+    int maux;            /* aux components per cell (1-D f-wave solver) */
     int nroe;
     double *u2v2, *u, *v, *enth, *a, *g1a2, *euv, *h;
 } rp_ctx;
@@ -350,6 +354,90 @@ static void rpn_shallow(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int m
         }
 }
 
+
+/* Stress-strain laws of the elasticity / p-system solvers (clawpack/riemann
+   rp1_nonlinear_elasticity_fwave.f, rpn2_psystem.f -- external, un-vendored; the
+   reference's apps define them through aux: apps/elasticity/1d/stegoton/stegoton.py:5-27,
+   test/psystem/psystem.py:20-33,99-100): law 1: sigma = E eps ; law 2: sigma = exp(E eps) - 1 */
+static inline double el_sigma(double eps, double E, double law)
+{
+    return (law == 1.0) ? E * eps : exp(E * eps) - 1.0;
+}
+static inline double el_sigmap(double eps, double E, double law)
+{
+    return (law == 1.0) ? E : E * exp(E * eps);
+}
+
+/* f-wave solver shared by the 1-D nonlinear elasticity system (eps_t - u_x = 0,
+   (rho u)_t - sigma_x = 0) and the normal direction of the 2-D p-system: the flux jump
+   (-du, -dsigma) is split into b1 (1, z_{i-1}) moving at -c_{i-1} and b2 (1, -z_i) moving
+   at +c_i, c = sqrt(sigma'/rho), z = rho c.  maux = aux components per cell. */
+static void rpn_elastic_fwave(const rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
+                              const double *ql, const double *qr, const double *auxl,
+                              const double *auxr, int maux, double *wave, double *s,
+                              double *amdq, double *apdq)
+{
+    int mu = (ixy <= 1) ? 1 : 2, mv = (ixy <= 1) ? 2 : 1;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double rhoi = auxl[0 + maux * IX(i)], rhoim = auxr[0 + maux * IX(i - 1)];
+        double Ei = auxl[1 + maux * IX(i)], Eim = auxr[1 + maux * IX(i - 1)];
+        double lawi = (c->rp_id == RP_PSYSTEM) ? auxl[2 + maux * IX(i)] : c->p[0];
+        double lawim = (c->rp_id == RP_PSYSTEM) ? auxr[2 + maux * IX(i - 1)] : c->p[0];
+        double epsi = Q2(ql, 0, i), epsim = Q2(qr, 0, i - 1);
+        double urhoi = Q2(ql, mu, i), urhoim = Q2(qr, mu, i - 1);
+        double bulki = el_sigmap(epsi, Ei, lawi);
+        double bulkim = el_sigmap(epsim, Eim, lawim);
+        double ci = sqrt(bulki / rhoi);
+        double cim = sqrt(bulkim / rhoim);
+        double zi = ci * rhoi;
+        double zim = cim * rhoim;
+        double du = urhoi / rhoi - urhoim / rhoim;
+        double dsig = el_sigma(epsi, Ei, lawi) - el_sigma(epsim, Eim, lawim);
+        double b1 = -(zi * du + dsig) / (zim + zi);
+        double b2 = -(zim * du - dsig) / (zim + zi);
+        WV(0, 0, i) = b1;
+        WV(mu, 0, i) = b1 * zim;
+        SP(0, i) = -cim;
+        WV(0, 1, i) = b2;
+        WV(mu, 1, i) = b2 * (-zi);
+        SP(1, i) = ci;
+        if (meqn == 3) { WV(mv, 0, i) = 0.0; WV(mv, 1, i) = 0.0; }
+        for (int m = 0; m < meqn; m++) {
+            Q2(amdq, m, i) = WV(m, 0, i);
+            Q2(apdq, m, i) = WV(m, 1, i);
+        }
+    }
+    (void)mwaves;
+}
+
+/* Transverse solver of the p-system: the fluctuation asdq is split with the eigenvectors of
+   the transverse Jacobian, (1, z) at speed -c and (1, -z) at speed +c, using the impedance
+   of the cell it leaves (aux2) and of the cell it enters (aux1 below, aux3 above); the
+   strain those need is the copy the app keeps in aux(4) (test/psystem/psystem.py:83-86). */
+static void rpt_psystem(int ixy, int meqn, int mbc, int mx, const double *aux1, const double *aux2,
+                        const double *aux3, int imp, const double *asdq, double *bmasdq,
+                        double *bpasdq)
+{
+    const int maux = 4;
+    int mu = (ixy == 1) ? 1 : 2, mv = (ixy == 1) ? 2 : 1;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int i1 = (imp == 1) ? i - 1 : i;
+        const double *am = aux1 + maux * IX(i1), *ac = aux2 + maux * IX(i1), *ap = aux3 + maux * IX(i1);
+        double cm = sqrt(el_sigmap(am[3], am[1], am[2]) / am[0]);
+        double cc = sqrt(el_sigmap(ac[3], ac[1], ac[2]) / ac[0]);
+        double cp = sqrt(el_sigmap(ap[3], ap[1], ap[2]) / ap[0]);
+        double zm = cm * am[0], zz = cc * ac[0], zp = cp * ap[0];
+        double a1 = (zz * Q2(asdq, 0, i) + Q2(asdq, mv, i)) / (zm + zz);
+        double a2 = (zz * Q2(asdq, 0, i) - Q2(asdq, mv, i)) / (zz + zp);
+        Q2(bmasdq, 0, i) = -cm * a1;
+        Q2(bmasdq, mu, i) = 0.0;
+        Q2(bmasdq, mv, i) = -cm * a1 * zm;
+        Q2(bpasdq, 0, i) = cp * a2;
+        Q2(bpasdq, mu, i) = 0.0;
+        Q2(bpasdq, mv, i) = cp * a2 * (-zp);
+    }
+}
+
 static void rpn_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
                        const double *ql, const double *qr, const double *auxl, const double *auxr,
                        double *wave, double *s, double *amdq, double *apdq);
@@ -363,6 +451,8 @@ static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
 {
     switch (c->rp_id) {
     case RP_SPHERE: rpn_sphere(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
+    case RP_NEL_FWAVE: rpn_elastic_fwave(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, c->maux, wave, s, amdq, apdq); break;
+    case RP_PSYSTEM: rpn_elastic_fwave(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, 4, wave, s, amdq, apdq); break;
     case RP_ACOUSTICS: rpn_acoustics(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_ADVECTION: rpn_advection(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_EULER5: rpn_euler5(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
@@ -380,6 +470,10 @@ static void rpt(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx, const
     int mu, mv;
     if (c->rp_id == RP_SPHERE) {
         rpt_sphere(c, ixy, meqn, mwaves, mbc, mx, ql, aux1, aux2, aux3, imp, asdq, bmasdq, bpasdq);
+        return;
+    }
+    if (c->rp_id == RP_PSYSTEM) {
+        rpt_psystem(ixy, meqn, mbc, mx, aux1, aux2, aux3, imp, asdq, bmasdq, bpasdq);
         return;
     }
     if (ixy == 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
@@ -750,7 +844,7 @@ double oracle_step1(int rp_id, const double *rp_params, int meqn, int mwaves, in
 {
     rp_ctx c;
     memset(&c, 0, sizeof(c));
-    c.rp_id = rp_id; c.ndim = 1;
+    c.rp_id = rp_id; c.ndim = 1; c.maux = maux;
     memcpy(c.p, rp_params, 8 * sizeof(double));
     int n = mx + 2 * mbc;
     ctx_alloc(&c, n);
@@ -786,7 +880,9 @@ double oracle_step1(int rp_id, const double *rp_params, int meqn, int mwaves, in
             for (int m = 0; m < meqn; m++)
                 for (int mw = 0; mw < mwaves; mw++) {
                     double dtdxave = 0.5 * (dtdx[IX(i - 1)] + dtdx[IX(i)]);
-                    Q2(f, m, i) = Q2(f, m, i) + 0.5 * fabs(SP(mw, i)) *
+                    /* step1.f:125-126 ; step1fw.f:135-136 with dsign(1,s) for f-waves */
+                    double lead = RP_IS_FWAVE(rp_id) ? copysign(1.0, SP(mw, i)) : fabs(SP(mw, i));
+                    Q2(f, m, i) = Q2(f, m, i) + 0.5 * lead *
                                   (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
                 }
         /* :136-138 (f(m,mx+2) is zero) */
@@ -878,9 +974,12 @@ static double flux2(rp_ctx *c, int ixy, int maxm, int meqn, int mwaves, int mbc,
             double dtdxave = 0.5 * (dtdx1d[IX(i - 1)] + dtdx1d[IX(i)]);
             for (int m = 0; m < meqn; m++) {
                 Q2(cqxx, m, i) = 0.0;
-                for (int mw = 0; mw < mwaves; mw++)
+                for (int mw = 0; mw < mwaves; mw++) {
+                    /* flux2.f:140-141 ; flux2fw.f:151-152 with dsign(1,s) for f-waves */
+                    double lead = RP_IS_FWAVE(c->rp_id) ? copysign(1.0, SP(mw, i)) : fabs(SP(mw, i));
                     Q2(cqxx, m, i) = Q2(cqxx, m, i) +
-                                     fabs(SP(mw, i)) * (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
+                                     lead * (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
+                }
                 Q2(fadd, m, i) = Q2(fadd, m, i) + 0.5 * Q2(cqxx, m, i);
             }
         }

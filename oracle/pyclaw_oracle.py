@@ -23,6 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
+RP_NEL_FWAVE, RP_PSYSTEM = 6, 7   # f-wave solvers (step1fw.f / flux2fw.f corrections)
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("CLAWB200_LIB") or os.path.join(_HERE, "csrc", "libcla
 
 MAXWAVES = 8
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
+RP_NEL_FWAVE, RP_PSYSTEM = 6, 7
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
 STAGE_AXPY, STAGE_CONVEX, STAGE_FINAL104, STAGE_DQ_ONLY = 0, 1, 2, 3
 

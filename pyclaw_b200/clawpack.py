@@ -140,8 +140,6 @@ class ClawSolver(Solver):
         if self.kernel_language not in ('Fortran', 'CUDA'):
             raise NotImplementedError("kernel_language=%r: only the CUDA kernels exist ('Fortran' is "
                                       "accepted as an alias); there is no Python/CPU path" % self.kernel_language)
-        if self.fwave:
-            raise NotImplementedError("f-wave solvers (classic*fw) are not implemented yet")
         state = solution.state
         state.set_mbc(self.mbc)
         self.check_cfl_settings()

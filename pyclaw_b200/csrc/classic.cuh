@@ -120,7 +120,13 @@ __device__ __forceinline__ void limit_waves(AR &ar, double (&wave)[RP::MEQN][RP:
     }
 }
 
-// flux2.f:127-145: cqxx(m) = sum_mw |s| (1 - |s| dtdxave) wave(m,mw)
+// flux2.f:127-145: cqxx(m) = sum_mw |s| (1 - |s| dtdxave) wave(m,mw);
+// flux2fw.f:151-152 for f-wave solvers: sign(s) in place of the leading |s|
+template <class RP>
+__device__ __forceinline__ double lead_factor(double s)
+{
+    return rp_is_fwave<RP>::value ? copysign(1.0, s) : fabs(s);
+}
 template <class RP>
 __device__ __forceinline__ void second_order(const double (&wave)[RP::MEQN][RP::MWAVES],
                                              const double (&s)[RP::MWAVES], double dtdxave,
@@ -131,7 +137,7 @@ __device__ __forceinline__ void second_order(const double (&wave)[RP::MEQN][RP::
         double c = 0.0;
 #pragma unroll
         for (int mw = 0; mw < RP::MWAVES; mw++)
-            if (RP::nz(m, mw)) c = c + fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[m][mw];
+            if (RP::nz(m, mw)) c = c + lead_factor<RP>(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[m][mw];
         cqxx[m] = c;
     }
 }
@@ -711,8 +717,11 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
 #pragma unroll
     for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; rr[m] = qs[m * QS + t + 1]; }
     double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+    // step1.f:80: rp1 gets the one aux array as both auxl and auxr; 1-D arrays have no rows
     const AuxCell nocell{nullptr, 0};
-    with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, nocell, nocell, wave, s, amdq, apdq, roe); });
+    const AuxCell axl = (RP::MAUX > 0) ? AuxCell{A.aux + (min(max(ii - 1, 1 - mbc), imax) + mbc - 1), A.amstride} : nocell;
+    const AuxCell axr = (RP::MAUX > 0) ? AuxCell{A.aux + (min(max(ii, 1 - mbc), imax) + mbc - 1), A.amstride} : nocell;
+    with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, axl, axr, wave, s, amdq, apdq, roe); });
     double cfl = 0.0;
     if (iface_ok) {
 #pragma unroll
@@ -762,7 +771,7 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
 #pragma unroll
             for (int mw = 0; mw < MW; mw++)
                 if (RP::nz(m, mw))
-                    f[m] = f[m] + 0.5 * fabs(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[m][mw];
+                    f[m] = f[m] + 0.5 * lead_factor<RP>(s[mw]) * (1.0 - fabs(s[mw]) * dtdxave) * wave[m][mw];
     }
 #pragma unroll
     for (int m = 0; m < MEQN; m++) {

@@ -58,11 +58,18 @@ static int check_problem(const clawb200_problem *p, int ndim)
 static int check_aux(const clawb200_problem *p, const double *aux, bool classic2d)
 {
     const bool capa = p->method[5] > 0;
-    const bool need_aux = capa || p->rp_id == CLAWB200_RP_SPHERE;
+    const bool fw = p->rp_id == CLAWB200_RP_NEL_FWAVE || p->rp_id == CLAWB200_RP_PSYSTEM;
+    const bool need_aux = capa || fw || p->rp_id == CLAWB200_RP_SPHERE;
     if (!need_aux) return 0;
+    if (!aux) return fail(CLAWB200_ERR_INVALID, "aux array required (mcapa > 0 or aux-dependent Riemann solver)");
+    if (fw) { // classic step1 / step2 / step2ds only (the callers check the solver's dimension)
+        if (capa) return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function is not compiled for the f-wave solvers");
+        if (p->rp_id == CLAWB200_RP_NEL_FWAVE ? p->maux < 2 : p->maux != 4)
+            return fail(CLAWB200_ERR_INVALID, "f-wave elasticity solvers: aux = {rho, K} (1-D) or {rho, E, law, eps} (2-D)");
+        return 0;
+    }
     if (!classic2d)
         return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function / aux-dependent solvers: 2-D classic sweeps only");
-    if (!aux) return fail(CLAWB200_ERR_INVALID, "aux array required (mcapa > 0 or aux-dependent Riemann solver)");
     if (p->rp_id == CLAWB200_RP_SPHERE && (p->maux < 16 || !capa))
         return fail(CLAWB200_ERR_INVALID, "the sphere solver needs its 16 aux components and mcapa");
     if (capa && !(p->rp_id == CLAWB200_RP_ACOUSTICS || p->rp_id == CLAWB200_RP_ADVECTION ||
@@ -174,6 +181,7 @@ static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
     case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS>(A, st);
     case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS>(A, st);
     case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS>(A, st);
+    case CLAWB200_RP_PSYSTEM: return launch_x<RpElasticFwave<2, 1>, TRANS>(A, st);
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
 }
@@ -193,6 +201,7 @@ static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
     case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS>(A, st);
     case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS>(A, st);
     case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS>(A, st);
+    case CLAWB200_RP_PSYSTEM: return launch_y<RpElasticFwave<2, 2>, TRANS>(A, st);
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
 }
@@ -206,12 +215,17 @@ static int check_rp_shape(const clawb200_problem *p)
     case CLAWB200_RP_EULER5: meqn = 5; mwaves = 5; break;
     case CLAWB200_RP_SHALLOW: meqn = 3; mwaves = 3; break;
     case CLAWB200_RP_SPHERE: meqn = 4; mwaves = 3; break;
+    case CLAWB200_RP_NEL_FWAVE: meqn = 2; mwaves = 2; break;
+    case CLAWB200_RP_PSYSTEM: meqn = 3; mwaves = 2; break;
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
     if (p->meqn != meqn || p->mwaves != mwaves)
         return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
-    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SHALLOW || p->rp_id == CLAWB200_RP_SPHERE) && p->ndim != 2)
+    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SHALLOW || p->rp_id == CLAWB200_RP_SPHERE ||
+         p->rp_id == CLAWB200_RP_PSYSTEM) && p->ndim != 2)
         return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 2-D only");
+    if (p->rp_id == CLAWB200_RP_NEL_FWAVE && p->ndim != 1)
+        return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 1-D only");
     return 0;
 }
 
@@ -224,7 +238,7 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
     if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
     if (q_in == q_out) return fail(CLAWB200_ERR_INVALID, "q_in and q_out must differ");
     if ((rc = check_aux(p, aux, false))) return rc;
-    SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev);
+    SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev, aux);
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int NT = 128, NC = NT - 3;
     dim3 grid((p->mx + NC - 1) / NC);
@@ -236,6 +250,11 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
     } break;
     case CLAWB200_RP_ADVECTION: {
         using RP = RpAdvection<1, 1>;
+        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
+        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
+    } break;
+    case CLAWB200_RP_NEL_FWAVE: {
+        using RP = RpElasticFwave<1, 1>;
         size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
         step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
     } break;
@@ -916,14 +935,16 @@ extern "C" int clawb200_step1_host(const clawb200_problem *p, double *q, const d
     if (!p || !q) return fail(CLAWB200_ERR_INVALID, "null argument");
     clawb200_problem P = host_layout(p);
     size_t n = (size_t)P.meqn * P.mstride;
-    int rc = g_hs.ensure(n);
+    int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
     if (rc) return rc;
     if ((rc = host_upload(P, q, g_hs.d_a))) return rc;
+    const double *d_aux;
+    if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
     // cells outside 1..mx keep their input values (the Fortran also updates cells 0 and
     // mx+1, which no caller reads: clawpack.py:406 keeps q[:, mbc:-mbc] only)
     CUDA_OK(cudaMemcpyAsync(g_hs.d_b, g_hs.d_a, n * sizeof(double), cudaMemcpyDeviceToDevice, g_hs.st));
     if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
-    if ((rc = clawb200_step1(&P, g_hs.d_a, g_hs.d_b, aux, dt, g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = clawb200_step1(&P, g_hs.d_a, g_hs.d_b, d_aux, dt, g_hs.d_cfl, g_hs.st))) return rc;
     if ((rc = host_download(P, g_hs.d_b, q))) return rc;
     return host_finish(cfl);
 }

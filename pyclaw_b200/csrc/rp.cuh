@@ -27,6 +27,16 @@
 #define CLAW_RP_SHALLOW 4
 
 #define CLAW_RP_SPHERE 5
+#define CLAW_RP_NEL_FWAVE 6
+#define CLAW_RP_PSYSTEM 7
+
+// Solvers that return f-waves (jumps in the flux) instead of waves: the sweeps then use the
+// second-order correction of step1fw.f:135-136 / flux2fw.f:151-152.  A member FWAVE = true
+// in the solver struct selects it; solvers without the member are wave solvers.
+template <class RP, class = void>
+struct rp_is_fwave { static constexpr bool value = false; };
+template <class RP>
+struct rp_is_fwave<RP, decltype((void)RP::FWAVE)> { static constexpr bool value = RP::FWAVE; };
 
 struct RpParams {
     double p[8];
@@ -763,5 +773,108 @@ struct RpSphere {
         qcv[1] = qcv[1] - qcn * erx;
         qcv[2] = qcv[2] - qcn * ery;
         qcv[3] = qcv[3] - qcn * erz;
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// Elasticity in a heterogeneous medium, f-wave solvers.
+//   1-D (NDIM = 1): eps_t - u_x = 0, (rho u)_t - sigma(eps, x)_x = 0
+//        clawpack/riemann rp1_nonlinear_elasticity_fwave.f (external); app
+//        apps/elasticity/1d/stegoton/stegoton.py: aux = {rho, K}, stress law from rp_params[0]
+//   2-D (NDIM = 2): the p-system, clawpack/riemann rpn2_psystem.f / rpt2_psystem.f (external);
+//        app test/psystem/psystem.py: aux = {rho, E, stress law, copy of eps}
+// Stress law 1: sigma = E eps ; law 2: sigma = exp(E eps) - 1.
+// The flux jump (-du, -dsigma) is split into b1 (1, z_{i-1}) at speed -c_{i-1} and
+// b2 (1, -z_i) at speed +c_i with c = sqrt(sigma'/rho), z = rho c.
+// exp() is the CUDA library's (<= 1 ulp): for law 2 parity with the CPU oracle is to
+// rounding error, for law 1 it is bit for bit.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double el_sigma(double eps, double E, double law)
+{
+    return (law == 1.0) ? E * eps : exp(E * eps) - 1.0;
+}
+__device__ __forceinline__ double el_sigmap(double eps, double E, double law)
+{
+    return (law == 1.0) ? E : E * exp(E * eps);
+}
+
+template <int NDIM, int IXY>
+struct RpElasticFwave {
+    static constexpr int ID = (NDIM == 1) ? CLAW_RP_NEL_FWAVE : CLAW_RP_PSYSTEM;
+    static constexpr int MEQN = NDIM + 1, MWAVES = 2, NROE = 1;
+    static constexpr int X_MINB = 4, Y_MINB = 3;
+    static constexpr int MAUX = (NDIM == 1) ? 2 : 4;
+    static constexpr bool QCOR = false;
+    static constexpr bool FWAVE = true;
+    static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
+    __host__ __device__ static constexpr bool nz(int m, int mw) { return m == 0 || m == MU; }
+
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[MEQN],
+                                                 const double (&r)[MEQN], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[MEQN][MWAVES],
+                                                 double (&s)[MWAVES], double (&amdq)[MEQN],
+                                                 double (&apdq)[MEQN], double (&roe)[NROE])
+    {
+        const double rhoi = axr(0), rhoim = axl(0);
+        const double Ei = axr(1), Eim = axl(1);
+        const double lawi = (NDIM == 2) ? axr(2) : P.p[0];
+        const double lawim = (NDIM == 2) ? axl(2) : P.p[0];
+        const double epsi = r[0], epsim = l[0];
+        const double urhoi = r[MU], urhoim = l[MU];
+        const Recip rri = ar.rcp(rhoi), rrim = ar.rcp(rhoim);
+        double bulki = el_sigmap(epsi, Ei, lawi);
+        double bulkim = el_sigmap(epsim, Eim, lawim);
+        double ci = ar.sqrt(ar.div(bulki, rri));
+        double cim = ar.sqrt(ar.div(bulkim, rrim));
+        double zi = ci * rhoi;
+        double zim = cim * rhoim;
+        double du = ar.div(urhoi, rri) - ar.div(urhoim, rrim);
+        double dsig = el_sigma(epsi, Ei, lawi) - el_sigma(epsim, Eim, lawim);
+        const Recip rz = ar.rcp(zim + zi);
+        double b1 = ar.div(-(zi * du + dsig), rz);
+        double b2 = ar.div(-(zim * du - dsig), rz);
+        wave[0][0] = b1;
+        wave[MU][0] = b1 * zim;
+        s[0] = -cim;
+        wave[0][1] = b2;
+        wave[MU][1] = b2 * (-zi);
+        s[1] = ci;
+        if (NDIM == 2) {
+            wave[NDIM == 2 ? MV : 0][0] = 0.0;
+            wave[NDIM == 2 ? MV : 0][1] = 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            amdq[m] = wave[m][0];
+            apdq[m] = wave[m][1];
+        }
+        roe[0] = 0.0;
+    }
+
+    // rpt2: asdq split with the transverse eigenvectors (1, z) at -c and (1, -z) at +c, using
+    // the impedance of the cell it leaves (ax2) and of the one it enters (ax1 below, ax3 above)
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[MEQN], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
+                                                      const double (&asdq)[MEQN],
+                                                      double (&bm)[MEQN], double (&bp)[MEQN])
+    {
+        constexpr int mv = (NDIM == 2) ? MV : 0, mu = (NDIM == 2) ? MU : 0;
+        const double rm = ax1(0), rc = ax2(0), rp = ax3(0);
+        double cm = ar.sqrt(ar.div(el_sigmap(ax1(3), ax1(1), ax1(2)), rm));
+        double cc = ar.sqrt(ar.div(el_sigmap(ax2(3), ax2(1), ax2(2)), rc));
+        double cp = ar.sqrt(ar.div(el_sigmap(ax3(3), ax3(1), ax3(2)), rp));
+        double zm = cm * rm, zz = cc * rc, zp = cp * rp;
+        double a1 = ar.div(zz * asdq[0] + asdq[mv], zm + zz);
+        double a2 = ar.div(zz * asdq[0] - asdq[mv], zz + zp);
+        bm[0] = -cm * a1;
+        bm[mu] = 0.0;
+        bm[mv] = -cm * a1 * zm;
+        bp[0] = cp * a2;
+        bp[mu] = 0.0;
+        bp[mv] = cp * a2 * (-zp);
     }
 };

@@ -6,14 +6,19 @@ its scripts never name the solver in Python.  Here ``solver.rp`` may be set to o
 these descriptors (or its name); if it is left unset the solver is inferred from the
 keys of ``state.aux_global`` (the cparam common block the script fills).
 """
-from .._lib import RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE
+from .._lib import (RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE, RP_NEL_FWAVE,
+                    RP_PSYSTEM)
 
 
 class RiemannSolver(object):
-    def __init__(self, name, rp_id, meqn, mwaves, param_names, ndims, optional=()):
+    def __init__(self, name, rp_id, meqn, mwaves, param_names, ndims, optional=(), defaults=None,
+                 fwave=False, maux=0):
         self.name, self.rp_id, self.mwaves, self.param_names, self.ndims = name, rp_id, mwaves, param_names, ndims
         self._meqn = meqn
         self.optional = set(optional)
+        self.defaults = dict(defaults or {})
+        self.fwave = fwave      # returns f-waves: pairs with the classic*fw modules (clawpack.py:222)
+        self.maux = maux        # aux components the solver reads
 
     def meqn(self, ndim):
         return self._meqn(ndim) if callable(self._meqn) else self._meqn
@@ -24,7 +29,7 @@ class RiemannSolver(object):
             # state.py:154-158: every cparam variable must be present in aux_global
             raise Exception("Some required value(s) in the cparam common block in the Riemann "
                             "solver have not been set in aux_global: %s" % missing)
-        return [float(aux_global.get(k, 0.0)) for k in self.param_names]
+        return [float(aux_global.get(k, self.defaults.get(k, 0.0))) for k in self.param_names]
 
     def __repr__(self):
         return "<riemann %s>" % self.name
@@ -40,7 +45,17 @@ shallow_roe_with_efix = RiemannSolver("shallow_roe_with_efix", RP_SHALLOW, 3, 3,
 shallow_sphere = RiemannSolver("shallow_sphere", RP_SPHERE, 4, 3, ["g", "dxcom", "dycom"], (2,),
                                optional=["dxcom", "dycom"])
 
-_BY_NAME = {s.name: s for s in (acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere)}
+# f-wave solvers (solver.fwave = True).  Stress law 1: sigma = K eps; 2: sigma = exp(K eps) - 1.
+#   1-D: aux = {rho, K}     (apps/elasticity/1d/stegoton/stegoton.py:17-27), law from
+#        aux_global['stress_law'] (default 2, the stegoton's)
+#   2-D: aux = {rho, E, stress law, copy of eps}   (test/psystem/psystem.py:35-86)
+nonlinear_elasticity_fwave = RiemannSolver("nonlinear_elasticity_fwave", RP_NEL_FWAVE, 2, 2, ["stress_law"],
+                                           (1,), optional=["stress_law"], defaults={"stress_law": 2.0},
+                                           fwave=True, maux=2)
+psystem = RiemannSolver("psystem", RP_PSYSTEM, 3, 2, [], (2,), fwave=True, maux=4)
+
+_BY_NAME = {s.name: s for s in (acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere,
+                                nonlinear_elasticity_fwave, psystem)}
 _BY_NAME.update({"euler": euler_5wave, "shallow": shallow_roe_with_efix})
 
 
@@ -59,7 +74,7 @@ rp_euler = _Module(euler_5wave, ["rp_euler_5wave_2d"])
 rp_shallow = _Module(shallow_roe_with_efix, ["rp_shallow_roe_with_efix_2d"])
 
 
-def resolve(rp, aux_global, ndim):
+def resolve(rp, aux_global, ndim, fwave=False):
     if isinstance(rp, RiemannSolver):
         return rp
     if isinstance(rp, str):
@@ -69,6 +84,9 @@ def resolve(rp, aux_global, ndim):
     if rp is not None:
         raise NotImplementedError("Python Riemann solvers are not supported: there is no CPU "
                                   "path; set solver.rp to a pyclaw.riemann descriptor")
+    if fwave:
+        # the only f-wave solvers the reference's applications link (stegoton, psystem)
+        return nonlinear_elasticity_fwave if ndim == 1 else psystem
     keys = set(aux_global.keys())
     if {"rho", "bulk", "cc", "zz"} <= keys:
         return acoustics

@@ -126,7 +126,16 @@ class Solver(object):
                                      "state lives on %s" % state.device)
         _lib.load()
         grid = state.grid
-        self._rp = riemann.resolve(self.rp, state.aux_global, grid.ndim)
+        fwave = bool(getattr(self, 'fwave', False))
+        self._rp = riemann.resolve(self.rp, state.aux_global, grid.ndim, fwave=fwave)
+        if self._rp.fwave != fwave:
+            # the reference links an f-wave solver into classic*fw.so and a wave solver into
+            # classic*.so (clawpack.py:221-222); mixing them gives wrong second-order terms
+            raise Exception("solver.fwave = %s but Riemann solver %s returns %s"
+                            % (fwave, self._rp.name, "f-waves" if self._rp.fwave else "waves"))
+        if state.maux < self._rp.maux:
+            raise Exception("Riemann solver %s reads %d aux components; state.maux = %d"
+                            % (self._rp.name, self._rp.maux, state.maux))
         if grid.ndim not in self._rp.ndims:
             raise Exception("Riemann solver %s has no %d-D version" % (self._rp.name, grid.ndim))
         if state.meqn != self._rp.meqn(grid.ndim):
