@@ -1352,15 +1352,16 @@ static void workS_free(workS *w)
     free(w->q1d); free(w->dq1d);
 }
 
-static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, double dxv,
-                       int ixy, int meqn, int mwaves, int mx, int mbc, int weno_variant,
-                       int zero_dq, workS *w)
+static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double dt, double dxv,
+                            int ixy, int meqn, int mwaves, int mx, int mbc, int weno_variant,
+                            int zero_dq, workS *w, const double *capa1d)
 {
     int n = mx + 2 * mbc;
     double *ql = w->ql, *qr = w->qr, *wave = w->wave, *s = w->s;
     double *amdq = w->amdq, *apdq = w->apdq, *amdq2 = w->amdq2, *apdq2 = w->apdq2;
     double *dtdx = w->dtdx;
-    for (int k = 0; k < n; k++) dtdx[k] = dt / dxv;
+    /* flux1.f90:59-63 */
+    for (int k = 0; k < n; k++) dtdx[k] = capa1d ? dt / (dxv * capa1d[k]) : dt / dxv;
     if (zero_dq)
         for (int k = 0; k < n * meqn; k++) dq1d[k] = 0.0;
     /* positions never reconstructed hold the cell average so that the Riemann
@@ -1390,6 +1391,13 @@ static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, do
     return cfl;
 }
 
+static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, double dxv,
+                       int ixy, int meqn, int mwaves, int mx, int mbc, int weno_variant,
+                       int zero_dq, workS *w)
+{
+    return sc_flux1_capa(c, q1d, dq1d, dt, dxv, ixy, meqn, mwaves, mx, mbc, weno_variant, zero_dq, w, NULL);
+}
+
 /* 1-D entry: sharpclaw1.flux1(q,auxbc,dt,t,ixy,mx,mbc,maxnx) -> (dq1d, cfl); dq1d zero on entry */
 double oracle_sc_flux1(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
                        int mx, const double *q, double *dq, double dx, double dt, int weno_variant)
@@ -1401,6 +1409,68 @@ double oracle_sc_flux1(int rp_id, const double *rp_params, int meqn, int mwaves,
     workS w;
     workS_alloc(&w, n, meqn, mwaves);
     double cfl = sc_flux1(&c, q, dq, dt, dx, 0, meqn, mwaves, mx, mbc, weno_variant, 0, &w);
+    workS_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* the same two entries with a capacity function: aux(maux, ...) padded like q, mcapa 1-based
+   (flux1.f90:59-63; flux2.f90:52-63,84-93 add dq1d unscaled in both branches) */
+double oracle_sc_flux1_capa(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
+                            int mx, const double *q, double *dq, double dx, double dt,
+                            int weno_variant, const double *aux, int maux, int mcapa)
+{
+    int n = mx + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    c.ndim = 1;
+    workS w;
+    workS_alloc(&w, n, meqn, mwaves);
+    double *capa = (double *)calloc(n, sizeof(double));
+    for (int k = 0; k < n; k++) capa[k] = aux[(mcapa - 1) + maux * k];
+    double cfl = sc_flux1_capa(&c, q, dq, dt, dx, 0, meqn, mwaves, mx, mbc, weno_variant, 0, &w, capa);
+    free(capa);
+    workS_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+double oracle_sc_flux2_capa(int rp_id, const double *rp_params, int meqn, int mwaves, int mbc,
+                            int mx, int my, const double *q, double *dq, double dx, double dy,
+                            double dt, int weno_variant, const double *aux, int maux, int mcapa)
+{
+    int maxm = mx > my ? mx : my;
+    int n = maxm + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    workS w;
+    workS_alloc(&w, n, meqn, mwaves);
+    double *capa = (double *)calloc(n, sizeof(double));
+    double cfl = 0.0;
+    double *q1d = w.q1d, *dq1d = w.dq1d;
+    for (int j = 0; j <= my + 1; j++) {
+        for (int i = 1 - mbc; i <= mx + mbc; i++) {
+            for (int m = 0; m < meqn; m++) Q2(q1d, m, i) = Q3(q, m, i, j);
+            capa[IX(i)] = AUX3(mcapa - 1, i, j);
+        }
+        double cfl1d = sc_flux1_capa(&c, q1d, dq1d, dt, dx, 1, meqn, mwaves, mx, mbc, weno_variant, 1, &w, capa);
+        cfl = dmax2(cfl, cfl1d);
+        for (int i = 1; i <= mx; i++)
+            for (int m = 0; m < meqn; m++)
+                Q3(dq, m, i, j) = Q3(dq, m, i, j) + Q2(dq1d, m, i);
+    }
+    for (int i = 0; i <= mx + 1; i++) {
+        for (int j = 1 - mbc; j <= my + mbc; j++) {
+            for (int m = 0; m < meqn; m++) Q2(q1d, m, j) = Q3(q, m, i, j);
+            capa[IX(j)] = AUX3(mcapa - 1, i, j);
+        }
+        double cfl1d = sc_flux1_capa(&c, q1d, dq1d, dt, dy, 2, meqn, mwaves, my, mbc, weno_variant, 1, &w, capa);
+        cfl = dmax2(cfl, cfl1d);
+        for (int j = 1; j <= my; j++)
+            for (int m = 0; m < meqn; m++)
+                Q3(dq, m, i, j) = Q3(dq, m, i, j) + Q2(dq1d, m, j);
+    }
+    free(capa);
     workS_free(&w);
     ctx_free(&c);
     return cfl;

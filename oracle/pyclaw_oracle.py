@@ -54,6 +54,10 @@ def lib():
         L.oracle_sc_flux1.argtypes = [i, _dp, i, i, i, i, _dp, _dp, d, d, i]
         L.oracle_sc_flux2.restype = d
         L.oracle_sc_flux2.argtypes = [i, _dp, i, i, i, i, i, _dp, _dp, d, d, d, i]
+        L.oracle_sc_flux1_capa.restype = d
+        L.oracle_sc_flux1_capa.argtypes = [i, _dp, i, i, i, i, _dp, _dp, d, d, i, _dp, i, i]
+        L.oracle_sc_flux2_capa.restype = d
+        L.oracle_sc_flux2_capa.argtypes = [i, _dp, i, i, i, i, i, _dp, _dp, d, d, d, i, _dp, i, i]
         L.oracle_step2_slabs.restype = d
         L.oracle_step2_slabs.argtypes = [i, _dp, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, _ip, _ip, i, i]
         L.oracle_sc_flux2_slabs.restype = d
@@ -134,15 +138,26 @@ def step2_slabs(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, me
                                     _pi(method), _pi(mthlim), nthreads, int(dimsplit))
 
 
-def sc_flux1(rp_id, rp_params, mwaves, mbc, mx, q, dx, dt, weno_variant):
+def sc_flux1(rp_id, rp_params, mwaves, mbc, mx, q, dx, dt, weno_variant, auxbc=None, mcapa=0):
+    """sharpclaw1.flux1 (sharpclaw.py:385); mcapa is 1-based as in clawparams.mcapa (0 = none)."""
     dq = np.zeros_like(q, order="F")
+    if mcapa > 0:
+        cfl = lib().oracle_sc_flux1_capa(rp_id, _p(_params(rp_params)), q.shape[0], mwaves, mbc, mx,
+                                         _p(q), _p(dq), dx, dt, weno_variant, _p(auxbc), auxbc.shape[0], mcapa)
+        return dq, cfl
     cfl = lib().oracle_sc_flux1(rp_id, _p(_params(rp_params)), q.shape[0], mwaves, mbc, mx,
                                 _p(q), _p(dq), dx, dt, weno_variant)
     return dq, cfl
 
 
-def sc_flux2(rp_id, rp_params, mwaves, mbc, mx, my, q, dx, dy, dt, weno_variant, nthreads=1):
+def sc_flux2(rp_id, rp_params, mwaves, mbc, mx, my, q, dx, dy, dt, weno_variant, nthreads=1,
+             auxbc=None, mcapa=0):
     dq = np.zeros_like(q, order="F")
+    if mcapa > 0:
+        cfl = lib().oracle_sc_flux2_capa(rp_id, _p(_params(rp_params)), q.shape[0], mwaves, mbc, mx, my,
+                                         _p(q), _p(dq), dx, dy, dt, weno_variant, _p(auxbc),
+                                         auxbc.shape[0], mcapa)
+        return dq, cfl
     if nthreads > 1:
         cfl = lib().oracle_sc_flux2_slabs(rp_id, _p(_params(rp_params)), q.shape[0], mwaves, mbc,
                                           mx, my, _p(q), _p(dq), dx, dy, dt, weno_variant, nthreads)
@@ -317,11 +332,12 @@ class OracleSolver(object):
         mbc = self.mbc
         if self.ndim == 1:
             dq, cfl = sc_flux1(self.rp_id, self.rp_params, self.mwaves, mbc, self.n[0], self.qbc,
-                               self.d[0], self.dt, self.weno_variant)
+                               self.d[0], self.dt, self.weno_variant, auxbc=self.auxbc,
+                               mcapa=self.mcapa + 1)
         else:
             dq, cfl = sc_flux2(self.rp_id, self.rp_params, self.mwaves, mbc, self.n[0], self.n[1],
                                self.qbc, self.d[0], self.d[1], self.dt, self.weno_variant,
-                               self.nthreads)
+                               self.nthreads, auxbc=self.auxbc, mcapa=self.mcapa + 1)
         self.cfl = cfl
         if cfl > self.cfl_max:
             raise _CFLError()

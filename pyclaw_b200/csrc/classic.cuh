@@ -35,6 +35,7 @@ struct SweepArgs {
     int pitch;
     int mx, my, mbc;
     double dtdx, dtdy; // dt/dx, dt/dy (used when dt_dev is null)
+    double dt;         // the time step itself (step1 with a capacity function)
     double dx, dy;
     const double *dt_dev; // if set, the time step is read from device memory: the launch
                           // sequence of a step is then independent of dt (CUDA-graph replay)
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
 // 1-D step (step1.f:4-142).  Same staging as the x-engine, one "row".
 // Update order: q - dtdx*apdq(i), then - dtdx*amdq(i+1), then - dtdx*(f(i+1)-f(i)).
 // ---------------------------------------------------------------------------
-template <class RP, int NT>
+template <class RP, int NT, bool CAPA = false>
 __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
 {
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
@@ -706,6 +707,13 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
     const bool order2 = (A.order != 1);
     double dtdx, dtdy_unused;
     load_dt(A, dtdx, dtdy_unused);
+    double dtdx_l = dtdx; // cell ii-1
+    if (CAPA) { // step1.f:62-73: dtdx(i) = dt / (dx * aux(mcapa, i))
+        const double *cap = A.aux + (long long)(A.mcapa - 1) * A.amstride;
+        const double dt = A.dt_dev ? __ldg(A.dt_dev) : A.dt;
+        dtdx_l = div1(dt, A.dx * __ldg(&cap[min(max(ii - 1, 1 - mbc), imax) + mbc - 1]));
+        dtdx = div1(dt, A.dx * __ldg(&cap[min(max(ii, 1 - mbc), imax) + mbc - 1]));
+    }
 
 #pragma unroll
     for (int m = 0; m < MEQN; m++) {
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
     double cfl = 0.0;
     if (iface_ok) {
 #pragma unroll
-        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx * s[mw]), -dtdx * s[mw]);
+        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx * s[mw]), -dtdx_l * s[mw]);
     }
     if (order2) {
 #pragma unroll
@@ -765,7 +773,7 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
             limit_waves<RP>(ar, wave, s, wnorm2, dotl, dotr, A.mthlim);
         });
         // step1.f:121-128
-        double dtdxave = 0.5 * (dtdx + dtdx);
+        double dtdxave = 0.5 * (dtdx_l + dtdx);
 #pragma unroll
         for (int m = 0; m < MEQN; m++)
 #pragma unroll

@@ -68,14 +68,16 @@ static int check_aux(const clawb200_problem *p, const double *aux, bool classic2
             return fail(CLAWB200_ERR_INVALID, "f-wave elasticity solvers: aux = {rho, K} (1-D) or {rho, E, law, eps} (2-D)");
         return 0;
     }
-    if (!classic2d)
-        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function / aux-dependent solvers: 2-D classic sweeps only");
-    if (p->rp_id == CLAWB200_RP_SPHERE && (p->maux < 16 || !capa))
-        return fail(CLAWB200_ERR_INVALID, "the sphere solver needs its 16 aux components and mcapa");
-    if (capa && !(p->rp_id == CLAWB200_RP_ACOUSTICS || p->rp_id == CLAWB200_RP_ADVECTION ||
-                  p->rp_id == CLAWB200_RP_SPHERE))
-        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function (mcapa) is compiled for the acoustics, "
-                                              "advection and sphere solvers only");
+    if (p->rp_id == CLAWB200_RP_SPHERE) {
+        if (!classic2d) return fail(CLAWB200_ERR_UNSUPPORTED, "the sphere solver is compiled for the 2-D classic sweeps only");
+        if (p->maux < 16 || !capa)
+            return fail(CLAWB200_ERR_INVALID, "the sphere solver needs its 16 aux components and mcapa");
+        return 0;
+    }
+    // capa: every solver in the 2-D classic sweeps; acoustics and advection in step1 and SharpClaw
+    if (!classic2d && !(p->rp_id == CLAWB200_RP_ACOUSTICS || p->rp_id == CLAWB200_RP_ADVECTION))
+        return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function (mcapa) in 1-D / SharpClaw is compiled for the "
+                                              "acoustics and advection solvers only");
     return 0;
 }
 
@@ -92,6 +94,7 @@ static SweepArgs make_args(const clawb200_problem *p, const double *qin, double 
     A.mx = p->mx; A.my = p->my; A.mbc = p->mbc;
     A.dtdx = dt / p->dx;
     A.dtdy = (p->ndim > 1) ? dt / p->dy : 0.0;
+    A.dt = dt;
     A.dx = p->dx;
     A.dy = (p->ndim > 1) ? p->dy : 1.0;
     A.dt_dev = p->dt_dev;
@@ -173,6 +176,8 @@ static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
         case CLAWB200_RP_ACOUSTICS: return launch_x<RpAcoustics<2, 1>, TRANS, true>(A, st);
         case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS, true>(A, st);
         case CLAWB200_RP_SPHERE: return launch_x<RpSphere<1>, TRANS, true>(A, st);
+        case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS, true>(A, st);
+        case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS, true>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
         }
     }
@@ -193,6 +198,8 @@ static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
         case CLAWB200_RP_ACOUSTICS: return launch_y<RpAcoustics<2, 2>, TRANS, true>(A, st);
         case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS, true>(A, st);
         case CLAWB200_RP_SPHERE: return launch_y<RpSphere<2>, TRANS, true>(A, st);
+        case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS, true>(A, st);
+        case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS, true>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
         }
     }
@@ -242,16 +249,19 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int NT = 128, NC = NT - 3;
     dim3 grid((p->mx + NC - 1) / NC);
+    const bool capa = A.mcapa > 0;
     switch (p->rp_id) {
     case CLAWB200_RP_ACOUSTICS: {
         using RP = RpAcoustics<1, 1>;
         size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
-        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
+        if (capa) step1_kernel<RP, NT, true><<<grid, NT, smem, st>>>(A);
+        else step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
     } break;
     case CLAWB200_RP_ADVECTION: {
         using RP = RpAdvection<1, 1>;
         size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
-        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
+        if (capa) step1_kernel<RP, NT, true><<<grid, NT, smem, st>>>(A);
+        else step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
     } break;
     case CLAWB200_RP_NEL_FWAVE: {
         using RP = RpElasticFwave<1, 1>;
@@ -529,12 +539,12 @@ static void weno_constants(ScArgs &A, int variant)
     A.epweno = (double)1.e-36f; // reconstruct.f90:7, a REAL(4) literal
 }
 
-template <class RPX, class RPY, bool OLD>
+template <class RPX, class RPY, bool OLD, bool CAPA = false>
 static int sc_launch2(const ScArgs &A, cudaStream_t st)
 {
     constexpr int NC = SNT - 2;
     size_t smem = sizeof(double) * (2 * RPX::MEQN * (SNT + 4) + 2 * RPX::MEQN * SNT);
-    auto k = sc2d_kernel<RPX, RPY, OLD, SNT>;
+    auto k = sc2d_kernel<RPX, RPY, OLD, SNT, CAPA>;
     CUDA_OK(set_smem(k, smem));
     dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);
     k<<<grid, SNT, smem, st>>>(A);
@@ -542,19 +552,19 @@ static int sc_launch2(const ScArgs &A, cudaStream_t st)
     return 0;
 }
 
-template <class RP, bool OLD>
+template <class RP, bool OLD, bool CAPA = false>
 static int sc_launch1(const ScArgs &A, cudaStream_t st)
 {
     constexpr int NC = SNT - 2;
     size_t smem = sizeof(double) * (RP::MEQN * (SNT + 4) + 2 * RP::MEQN * SNT);
-    sc1d_kernel<RP, OLD, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
+    sc1d_kernel<RP, OLD, SNT, CAPA><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 static int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *qa, double *out,
                             double *dq_out, double dt, int mode, double ca, double cb, double div,
-                            double *cfl_dev, cudaStream_t st)
+                            double *cfl_dev, cudaStream_t st, const double *aux = nullptr)
 {
     ScArgs A;
     memset(&A, 0, sizeof(A));
@@ -568,6 +578,28 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
     A.mode = mode; A.ca = ca; A.cb = cb; A.div = div;
     A.cfl_bits = (unsigned long long *)cfl_dev;
     const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
+    if (p->method[5] > 0) {
+        // capacity function (flux1.f90:59-63): compiled for the acoustics and advection solvers
+        A.capa = aux + (long long)(p->method[5] - 1) * p->mstride;
+        A.dt = dt; A.dx = p->dx; A.dy = (p->ndim > 1) ? p->dy : 1.0;
+        if (p->ndim == 1) {
+            switch (p->rp_id) {
+            case CLAWB200_RP_ACOUSTICS:
+                return old ? sc_launch1<RpAcoustics<1, 1>, true, true>(A, st) : sc_launch1<RpAcoustics<1, 1>, false, true>(A, st);
+            case CLAWB200_RP_ADVECTION:
+                return old ? sc_launch1<RpAdvection<1, 1>, true, true>(A, st) : sc_launch1<RpAdvection<1, 1>, false, true>(A, st);
+            default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
+            }
+        }
+        A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+        switch (p->rp_id) {
+        case CLAWB200_RP_ACOUSTICS: return old ? sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, true, true>(A, st)
+                                               : sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, false, true>(A, st);
+        case CLAWB200_RP_ADVECTION: return old ? sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, true, true>(A, st)
+                                               : sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, false, true>(A, st);
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
+        }
+    }
     if (p->ndim == 1) {
         switch (p->rp_id) {
         case CLAWB200_RP_ACOUSTICS:
@@ -608,7 +640,7 @@ extern "C" int clawb200_sharpclaw_stage(const clawb200_problem *p, const double 
     if ((mode == 1 || mode == 2) && !qa) return fail(CLAWB200_ERR_INVALID, "this stage mode needs qa");
     if (out == q) return fail(CLAWB200_ERR_INVALID, "out must not alias q");
     if ((rc = check_aux(p, aux, false))) return rc;
-    return sharpclaw_launch(p, q, qa, out, dq_out, dt, mode, ca, cb, div, cfl_dev, (cudaStream_t)stream);
+    return sharpclaw_launch(p, q, qa, out, dq_out, dt, mode, ca, cb, div, cfl_dev, (cudaStream_t)stream, aux);
 }
 
 // ---------------------------------------------------------------------------
@@ -1004,12 +1036,14 @@ extern "C" int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const doubl
     if (!p || !q || !dq) return fail(CLAWB200_ERR_INVALID, "null argument");
     clawb200_problem P = host_layout(p);
     size_t n = (size_t)P.meqn * P.mstride;
-    int rc = g_hs.ensure(n);
+    int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
     if (rc) return rc;
     if ((rc = host_upload(P, q, g_hs.d_a))) return rc;
+    const double *d_aux;
+    if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
     CUDA_OK(cudaMemsetAsync(g_hs.d_b, 0, n * sizeof(double), g_hs.st));
     if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
-    if ((rc = clawb200_sharpclaw_stage(&P, g_hs.d_a, nullptr, nullptr, g_hs.d_b, aux, dt,
+    if ((rc = clawb200_sharpclaw_stage(&P, g_hs.d_a, nullptr, nullptr, g_hs.d_b, d_aux, dt,
                                        CLAWB200_STAGE_DQ_ONLY, 0.0, 0.0, 1.0, g_hs.d_cfl, g_hs.st)))
         return rc;
     if ((rc = host_download(P, g_hs.d_b, dq))) return rc;

@@ -33,7 +33,20 @@ struct ScArgs {
     double ca, cb, div;
     unsigned long long *cfl_bits;
     int rows_per_cta;
+    // capacity function (flux1.f90:59-63): dtdx(i) = dt / (dx * aux(mcapa, i))
+    const double *capa; // the capa component of aux, padded like q (or null)
+    double dt, dx, dy;
 };
+
+// dt / (d * capa) with one correctly rounded division, fast path first
+__device__ __forceinline__ double sc_dtd(double dt, double d, double capa)
+{
+    FastArith fa;
+    double den = d * capa;
+    double v = fa.div(dt, den);
+    if (fa.bad()) v = dt / den;
+    return v;
+}
 
 // weno.f90:35-98 for one component of one cell: ql = value at the left edge, qr at the right.
 // The six weights are quotients over three denominators and two normalisations, i.e. five
@@ -168,7 +181,7 @@ __device__ __forceinline__ void stage_store(const ScArgs &A, long long idx, cons
 template <class RP, bool OLD, int NT>
 __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, double *x1, double *x2,
                                         int t, bool iface_cfl, bool full, double &cfl,
-                                        double (&dqx)[RP::MEQN])
+                                        double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l)
 {
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
     constexpr int QS = NT + 4;
@@ -190,7 +203,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
     with_arith([&](auto &ar) { RP::solve(ar, A.rp, left, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
     if (iface_cfl) {
 #pragma unroll
-        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, A.dtdx * s[mw]), -A.dtdx * s[mw]);
+        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx_c * s[mw]), -dtdx_l * s[mw]);
     }
 #pragma unroll
     for (int m = 0; m < MEQN; m++) x2[m * NT + t] = amdq[m];
@@ -201,7 +214,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             double an = x2[m * NT + (t < NT - 1 ? t + 1 : t)];
-            dqx[m] = 0.0 - A.dtdx * (an + apdq[m] + amdq2[m] + apdq2[m]);
+            dqx[m] = 0.0 - dtdx_c * (an + apdq[m] + amdq2[m] + apdq2[m]);
         }
     }
 }
@@ -212,7 +225,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
 #ifndef CLAW_SC_MINB
 #define CLAW_SC_MINB 2
 #endif
-template <class RPX, class RPY, bool OLD, int NT>
+template <class RPX, class RPY, bool OLD, int NT, bool CAPA = false>
 __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_kernel(const ScArgs A)
 {
     constexpr int MEQN = RPX::MEQN, MW = RPX::MWAVES, NROE = RPX::NROE;
@@ -238,6 +251,7 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
     const int j1 = min(j0 + A.rows_per_cta, A.my + 1);
 
     double cfl = 0.0;
+    double dtdy_c = A.dtdy, dtdy_p = A.dtdy; // dt/(dy capa) of rows c and c-1
     double w0[MEQN], w1[MEQN], w2[MEQN], w3[MEQN], w4[MEQN];
     double dx1[MEQN], dx2[MEQN], dx3[MEQN], dx4[MEQN];
     double qr_prev[MEQN], apdq_prev[MEQN], amdq2_prev[MEQN], apdq2_prev[MEQN];
@@ -285,12 +299,22 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
         const bool xfull = (k >= j0) && (k < j1);
         const bool xcfl_only = (k == 0 && j0 == 1) || (k == A.my + 1 && j1 == A.my + 1);
         if (xfull || xcfl_only) {
-            sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1);
+            double dtdx_c = A.dtdx, dtdx_l = A.dtdx;
+            if (CAPA) {
+                const int il = min(max(ic - 1, 1 - mbc), imax) + mbc - 1;
+                dtdx_c = sc_dtd(A.dt, A.dx, __ldg(&A.capa[rowoff + icl]));
+                dtdx_l = sc_dtd(A.dt, A.dx, __ldg(&A.capa[rowoff + il]));
+            }
+            sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1, dtdx_c, dtdx_l);
         }
 
         // y-direction: reconstruct cell c = k-2 from rows k-4 .. k
         const int c = k - 2;
         if (c >= j0 - 1) {
+            if (CAPA) {
+                dtdy_p = dtdy_c;
+                dtdy_c = sc_dtd(A.dt, A.dy, __ldg(&A.capa[(long long)A.pitch * (c + mbc - 1) + icl]));
+            }
             double ql[MEQN], qr[MEQN];
             with_arith([&](auto &ar) {
 #pragma unroll
@@ -306,7 +330,7 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
                 if (ycol && c >= 1 && c <= A.my + 1) {
 #pragma unroll
                     for (int mw = 0; mw < MW; mw++)
-                        cfl = dmax2(dmax2(cfl, A.dtdy * s[mw]), -A.dtdy * s[mw]);
+                        cfl = dmax2(dmax2(cfl, dtdy_c * s[mw]), -dtdy_p * s[mw]);
                 }
                 if (c < j1)
                     with_arith([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
@@ -316,7 +340,7 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
                     double dq[MEQN];
 #pragma unroll
                     for (int m = 0; m < MEQN; m++) {
-                        double dqy = 0.0 - A.dtdy * (amdq[m] + apdq_prev[m] + amdq2_prev[m] + apdq2_prev[m]);
+                        double dqy = 0.0 - dtdy_p * (amdq[m] + apdq_prev[m] + amdq2_prev[m] + apdq2_prev[m]);
                         dq[m] = (0.0 + dx4[m]) + dqy;
                     }
                     stage_store<MEQN>(A, (long long)A.pitch * (jc + mbc - 1) + icl, w1, dq);
@@ -335,7 +359,7 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
 // ---------------------------------------------------------------------------
 // 1-D: one row, x-direction only.
 // ---------------------------------------------------------------------------
-template <class RP, bool OLD, int NT>
+template <class RP, bool OLD, int NT, bool CAPA = false>
 __global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
 {
     constexpr int MEQN = RP::MEQN;
@@ -365,7 +389,13 @@ __global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
         dqx[m] = 0.0;
     }
     __syncthreads();
-    sc_xrow<RP, OLD, NT>(A, qs, x1, x2, t, xiface, true, cfl, dqx);
+    double dtdx_c = A.dtdx, dtdx_l = A.dtdx;
+    if (CAPA) {
+        const int il = min(max(ic - 1, 1 - mbc), imax) + mbc - 1;
+        dtdx_c = sc_dtd(A.dt, A.dx, __ldg(&A.capa[icl]));
+        dtdx_l = sc_dtd(A.dt, A.dx, __ldg(&A.capa[il]));
+    }
+    sc_xrow<RP, OLD, NT>(A, qs, x1, x2, t, xiface, true, cfl, dqx, dtdx_c, dtdx_l);
     if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
     sc_cfl_commit(cfl, A.cfl_bits);
 }

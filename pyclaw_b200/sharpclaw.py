@@ -53,7 +53,7 @@ class SharpClawSolver(Solver):
     # ---- one dq evaluation fused with a stage update ----
     def _stage(self, q_buf, qa_buf, out_buf, mode, ca, cb, div, slot, dq_buf=None):
         _lib.call("clawb200_sharpclaw_stage", ctypes.byref(self._problem), _ptr(q_buf), _ptr(qa_buf),
-                  _ptr(out_buf), _ptr(dq_buf), None, float(self.dt), mode, float(ca), float(cb),
+                  _ptr(out_buf), _ptr(dq_buf), self._aux_ptr, float(self.dt), mode, float(ca), float(cb),
                   float(div), ctypes.c_void_p(self._cfl_dev.data_ptr() + 8 * slot), _stream())
 
     def _bcs_on(self, state, buf, t=None):
@@ -221,8 +221,11 @@ class SharpClawSolver(Solver):
         state.set_mbc(self.mbc)
         self.allocate_rk_stages(solution)
         self.set_mthlim()
-        self._setup_device(state, weno_variant=variant)
+        # clawparams.mcapa = state.mcapa + 1 (sharpclaw.py:270)
+        method = [int(self.dt_variable), 2, 0, 0, 0, state.mcapa + 1, state.maux]
+        self._setup_device(state, method=method, weno_variant=variant)
         self.allocate_bc_arrays(state)
+        self._aux_ptr = _ptr(state._aux.cur if state._aux is not None else None)
         self._dq_field = None
 
     def teardown(self):

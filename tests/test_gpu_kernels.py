@@ -188,7 +188,7 @@ def test_f2py_shaped_modules():
         classic2.step2(max(mx, my), mbc, mx, my, np.ascontiguousarray(q), qnew, None, dx, dy, dt, method, lim)
 
 
-@pytest.mark.parametrize("rp", ["acoustics", "advection"])
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "euler", "shallow"])
 @pytest.mark.parametrize("shape", [(37, 29), (130, 70)])
 @pytest.mark.parametrize("trans", [-1, 0, 1, 2])
 def test_capacity_function(rp, shape, trans):
@@ -446,3 +446,71 @@ def test_fwave_solver_argument_checks():
     a2 = np.ones((3, mx + 4, 12), order="F")
     with pytest.raises(_lib.ClawB200Error, match="aux"):
         _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q2), _ptr(q2.copy("F")), _ptr(a2), 0.01, ctypes.byref(cfl))
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection"])
+@pytest.mark.parametrize("mx", [7, 300, 1001])
+@pytest.mark.parametrize("order", [1, 2])
+def test_step1_capacity_function(rp, mx, order):
+    """step1.f:62-73: dtdx(i) = dt / (dx * aux(mcapa, i)); mcapa is the second aux component."""
+    rp_id, params, _, mwaves, lim = RPS[rp]
+    meqn = 2 if rp == "acoustics" else 1
+    params = [1.0, 1.0, 1.0, 1.0] if rp == "acoustics" else params
+    mbc = 2
+    dx, dt = 1.0 / mx, 0.3 / mx
+    method = [1, order, 0, 0, 0, 2, 2]
+    q = _random_padded(rp, mx, 0, mbc, seed=mx)
+    aux = np.asfortranarray(np.random.RandomState(mx).uniform(0.5, 1.5, (2, mx + 2 * mbc)))
+    P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, method, lim, maux=2)
+    q_o = q.copy("F")
+    cfl_o = po.step1(rp_id, params, mbc, mx, q_o, aux, dx, dt, method, lim)
+    q_g = q.copy("F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_step1_host", ctypes.byref(P), _ptr(q_g), _ptr(aux), dt, ctypes.byref(cfl_g))
+    assert np.array_equal(q_g[:, mbc:-mbc], q_o[:, mbc:-mbc])
+    assert cfl_g.value == cfl_o
+    # and it is not the uniform-grid result
+    q_u = q.copy("F")
+    po.step1(rp_id, params, mbc, mx, q_u, None, dx, dt, [1, order, 0, 0, 0, 0, 0], lim)
+    assert np.abs(q_u - q_o)[:, mbc:-mbc].max() > 1e-4
+
+
+@pytest.mark.parametrize("rp", ["acoustics", "advection"])
+@pytest.mark.parametrize("variant", [0, 2])
+def test_sharpclaw_capacity_function(rp, variant):
+    """flux1.f90:59-63: dtdx = dt / (dx(ixy) * aux(mcapa, :)) in both sweep directions."""
+    rp_id, params, meqn2, mwaves, _ = RPS[rp]
+    mbc = 3
+    dt = 0.0011
+    rng = np.random.RandomState(11)
+    cfl_g = ctypes.c_double()
+    # 2-D
+    for mx, my in ((37, 29), (130, 70)):
+        dx, dy = 0.01, 0.013
+        q = _random_padded(rp, mx, my, mbc, seed=mx + variant, smooth=True)
+        aux = np.asfortranarray(rng.uniform(0.5, 1.5, (2, mx + 2 * mbc, my + 2 * mbc)))
+        method = [1, 2, 0, 0, 0, 2, 2]
+        P = _lib.make_problem(2, meqn2, mwaves, mbc, mx, my, dx, dy, rp_id, params, method=method,
+                              maux=2, weno_variant=variant)
+        dq_o, cfl_o = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, variant, auxbc=aux, mcapa=2)
+        dq_g = np.zeros_like(q, order="F")
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), _ptr(aux), dt,
+                  ctypes.byref(cfl_g))
+        inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+        assert np.array_equal(dq_g[inner], dq_o[inner]) and cfl_g.value == cfl_o
+        dq_u, _ = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, variant)
+        assert np.abs(dq_u - dq_o)[inner].max() > 1e-4
+    # 1-D
+    meqn = 2 if rp == "acoustics" else 1
+    params1 = [1.0, 1.0, 1.0, 1.0] if rp == "acoustics" else params
+    for mx in (9, 500):
+        dx = 1.0 / mx
+        q = _random_padded(rp, mx, 0, mbc, seed=mx, smooth=True)
+        aux = np.asfortranarray(rng.uniform(0.5, 1.5, (2, mx + 2 * mbc)))
+        P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params1, method=[1, 2, 0, 0, 0, 1, 2],
+                              maux=2, weno_variant=variant)
+        dq_o, cfl_o = po.sc_flux1(rp_id, params1, mwaves, mbc, mx, q, dx, dt, variant, auxbc=aux, mcapa=1)
+        dq_g = np.zeros_like(q, order="F")
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), _ptr(aux), dt,
+                  ctypes.byref(cfl_g))
+        assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]) and cfl_g.value == cfl_o
