@@ -430,18 +430,28 @@ def main():
     kms, bpc = kern[dom]
     achieved = bpc * cells_per_rank / (kms * 1e-3) / 1e9
     traffic = None
+    fp64 = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            tr = json.load(f).get(args.workload, {}).get(dom)
+            prof = json.load(f)
+            tr = prof.get(args.workload, {}).get(dom)
             if tr:  # measured DRAM bytes per cell per launch (ncu), scaled to this launch's cells
                 traffic = tr["bytes_per_cell"] * cells_per_rank
+            if tr and "fp64_inst_per_cell" in tr:
+                # the resource that actually binds: FP64-pipe instructions the
+                # kernel executes (ncu count, -fmad=false so one instruction = one flop) per second,
+                # against the FP64 issue rate measured on this GPU type by scratch/fp64_peak.cu
+                rate = tr["fp64_inst_per_cell"] * cells_per_rank / (kms * 1e-3)
+                fp64 = {"achieved": rate / 1e12, "peak": prof["_fp64_peak_inst_per_s"] / 1e12,
+                        "unit": "T FP64 inst/s", "frac": rate / prof["_fp64_peak_inst_per_s"],
+                        "inst_per_cell_per_launch": tr["fp64_inst_per_cell"]}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "kernel_ms": kms, "algorithmic_bytes_per_cell_per_launch": bpc,
                 "all_kernels_ms": {k: v[0] for k, v in kern.items()},
                 "step_frac": value / world * wl["balg"] / 1e9 / peak,
-                "step_algorithmic_bytes_per_cell": wl["balg"]}
+                "step_algorithmic_bytes_per_cell": wl["balg"], "fp64_pipe": fp64}
 
     # ---- e2e: the f2py-shaped C ABI call with HOST buffers (H2D + kernels + D2H timed) ----
     e2e = None
