@@ -485,7 +485,7 @@ def main():
         nbytes = host_in.numel() * 8
         e2e = {"value": cells_per_rank * k / el, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes + 8, "steps": k,
-               "what": "clawb200_step2_host (the f2py-shaped call): pinned host qold -> H2D -> layout kernel -> sweeps -> layout kernel -> D2H qnew every step, as a 3-stream pipeline of 512-row slabs",
+               "what": "clawb200_step2_host (the f2py-shaped call): pinned host qold -> H2D -> layout kernel -> sweeps -> layout kernel -> D2H qnew every step, as a 3-stream pipeline of 128-row slabs",
                "resident_api": {"value": value, "unit": "cell-updates/s",
                                 "what": "solver.evolve_to_time through the pyclaw API, q resident in HBM, "
                                         "8-byte CFL read back per step"}}

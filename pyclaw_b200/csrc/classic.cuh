@@ -308,6 +308,13 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq[m] + cqxx[m]) : amdq[m];
                         RP::transverse(ar, A.rp, roe, l, AUXRP ? aux_cell(A, ii - 1, r - 1) : nocell, axl,
                                        AUXRP ? aux_cell(A, ii - 1, r + 1) : nocell, asdq, bmm, bpm);
+                        // hand the "goes into the left cell" parts to thread t-1 right away: they
+                        // are dead in this thread, and the second solve needs the registers
+#pragma unroll
+                        for (int m = 0; m < MEQN; m++) {
+                            xs[(2 * MEQN + m) * NT + t] = bmm[m];
+                            xs[(3 * MEQN + m) * NT + t] = bpm[m];
+                        }
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq[m] - cqxx[m]) : apdq[m];
                         RP::transverse(ar, A.rp, roe, rr, AUXRP ? aux_cell(A, ii, r - 1) : nocell, axr,
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
 #pragma unroll
         for (int m = 0; m < MEQN; m++) F[m] = 0.5 * cqxx[m];
 
-        if (TRANS) {
+        if (TRANS && !(A.trans > 0)) { // (otherwise stored right after the first transverse solve)
 #pragma unroll
             for (int m = 0; m < MEQN; m++) {
                 xs[(2 * MEQN + m) * NT + t] = bmm[m];

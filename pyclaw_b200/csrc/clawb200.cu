@@ -5,6 +5,7 @@
 // contraction and results must match it bit for bit ("hard parts").
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -882,7 +883,14 @@ static int host_pipeline(const clawb200_problem *p, const double *qold, double *
     const int out0 = (mode == 1) ? 0 : mbc;
     const int out1 = (mode == 1) ? ny_tot : mbc + p->my;
     const int halo = (mode == 1) ? 0 : mbc; // input rows needed beyond the output rows
-    int nslab = (out1 - out0 + 511) / 512;
+    // slab height: PCIe time is the bound, the first upload and the last download are the only
+    // transfers that do not overlap, so slabs are kept small (CLAWB200_SLAB_ROWS overrides)
+    static const int slab_rows = [] {
+        const char *e = getenv("CLAWB200_SLAB_ROWS");
+        int v = e ? atoi(e) : 0;
+        return (v >= 16) ? v : 128;
+    }();
+    int nslab = (out1 - out0 + slab_rows - 1) / slab_rows;
     if (nslab < 1) nslab = 1;
     const int rows_per = (out1 - out0 + nslab - 1) / nslab;
     const size_t nmax = rowd * (size_t)(rows_per + 2 * mbc);
