@@ -68,6 +68,24 @@ def run(pc, kind, q0, aux0, mx, my, opts):
     return np.asarray(q), status['numsteps']
 
 
+def run_sphere(pc, mx, my):
+    """BASELINE config 5 on a slab partition: periodic x, pole-fold custom y BCs on the edge
+    ranks, 16 aux components with capa, Strang-split fused src2."""
+    from pyclaw_b200.apps import shallow_sphere as app
+    state, solver = app.setup(pc, mx, my)
+    solver.dt_initial = 0.1 * state.grid.d[0] / 4.0
+    claw = pc.Controller()
+    claw.output_format = None
+    claw.tfinal = 0.02
+    claw.nout = 2
+    claw.solution = pc.Solution(state)
+    claw.solver = solver
+    status = claw.run()
+    part = state._partition
+    q = part.gather_interior(state) if part is not None else np.asarray(state.q)
+    return np.asarray(q), status['numsteps']
+
+
 def main():
     import petclaw
     rank, world = petclaw.init('nccl')
@@ -88,6 +106,13 @@ def main():
             print("case %s %s: %d ranks, %d steps, bit-identical=%s maxdiff=%g"
                   % (kind, opts, world, nsteps, same, np.abs(qp - qser).max()), flush=True)
             ok &= same
+    qp, nsteps = run_sphere(petclaw, 64, 32)
+    if rank == 0:
+        qser, nser = run_sphere(pyclaw, 64, 32)
+        same = np.array_equal(qp, qser) and nsteps == nser and not np.isnan(qser).any() and nser >= 3
+        print("case sphere: %d ranks, %d steps, bit-identical=%s maxdiff=%g"
+              % (world, nsteps, same, np.abs(qp - qser).max()), flush=True)
+        ok &= same
     flag = torch.tensor([1.0 if ok else 0.0], device='cuda')
     dist.broadcast(flag, 0)
     dist.barrier()
