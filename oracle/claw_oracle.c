@@ -271,6 +271,74 @@ static void rpn_euler5(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx
         }
 }
 
+/* clawpack/riemann rp1_shallow_roe_with_efix.f (external, un-vendored; app apps/shallow/1d,
+   Makefile:3): the 1-D Roe solver with the same entropy fix; restated from the published
+   algorithm (LeVeque 2002, sec. 15.3.3 / 15.3.5), parity unpinned. */
+static void rpn_shallow1d(rp_ctx *c, int meqn, int mwaves, int mbc, int mx,
+                          const double *ql, const double *qr,
+                          double *wave, double *s, double *amdq, double *apdq)
+{
+    const double grav = c->p[0];
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double hl = Q2(qr, 0, i - 1), hr = Q2(ql, 0, i);
+        double hul = Q2(qr, 1, i - 1), hur = Q2(ql, 1, i);
+        double hsqrtl = sqrt(hl);
+        double hsqrtr = sqrt(hr);
+        double hsq2 = hsqrtl + hsqrtr;
+        double ubar = (hul / hsqrtl + hur / hsqrtr) / hsq2;
+        double cbar = sqrt(0.5 * grav * (hl + hr));
+        double d1 = hr - hl;
+        double d2 = hur - hul;
+        double a1 = 0.5 * (-d2 + (ubar + cbar) * d1) / cbar;
+        double a2 = 0.5 * (d2 - (ubar - cbar) * d1) / cbar;
+        WV(0, 0, i) = a1;
+        WV(1, 0, i) = a1 * (ubar - cbar);
+        SP(0, i) = ubar - cbar;
+        WV(0, 1, i) = a2;
+        WV(1, 1, i) = a2 * (ubar + cbar);
+        SP(1, i) = ubar + cbar;
+        /* entropy fix: as in rpn_shallow above, without the shear wave */
+        int done = 0;
+        double s0 = hul / hl - sqrt(grav * hl);
+        if (s0 > 0.0 && SP(0, i) > 0.0) {
+            for (int m = 0; m < 2; m++) Q2(amdq, m, i) = 0.0;
+            done = 1;
+        }
+        if (!done) {
+            double h1 = hl + WV(0, 0, i);
+            double hu1 = hul + WV(1, 0, i);
+            double s1 = hu1 / h1 - sqrt(grav * h1);
+            double sfract;
+            if (s0 < 0.0 && s1 > 0.0)
+                sfract = s0 * ((s1 - SP(0, i)) / (s1 - s0));
+            else if (SP(0, i) < 0.0)
+                sfract = SP(0, i);
+            else
+                sfract = 0.0;
+            for (int m = 0; m < 2; m++) Q2(amdq, m, i) = sfract * WV(m, 0, i);
+            double s03 = hur / hr + sqrt(grav * hr);
+            double h3 = hr - WV(0, 1, i);
+            double hu3 = hur - WV(1, 1, i);
+            double s3 = hu3 / h3 + sqrt(grav * h3);
+            int add = 1;
+            if (s3 < 0.0 && s03 > 0.0)
+                sfract = s3 * ((s03 - SP(1, i)) / (s03 - s3));
+            else if (SP(1, i) < 0.0)
+                sfract = SP(1, i);
+            else
+                add = 0;
+            if (add)
+                for (int m = 0; m < 2; m++) Q2(amdq, m, i) = Q2(amdq, m, i) + sfract * WV(m, 1, i);
+        }
+        for (int m = 0; m < 2; m++) {
+            double df = 0.0;
+            for (int mw = 0; mw < 2; mw++) df = df + SP(mw, i) * WV(m, mw, i);
+            Q2(apdq, m, i) = df - Q2(amdq, m, i);
+        }
+    }
+    (void)meqn; (void)mwaves;
+}
+
 /* clawpack/riemann rpn2_shallow_roe_with_efix.f (external) */
 static void rpn_shallow(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
                         const double *ql, const double *qr,
@@ -456,7 +524,10 @@ static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
     case RP_ACOUSTICS: rpn_acoustics(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_ADVECTION: rpn_advection(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_EULER5: rpn_euler5(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
-    case RP_SHALLOW: rpn_shallow(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
+    case RP_SHALLOW:
+        if (ixy == 0) rpn_shallow1d(c, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq);
+        else rpn_shallow(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq);
+        break;
     }
 }
 

@@ -221,7 +221,7 @@ static int check_rp_shape(const clawb200_problem *p)
     case CLAWB200_RP_ACOUSTICS: meqn = p->ndim + 1; mwaves = 2; break;
     case CLAWB200_RP_ADVECTION: meqn = 1; mwaves = 1; break;
     case CLAWB200_RP_EULER5: meqn = 5; mwaves = 5; break;
-    case CLAWB200_RP_SHALLOW: meqn = 3; mwaves = 3; break;
+    case CLAWB200_RP_SHALLOW: meqn = p->ndim + 1; mwaves = p->ndim + 1; break;
     case CLAWB200_RP_SPHERE: meqn = 4; mwaves = 3; break;
     case CLAWB200_RP_NEL_FWAVE: meqn = 2; mwaves = 2; break;
     case CLAWB200_RP_PSYSTEM: meqn = 3; mwaves = 2; break;
@@ -229,7 +229,7 @@ static int check_rp_shape(const clawb200_problem *p)
     }
     if (p->meqn != meqn || p->mwaves != mwaves)
         return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
-    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SHALLOW || p->rp_id == CLAWB200_RP_SPHERE ||
+    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SPHERE ||
          p->rp_id == CLAWB200_RP_PSYSTEM) && p->ndim != 2)
         return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 2-D only");
     if (p->rp_id == CLAWB200_RP_NEL_FWAVE && p->ndim != 1)
@@ -263,6 +263,12 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
         size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
         if (capa) step1_kernel<RP, NT, true><<<grid, NT, smem, st>>>(A);
         else step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
+    } break;
+    case CLAWB200_RP_SHALLOW: {
+        using RP = RpShallow1D;
+        if (capa) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
+        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
+        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
     } break;
     case CLAWB200_RP_NEL_FWAVE: {
         using RP = RpElasticFwave<1, 1>;
@@ -607,6 +613,8 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
             return old ? sc_launch1<RpAcoustics<1, 1>, true>(A, st) : sc_launch1<RpAcoustics<1, 1>, false>(A, st);
         case CLAWB200_RP_ADVECTION:
             return old ? sc_launch1<RpAdvection<1, 1>, true>(A, st) : sc_launch1<RpAdvection<1, 1>, false>(A, st);
+        case CLAWB200_RP_SHALLOW:
+            return old ? sc_launch1<RpShallow1D, true>(A, st) : sc_launch1<RpShallow1D, false>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
     }

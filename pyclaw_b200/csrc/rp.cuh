@@ -778,6 +778,97 @@ struct RpSphere {
 
 
 // ---------------------------------------------------------------------------
+// 1-D shallow water, Roe solver with entropy fix.  clawpack/riemann
+// rp1_shallow_roe_with_efix.f (external; app apps/shallow/1d).  cparam{grav}.
+// ---------------------------------------------------------------------------
+struct RpShallow1D {
+    static constexpr int ID = CLAW_RP_SHALLOW;
+    static constexpr int MEQN = 2, MWAVES = 2, NROE = 1;
+    static constexpr int X_MINB = 4, Y_MINB = 4;
+    static constexpr int MAUX = 0;
+    static constexpr bool QCOR = false;
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[2],
+                                                 const double (&r)[2], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[2][2], double (&s)[2], double (&amdq)[2],
+                                                 double (&apdq)[2], double (&roe)[NROE])
+    {
+        const double grav = P.p[0];
+        const double hl = l[0], hr = r[0], hul = l[1], hur = r[1];
+        double hsqrtl = ar.sqrt(hl);
+        double hsqrtr = ar.sqrt(hr);
+        double hsq2 = hsqrtl + hsqrtr;
+        double ubar = ar.div(ar.div(hul, hsqrtl) + ar.div(hur, hsqrtr), hsq2);
+        double cbar = ar.sqrt(0.5 * grav * (hl + hr));
+        const Recip rc = ar.rcp(cbar);
+        double d1 = hr - hl;
+        double d2 = hur - hul;
+        double a1 = ar.div(0.5 * (-d2 + (ubar + cbar) * d1), rc);
+        double a2 = ar.div(0.5 * (d2 - (ubar - cbar) * d1), rc);
+        wave[0][0] = a1;
+        wave[1][0] = a1 * (ubar - cbar);
+        s[0] = ubar - cbar;
+        wave[0][1] = a2;
+        wave[1][1] = a2 * (ubar + cbar);
+        s[1] = ubar + cbar;
+        bool done = false;
+        double s0 = ar.div(hul, hl) - ar.sqrt(grav * hl);
+        if (s0 > 0.0 && s[0] > 0.0) {
+            amdq[0] = 0.0; amdq[1] = 0.0;
+            done = true;
+        }
+        if (!done) {
+            double h1 = hl + wave[0][0];
+            double hu1 = hul + wave[1][0];
+            double s1 = ar.div(hu1, h1) - ar.sqrt(grav * h1);
+            double sfract;
+            if (s0 < 0.0 && s1 > 0.0)
+                sfract = s0 * ar.div(s1 - s[0], s1 - s0);
+            else if (s[0] < 0.0)
+                sfract = s[0];
+            else
+                sfract = 0.0;
+            amdq[0] = sfract * wave[0][0];
+            amdq[1] = sfract * wave[1][0];
+            double s03 = ar.div(hur, hr) + ar.sqrt(grav * hr);
+            double h3 = hr - wave[0][1];
+            double hu3 = hur - wave[1][1];
+            double s3 = ar.div(hu3, h3) + ar.sqrt(grav * h3);
+            bool add = true;
+            if (s3 < 0.0 && s03 > 0.0)
+                sfract = s3 * ar.div(s03 - s[1], s03 - s3);
+            else if (s[1] < 0.0)
+                sfract = s[1];
+            else
+                add = false;
+            if (add) {
+                amdq[0] = amdq[0] + sfract * wave[0][1];
+                amdq[1] = amdq[1] + sfract * wave[1][1];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            double df = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 2; mw++) df = df + s[mw] * wave[m][mw];
+            apdq[m] = df - amdq[m];
+        }
+        roe[0] = 0.0;
+    }
+
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &, const RpParams &, const double (&)[NROE],
+                                                      const double (&)[2], const AuxCell &, const AuxCell &,
+                                                      const AuxCell &, const double (&)[2], double (&bm)[2],
+                                                      double (&bp)[2])
+    {
+        bm[0] = bm[1] = bp[0] = bp[1] = 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // Elasticity in a heterogeneous medium, f-wave solvers.
 //   1-D (NDIM = 1): eps_t - u_x = 0, (rho u)_t - sigma(eps, x)_x = 0
 //        clawpack/riemann rp1_nonlinear_elasticity_fwave.f (external); app

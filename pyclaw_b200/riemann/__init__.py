@@ -13,8 +13,10 @@ from .._lib import (RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE
 class RiemannSolver(object):
     def __init__(self, name, rp_id, meqn, mwaves, param_names, ndims, optional=(), defaults=None,
                  fwave=False, maux=0):
-        self.name, self.rp_id, self.mwaves, self.param_names, self.ndims = name, rp_id, mwaves, param_names, ndims
+        self.name, self.rp_id, self.param_names, self.ndims = name, rp_id, param_names, ndims
         self._meqn = meqn
+        self._mwaves = mwaves
+        self.mwaves = self.nwaves(max(ndims))
         self.optional = set(optional)
         self.defaults = dict(defaults or {})
         self.fwave = fwave      # returns f-waves: pairs with the classic*fw modules (clawpack.py:222)
@@ -22,6 +24,9 @@ class RiemannSolver(object):
 
     def meqn(self, ndim):
         return self._meqn(ndim) if callable(self._meqn) else self._meqn
+
+    def nwaves(self, ndim):
+        return self._mwaves(ndim) if callable(self._mwaves) else self._mwaves
 
     def params(self, aux_global):
         missing = [k for k in self.param_names if k not in aux_global and k not in self.optional]
@@ -38,7 +43,8 @@ class RiemannSolver(object):
 acoustics = RiemannSolver("acoustics", RP_ACOUSTICS, lambda ndim: ndim + 1, 2, ["rho", "bulk", "cc", "zz"], (1, 2))
 advection = RiemannSolver("advection", RP_ADVECTION, 1, 1, ["u", "v"], (1, 2), optional=["v"])
 euler_5wave = RiemannSolver("euler_5wave", RP_EULER5, 5, 5, ["gamma", "gamma1"], (2,))
-shallow_roe_with_efix = RiemannSolver("shallow_roe_with_efix", RP_SHALLOW, 3, 3, ["grav"], (2,))
+shallow_roe_with_efix = RiemannSolver("shallow_roe_with_efix", RP_SHALLOW, lambda ndim: ndim + 1,
+                                      lambda ndim: ndim + 1, ["grav"], (1, 2))
 
 # shallow water on the sphere (apps/shallow-sphere): `g` is the reference's common /sw/ g;
 # dxcom / dycom (common /comxyt/) default to the grid spacing

@@ -140,9 +140,9 @@ class Solver(object):
             raise Exception("Riemann solver %s has no %d-D version" % (self._rp.name, grid.ndim))
         if state.meqn != self._rp.meqn(grid.ndim):
             raise Exception("state.meqn = %d does not match Riemann solver %s" % (state.meqn, self._rp.name))
-        if self.mwaves != self._rp.mwaves:
+        if self.mwaves != self._rp.nwaves(grid.ndim):
             raise Exception("solver.mwaves = %s does not match Riemann solver %s (%d)"
-                            % (self.mwaves, self._rp.name, self._rp.mwaves))
+                            % (self.mwaves, self._rp.name, self._rp.nwaves(grid.ndim)))
         ng, d = grid.ng, grid.d
         self._problem = _lib.make_problem(
             grid.ndim, state.meqn, self.mwaves, self.mbc, ng[0], ng[1] if grid.ndim > 1 else 1,

@@ -491,3 +491,45 @@ def test_sphere_src2_kernel_vs_tensor_ops_vs_oracle():
     # the oracle recomputes the radial vector with libm-free mapc2p: identical to aux(14:16)
     # only if aux came from the same mapc2p; here aux is numpy's -> compare to round-off
     assert np.abs(a - qo).max() < 1e-15
+
+
+@pytest.mark.parametrize("solver_type,ic", [('classic', '2-shock'), ('classic', 'dam-break'), ('sharpclaw', 'dam-break')])
+def test_shallow1d_app_vs_oracle(solver_type, ic):
+    """apps/shallow/1d/shallow1D.py, line by line, against the oracle driver (the reference has no
+    golden for it; the 1-D Roe solver is external: parity unpinned, GPU vs oracle bit for bit)."""
+    import pyclaw
+    solver = pyclaw.ClawSolver1D() if solver_type == 'classic' else pyclaw.SharpClawSolver1D()
+    solver.mwaves = 2
+    solver.limiters = pyclaw.limiters.tvd.vanleer
+    solver.kernel_language = 'Fortran'
+    solver.bc_lower[0] = pyclaw.BC.outflow
+    solver.bc_upper[0] = pyclaw.BC.outflow
+    if solver_type == 'sharpclaw':
+        solver.cfl_max, solver.cfl_desired = 1.3, 1.2
+    mx = 500
+    grid = pyclaw.Grid(pyclaw.Dimension('x', -5.0, 5.0, mx))
+    state = pyclaw.State(grid, 2)
+    state.aux_global['grav'] = 1.0
+    xc = grid.x.center
+    hl, ul, hr, ur = (3., 0., 1., 0.) if ic == 'dam-break' else (1., 1., 1., -1.)
+    q0 = np.zeros((2, mx), order='F')
+    q0[0] = hl * (xc <= 0.) + hr * (xc > 0.)
+    q0[1] = hl * ul * (xc <= 0.) + hr * ur * (xc > 0.)
+    state.q[...] = q0
+    claw = pyclaw.Controller()
+    claw.keep_copy, claw.output_format, claw.tfinal = True, None, 2.0
+    claw.solution, claw.solver = pyclaw.Solution(state), solver
+    claw.run()
+    qg = np.asarray(claw.frames[-1].q)
+
+    s = po.OracleSolver(solver_type, 1, po.RP_SHALLOW, [1.0], 2)
+    s.bc_lower = s.bc_upper = [po.BC_OUTFLOW]
+    if solver_type == 'classic':
+        s.limiters = 3
+    else:
+        s.cfl_max, s.cfl_desired = 1.3, 1.2
+    qo = s.run(q0, None, [grid.d[0]], 2.0, 10)[-1]
+    assert not np.isnan(qo).any()
+    assert np.array_equal(qg, qo)
+    if ic == 'dam-break':       # exact middle state of the 3:1 dam break with g = 1
+        assert abs(qg[0, mx // 2] - 1.848576) < 2e-3

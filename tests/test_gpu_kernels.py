@@ -514,3 +514,44 @@ def test_sharpclaw_capacity_function(rp, variant):
         _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), _ptr(aux), dt,
                   ctypes.byref(cfl_g))
         assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]) and cfl_g.value == cfl_o
+
+
+# ---------------------------------------------------------------------------
+# 1-D shallow water (rp1_shallow_roe_with_efix; apps/shallow/1d)
+# ---------------------------------------------------------------------------
+def _shallow1d_data(mx, mbc, seed, smooth):
+    q2 = _random_padded("shallow", mx, 0, mbc, seed=seed, smooth=smooth)   # (3, n): h, hu, hv
+    return np.asfortranarray(q2[:2])
+
+
+@pytest.mark.parametrize("mx", [5, 100, 1001])
+@pytest.mark.parametrize("order,lim", [(1, [0, 0]), (2, [4, 4]), (2, [1, 3])])
+def test_step1_shallow(mx, order, lim):
+    mbc = 2
+    dx, dt = 1.0 / mx, 0.1 / mx
+    method = [1, order, 0, 0, 0, 0, 0]
+    q = _shallow1d_data(mx, mbc, mx, False)
+    P = _lib.make_problem(1, 2, 2, mbc, mx, 1, dx, 1.0, 4, [1.0], method, lim)
+    q_o = q.copy("F")
+    cfl_o = po.step1(4, [1.0], mbc, mx, q_o, None, dx, dt, method, lim)
+    q_g = q.copy("F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_step1_host", ctypes.byref(P), _ptr(q_g), None, dt, ctypes.byref(cfl_g))
+    assert not np.isnan(q_o).any() and cfl_o > 0.05
+    assert np.array_equal(q_g[:, mbc:-mbc], q_o[:, mbc:-mbc])
+    assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("mx", [9, 500])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_sharpclaw_dq1_shallow(mx, variant):
+    mbc = 3
+    dx, dt = 1.0 / mx, 0.1 / mx
+    q = _shallow1d_data(mx, mbc, mx + variant, True)
+    P = _lib.make_problem(1, 2, 2, mbc, mx, 1, dx, 1.0, 4, [1.0], weno_variant=variant)
+    dq_o, cfl_o = po.sc_flux1(4, [1.0], 2, mbc, mx, q, dx, dt, variant)
+    dq_g = np.zeros_like(q, order="F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
+    assert not np.isnan(dq_o).any()
+    assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]) and cfl_g.value == cfl_o
