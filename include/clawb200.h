@@ -49,6 +49,8 @@ extern "C" {
 #define CLAWB200_RP_NEL_FWAVE 6 /* rp1_nonlinear_elasticity_fwave (apps/elasticity/1d/stegoton);
                                    aux {rho, K}; params {stress law: 1 linear, 2 exponential} */
 #define CLAWB200_RP_PSYSTEM 7   /* rpn2/rpt2_psystem (test/psystem); aux {rho, E, law, eps} */
+#define CLAWB200_RP_ACOUSTICS3D_VC 8 /* rpn3_vc_acoustics (test/acoustics/3d); aux {impedance, c};
+                                        3-D, dimensional splitting only */
 
 /* Boundary condition ids = pyclaw.BC (src/pyclaw/solver.py:17-23) */
 #define CLAWB200_BC_CUSTOM 0
@@ -162,6 +164,18 @@ int clawb200_sphere_src2(const clawb200_problem *p, double *q, const double *aux
 int clawb200_bc_fill(const clawb200_problem *p, double *q, int narr, int idim, int side,
                      int bctype, int negate, void *stream);
 
+/* classic3.step3ds (src/fortran/3d/classic/step3ds.f:2-376 with flux3.f:176-237, method(3) < 0;
+ * called at clawpack.py:656-676): one directional sweep of the dimensionally split 3-D
+ * algorithm, idir = 1, 2, 3.  p->ndim = 3; p->mx, my, dx, dy as usual, the third dimension
+ * travels as (mz, dz); the field is q[m][k][j][i] with p->pitch = padded row length and
+ * p->mstride >= pitch*(my+2mbc)*(mz+2mbc).  q_out receives qold in cells the sweep does not
+ * touch; q_in != q_out.  Unsplit 3-D (step3.f / flux3.f with rpt3, rptt3) is not built. */
+int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, const double *q_in, double *q_out,
+                     const double *aux, double dt, int idir, double *cfl_dev, void *stream);
+/* qbc_lower / qbc_upper for a 3-D field (idim = 0, 1, 2). */
+int clawb200_bc_fill3(const clawb200_problem *p, int mz, double *q, int narr, int idim, int side,
+                      int bctype, int negate, void *stream);
+
 /* Layout converters between the reference's host layout (component fastest) and the
  * device layout, both on DEVICE memory; nx, ny include ghost cells. */
 int clawb200_aos_to_soa(const double *aos, double *soa, int ncomp, int nx, int ny,
@@ -198,6 +212,11 @@ int clawb200_step2_host(const clawb200_problem *p, const double *qold, double *q
  * (dq, cfl) = sharpclaw2.flux2(q, auxbc, dt, t, mbc, maxm, mx, my)     (ndim = 2) */
 int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const double *q, double *dq,
                                const double *aux, double dt, double *cfl);
+
+/* (qnew, cfl) = classic3.step3ds(maxm, mbc, mx, my, mz, qold, qnew, auxbc, dx, dy, dz, dt, method,
+ *                                mthlim, aux1, aux2, aux3, work, idir) */
+int clawb200_step3ds_host(const clawb200_problem *p, int mz, double dz, const double *qold,
+                          double *qnew, const double *aux, double dt, int idir, double *cfl);
 
 #ifdef __cplusplus
 }

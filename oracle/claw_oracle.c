@@ -39,6 +39,7 @@
 #define RP_SPHERE 5 /* shallow water on the sphere: params g, dxcom, dycom ; 16 aux ; step2qcor */
 #define RP_NEL_FWAVE 6 /* 1-D nonlinear elasticity, f-waves: aux = rho, K ; params[0] = stress law */
 #define RP_PSYSTEM 7   /* 2-D p-system, f-waves: aux = rho, E, stress law, eps ; rpt2 */
+#define RP_ACOUSTICS3D_VC 8 /* 3-D variable-coefficient acoustics: aux = impedance, sound speed */
 #define RP_IS_FWAVE(id) ((id) == RP_NEL_FWAVE || (id) == RP_PSYSTEM)
 
 #define WENO_PYWENO_F32 0 /* weno.f90 literals read as REAL(4), as gfortran does */
@@ -506,6 +507,36 @@ static void rpt_psystem(int ixy, int meqn, int mbc, int mx, const double *aux1, 
     }
 }
 
+/* clawpack/riemann rpn3_vc_acoustics.f (external, un-vendored; test/acoustics/3d/Makefile:3):
+   q = (p, u, v, w), aux(1) = impedance Z, aux(2) = sound speed c of each cell
+   (test/acoustics/3d/acoustics.py:66-67).  ixyz = 1, 2, 3 selects the normal velocity. */
+static void rpn3_vc_acoustics(int ixyz, int meqn, int mwaves, int mbc, int mx, int maux,
+                              const double *ql, const double *qr, const double *auxl,
+                              const double *auxr, double *wave, double *s, double *amdq,
+                              double *apdq)
+{
+    const int mu = ixyz;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double delta1 = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        double delta2 = Q2(ql, mu, i) - Q2(qr, mu, i - 1);
+        double zi = auxl[0 + maux * IX(i)], zim = auxr[0 + maux * IX(i - 1)];
+        double a1 = (-delta1 + zi * delta2) / (zim + zi);
+        double a2 = (delta1 + zim * delta2) / (zim + zi);
+        for (int m = 0; m < meqn; m++) { WV(m, 0, i) = 0.0; WV(m, 1, i) = 0.0; }
+        WV(0, 0, i) = -a1 * zim;
+        WV(mu, 0, i) = a1;
+        SP(0, i) = -auxr[1 + maux * IX(i - 1)];
+        WV(0, 1, i) = a2 * zi;
+        WV(mu, 1, i) = a2;
+        SP(1, i) = auxl[1 + maux * IX(i)];
+        for (int m = 0; m < meqn; m++) {
+            Q2(amdq, m, i) = SP(0, i) * WV(m, 0, i);
+            Q2(apdq, m, i) = SP(1, i) * WV(m, 1, i);
+        }
+    }
+    (void)mwaves;
+}
+
 static void rpn_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
                        const double *ql, const double *qr, const double *auxl, const double *auxr,
                        double *wave, double *s, double *amdq, double *apdq);
@@ -520,6 +551,7 @@ static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
     switch (c->rp_id) {
     case RP_SPHERE: rpn_sphere(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
     case RP_NEL_FWAVE: rpn_elastic_fwave(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, c->maux, wave, s, amdq, apdq); break;
+    case RP_ACOUSTICS3D_VC: rpn3_vc_acoustics(ixy, meqn, mwaves, mbc, mx, c->maux, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
     case RP_PSYSTEM: rpn_elastic_fwave(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, 4, wave, s, amdq, apdq); break;
     case RP_ACOUSTICS: rpn_acoustics(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_ADVECTION: rpn_advection(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
@@ -1171,6 +1203,101 @@ double oracle_step2ds(int rp_id, const double *rp_params, int maxm, int meqn, in
             }
         }
     }
+    work2_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+
+/* ------------------------------------------------------------------------- */
+/* step3ds.f:2-376 with flux3.f:176-237 (method(3) < 0: the normal solve, limiter and      */
+/* second-order correction only).  idir = 1, 2, 3; sweeps cover one ghost layer of the     */
+/* other two directions (k = 0..mz+1, j = 0..my+1, ...), not all of them as step2ds does.  */
+/* q(meqn, 1-mbc:mx+mbc, 1-mbc:my+mbc, 1-mbc:mz+mbc), Fortran order.                       */
+/* ------------------------------------------------------------------------- */
+static double flux3_ds(rp_ctx *c, int ixyz, int meqn, int mwaves, int mbc, int mx,
+                       const double *q1d, const double *dtdx1d, const int *method,
+                       const int *mthlim, work2 *w)
+{
+    double *wave = w->wave, *s = w->s, *amdq = w->amdq, *apdq = w->apdq, *cqxx = w->cqxx;
+    double *qadd = w->qadd, *fadd = w->fadd;
+    int limit = 0;
+    for (int mw = 0; mw < mwaves; mw++) if (mthlim[mw] > 0) limit = 1;
+    for (int i = 1 - mbc; i <= mx + mbc; i++)
+        for (int m = 0; m < meqn; m++) { Q2(qadd, m, i) = 0.0; Q2(fadd, m, i) = 0.0; }
+    rpn(c, ixyz, meqn, mwaves, mbc, mx, q1d, q1d, w->aux2, w->aux2, wave, s, amdq, apdq);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(qadd, m, i) = Q2(qadd, m, i) - dtdx1d[IX(i)] * Q2(apdq, m, i);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(qadd, m, i - 1) = Q2(qadd, m, i - 1) - dtdx1d[IX(i - 1)] * Q2(amdq, m, i);
+    double cfl1d = 0.0;
+    for (int i = 1; i <= mx + 1; i++)
+        for (int mw = 0; mw < mwaves; mw++)
+            cfl1d = dmax2(dmax2(cfl1d, dtdx1d[IX(i)] * SP(mw, i)), -dtdx1d[IX(i - 1)] * SP(mw, i));
+    if (method[1] == 1) return cfl1d;
+    if (limit) limiter(mx, meqn, mwaves, mbc, mx, wave, s, mthlim);
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double dtdxave = 0.5 * (dtdx1d[IX(i - 1)] + dtdx1d[IX(i)]);
+        for (int m = 0; m < meqn; m++) Q2(cqxx, m, i) = 0.0;
+        for (int mw = 0; mw < mwaves; mw++)
+            for (int m = 0; m < meqn; m++)
+                Q2(cqxx, m, i) = Q2(cqxx, m, i) + 0.5 * fabs(SP(mw, i)) *
+                                 (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
+        for (int m = 0; m < meqn; m++) Q2(fadd, m, i) = Q2(fadd, m, i) + Q2(cqxx, m, i);
+    }
+    return cfl1d;
+}
+
+double oracle_step3ds(int rp_id, const double *rp_params, int meqn, int mwaves, int maux, int mbc,
+                      int mx, int my, int mz, const double *qold, double *qnew, const double *aux,
+                      double dx, double dy, double dz, double dt, const int *method,
+                      const int *mthlim, int idir)
+{
+    int maxm = mx > my ? mx : my;
+    if (mz > maxm) maxm = mz;
+    int n = maxm + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n);
+    c.ndim = 3; c.maux = maux;
+    work2 w;
+    work2_alloc(&w, n, meqn, mwaves);
+    work2_alloc_aux(&w, n, maux);
+    const size_t NXs = mx + 2 * mbc, NYs = my + 2 * mbc;
+#define Q4(arr, m, i, j, k) arr[(m) + (size_t)meqn * (((i) + mbc - 1) + NXs * (((j) + mbc - 1) + NYs * ((k) + mbc - 1)))]
+#define AUX4(ma, i, j, k) aux[(ma) + (size_t)maux * (((i) + mbc - 1) + NXs * (((j) + mbc - 1) + NYs * ((k) + mbc - 1)))]
+    const int mcapa = method[5];
+    const double dtd[3] = {dt / dx, dt / dy, dt / dz};
+    const int len[3] = {mx, my, mz};
+    double cfl = 0.0;
+    double *q1d = w.q1d, *qadd = w.qadd, *fadd = w.fadd;
+    const int d = idir - 1;              /* sweep direction */
+    const int o1 = (d == 0) ? 1 : 0;     /* the two other directions, lower index first */
+    const int o2 = (d == 2) ? 1 : 2;
+    int idx[3];
+    for (idx[o2] = 0; idx[o2] <= len[o2] + 1; idx[o2]++)
+        for (idx[o1] = 0; idx[o1] <= len[o1] + 1; idx[o1]++) {
+            for (int l = 1 - mbc; l <= len[d] + mbc; l++) {
+                idx[d] = l;
+                for (int m = 0; m < meqn; m++) Q2(q1d, m, l) = Q4(qold, m, idx[0], idx[1], idx[2]);
+                w.dtdx1d[IX(l)] = (mcapa > 0) ? dtd[d] / AUX4(mcapa - 1, idx[0], idx[1], idx[2]) : dtd[d];
+                for (int ma = 0; ma < maux; ma++)
+                    w.aux2[ma + maux * IX(l)] = AUX4(ma, idx[0], idx[1], idx[2]);
+            }
+            double cfl1d = flux3_ds(&c, idir, meqn, mwaves, mbc, len[d], q1d, w.dtdx1d, method, mthlim, &w);
+            cfl = dmax2(cfl, cfl1d);
+            for (int l = 1; l <= len[d]; l++) {
+                idx[d] = l;
+                for (int m = 0; m < meqn; m++) {
+                    double upd = dtd[d] * (Q2(fadd, m, l + 1) - Q2(fadd, m, l));
+                    if (mcapa > 0) upd = upd / AUX4(mcapa - 1, idx[0], idx[1], idx[2]);
+                    Q4(qnew, m, idx[0], idx[1], idx[2]) =
+                        Q4(qnew, m, idx[0], idx[1], idx[2]) + Q2(qadd, m, l) - upd;
+                }
+            }
+        }
+#undef Q4
+#undef AUX4
     work2_free(&w);
     ctx_free(&c);
     return cfl;

@@ -24,6 +24,7 @@ _LIB = None
 
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 RP_NEL_FWAVE, RP_PSYSTEM = 6, 7   # f-wave solvers (step1fw.f / flux2fw.f corrections)
+RP_ACOUSTICS3D_VC = 8              # 3-D variable-coefficient acoustics (dimensional splitting)
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 
@@ -50,6 +51,8 @@ def lib():
         L.oracle_step2ds.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, _ip, _ip, i]
         L.oracle_step2.restype = d
         L.oracle_step2.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, _ip, _ip]
+        L.oracle_step3ds.restype = d
+        L.oracle_step3ds.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, d, _ip, _ip, i]
         L.oracle_sc_flux1.restype = d
         L.oracle_sc_flux1.argtypes = [i, _dp, i, i, i, i, _dp, _dp, d, d, i]
         L.oracle_sc_flux2.restype = d
@@ -123,6 +126,18 @@ def step2(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method, 
     return lib().oracle_step2(rp_id, _p(_params(rp_params)), max(mx, my), meqn, len(mthlim), maux,
                               mbc, mx, my, _p(qold), _p(qnew), _p(aux), dx, dy, dt,
                               _pi(method), _pi(mthlim))
+
+
+def step3ds(rp_id, rp_params, mbc, mx, my, mz, qold, qnew, auxbc, dx, dy, dz, dt, method, mthlim, idir):
+    """classic3.step3ds (clawpack.py:656-676): one directional sweep; qnew updated in place."""
+    meqn = qold.shape[0]
+    maux = 0 if auxbc is None else auxbc.shape[0]
+    aux = np.zeros(1) if maux == 0 else auxbc
+    method = np.ascontiguousarray(method, dtype=np.int32)
+    mthlim = np.ascontiguousarray(mthlim, dtype=np.int32)
+    assert qold.flags["F_CONTIGUOUS"] and qnew.flags["F_CONTIGUOUS"]
+    return lib().oracle_step3ds(rp_id, _p(_params(rp_params)), meqn, len(mthlim), maux, mbc, mx, my, mz,
+                                _p(qold), _p(qnew), _p(aux), dx, dy, dz, dt, _pi(method), _pi(mthlim), idir)
 
 
 def step2_slabs(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method, mthlim,
@@ -292,6 +307,17 @@ class OracleSolver(object):
         if self.ndim == 1:
             cfl = step1(self.rp_id, self.rp_params, mbc, self.n[0], self.qbc, self.auxbc,
                         self.d[0], self.dt, self.method, self.mthlim)
+        elif self.ndim == 3:
+            # clawpack.py:656-676: three aliased step3ds calls; only dim_split is restated
+            assert self.dim_split
+            mx, my, mz = self.n
+            dx, dy, dz = self.d
+            q = self.qbc
+            cfl = 0.0
+            for idir in (1, 2, 3):
+                qold = q.copy("F")
+                cfl = max(cfl, step3ds(self.rp_id, self.rp_params, mbc, mx, my, mz, qold, q, self.auxbc,
+                                       dx, dy, dz, self.dt, self.method, self.mthlim, idir))
         else:
             mx, my = self.n
             dx, dy = self.d

@@ -9,11 +9,11 @@ from .solution import Solution
 from .grid import Dimension, Grid
 from .state import State
 from .cfl import CFL
-from .clawpack import ClawSolver1D, ClawSolver2D
+from .clawpack import ClawSolver1D, ClawSolver2D, ClawSolver3D
 from .sharpclaw import SharpClawSolver1D, SharpClawSolver2D
 from .solver import BC, CFLError
 from .limiters import tvd
 
 __all__ = ['Controller', 'Dimension', 'Grid', 'Solution', 'State', 'CFL', 'riemann',
-           'ClawSolver1D', 'ClawSolver2D', 'SharpClawSolver1D', 'SharpClawSolver2D',
+           'ClawSolver1D', 'ClawSolver2D', 'ClawSolver3D', 'SharpClawSolver1D', 'SharpClawSolver2D',
            'limiters', 'tvd', 'BC']

@@ -257,3 +257,43 @@ class ClawSolver2D(ClawSolver):
             state._q.put_spare(tmp)
         state._commit(qnew)
         self.cfl.update_global_max(cfl)
+
+
+class ClawSolver3D(ClawSolver):
+    """clawpack.py:563-702.  Only the dimensionally split algorithm (``dim_split=True``, the
+    reference's default: three ``step3ds`` sweeps) is built; the unsplit ``step3`` with its
+    transverse and double-transverse solves raises NotImplementedError."""
+    no_trans = 0
+    trans_inc = 11
+    trans_cor = 22
+
+    def __init__(self, data=None):
+        self._extra_defaults = {'dim_split': True, 'order_trans': self.trans_cor}
+        self.ndim = 3
+        super(ClawSolver3D, self).__init__(data)
+
+    def setup(self, solution):
+        if not self.dim_split:
+            raise NotImplementedError("ClawSolver3D: only dim_split=True (step3ds) is implemented; the "
+                                      "unsplit step3 / flux3 with rpt3 and rptt3 is not")
+        super(ClawSolver3D, self).setup(solution)
+
+    def step_hyperbolic(self, solution):
+        state = solution.states[0]
+        aux = _ptr(state._aux.cur if state._aux is not None else None)
+        dt = float(self.dt)
+        F = state._q
+        qold, b1, b2 = F.cur, F.get_spare(), F.get_spare()
+        mz, dz = int(self._mz), float(self._dz)
+
+        def launch(P, cfl, st):
+            # step3ds three times (clawpack.py:656-676); the Fortran's aliased calls become a
+            # rotation qold -> b1 (x) -> b2 (y) -> b1 (z)
+            _lib.call("clawb200_step3ds", P, mz, dz, _ptr(qold), _ptr(b1), aux, dt, 1, cfl, st)
+            _lib.call("clawb200_step3ds", P, mz, dz, _ptr(b1), _ptr(b2), aux, dt, 2, cfl, st)
+            _lib.call("clawb200_step3ds", P, mz, dz, _ptr(b2), _ptr(b1), aux, dt, 3, cfl, st)
+        self._graph_key = (qold.data_ptr(), b1.data_ptr(), b2.data_ptr())
+        cfl = self._hyperbolic_sequence(state, launch)
+        F.put_spare(b2)
+        state._commit(b1)
+        self.cfl.update_global_max(cfl)

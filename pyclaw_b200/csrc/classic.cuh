@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     const int ic = TRANS ? i0 - 1 + t : i0 + t;      // this thread's column (Fortran index)
     const int icl = min(ic, A.mx + mbc) + mbc - 1;   // clamped array column
     const bool col_out = TRANS ? (t >= 1 && t <= NC && ic <= A.ihi) : (ic <= A.ihi);
-    const bool col_cfl = TRANS ? (ic >= 0 && ic <= A.mx + 1) : (ic <= A.mx + mbc);
+    const bool col_cfl = TRANS ? (ic >= 0 && ic <= A.mx + 1) : (ic <= A.ihi);
     const int j0 = A.jlo + blockIdx.y * A.rows_per_cta;
     const int j1 = min(j0 + A.rows_per_cta, A.jhi + 1);
     const bool order2 = (A.order != 1);

@@ -309,6 +309,100 @@ extern "C" int clawb200_step2ds(const clawb200_problem *p, const double *q_in, d
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// 3-D, dimensional splitting (step3ds.f:2-376; clawpack.py:656-676).  A 3-D field is
+// q[m][k][j][i]; every sweep is a set of independent 1-D problems, so the 2-D engines do the
+// work on 2-D views of the array: x- and y-sweeps plane by plane (k = 0..mz+1), z-sweeps on
+// the (i, k) slices j = 0..my+1 (row stride = one plane).  The arithmetic of flux3.f with
+// method(3) < 0 is that of flux2.f (the 0.5 of the correction flux is applied per term
+// instead of to the sum, an exact scaling).
+// ---------------------------------------------------------------------------
+extern "C" int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, const double *q_in,
+                                double *q_out, const double *aux, double dt, int idir,
+                                double *cfl_dev, void *stream)
+{
+    int rc = check_problem(p, 3);
+    if (rc) return rc;
+    if (p->rp_id != CLAWB200_RP_ACOUSTICS3D_VC)
+        return fail(CLAWB200_ERR_UNSUPPORTED, "no 3-D version of this Riemann solver");
+    if (p->meqn != 4 || p->mwaves != 2) return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
+    if (p->maux < 2 || !aux) return fail(CLAWB200_ERR_INVALID, "aux array required: {impedance, sound speed}");
+    if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for the 3-D sweeps");
+    if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
+    if (mz < 1 || !(dz > 0.0)) return fail(CLAWB200_ERR_INVALID, "mz, dz must be positive");
+    if (q_in == q_out) return fail(CLAWB200_ERR_INVALID, "q_in and q_out must differ");
+    if (idir < 1 || idir > 3) return fail(CLAWB200_ERR_INVALID, "idir must be 1, 2 or 3");
+    const int mbc = p->mbc, nx = p->pitch, ny = p->my + 2 * mbc, nz = mz + 2 * mbc;
+    const long long plane = (long long)nx * ny;
+    if (p->mstride < plane * nz) return fail(CLAWB200_ERR_INVALID, "mstride smaller than the padded field");
+    cudaStream_t st = (cudaStream_t)stream;
+    // step3ds.f: "qold and qnew are identical on entry"; cells the sweep does not touch keep qold
+    CUDA_OK(cudaMemcpyAsync(q_out, q_in, sizeof(double) * (size_t)p->meqn * p->mstride,
+                            cudaMemcpyDeviceToDevice, st));
+    clawb200_problem P2 = *p;
+    P2.ndim = 2;
+    if (idir == 1 || idir == 2) {
+        for (int k = 0; k <= mz + 1; k++) {
+            const long long off = plane * (k + mbc - 1);
+            SweepArgs A = make_args(&P2, q_in + off, q_out + off, dt, cfl_dev, aux + off);
+            A.trans = -1;
+            if (idir == 1) {
+                A.ilo = 1; A.ihi = p->mx; A.jlo = 0; A.jhi = p->my + 1;
+                A.rows_per_cta = pick_rows(A.jhi - A.jlo + 1, (p->mx + XNT - 4) / (XNT - 3));
+                if ((rc = launch_x<RpAcoustics3D<1>, false>(A, st))) return rc;
+            } else {
+                A.ilo = 0; A.ihi = p->mx + 1; A.jlo = 1; A.jhi = p->my;
+                A.rows_per_cta = pick_rows(p->my, (p->mx + 2 + YNT - 1) / YNT);
+                if ((rc = launch_y<RpAcoustics3D<2>, false>(A, st))) return rc;
+            }
+        }
+    } else {
+        clawb200_problem P3 = P2;
+        P3.my = mz;
+        P3.dy = dz;
+        P3.pitch = (int)plane;
+        for (int j = 0; j <= p->my + 1; j++) {
+            const long long off = (long long)nx * (j + mbc - 1);
+            SweepArgs A = make_args(&P3, q_in + off, q_out + off, dt, cfl_dev, aux + off);
+            A.trans = -1;
+            A.ilo = 0; A.ihi = p->mx + 1; A.jlo = 1; A.jhi = mz;
+            A.rows_per_cta = pick_rows(mz, (p->mx + 2 + YNT - 1) / YNT);
+            if ((rc = launch_y<RpAcoustics3D<3>, false>(A, st))) return rc;
+        }
+    }
+    return 0;
+}
+
+__global__ void bc_kernel(double *q, long long mstride, int pitch, int narr, int nx, int ny,
+                          int mbc, int idim, int side, int bctype, int negate);
+
+// Ghost cells of a 3-D field, one side of one dimension (solver.py:384-452 in 3-D).
+extern "C" int clawb200_bc_fill3(const clawb200_problem *p, int mz, double *q, int narr, int idim,
+                                 int side, int bctype, int negate, void *stream)
+{
+    if (!p || !q) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (p->ndim != 3 || idim < 0 || idim > 2 || side < 0 || side > 1)
+        return fail(CLAWB200_ERR_INVALID, "bad ndim/idim/side");
+    if (bctype < CLAWB200_BC_OUTFLOW || bctype > CLAWB200_BC_REFLECTING)
+        return fail(CLAWB200_ERR_INVALID, "bc_fill handles outflow, periodic and reflecting");
+    const int mbc = p->mbc, nx = p->pitch, ny = p->my + 2 * mbc, nz = mz + 2 * mbc;
+    const long long plane = (long long)nx * ny;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto launch = [&](double *base, int pitch, int ex, int ey, int dim2) {
+        const long long total = (long long)((dim2 == 0) ? ey : ex) * mbc * narr;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks < 1) blocks = 1;
+        bc_kernel<<<blocks, 256, 0, st>>>(base, p->mstride, pitch, narr, ex, ey, mbc, dim2, side, bctype, negate);
+    };
+    if (idim == 0) launch(q, nx, nx, ny * nz, 0);             // ghost columns of every (j, k) row
+    else if (idim == 2) launch(q, (int)plane, (int)plane, nz, 1); // ghost planes: "rows" of nx*ny cells
+    else
+        for (int k = 0; k < nz; k++) launch(q + plane * k, nx, nx, ny, 1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int step2_impl(const clawb200_problem *p, const double *qold, double *qnew, const double *aux,
                       double dt, int parts, int jlo, int jhi, double *cfl_dev, void *stream)
 {
@@ -1063,5 +1157,27 @@ extern "C" int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const doubl
                                        CLAWB200_STAGE_DQ_ONLY, 0.0, 0.0, 1.0, g_hs.d_cfl, g_hs.st)))
         return rc;
     if ((rc = host_download(P, g_hs.d_b, dq))) return rc;
+    return host_finish(cfl);
+}
+
+// classic3.step3ds with host arrays q(meqn, mx+2mbc, my+2mbc, mz+2mbc) (clawpack.py:656-676)
+extern "C" int clawb200_step3ds_host(const clawb200_problem *p, int mz, double dz, const double *qold,
+                                     double *qnew, const double *aux, double dt, int idir, double *cfl)
+{
+    if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (p->ndim != 3 || mz < 1) return fail(CLAWB200_ERR_INVALID, "3-D problem expected");
+    clawb200_problem P = *p;
+    P.dt_dev = nullptr;
+    const int nx = p->mx + 2 * p->mbc, ny = p->my + 2 * p->mbc, nz = mz + 2 * p->mbc;
+    P.pitch = nx;
+    P.mstride = (long long)nx * ny * nz;
+    int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
+    if (rc) return rc;
+    if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
+    const double *d_aux;
+    if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
+    if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = clawb200_step3ds(&P, mz, dz, g_hs.d_a, g_hs.d_b, d_aux, dt, idir, g_hs.d_cfl, g_hs.st))) return rc;
+    if ((rc = host_download(P, g_hs.d_b, qnew))) return rc;
     return host_finish(cfl);
 }

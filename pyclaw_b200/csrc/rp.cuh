@@ -29,6 +29,7 @@
 #define CLAW_RP_SPHERE 5
 #define CLAW_RP_NEL_FWAVE 6
 #define CLAW_RP_PSYSTEM 7
+#define CLAW_RP_ACOUSTICS3D_VC 8
 
 // Solvers that return f-waves (jumps in the flux) instead of waves: the sweeps then use the
 // second-order correction of step1fw.f:135-136 / flux2fw.f:151-152.  A member FWAVE = true
@@ -967,5 +968,61 @@ struct RpElasticFwave {
         bp[0] = cp * a2;
         bp[mu] = 0.0;
         bp[mv] = cp * a2 * (-zp);
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// 3-D acoustics in a heterogeneous medium.  clawpack/riemann rpn3_vc_acoustics.f (external;
+// test/acoustics/3d).  q = (p, u, v, w); aux = {impedance Z, sound speed c} of each cell.
+// IXYZ = 1, 2, 3 is the sweep direction.  Normal solve only: the 3-D path here is the
+// dimensionally split one (step3ds.f), which never calls rpt3 / rptt3.
+// ---------------------------------------------------------------------------
+template <int IXYZ>
+struct RpAcoustics3D {
+    static constexpr int ID = CLAW_RP_ACOUSTICS3D_VC;
+    static constexpr int MEQN = 4, MWAVES = 2, NROE = 1;
+    static constexpr int X_MINB = 4, Y_MINB = 4;
+    static constexpr int MAUX = 2;
+    static constexpr bool QCOR = false;
+    static constexpr int MU = IXYZ;
+    __host__ __device__ static constexpr bool nz(int m, int mw) { return m == 0 || m == MU; }
+
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[4],
+                                                 const double (&r)[4], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[4][2], double (&s)[2], double (&amdq)[4],
+                                                 double (&apdq)[4], double (&roe)[NROE])
+    {
+        const double zi = axr(0), zim = axl(0);
+        double delta1 = r[0] - l[0];
+        double delta2 = r[MU] - l[MU];
+        const Recip rz = ar.rcp(zim + zi);
+        double a1 = ar.div(-delta1 + zi * delta2, rz);
+        double a2 = ar.div(delta1 + zim * delta2, rz);
+#pragma unroll
+        for (int m = 0; m < 4; m++) { wave[m][0] = 0.0; wave[m][1] = 0.0; }
+        wave[0][0] = -a1 * zim;
+        wave[MU][0] = a1;
+        s[0] = -axl(1);
+        wave[0][1] = a2 * zi;
+        wave[MU][1] = a2;
+        s[1] = axr(1);
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            amdq[m] = s[0] * wave[m][0];
+            apdq[m] = s[1] * wave[m][1];
+        }
+        roe[0] = 0.0;
+    }
+
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &, const RpParams &, const double (&)[NROE],
+                                                      const double (&)[4], const AuxCell &, const AuxCell &,
+                                                      const AuxCell &, const double (&)[4], double (&bm)[4],
+                                                      double (&bp)[4])
+    {
+#pragma unroll
+        for (int m = 0; m < 4; m++) { bm[m] = 0.0; bp[m] = 0.0; }
     }
 };

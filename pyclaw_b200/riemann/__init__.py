@@ -7,7 +7,7 @@ these descriptors (or its name); if it is left unset the solver is inferred from
 keys of ``state.aux_global`` (the cparam common block the script fills).
 """
 from .._lib import (RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE, RP_NEL_FWAVE,
-                    RP_PSYSTEM)
+                    RP_PSYSTEM, RP_ACOUSTICS3D_VC)
 
 
 class RiemannSolver(object):
@@ -60,7 +60,10 @@ nonlinear_elasticity_fwave = RiemannSolver("nonlinear_elasticity_fwave", RP_NEL_
                                            fwave=True, maux=2)
 psystem = RiemannSolver("psystem", RP_PSYSTEM, 3, 2, [], (2,), fwave=True, maux=4)
 
-_BY_NAME = {s.name: s for s in (acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere,
+# 3-D acoustics in a heterogeneous medium (test/acoustics/3d): aux = {impedance, sound speed}
+vc_acoustics_3d = RiemannSolver("vc_acoustics_3d", RP_ACOUSTICS3D_VC, 4, 2, [], (3,), maux=2)
+
+_BY_NAME = {s.name: s for s in (vc_acoustics_3d, acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere,
                                 nonlinear_elasticity_fwave, psystem)}
 _BY_NAME.update({"euler": euler_5wave, "shallow": shallow_roe_with_efix})
 
@@ -90,6 +93,8 @@ def resolve(rp, aux_global, ndim, fwave=False):
     if rp is not None:
         raise NotImplementedError("Python Riemann solvers are not supported: there is no CPU "
                                   "path; set solver.rp to a pyclaw.riemann descriptor")
+    if ndim == 3:
+        return vc_acoustics_3d       # the only 3-D solver the reference's applications link
     if fwave:
         # the only f-wave solvers the reference's applications link (stegoton, psystem)
         return nonlinear_elasticity_fwave if ndim == 1 else psystem

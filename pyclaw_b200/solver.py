@@ -144,6 +144,8 @@ class Solver(object):
             raise Exception("solver.mwaves = %s does not match Riemann solver %s (%d)"
                             % (self.mwaves, self._rp.name, self._rp.nwaves(grid.ndim)))
         ng, d = grid.ng, grid.d
+        self._mz = ng[2] if grid.ndim > 2 else 1
+        self._dz = d[2] if grid.ndim > 2 else 1.0
         self._problem = _lib.make_problem(
             grid.ndim, state.meqn, self.mwaves, self.mbc, ng[0], ng[1] if grid.ndim > 1 else 1,
             d[0], d[1] if grid.ndim > 1 else 1.0, self._rp.rp_id, self._rp.params(state.aux_global),
@@ -190,8 +192,12 @@ class Solver(object):
                     pass  # wrap-around comes with the halo exchange (solver.py:366-367)
                 elif bc in (BC.outflow, BC.periodic, BC.reflecting):
                     negate = idim + 1 if (is_q and bc == BC.reflecting) else -1
-                    _lib.call("clawb200_bc_fill", ctypes.byref(P), _ptr(arr_field.cur), arr_field.ncomp,
-                              idim, side, bc, negate, _stream())
+                    if grid.ndim == 3:
+                        _lib.call("clawb200_bc_fill3", ctypes.byref(P), self._mz, _ptr(arr_field.cur),
+                                  arr_field.ncomp, idim, side, bc, negate, _stream())
+                    else:
+                        _lib.call("clawb200_bc_fill", ctypes.byref(P), _ptr(arr_field.cur), arr_field.ncomp,
+                                  idim, side, bc, negate, _stream())
                 elif bc is None:
                     raise Exception("One or more of the boundary conditions has not been specified.")
                 else:

@@ -37,8 +37,10 @@ class _Field(object):
 
     @staticmethod
     def user_view(t):
-        """[m][j][i] storage -> [m,i,j] indexing"""
-        return as_claw(t if t.dim() == 2 else t.permute(0, 2, 1))
+        """[m][j][i] / [m][k][j][i] storage -> [m,i,j] / [m,i,j,k] indexing"""
+        if t.dim() == 2:
+            return as_claw(t)
+        return as_claw(t.permute(0, 2, 1) if t.dim() == 3 else t.permute(0, 3, 2, 1))
 
     def padded(self, t=None):
         return self.user_view(self.cur if t is None else t)

@@ -159,3 +159,24 @@ def test_shallow_sphere_golden():
     # src2 + setaux + qinit reproduce all 18 printed digits (heights are O(1e-3))
     assert s.total == {"numsteps": 764, "rejected": 1}
     assert diff < 1e-15 and np.abs(frames[-1][0] - gold).max() < 1e-16
+
+
+def test_acoustics3d_homogeneous_scalar():
+    """test/test_examples.py:474-488 (test/acoustics/3d/acoustics.py, test='hom'): dimensionally
+    split 3-D classic solver, 256x4x4, periodic; |p(T) - p(0)|_1 dx dy dz = 0.00286 +- 1e-4."""
+    mx, my, mz = 256, 4, 4
+    x = (np.arange(mx) + 0.5) * (2.0 / mx) - 1.0
+    X = np.broadcast_to(x[:, None, None], (mx, my, mz))
+    aux = np.ones((2, mx, my, mz), order="F")
+    q0 = np.zeros((4, mx, my, mz), order="F")
+    r = np.sqrt((X + 0.5) ** 2)
+    q0[0] = (np.abs(r) <= 0.2) * (1. + np.cos(np.pi * r / 0.2))
+    s = po.OracleSolver("classic", 3, po.RP_ACOUSTICS3D_VC, [], 2)
+    s.limiters = 4
+    s.bc_lower = s.bc_upper = [po.BC_PERIODIC] * 3
+    s.aux_bc_lower = s.aux_bc_upper = [po.BC_PERIODIC] * 3
+    s.dim_split = True
+    d = [2.0 / mx, 2.0 / my, 2.0 / mz]
+    qf = s.run(q0, aux, d, 2.0, 10)[-1]
+    err = np.prod(d) * np.abs(qf[0] - q0[0]).sum()
+    assert abs(err - 0.00286) < 1e-4, err
