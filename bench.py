@@ -157,7 +157,8 @@ def build_problem(pyclaw, workload, n, nranks, torch):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md): NVML every
+    20 ms when the bindings load, else the recipe's nvidia-smi query every 200 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -165,32 +166,63 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._halt = index, [], threading.Event()
+        self.reasons, self.smax, self.source = set(), None, "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            r = int(get(self._h))
+            for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                              ("hw_thermal_slowdown", 0x40)):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if not out:
+            return
+        f = [x.strip() for x in out.split(",")]
+        if f[0].replace('.', '').isdigit():
+            self.samples.append(int(float(f[0])))
+        if self.smax is None and f[1].replace('.', '').isdigit():
+            self.smax = int(float(f[1]))
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02 if self._nvml is not None else 0.2)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace('.', '').isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for nme, v in zip(names, s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        smax = int(float(self.samples[0][1])) if self.samples else None
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------
