@@ -899,14 +899,16 @@ static double philim(double a, double b, int meth)
 {
     double r = b / a;
     switch (meth) {
-    case 1: return dmax2(0.0, dmin2(1.0, r));
     case 2: return dmax2(dmax2(0.0, dmin2(1.0, 2.0 * r)), dmin2(2.0, r));
     case 3: return (r + fabs(r)) / (1.0 + fabs(r));
     case 4: {
         double c = (1.0 + r) / 2.0;
         return dmax2(0.0, dmin2(dmin2(c, 2.0), 2.0 * r));
     }
-    default: return r;
+    case 5: return r;
+    /* philim.f:19: a computed GO TO whose index is outside 1..5 falls through to the
+       statement that follows it, label 10 (minmod) */
+    default: return dmax2(0.0, dmin2(1.0, r));
     }
 }
 

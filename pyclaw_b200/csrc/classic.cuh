@@ -89,14 +89,15 @@ __device__ __forceinline__ double philim(AR &ar, double a, double b, int meth)
 {
     double r = ar.div(b, a);
     switch (meth) {
-    case 1: return dmax2(0.0, dmin2(1.0, r));
     case 2: return dmax2(dmax2(0.0, dmin2(1.0, 2.0 * r)), dmin2(2.0, r));
     case 3: return ar.div(r + fabs(r), 1.0 + fabs(r));
     case 4: {
         double c = (1.0 + r) / 2.0;
         return dmax2(0.0, dmin2(dmin2(c, 2.0), 2.0 * r));
     }
-    default: return r;
+    case 5: return r;
+    // philim.f:19: a computed GO TO with an index outside 1..5 falls through to label 10
+    default: return dmax2(0.0, dmin2(1.0, r));
     }
 }
 

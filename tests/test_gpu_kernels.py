@@ -555,3 +555,26 @@ def test_sharpclaw_dq1_shallow(mx, variant):
     _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
     assert not np.isnan(dq_o).any()
     assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]) and cfl_g.value == cfl_o
+
+
+def test_limiter_id_range():
+    """philim.f:19 is a computed GO TO: ids 1..5 select minmod, superbee, van Leer, MC and
+    Beam-Warming; any other positive id falls through to minmod."""
+    rp_id, params, meqn, mwaves, _ = RPS["acoustics"]
+    mx, my, mbc = 60, 21, 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    method = [1, 2, 2, 0, 0, 0, 0]
+    q = _random_padded("acoustics", mx, my, mbc, seed=3)
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    out = {}
+    for lim in ([5, 3], [9, 23], [1, 1]):
+        P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+        qn_o = q.copy("F")
+        po.step2(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim)
+        qn_g = q.copy("F")
+        cfl_g = ctypes.c_double()
+        _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), None, dt, ctypes.byref(cfl_g))
+        assert np.array_equal(qn_g[inner], qn_o[inner]), lim
+        out[tuple(lim)] = qn_g[inner].copy()
+    assert np.array_equal(out[(9, 23)], out[(1, 1)])
+    assert not np.array_equal(out[(5, 3)], out[(1, 1)])
