@@ -62,6 +62,8 @@ extern "C" {
 #define CLAWB200_WENO_PYWENO_F32 0 /* weno.f90:35-98 with its kind-less literals read as REAL(4) */
 #define CLAWB200_WENO_PYWENO_F64 1 /* same formulas, literals read as doubles                    */
 #define CLAWB200_WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)                     */
+#define CLAWB200_WENO_TABLES 3     /* weno.f90:104-2425, orders 7..17 (1-D): coefficient tables set
+                                      with clawb200_set_weno_tables                               */
 
 #define CLAWB200_ERR_INVALID (-1)
 #define CLAWB200_ERR_UNSUPPORTED (-2)

@@ -45,6 +45,7 @@
 #define WENO_PYWENO_F32 0 /* weno.f90 literals read as REAL(4), as gfortran does */
 #define WENO_PYWENO_F64 1 /* same formulas, literals read as doubles            */
 #define WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)              */
+#define WENO_TABLES 3     /* weno.f90:104-2425 (orders 7..17) through coefficient tables */
 
 typedef struct {
     int rp_id;
@@ -1482,6 +1483,83 @@ static void weno5_pyweno(const double *q, double *ql, double *qr, int meqn, int 
     }
 }
 
+/* weno.f90:104-2425: the PyWENO-generated subroutines weno7 .. weno17 all have the shape of
+   weno5 above with k = (order+1)/2 stencils.  Their ~2000 literals are not copied: the caller
+   supplies the tables (regenerated from the formulas' definition and spot-checked against
+   literals of the reference in tests/test_oracle_golden.py), this routine is the arithmetic.
+   S[r][pair(a<=b)], CL/CR[r][j], WL/WR[r]; stencil r = cells i-r .. i-r+k-1. */
+static struct {
+    int k;
+    double S[9][45], CL[9][9], CR[9][9], WL[9], WR[9], eps;
+} g_weno;
+
+void oracle_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
+                            const double *WL, const double *WR, double eps)
+{
+    const int npair = k * (k + 1) / 2;
+    g_weno.k = k;
+    g_weno.eps = eps;
+    for (int r = 0; r < k; r++) {
+        for (int n = 0; n < npair; n++) g_weno.S[r][n] = S[r * npair + n];
+        for (int j = 0; j < k; j++) { g_weno.CL[r][j] = CL[r * k + j]; g_weno.CR[r][j] = CR[r * k + j]; }
+        g_weno.WL[r] = WL[r];
+        g_weno.WR[r] = WR[r];
+    }
+}
+
+static void weno_tables(const double *q, double *ql, double *qr, int meqn, int mx, int mbc)
+{
+    const int k = g_weno.k;
+    const double eps = g_weno.eps;
+    for (int p = mbc; p <= mx + mbc + 1; p++) {
+        for (int m = 0; m < meqn; m++) {
+            double sigma[9], omega[18], fr[18];
+            for (int r = 0; r < k; r++) {
+                double sg = 0.0;
+                int n = 0;
+                for (int a = 0; a < k; a++)
+                    for (int b = a; b < k; b++) {
+                        double t = ((g_weno.S[r][n]) * QP(q, m, p - r + a)) * QP(q, m, p - r + b);
+                        sg = (n == 0) ? t : sg + t;
+                        n++;
+                    }
+                sigma[r] = sg;
+            }
+            double acc = 0.0;
+            for (int r = 0; r < k; r++) {
+                omega[r] = g_weno.WL[r] / ((sigma[r] + eps) * (sigma[r] + eps));
+                acc = acc + omega[r];
+            }
+            for (int r = 0; r < k; r++) omega[r] = omega[r] / acc;
+            acc = 0.0;
+            for (int r = 0; r < k; r++) {
+                omega[k + r] = g_weno.WR[r] / ((sigma[r] + eps) * (sigma[r] + eps));
+                acc = acc + omega[k + r];
+            }
+            for (int r = 0; r < k; r++) omega[k + r] = omega[k + r] / acc;
+            for (int r = 0; r < k; r++) {
+                double fl = 0.0, fq = 0.0;
+                for (int j = 0; j < k; j++) {
+                    double tl = (g_weno.CL[r][j]) * QP(q, m, p - r + j);
+                    double tr = (g_weno.CR[r][j]) * QP(q, m, p - r + j);
+                    fl = (j == 0) ? tl : fl + tl;
+                    fq = (j == 0) ? tr : fq + tr;
+                }
+                fr[r] = fl;
+                fr[k + r] = fq;
+            }
+            double fs0 = 0.0, fs1 = 0.0;
+            for (int r = 0; r < k; r++) {
+                double t0 = (omega[r]) * (fr[r]), t1 = (omega[k + r]) * (fr[k + r]);
+                fs0 = (r == 0) ? t0 : fs0 + t0;
+                fs1 = (r == 0) ? t1 : fs1 + t1;
+            }
+            QP(ql, m, p) = fs0;
+            QP(qr, m, p) = fs1;
+        }
+    }
+}
+
 /* reconstruct.f90:120-185 (hand-written weno5, lim_type = 3) */
 static void weno5_old(const double *q, double *ql, double *qr, int meqn, int mx, int mbc,
                       double *dq1m, double *uu)
@@ -1570,6 +1648,7 @@ static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double d
     memcpy(ql, q1d, sizeof(double) * n * meqn);
     memcpy(qr, q1d, sizeof(double) * n * meqn);
     if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
+    else if (weno_variant == WENO_TABLES) weno_tables(q1d, ql, qr, meqn, mx, mbc);
     else weno5_pyweno(q1d, ql, qr, meqn, mx, mbc, weno_variant == WENO_PYWENO_F32);
     rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, NULL, NULL, wave, s, amdq, apdq);
     double cfl = 0.0;

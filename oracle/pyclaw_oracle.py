@@ -25,7 +25,7 @@ _LIB = None
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 RP_NEL_FWAVE, RP_PSYSTEM = 6, 7   # f-wave solvers (step1fw.f / flux2fw.f corrections)
 RP_ACOUSTICS3D_VC = 8              # 3-D variable-coefficient acoustics (dimensional splitting)
-WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
+WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES = 0, 1, 2, 3
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -51,6 +51,8 @@ def lib():
         L.oracle_step2ds.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, _ip, _ip, i]
         L.oracle_step2.restype = d
         L.oracle_step2.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, _ip, _ip]
+        L.oracle_set_weno_tables.restype = None
+        L.oracle_set_weno_tables.argtypes = [i, _dp, _dp, _dp, _dp, _dp, d]
         L.oracle_step3ds.restype = d
         L.oracle_step3ds.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, d, _ip, _ip, i]
         L.oracle_sc_flux1.restype = d
@@ -151,6 +153,14 @@ def step2_slabs(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, me
     return lib().oracle_step2_slabs(rp_id, _p(_params(rp_params)), meqn, len(mthlim), maux, mbc,
                                     mx, my, _p(qold), _p(qnew), _p(aux), dx, dy, dt,
                                     _pi(method), _pi(mthlim), nthreads, int(dimsplit))
+
+
+def set_weno_tables(tab):
+    """Coefficient tables for weno_variant = WENO_TABLES (orders 7..17): dict with k, S[k][k(k+1)/2],
+    CL/CR[k][k], WL/WR[k], eps (see oracle_set_weno_tables in claw_oracle.c)."""
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    S, CL, CR, WL, WR = c(tab['S']), c(tab['CL']), c(tab['CR']), c(tab['WL']), c(tab['WR'])
+    lib().oracle_set_weno_tables(int(tab['k']), _p(S), _p(CL), _p(CR), _p(WL), _p(WR), float(tab['eps']))
 
 
 def sc_flux1(rp_id, rp_params, mwaves, mbc, mx, q, dx, dt, weno_variant, auxbc=None, mcapa=0):
@@ -264,6 +274,7 @@ class OracleSolver(object):
         else:
             self.mbc, self.cfl_max, self.cfl_desired = 3, 2.5, 2.45
             self.time_integrator, self.weno_variant = "SSP104", WENO_PYWENO_F32
+            self.weno_order, self.weno_tables = 5, None
         self.mcapa = -1
         self.cfl = self.cfl_desired
         self.status = {}
@@ -272,6 +283,12 @@ class OracleSolver(object):
     # ---- setup (clawpack.py:214-238, sharpclaw.py:303-326) ----
     def setup(self, q, aux, d):
         self.d = list(d)
+        if self.kind == "sharpclaw" and self.weno_order != 5:
+            # sharpclaw.py:303-304 mbc = (weno_order+1)/2 ; reconstruct.f90:96-113 selects weno<order>;
+            # the caller supplies the coefficient tables (set_weno_tables)
+            self.mbc = (self.weno_order + 1) // 2
+            set_weno_tables(self.weno_tables)
+            self.weno_variant = WENO_TABLES
         mbc = self.mbc
         self.n = list(q.shape[1:])
         self.qbc = np.zeros([q.shape[0]] + [n + 2 * mbc for n in self.n], order="F")

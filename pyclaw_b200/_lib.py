@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("CLAWB200_LIB") or os.path.join(_HERE, "csrc", "libcla
 MAXWAVES = 8
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 RP_NEL_FWAVE, RP_PSYSTEM, RP_ACOUSTICS3D_VC = 6, 7, 8
-WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD = 0, 1, 2
+WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES = 0, 1, 2, 3
 STAGE_AXPY, STAGE_CONVEX, STAGE_FINAL104, STAGE_DQ_ONLY = 0, 1, 2, 3
 
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "clawb200_step2ds_host": [_pp, _dp, _dp, _dp, _d, _i, _dref],
     "clawb200_step2_host": [_pp, _dp, _dp, _dp, _d, _dref],
     "clawb200_sharpclaw_dq_host": [_pp, _dp, _dp, _dp, _d, _dref],
+    "clawb200_set_weno_tables": [_i, _dp, _dp, _dp, _dp, _dp, _d, _vp],
     "clawb200_step3ds": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dp, _vp],
     "clawb200_bc_fill3": [_pp, _i, _dp, _i, _i, _i, _i, _i, _vp],
     "clawb200_step3ds_host": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dref],

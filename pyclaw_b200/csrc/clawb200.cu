@@ -624,6 +624,42 @@ extern "C" int clawb200_halo_unpack(const clawb200_problem *p, double *q, int na
 // ---------------------------------------------------------------------------
 constexpr int SNT = 128;
 
+static int g_weno_k = 0; // stencils of the table-driven WENO currently in constant memory
+
+extern "C" int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
+                                        const double *WL, const double *WR, double eps, void *stream)
+{
+    if (k < 3 || k > 9) return fail(CLAWB200_ERR_INVALID, "weno_order must be an odd number between 5 and 17");
+    if (!S || !CL || !CR || !WL || !WR) return fail(CLAWB200_ERR_INVALID, "null table");
+    static WenoTab h; // staging copy: must outlive the asynchronous upload
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    memset(&h, 0, sizeof(h));
+    const int npair = k * (k + 1) / 2;
+    h.k = k;
+    h.eps = eps;
+    for (int r = 0; r < k; r++) {
+        for (int n = 0; n < npair; n++) h.S[r][n] = S[r * npair + n];
+        for (int j = 0; j < k; j++) { h.CL[r][j] = CL[r * k + j]; h.CR[r][j] = CR[r * k + j]; }
+        h.WL[r] = WL[r];
+        h.WR[r] = WR[r];
+    }
+    CUDA_OK(cudaMemcpyToSymbolAsync(c_weno, &h, sizeof(h), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    g_weno_k = k;
+    return 0;
+}
+
+template <class RP>
+static int sc_launch1_tab(const ScArgs &A, cudaStream_t st)
+{
+    constexpr int NC = SNT - 2;
+    const int H = g_weno_k - 1;
+    size_t smem = sizeof(double) * (RP::MEQN * (SNT + 2 * H) + 2 * RP::MEQN * SNT);
+    sc1d_tab_kernel<RP, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static void weno_constants(ScArgs &A, int variant)
 {
     const bool f32 = (variant == CLAWB200_WENO_PYWENO_F32);
@@ -679,6 +715,18 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
     A.mode = mode; A.ca = ca; A.cb = cb; A.div = div;
     A.cfl_bits = (unsigned long long *)cfl_dev;
     const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
+    if (p->weno_variant == CLAWB200_WENO_TABLES) {
+        if (p->ndim != 1) return fail(CLAWB200_ERR_UNSUPPORTED, "WENO orders above 5 are compiled for 1-D only");
+        if (g_weno_k < 3) return fail(CLAWB200_ERR_INVALID, "call clawb200_set_weno_tables first");
+        if (p->mbc < g_weno_k) return fail(CLAWB200_ERR_INVALID, "WENO of order 2k-1 needs mbc >= k");
+        if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for WENO orders above 5");
+        switch (p->rp_id) {
+        case CLAWB200_RP_ACOUSTICS: return sc_launch1_tab<RpAcoustics<1, 1>>(A, st);
+        case CLAWB200_RP_ADVECTION: return sc_launch1_tab<RpAdvection<1, 1>>(A, st);
+        case CLAWB200_RP_SHALLOW: return sc_launch1_tab<RpShallow1D>(A, st);
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
+        }
+    }
     if (p->method[5] > 0) {
         // capacity function (flux1.f90:59-63): compiled for the acoustics and advection solvers
         A.capa = aux + (long long)(p->method[5] - 1) * p->mstride;

@@ -178,12 +178,21 @@ __device__ __forceinline__ void stage_store(const ScArgs &A, long long idx, cons
 // x-direction of one row, shared by the 1-D and 2-D kernels.  On entry qs holds the
 // staged row (index k <-> cell i0-3+k).  Returns dq_x for the thread's cell; full=false
 // computes only the interface solve (rows 0 and my+1 contribute to the CFL number only).
+// Everything of flux1.f90 after the reconstruction (:129-192), for the cell / interface of
+// thread t: interface solve with the left neighbour's right-edge value, CFL, in-cell solve,
+// fluctuation sum.
+template <class RP, int NT>
+__device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql)[RP::MEQN],
+                                              const double (&qr)[RP::MEQN], double *x1, double *x2,
+                                              int t, bool iface_cfl, bool full, double &cfl,
+                                              double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l);
+
 template <class RP, bool OLD, int NT>
 __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, double *x1, double *x2,
                                         int t, bool iface_cfl, bool full, double &cfl,
                                         double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l)
 {
-    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    constexpr int MEQN = RP::MEQN;
     constexpr int QS = NT + 4;
     double ql[MEQN], qr[MEQN];
     with_arith([&](auto &ar) {
@@ -193,6 +202,16 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
             weno5<OLD>(ar, A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m]);
         }
     });
+    sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, iface_cfl, full, cfl, dqx, dtdx_c, dtdx_l);
+}
+
+template <class RP, int NT>
+__device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql)[RP::MEQN],
+                                              const double (&qr)[RP::MEQN], double *x1, double *x2,
+                                              int t, bool iface_cfl, bool full, double &cfl,
+                                              double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l)
+{
+    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
 #pragma unroll
     for (int m = 0; m < MEQN; m++) x1[m * NT + t] = qr[m];
     __syncthreads();
@@ -400,3 +419,107 @@ __global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
     sc_cfl_commit(cfl, A.cfl_bits);
 }
 
+
+
+// ---------------------------------------------------------------------------
+// WENO of order 7 .. 17 (weno.f90:104-2425), 1-D.  The generated subroutines all have the
+// shape of weno5 with k = (order+1)/2 stencils; the kernel walks coefficient tables held in
+// constant memory (regenerated on the host from the formulas' definition,
+// pyclaw_b200/weno_tables.py) in the order the generated code evaluates its terms.
+// ---------------------------------------------------------------------------
+struct WenoTab {
+    int k;
+    double S[9][45], CL[9][9], CR[9][9], WL[9], WR[9], eps;
+};
+__constant__ WenoTab c_weno;
+
+template <class AR>
+__device__ __forceinline__ void weno_tab(AR &ar, const double *row /* cell i at row[0] */, double &ql, double &qr)
+{
+    const int k = c_weno.k;
+    const double eps = c_weno.eps;
+    double sigma[9], omega[18];
+    for (int r = 0; r < k; r++) {
+        double sg = 0.0;
+        int n = 0;
+        for (int a = 0; a < k; a++)
+            for (int b = a; b < k; b++) {
+                double tt = ((c_weno.S[r][n]) * row[a - r]) * row[b - r];
+                sg = (n == 0) ? tt : sg + tt;
+                n++;
+            }
+        sigma[r] = sg;
+    }
+    double acc = 0.0;
+    for (int r = 0; r < k; r++) {
+        omega[r] = ar.div(c_weno.WL[r], (sigma[r] + eps) * (sigma[r] + eps));
+        acc = acc + omega[r];
+    }
+    {
+        const Recip ra = ar.rcp(acc);
+        for (int r = 0; r < k; r++) omega[r] = ar.div(omega[r], ra);
+    }
+    acc = 0.0;
+    for (int r = 0; r < k; r++) {
+        omega[k + r] = ar.div(c_weno.WR[r], (sigma[r] + eps) * (sigma[r] + eps));
+        acc = acc + omega[k + r];
+    }
+    {
+        const Recip ra = ar.rcp(acc);
+        for (int r = 0; r < k; r++) omega[k + r] = ar.div(omega[k + r], ra);
+    }
+    double fs0 = 0.0, fs1 = 0.0;
+    for (int r = 0; r < k; r++) {
+        double fl = 0.0, fq = 0.0;
+        for (int j = 0; j < k; j++) {
+            double tl = (c_weno.CL[r][j]) * row[j - r];
+            double tr = (c_weno.CR[r][j]) * row[j - r];
+            fl = (j == 0) ? tl : fl + tl;
+            fq = (j == 0) ? tr : fq + tr;
+        }
+        double t0 = (omega[r]) * (fl), t1 = (omega[k + r]) * (fq);
+        fs0 = (r == 0) ? t0 : fs0 + t0;
+        fs1 = (r == 0) ? t1 : fs1 + t1;
+    }
+    ql = fs0;
+    qr = fs1;
+}
+
+template <class RP, int NT>
+__global__ void __launch_bounds__(NT) sc1d_tab_kernel(const ScArgs A)
+{
+    constexpr int MEQN = RP::MEQN;
+    constexpr int NC = NT - 2;
+    const int k = c_weno.k;
+    const int H = k - 1;            // halo cells of the stencil on each side
+    const int QS = NT + 2 * H;
+    extern __shared__ double sm[];
+    double *qs = sm;                // [MEQN][NT + 2H], index e <-> cell i0-1-H+e
+    double *x1 = qs + MEQN * QS;
+    double *x2 = x1 + MEQN * NT;
+    const int t = threadIdx.x;
+    const int mbc = A.mbc;
+    const int i0 = 1 + blockIdx.x * NC;
+    const int ic = i0 - 1 + t;
+    const int imax = A.mx + mbc;
+    const int icl = min(ic, imax) + mbc - 1;
+    const bool col_out = (t >= 1) && (t <= NC) && (ic <= A.mx);
+    const bool xiface = (t >= 1) && (ic >= 1) && (ic <= A.mx + 1);
+    for (int e = t; e < QS; e += NT) {
+        const int c = min(max(i0 - 1 - H + e, 1 - mbc), imax) + mbc - 1;
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) qs[m * QS + e] = A.q[m * A.mstride + c];
+    }
+    __syncthreads();
+    double cfl = 0.0;
+    double q0[MEQN], ql[MEQN], qr[MEQN], dqx[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) { q0[m] = qs[m * QS + t + H]; dqx[m] = 0.0; }
+    with_arith([&](auto &ar) {
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) weno_tab(ar, qs + m * QS + t + H, ql[m], qr[m]);
+    });
+    sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, xiface, true, cfl, dqx, A.dtdx, A.dtdx);
+    if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
+    sc_cfl_commit(cfl, A.cfl_bits);
+}

@@ -205,9 +205,19 @@ class SharpClawSolver(Solver):
         """sharpclaw.py:303-326 / 475-498"""
         if self.kernel_language not in ('Fortran', 'CUDA'):
             raise NotImplementedError("only the CUDA kernels exist; there is no Python/CPU path")
+        if self.weno_order not in (5, 7, 9, 11, 13, 15, 17):
+            # reconstruct.f90:111-113
+            raise Exception("weno_order must be an odd number between 5 and 17 (inclusive).")
         if self.weno_order != 5:
-            raise NotImplementedError("weno_order=%s: only WENO5 is implemented" % self.weno_order)
-        if self.lim_type == 2 and self.char_decomp == 0:
+            # weno7 .. weno17 (weno.f90:104-2425): table-driven kernel, 1-D component-wise only
+            if self.ndim != 1 or self.lim_type != 2 or self.char_decomp != 0:
+                raise NotImplementedError("weno_order > 5 is implemented for SharpClawSolver1D with "
+                                          "lim_type=2, char_decomp=0")
+            from .weno_tables import tables
+            import numpy as np
+            tab = tables((self.weno_order + 1) // 2, self.weno_literals)
+            variant = _lib.WENO_TABLES
+        elif self.lim_type == 2 and self.char_decomp == 0:
             variant = _lib.WENO_PYWENO_F32 if self.weno_literals == 'f32' else _lib.WENO_PYWENO_F64
         elif self.lim_type == 3:
             variant = _lib.WENO_OLD
@@ -224,6 +234,10 @@ class SharpClawSolver(Solver):
         # clawparams.mcapa = state.mcapa + 1 (sharpclaw.py:270)
         method = [int(self.dt_variable), 2, 0, 0, 0, state.mcapa + 1, state.maux]
         self._setup_device(state, method=method, weno_variant=variant)
+        if variant == _lib.WENO_TABLES:
+            arr = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('S', 'CL', 'CR', 'WL', 'WR')]
+            _lib.call("clawb200_set_weno_tables", int(tab['k']),
+                      *[ctypes.c_void_p(a.ctypes.data) for a in arr], float(tab['eps']), _stream())
         self.allocate_bc_arrays(state)
         self._aux_ptr = _ptr(state._aux.cur if state._aux is not None else None)
         self._dq_field = None

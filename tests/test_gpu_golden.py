@@ -60,6 +60,21 @@ def test_acoustics1d_classic():
     assert abs(err - 0.00104856594174) < 1e-14          # test_examples.py:59-66 (tolerance 1e-5)
 
 
+def test_acoustics1d_sharpclaw_weno17():
+    # test_examples.py:162-169: 0.000163221216565 within the reference's own 1e-5
+    err, claw = _acoustics1d('sharpclaw', weno_order=17)
+    assert abs(err - 0.000163221216565) < 1e-5, err
+    # and the oracle driver with the same tables gives the same frames bit for bit
+    from pyclaw_b200.weno_tables import tables
+    pb = problems.acoustics1d(100)
+    s = po.OracleSolver("sharpclaw", 1, po.RP_ACOUSTICS, pb["params"], 2)
+    s.bc_lower = s.bc_upper = [po.BC_PERIODIC]
+    s.dt_initial = pb["dt_initial"]
+    s.weno_order, s.weno_tables = 17, tables(9, 'f32')
+    fr = s.run(pb["q"], None, pb["d"], 1.0, 5)
+    assert np.array_equal(np.asarray(claw.frames[-1].state.q), fr[-1])
+
+
 def test_acoustics1d_sharpclaw():
     err, _ = _acoustics1d('sharpclaw', weno_literals='f64')
     assert abs(err - 0.000298935748775) < 1e-12          # test_examples.py:125-150 (tolerance 1e-5)

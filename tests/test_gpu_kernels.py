@@ -578,3 +578,40 @@ def test_limiter_id_range():
         out[tuple(lim)] = qn_g[inner].copy()
     assert np.array_equal(out[(9, 23)], out[(1, 1)])
     assert not np.array_equal(out[(5, 3)], out[(1, 1)])
+
+
+# ---------------------------------------------------------------------------
+# WENO of order 7 .. 17 (weno.f90:104-2425), 1-D, table driven
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [7, 9, 11, 13, 15, 17])
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "shallow"])
+@pytest.mark.parametrize("literals", ["f32", "f64"])
+def test_sharpclaw_high_order_weno(order, rp, literals):
+    from pyclaw_b200.weno_tables import tables
+    k = (order + 1) // 2
+    mbc = k
+    rp_id, params, _, mwaves, _ = RPS[rp]
+    meqn = {"acoustics": 2, "advection": 1, "shallow": 2}[rp]
+    mwaves = {"acoustics": 2, "advection": 1, "shallow": 2}[rp]
+    params = [1.0, 1.0, 1.0, 1.0] if rp == "acoustics" else params
+    tab = tables(k, literals)
+    po.set_weno_tables(tab)
+    arr = [np.ascontiguousarray(tab[n], dtype=np.float64) for n in ('S', 'CL', 'CR', 'WL', 'WR')]
+    _lib.call("clawb200_set_weno_tables", k, *[_ptr(a) for a in arr], float(tab['eps']), None)
+    for mx in (11, 300):
+        dx, dt = 1.0 / mx, 0.1 / mx
+        q = _shallow1d_data(mx, mbc, mx + order, True) if rp == "shallow" else \
+            _random_padded(rp, mx, 0, mbc, seed=mx + order, smooth=True)
+        P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, weno_variant=_lib.WENO_TABLES)
+        dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, po.WENO_TABLES)
+        dq_g = np.zeros_like(q, order="F")
+        cfl_g = ctypes.c_double()
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
+        assert not np.isnan(dq_o).any()
+        assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]), np.abs(dq_g - dq_o)[:, mbc:-mbc].max()
+        assert cfl_g.value == cfl_o
+    # orders above 5 are refused in 2-D, and too few ghost cells are refused
+    P2 = _lib.make_problem(2, 3, 2, mbc, 20, 20, 0.1, 0.1, 1, [1.0, 4.0, 2.0, 2.0], weno_variant=_lib.WENO_TABLES)
+    q2 = np.zeros((3, 20 + 2 * mbc, 20 + 2 * mbc), order="F")
+    with pytest.raises(_lib.ClawB200Error, match="1-D"):
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P2), _ptr(q2), _ptr(q2.copy("F")), None, 0.01, ctypes.byref(cfl_g))

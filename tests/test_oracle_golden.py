@@ -180,3 +180,52 @@ def test_acoustics3d_homogeneous_scalar():
     qf = s.run(q0, aux, d, 2.0, 10)[-1]
     err = np.prod(d) * np.abs(qf[0] - q0[0]).sum()
     assert abs(err - 0.00286) < 1e-4, err
+
+
+def test_weno_tables_match_the_reference_literals():
+    """The regenerated WENO coefficients against literals of the reference's generated code
+    (src/fortran/1d/sharpclaw/weno.f90): weno5 :35-90, weno7 :139-215, weno17 :1779-2240."""
+    from pyclaw_b200.weno_tables import exact_tables, tables
+    T = exact_tables(3)
+    assert [float(v) for v in T['WL']] == [0.1, 0.6, 0.3] and [float(v) for v in T['WR']] == [0.3, 0.6, 0.1]
+    lit = lambda x, ref: abs(float(x) - ref) <= 0.6e-14 * max(1.0, abs(ref)) * 10
+    assert lit(T['S'][0][(0, 0)], 3.33333333333333) and lit(T['S'][0][(0, 1)], -10.3333333333333)
+    assert lit(T['CL'][0][0], 1.83333333333333) and lit(T['CR'][0][2], -0.166666666666667)
+    T = exact_tables(4)
+    for (r, ab), ref in {(0, (0, 0)): 8.77916666666667, (0, (0, 1)): -39.175, (0, (1, 2)): -71.8583333333333,
+                         (1, (0, 0)): 2.27916666666667, (1, (2, 3)): -6.84166666666667,
+                         (2, (0, 2)): 6.675, (3, (0, 1)): -16.175}.items():
+        assert lit(T['S'][r][ab], ref), (r, ab)
+    assert lit(T['WL'][3], 0.114285714285714) and lit(T['WR'][1], 0.514285714285714)
+    assert lit(T['WR'][3], 0.0285714285714286)
+    assert [lit(a, b) for a, b in zip(T['CL'][0], [2.08333333333333, -1.91666666666667, 1.08333333333333, -0.25])] == [True] * 4
+    assert [lit(a, b) for a, b in zip(T['CR'][1], [-0.0833333333333333, 0.583333333333333, 0.583333333333333, -0.0833333333333333])] == [True] * 4
+    T = exact_tables(9)
+    assert lit(T['S'][0][(0, 0)], 669.714981108808) and lit(T['S'][0][(0, 1)], -8893.78045641284)
+    assert lit(T['WL'][0], 4.11353352529823e-05) and lit(T['WR'][0], 0.000370218017276841)
+    assert lit(T['WR'][8], 4.11353352529823e-05)
+    assert lit(T['CL'][0][0], 2.82896825396825) and lit(T['CL'][0][1], -6.17103174603175)
+    for k in range(3, 10):
+        T = exact_tables(k)
+        assert sum(T['WL']) == 1 and sum(T['WR']) == 1
+        assert all(sum(row) == 1 for row in T['CL']) and all(sum(row) == 1 for row in T['CR'])
+    # table-driven arithmetic with k = 3 is the dedicated weno5 code, bit for bit
+    q = problems.smooth_state('acoustics', (206,), seed=4)
+    po.set_weno_tables(tables(3, 'f32'))
+    a, ca = po.sc_flux1(1, [1, 1, 1, 1], 2, 3, 200, q, 0.005, 0.0015, po.WENO_PYWENO_F32)
+    b, cb = po.sc_flux1(1, [1, 1, 1, 1], 2, 3, 200, q, 0.005, 0.0015, po.WENO_TABLES)
+    assert np.array_equal(a, b) and ca == cb
+
+
+def test_acoustics1d_weno17_scalar():
+    """test/test_examples.py:162-169: SharpClaw SSP104 with weno_order=17, 1-D acoustics, 100 cells:
+    0.000163221216565 +- 1e-5 (the reference's own tolerance; REAL(4) literals give 0.0001609)."""
+    from pyclaw_b200.weno_tables import tables
+    pb = problems.acoustics1d(100)
+    s = po.OracleSolver("sharpclaw", 1, po.RP_ACOUSTICS, pb["params"], 2)
+    s.bc_lower = s.bc_upper = [po.BC_PERIODIC]
+    s.dt_initial = pb["dt_initial"]
+    s.weno_order, s.weno_tables = 17, tables(9, 'f32')
+    fr = s.run(pb["q"], None, pb["d"], 1.0, 5)
+    err = pb["d"][0] * np.abs(fr[-1] - fr[0]).sum()
+    assert abs(err - 0.000163221216565) < 1e-5, err
