@@ -155,6 +155,14 @@ int clawb200_sharpclaw_stage(const clawb200_problem *p, const double *q, const d
  * over n contiguous doubles (whole padded buffers). */
 int clawb200_ssp104_combine(const double *q, double *s1, double *s2, long long n, void *stream);
 
+/* Coefficient tables for weno_variant = CLAWB200_WENO_TABLES: k = (weno_order+1)/2 in 3..9
+ * stencils; S[k][k(k+1)/2] smoothness quadratic forms (pairs a <= b in stencil order),
+ * CL/CR[k][k] left / right edge reconstruction, WL/WR[k] ideal weights, eps (the 1e-36 of the
+ * generated code).  Replaces the literals of weno7 .. weno17 (weno.f90:104-2425), selected
+ * at reconstruct.f90:96-113.  Host pointers; the call returns after the upload. */
+int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
+                             const double *WL, const double *WR, double eps, void *stream);
+
 /* apps/shallow-sphere/src2.f:2-147 (the f2py `problem.src2` the reference script wraps as
  * solver.step_src): Coriolis source term with tangent-plane projection, in place on the
  * interior cells of q; aux is the 16-component sphere array. */
