@@ -195,7 +195,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
     constexpr int MEQN = RP::MEQN;
     constexpr int QS = NT + 4;
     double ql[MEQN], qr[MEQN];
-    with_arith([&](auto &ar) {
+    with_arith_fz([&](auto &ar) {
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             const double *row = qs + m * QS + t;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql
     double left[MEQN];
 #pragma unroll
     for (int m = 0; m < MEQN; m++) left[m] = x1[m * NT + (t > 0 ? t - 1 : 0)];
-    with_arith([&](auto &ar) { RP::solve(ar, A.rp, left, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
+    with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, left, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
     if (iface_cfl) {
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx_c * s[mw]), -dtdx_l * s[mw]);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql
     __syncthreads();
     if (full) {
         double amdq2[MEQN], apdq2[MEQN];
-        with_arith([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
+        with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             double an = x2[m * NT + (t < NT - 1 ? t + 1 : t)];
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
                 dtdy_c = sc_dtd(A.dt, A.dy, __ldg(&A.capa[(long long)A.pitch * (c + mbc - 1) + icl]));
             }
             double ql[MEQN], qr[MEQN];
-            with_arith([&](auto &ar) {
+            with_arith_fz([&](auto &ar) {
 #pragma unroll
                 for (int m = 0; m < MEQN; m++)
                     weno5<OLD>(ar, A, w0[m], w1[m], w2[m], w3[m], w4[m], ql[m], qr[m]);
@@ -345,14 +345,14 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
 #pragma unroll
             for (int m = 0; m < MEQN; m++) { amdq[m] = apdq[m] = amdq2[m] = apdq2[m] = 0.0; }
             if (c >= j0) {
-                with_arith([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
+                with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
                 if (ycol && c >= 1 && c <= A.my + 1) {
 #pragma unroll
                     for (int mw = 0; mw < MW; mw++)
                         cfl = dmax2(dmax2(cfl, dtdy_c * s[mw]), -dtdy_p * s[mw]);
                 }
                 if (c < j1)
-                    with_arith([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
+                    with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
                 // cell c-1 = k-3 is complete
                 const int jc = c - 1;
                 if (jc >= j0 && jc < j1 && col_out) {
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(NT) sc1d_tab_kernel(const ScArgs A)
     double q0[MEQN], ql[MEQN], qr[MEQN], dqx[MEQN];
 #pragma unroll
     for (int m = 0; m < MEQN; m++) { q0[m] = qs[m * QS + t + H]; dqx[m] = 0.0; }
-    with_arith([&](auto &ar) {
+    with_arith_fz([&](auto &ar) {
 #pragma unroll
         for (int m = 0; m < MEQN; m++) weno_tab(ar, qs + m * QS + t + H, ql[m], qr[m]);
     });
