@@ -49,6 +49,12 @@ extern "C" {
 #define CLAWB200_RP_NEL_FWAVE 6 /* rp1_nonlinear_elasticity_fwave (apps/elasticity/1d/stegoton);
                                    aux {rho, K}; params {stress law: 1 linear, 2 exponential} */
 #define CLAWB200_RP_PSYSTEM 7   /* rpn2/rpt2_psystem (test/psystem); aux {rho, E, law, eps} */
+/* further solvers of the reference's applications (external clawpack/riemann sources) */
+#define CLAWB200_RP_VC_ACOUSTICS 9    /* rpn2/rpt2_vc_acoustics (apps/acoustics/2d/variable); aux {rho, c} */
+#define CLAWB200_RP_BURGERS 10        /* rp1_burgers with entropy fix (apps/burgers/1d)                   */
+#define CLAWB200_RP_ADVECTION_COLOR 11 /* rp1_advection_color (apps/advection/1d/variable); aux {u}        */
+#define CLAWB200_RP_VC_ADVECTION 12   /* rpn2/rpt2_vc_advection (apps/advection/2d/annulus); aux {u, v[, capa]} */
+#define CLAWB200_RP_EULER1D 13        /* rp1_euler_with_efix (apps/euler/1d/wcblast); params {gamma,gamma1} */
 #define CLAWB200_RP_ACOUSTICS3D_VC 8 /* rpn3_vc_acoustics (test/acoustics/3d); aux {impedance, c};
                                         3-D, dimensional splitting only */
 

@@ -40,6 +40,11 @@
 #define RP_NEL_FWAVE 6 /* 1-D nonlinear elasticity, f-waves: aux = rho, K ; params[0] = stress law */
 #define RP_PSYSTEM 7   /* 2-D p-system, f-waves: aux = rho, E, stress law, eps ; rpt2 */
 #define RP_ACOUSTICS3D_VC 8 /* 3-D variable-coefficient acoustics: aux = impedance, sound speed */
+#define RP_VC_ACOUSTICS 9    /* 2-D acoustics, aux = rho, c (apps/acoustics/2d/variable)           */
+#define RP_BURGERS 10        /* 1-D Burgers with entropy fix (apps/burgers/1d)                     */
+#define RP_ADVECTION_COLOR 11 /* 1-D colour equation, aux(1) = velocity (apps/advection/1d/variable) */
+#define RP_VC_ADVECTION 12   /* 2-D colour equation, aux = edge velocities (apps/advection/2d/annulus) */
+#define RP_EULER1D 13        /* 1-D Euler, Roe + entropy fix (apps/euler/1d/wcblast)                */
 #define RP_IS_FWAVE(id) ((id) == RP_NEL_FWAVE || (id) == RP_PSYSTEM)
 
 #define WENO_PYWENO_F32 0 /* weno.f90 literals read as REAL(4), as gfortran does */
@@ -538,6 +543,179 @@ static void rpn3_vc_acoustics(int ixyz, int meqn, int mwaves, int mbc, int mx, i
     (void)mwaves;
 }
 
+/* ---- further solvers of the reference's applications; all external (clawpack/riemann,
+   un-vendored, no pinned version, no golden data in the reference): restated from the
+   published algorithms (LeVeque 2002), parity unpinned ---- */
+
+/* rpn2_vc_acoustics.f: aux(1) = density, aux(2) = sound speed (apps/acoustics/2d/variable/acoustics.py:56-57) */
+static void rpn_vc_acoustics(int ixy, int meqn, int mwaves, int mbc, int mx, int maux,
+                             const double *ql, const double *qr, const double *auxl, const double *auxr,
+                             double *wave, double *s, double *amdq, double *apdq)
+{
+    int mu = (ixy == 1) ? 1 : 2, mv = (ixy == 1) ? 2 : 1;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double delta1 = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        double delta2 = Q2(ql, mu, i) - Q2(qr, mu, i - 1);
+        double zi = auxl[0 + maux * IX(i)] * auxl[1 + maux * IX(i)];
+        double zim = auxr[0 + maux * IX(i - 1)] * auxr[1 + maux * IX(i - 1)];
+        double a1 = (-delta1 + zi * delta2) / (zim + zi);
+        double a2 = (delta1 + zim * delta2) / (zim + zi);
+        WV(0, 0, i) = -a1 * zim;
+        WV(mu, 0, i) = a1;
+        WV(mv, 0, i) = 0.0;
+        SP(0, i) = -auxr[1 + maux * IX(i - 1)];
+        WV(0, 1, i) = a2 * zi;
+        WV(mu, 1, i) = a2;
+        WV(mv, 1, i) = 0.0;
+        SP(1, i) = auxl[1 + maux * IX(i)];
+        for (int m = 0; m < meqn; m++) {
+            Q2(amdq, m, i) = SP(0, i) * WV(m, 0, i);
+            Q2(apdq, m, i) = SP(1, i) * WV(m, 1, i);
+        }
+    }
+    (void)mwaves;
+}
+
+/* rpt2_vc_acoustics.f */
+static void rpt_vc_acoustics(int ixy, int meqn, int mbc, int mx, int maux, const double *aux1,
+                             const double *aux2, const double *aux3, int imp, const double *asdq,
+                             double *bmasdq, double *bpasdq)
+{
+    int mu = (ixy == 1) ? 1 : 2, mv = (ixy == 1) ? 2 : 1;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int i1 = (imp == 1) ? i - 1 : i;
+        double cm = aux1[1 + maux * IX(i1)], cp = aux3[1 + maux * IX(i1)];
+        double zm = aux1[0 + maux * IX(i1)] * aux1[1 + maux * IX(i1)];
+        double zz = aux2[0 + maux * IX(i1)] * aux2[1 + maux * IX(i1)];
+        double zp = aux3[0 + maux * IX(i1)] * aux3[1 + maux * IX(i1)];
+        double a1 = (-Q2(asdq, 0, i) + Q2(asdq, mv, i) * zz) / (zm + zz);
+        double a2 = (Q2(asdq, 0, i) + Q2(asdq, mv, i) * zz) / (zz + zp);
+        Q2(bmasdq, 0, i) = cm * a1 * zm;
+        Q2(bmasdq, mu, i) = 0.0;
+        Q2(bmasdq, mv, i) = -cm * a1;
+        Q2(bpasdq, 0, i) = cp * a2 * zp;
+        Q2(bpasdq, mu, i) = 0.0;
+        Q2(bpasdq, mv, i) = cp * a2;
+    }
+    (void)meqn;
+}
+
+/* rp1_burgers.f90 with the entropy fix for the transonic rarefaction */
+static void rpn_burgers(int mbc, int mx, const double *ql, const double *qr, double *wave,
+                        double *s, double *amdq, double *apdq)
+{
+    const int meqn = 1, mwaves = 1;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double l = Q2(qr, 0, i - 1), r = Q2(ql, 0, i);
+        WV(0, 0, i) = r - l;
+        SP(0, i) = 0.5 * (l + r);
+        Q2(amdq, 0, i) = dmin2(SP(0, i), 0.0) * WV(0, 0, i);
+        Q2(apdq, 0, i) = dmax2(SP(0, i), 0.0) * WV(0, 0, i);
+        if (l < 0.0 && r > 0.0) {
+            Q2(amdq, 0, i) = -0.5 * (l * l);
+            Q2(apdq, 0, i) = 0.5 * (r * r);
+        }
+    }
+}
+
+/* rp1_advection_color.f / rpn2_vc_advection.f: q_t + u q_x (+ v q_y) = 0 with the edge velocity
+   of the sweep direction in aux(ixy) of the cell to the right of the interface */
+static void rpn_color(int ixy, int mbc, int mx, int maux, const double *ql, const double *qr,
+                      const double *auxl, double *wave, double *s, double *amdq, double *apdq)
+{
+    const int meqn = 1, mwaves = 1;
+    const int ma = (ixy <= 1) ? 0 : 1;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double u = auxl[ma + maux * IX(i)];
+        WV(0, 0, i) = Q2(ql, 0, i) - Q2(qr, 0, i - 1);
+        SP(0, i) = u;
+        Q2(amdq, 0, i) = dmin2(u, 0.0) * WV(0, 0, i);
+        Q2(apdq, 0, i) = dmax2(u, 0.0) * WV(0, 0, i);
+    }
+}
+
+/* rpt2_vc_advection.f: transverse velocity = the other edge velocity, taken at the bottom edge
+   of this row for down-going and of the row above for up-going parts */
+static void rpt_color(int ixy, int mbc, int mx, int maux, const double *aux2, const double *aux3,
+                      int imp, const double *asdq, double *bmasdq, double *bpasdq)
+{
+    const int meqn = 1;
+    const int kv = (ixy == 1) ? 1 : 0;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int i1 = (imp == 1) ? i - 1 : i;
+        Q2(bmasdq, 0, i) = dmin2(aux2[kv + maux * IX(i1)], 0.0) * Q2(asdq, 0, i);
+        Q2(bpasdq, 0, i) = dmax2(aux3[kv + maux * IX(i1)], 0.0) * Q2(asdq, 0, i);
+    }
+}
+
+/* rp1_euler_with_efix.f: the 1-D twin of rpn_euler5 above (3 waves, same entropy fix) */
+static void rpn_euler1d(rp_ctx *c, int mbc, int mx, const double *ql, const double *qr,
+                        double *wave, double *s, double *amdq, double *apdq)
+{
+    const int meqn = 3, mwaves = 3;
+    const double gamma1 = c->p[1];
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        double rl = Q2(qr, 0, i - 1), rr = Q2(ql, 0, i);
+        double ml = Q2(qr, 1, i - 1), mr = Q2(ql, 1, i);
+        double el = Q2(qr, 2, i - 1), er = Q2(ql, 2, i);
+        double rhsqrtl = sqrt(rl), rhsqrtr = sqrt(rr);
+        double pl = gamma1 * (el - 0.5 * (ml * ml) / rl);
+        double pr = gamma1 * (er - 0.5 * (mr * mr) / rr);
+        double rhsq2 = rhsqrtl + rhsqrtr;
+        double u = (ml / rhsqrtl + mr / rhsqrtr) / rhsq2;
+        double enth = (((el + pl) / rhsqrtl + (er + pr) / rhsqrtr)) / rhsq2;
+        double a2s = gamma1 * (enth - 0.5 * (u * u));
+        double a = sqrt(a2s);
+        double d1 = rr - rl, d2 = mr - ml, d3 = er - el;
+        double a2 = gamma1 / (a * a) * ((enth - u * u) * d1 + u * d2 - d3);
+        double a3 = (d2 + (a - u) * d1 - a * a2) / (2.0 * a);
+        double a1 = d1 - a2 - a3;
+        WV(0, 0, i) = a1; WV(1, 0, i) = a1 * (u - a); WV(2, 0, i) = a1 * (enth - u * a); SP(0, i) = u - a;
+        WV(0, 1, i) = a2; WV(1, 1, i) = a2 * u;       WV(2, 1, i) = a2 * 0.5 * (u * u);  SP(1, i) = u;
+        WV(0, 2, i) = a3; WV(1, 2, i) = a3 * (u + a); WV(2, 2, i) = a3 * (enth + u * a); SP(2, i) = u + a;
+        /* entropy fix (Harten-Hyman), left-going fluctuation first */
+        int done = 0;
+        double cl = sqrt(gamma1 * (gamma1 + 1.0) * (el / rl - 0.5 * ((ml / rl) * (ml / rl))));
+        double s0 = ml / rl - cl;
+        if (s0 >= 0.0 && SP(0, i) > 0.0) {
+            for (int m = 0; m < 3; m++) Q2(amdq, m, i) = 0.0;
+            done = 1;
+        }
+        if (!done) {
+            double rho1 = rl + WV(0, 0, i), rhou1 = ml + WV(1, 0, i), en1 = el + WV(2, 0, i);
+            double p1 = gamma1 * (en1 - 0.5 * (rhou1 * rhou1) / rho1);
+            double c1 = sqrt((gamma1 + 1.0) * p1 / rho1);
+            double s1 = rhou1 / rho1 - c1;
+            double sfract;
+            if (s0 < 0.0 && s1 > 0.0) sfract = s0 * (s1 - SP(0, i)) / (s1 - s0);
+            else if (SP(0, i) < 0.0) sfract = SP(0, i);
+            else sfract = 0.0;
+            for (int m = 0; m < 3; m++) Q2(amdq, m, i) = sfract * WV(m, 0, i);
+            if (SP(1, i) >= 0.0) done = 1;
+        }
+        if (!done) {
+            for (int m = 0; m < 3; m++) Q2(amdq, m, i) = Q2(amdq, m, i) + SP(1, i) * WV(m, 1, i);
+            double cr = sqrt(gamma1 * (gamma1 + 1.0) * (er / rr - 0.5 * ((mr / rr) * (mr / rr))));
+            double s3 = mr / rr + cr;
+            double rho2 = rr - WV(0, 2, i), rhou2 = mr - WV(1, 2, i), en2 = er - WV(2, 2, i);
+            double p2 = gamma1 * (en2 - 0.5 * (rhou2 * rhou2) / rho2);
+            double c2 = sqrt((gamma1 + 1.0) * p2 / rho2);
+            double s2 = rhou2 / rho2 + c2;
+            double sfract;
+            int add = 1;
+            if (s2 < 0.0 && s3 > 0.0) sfract = s2 * (s3 - SP(2, i)) / (s3 - s2);
+            else if (SP(2, i) < 0.0) sfract = SP(2, i);
+            else { sfract = 0.0; add = 0; }
+            if (add) for (int m = 0; m < 3; m++) Q2(amdq, m, i) = Q2(amdq, m, i) + sfract * WV(m, 2, i);
+        }
+        for (int m = 0; m < 3; m++) {
+            double df = 0.0;
+            for (int mw = 0; mw < 3; mw++) df = df + SP(mw, i) * WV(m, mw, i);
+            Q2(apdq, m, i) = df - Q2(amdq, m, i);
+        }
+    }
+}
+
 static void rpn_sphere(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
                        const double *ql, const double *qr, const double *auxl, const double *auxr,
                        double *wave, double *s, double *amdq, double *apdq);
@@ -552,6 +730,11 @@ static void rpn(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx,
     switch (c->rp_id) {
     case RP_SPHERE: rpn_sphere(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
     case RP_NEL_FWAVE: rpn_elastic_fwave(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, c->maux, wave, s, amdq, apdq); break;
+    case RP_VC_ACOUSTICS: rpn_vc_acoustics(ixy, meqn, mwaves, mbc, mx, c->maux, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
+    case RP_BURGERS: rpn_burgers(mbc, mx, ql, qr, wave, s, amdq, apdq); break;
+    case RP_ADVECTION_COLOR: rpn_color(ixy, mbc, mx, c->maux, ql, qr, auxl, wave, s, amdq, apdq); break;
+    case RP_VC_ADVECTION: rpn_color(ixy, mbc, mx, c->maux, ql, qr, auxl, wave, s, amdq, apdq); break;
+    case RP_EULER1D: rpn_euler1d(c, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
     case RP_ACOUSTICS3D_VC: rpn3_vc_acoustics(ixy, meqn, mwaves, mbc, mx, c->maux, ql, qr, auxl, auxr, wave, s, amdq, apdq); break;
     case RP_PSYSTEM: rpn_elastic_fwave(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl, auxr, 4, wave, s, amdq, apdq); break;
     case RP_ACOUSTICS: rpn_acoustics(c, ixy, meqn, mwaves, mbc, mx, ql, qr, wave, s, amdq, apdq); break;
@@ -578,6 +761,14 @@ static void rpt(rp_ctx *c, int ixy, int meqn, int mwaves, int mbc, int mx, const
     }
     if (c->rp_id == RP_PSYSTEM) {
         rpt_psystem(ixy, meqn, mbc, mx, aux1, aux2, aux3, imp, asdq, bmasdq, bpasdq);
+        return;
+    }
+    if (c->rp_id == RP_VC_ACOUSTICS) {
+        rpt_vc_acoustics(ixy, meqn, mbc, mx, c->maux, aux1, aux2, aux3, imp, asdq, bmasdq, bpasdq);
+        return;
+    }
+    if (c->rp_id == RP_VC_ADVECTION) {
+        rpt_color(ixy, mbc, mx, c->maux, aux2, aux3, imp, asdq, bmasdq, bpasdq);
         return;
     }
     if (ixy == 1) { mu = 1; mv = 2; } else { mu = 2; mv = 1; }
@@ -1137,6 +1328,7 @@ double oracle_step2ds(int rp_id, const double *rp_params, int maxm, int meqn, in
     int n = maxm + 2 * mbc;
     rp_ctx c;
     rp_ctx_init(&c, rp_id, rp_params, n);
+    c.maux = maux;
     work2 w;
     work2_alloc(&w, n, meqn, mwaves);
     work2_alloc_aux(&w, n, maux);
@@ -1317,6 +1509,7 @@ double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int 
     int n = maxm + 2 * mbc;
     rp_ctx c;
     rp_ctx_init(&c, rp_id, rp_params, n);
+    c.maux = maux;
     work2 w;
     work2_alloc(&w, n, meqn, mwaves);
     work2_alloc_aux(&w, n, maux);

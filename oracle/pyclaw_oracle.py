@@ -25,6 +25,7 @@ _LIB = None
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 RP_NEL_FWAVE, RP_PSYSTEM = 6, 7   # f-wave solvers (step1fw.f / flux2fw.f corrections)
 RP_ACOUSTICS3D_VC = 8              # 3-D variable-coefficient acoustics (dimensional splitting)
+RP_VC_ACOUSTICS, RP_BURGERS, RP_ADVECTION_COLOR, RP_VC_ADVECTION, RP_EULER1D = 9, 10, 11, 12, 13
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES = 0, 1, 2, 3
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 

@@ -15,6 +15,8 @@
 #include "classic.cuh"
 #include "sharpclaw.cuh"
 
+using RpColor1D = RpColor<1, 1>; // (a template-id with a comma cannot be a macro argument)
+
 static thread_local std::string g_err;
 
 static int fail(int code, const char *msg)
@@ -60,13 +62,22 @@ static int check_aux(const clawb200_problem *p, const double *aux, bool classic2
 {
     const bool capa = p->method[5] > 0;
     const bool fw = p->rp_id == CLAWB200_RP_NEL_FWAVE || p->rp_id == CLAWB200_RP_PSYSTEM;
-    const bool need_aux = capa || fw || p->rp_id == CLAWB200_RP_SPHERE;
+    const bool vc = p->rp_id == CLAWB200_RP_VC_ACOUSTICS || p->rp_id == CLAWB200_RP_ADVECTION_COLOR ||
+                    p->rp_id == CLAWB200_RP_VC_ADVECTION;
+    const bool need_aux = capa || fw || vc || p->rp_id == CLAWB200_RP_SPHERE;
     if (!need_aux) return 0;
     if (!aux) return fail(CLAWB200_ERR_INVALID, "aux array required (mcapa > 0 or aux-dependent Riemann solver)");
     if (fw) { // classic step1 / step2 / step2ds only (the callers check the solver's dimension)
         if (capa) return fail(CLAWB200_ERR_UNSUPPORTED, "capacity function is not compiled for the f-wave solvers");
         if (p->rp_id == CLAWB200_RP_NEL_FWAVE ? p->maux < 2 : p->maux != 4)
             return fail(CLAWB200_ERR_INVALID, "f-wave elasticity solvers: aux = {rho, K} (1-D) or {rho, E, law, eps} (2-D)");
+        return 0;
+    }
+    if (vc) { // variable-coefficient solvers read aux in the classic sweeps (step1 / step2 / step2ds)
+        const int need = (p->rp_id == CLAWB200_RP_ADVECTION_COLOR) ? 1 : 2;
+        if (p->maux < need) return fail(CLAWB200_ERR_INVALID, "this Riemann solver reads more aux components than maux");
+        if (capa && p->rp_id != CLAWB200_RP_VC_ADVECTION)
+            return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
         return 0;
     }
     if (p->rp_id == CLAWB200_RP_SPHERE) {
@@ -179,6 +190,7 @@ static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
         case CLAWB200_RP_SPHERE: return launch_x<RpSphere<1>, TRANS, true>(A, st);
         case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS, true>(A, st);
         case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS, true>(A, st);
+        case CLAWB200_RP_VC_ADVECTION: return launch_x<RpColor<2, 1>, TRANS, true>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
         }
     }
@@ -188,6 +200,8 @@ static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
     case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS>(A, st);
     case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS>(A, st);
     case CLAWB200_RP_PSYSTEM: return launch_x<RpElasticFwave<2, 1>, TRANS>(A, st);
+    case CLAWB200_RP_VC_ACOUSTICS: return launch_x<RpVcAcoustics<1>, TRANS>(A, st);
+    case CLAWB200_RP_VC_ADVECTION: return launch_x<RpColor<2, 1>, TRANS>(A, st);
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
 }
@@ -201,6 +215,7 @@ static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
         case CLAWB200_RP_SPHERE: return launch_y<RpSphere<2>, TRANS, true>(A, st);
         case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS, true>(A, st);
         case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS, true>(A, st);
+        case CLAWB200_RP_VC_ADVECTION: return launch_y<RpColor<2, 2>, TRANS, true>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
         }
     }
@@ -210,6 +225,8 @@ static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
     case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS>(A, st);
     case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS>(A, st);
     case CLAWB200_RP_PSYSTEM: return launch_y<RpElasticFwave<2, 2>, TRANS>(A, st);
+    case CLAWB200_RP_VC_ACOUSTICS: return launch_y<RpVcAcoustics<2>, TRANS>(A, st);
+    case CLAWB200_RP_VC_ADVECTION: return launch_y<RpColor<2, 2>, TRANS>(A, st);
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
 }
@@ -225,14 +242,20 @@ static int check_rp_shape(const clawb200_problem *p)
     case CLAWB200_RP_SPHERE: meqn = 4; mwaves = 3; break;
     case CLAWB200_RP_NEL_FWAVE: meqn = 2; mwaves = 2; break;
     case CLAWB200_RP_PSYSTEM: meqn = 3; mwaves = 2; break;
+    case CLAWB200_RP_VC_ACOUSTICS: meqn = 3; mwaves = 2; break;
+    case CLAWB200_RP_BURGERS: meqn = 1; mwaves = 1; break;
+    case CLAWB200_RP_ADVECTION_COLOR: meqn = 1; mwaves = 1; break;
+    case CLAWB200_RP_VC_ADVECTION: meqn = 1; mwaves = 1; break;
+    case CLAWB200_RP_EULER1D: meqn = 3; mwaves = 3; break;
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
     if (p->meqn != meqn || p->mwaves != mwaves)
         return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
-    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SPHERE ||
-         p->rp_id == CLAWB200_RP_PSYSTEM) && p->ndim != 2)
+    if ((p->rp_id == CLAWB200_RP_EULER5 || p->rp_id == CLAWB200_RP_SPHERE || p->rp_id == CLAWB200_RP_PSYSTEM ||
+         p->rp_id == CLAWB200_RP_VC_ACOUSTICS || p->rp_id == CLAWB200_RP_VC_ADVECTION) && p->ndim != 2)
         return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 2-D only");
-    if (p->rp_id == CLAWB200_RP_NEL_FWAVE && p->ndim != 1)
+    if ((p->rp_id == CLAWB200_RP_NEL_FWAVE || p->rp_id == CLAWB200_RP_BURGERS ||
+         p->rp_id == CLAWB200_RP_ADVECTION_COLOR || p->rp_id == CLAWB200_RP_EULER1D) && p->ndim != 1)
         return fail(CLAWB200_ERR_UNSUPPORTED, "this Riemann solver is 1-D only");
     return 0;
 }
@@ -275,6 +298,18 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
         size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
         step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
     } break;
+#define STEP1_PLAIN(RPT)                                                                                     \
+    {                                                                                                        \
+        using RP = RPT;                                                                                      \
+        if (capa) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");               \
+        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT); \
+        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);                                                     \
+    }                                                                                                        \
+    break
+    case CLAWB200_RP_BURGERS: STEP1_PLAIN(RpBurgers);
+    case CLAWB200_RP_ADVECTION_COLOR: STEP1_PLAIN(RpColor1D);
+    case CLAWB200_RP_EULER1D: STEP1_PLAIN(RpEuler1D);
+#undef STEP1_PLAIN
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
     }
     CUDA_OK(cudaGetLastError());
@@ -724,6 +759,8 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
         case CLAWB200_RP_ACOUSTICS: return sc_launch1_tab<RpAcoustics<1, 1>>(A, st);
         case CLAWB200_RP_ADVECTION: return sc_launch1_tab<RpAdvection<1, 1>>(A, st);
         case CLAWB200_RP_SHALLOW: return sc_launch1_tab<RpShallow1D>(A, st);
+        case CLAWB200_RP_BURGERS: return sc_launch1_tab<RpBurgers>(A, st);
+        case CLAWB200_RP_EULER1D: return sc_launch1_tab<RpEuler1D>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
     }
@@ -757,6 +794,10 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
             return old ? sc_launch1<RpAdvection<1, 1>, true>(A, st) : sc_launch1<RpAdvection<1, 1>, false>(A, st);
         case CLAWB200_RP_SHALLOW:
             return old ? sc_launch1<RpShallow1D, true>(A, st) : sc_launch1<RpShallow1D, false>(A, st);
+        case CLAWB200_RP_BURGERS:
+            return old ? sc_launch1<RpBurgers, true>(A, st) : sc_launch1<RpBurgers, false>(A, st);
+        case CLAWB200_RP_EULER1D:
+            return old ? sc_launch1<RpEuler1D, true>(A, st) : sc_launch1<RpEuler1D, false>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
     }

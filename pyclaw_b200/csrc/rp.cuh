@@ -30,6 +30,11 @@
 #define CLAW_RP_NEL_FWAVE 6
 #define CLAW_RP_PSYSTEM 7
 #define CLAW_RP_ACOUSTICS3D_VC 8
+#define CLAW_RP_VC_ACOUSTICS 9
+#define CLAW_RP_BURGERS 10
+#define CLAW_RP_ADVECTION_COLOR 11
+#define CLAW_RP_VC_ADVECTION 12
+#define CLAW_RP_EULER1D 13
 
 // Solvers that return f-waves (jumps in the flux) instead of waves: the sweeps then use the
 // second-order correction of step1fw.f:135-136 / flux2fw.f:151-152.  A member FWAVE = true
@@ -1024,5 +1029,227 @@ struct RpAcoustics3D {
     {
 #pragma unroll
         for (int m = 0; m < 4; m++) { bm[m] = 0.0; bp[m] = 0.0; }
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// Further solvers of the reference's applications (all external: clawpack/riemann,
+// un-vendored; restated from the published algorithms, parity unpinned).
+// ---------------------------------------------------------------------------
+
+// 2-D acoustics in a heterogeneous medium: rpn2_vc_acoustics.f / rpt2_vc_acoustics.f
+// (apps/acoustics/2d/variable).  aux = {density, sound speed}.
+template <int IXY>
+struct RpVcAcoustics {
+    static constexpr int ID = CLAW_RP_VC_ACOUSTICS;
+    static constexpr int MEQN = 3, MWAVES = 2, NROE = 1;
+    static constexpr int X_MINB = 4, Y_MINB = 3;
+    static constexpr int MAUX = 2;
+    static constexpr bool QCOR = false;
+    static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;
+    __host__ __device__ static constexpr bool nz(int m, int mw) { return m == 0 || m == MU; }
+
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[3],
+                                                 const double (&r)[3], const AuxCell &axl, const AuxCell &axr,
+                                                 double (&wave)[3][2], double (&s)[2], double (&amdq)[3],
+                                                 double (&apdq)[3], double (&roe)[NROE])
+    {
+        const double ci = axr(1), cim = axl(1);
+        const double zi = axr(0) * ci, zim = axl(0) * cim;
+        double delta1 = r[0] - l[0];
+        double delta2 = r[MU] - l[MU];
+        const Recip rz = ar.rcp(zim + zi);
+        double a1 = ar.div(-delta1 + zi * delta2, rz);
+        double a2 = ar.div(delta1 + zim * delta2, rz);
+        wave[0][0] = -a1 * zim; wave[MU][0] = a1; wave[MV][0] = 0.0; s[0] = -cim;
+        wave[0][1] = a2 * zi;   wave[MU][1] = a2; wave[MV][1] = 0.0; s[1] = ci;
+#pragma unroll
+        for (int m = 0; m < 3; m++) { amdq[m] = s[0] * wave[m][0]; apdq[m] = s[1] * wave[m][1]; }
+        roe[0] = 0.0;
+    }
+
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
+                                                      const double (&qc)[3], const AuxCell &ax1,
+                                                      const AuxCell &ax2, const AuxCell &ax3,
+                                                      const double (&asdq)[3], double (&bm)[3], double (&bp)[3])
+    {
+        const double cm = ax1(1), cp = ax3(1);
+        const double zm = ax1(0) * cm, zz = ax2(0) * ax2(1), zp = ax3(0) * cp;
+        double a1 = ar.div(-asdq[0] + asdq[MV] * zz, zm + zz);
+        double a2 = ar.div(asdq[0] + asdq[MV] * zz, zz + zp);
+        bm[0] = cm * a1 * zm; bm[MU] = 0.0; bm[MV] = -cm * a1;
+        bp[0] = cp * a2 * zp; bp[MU] = 0.0; bp[MV] = cp * a2;
+    }
+};
+
+// 1-D Burgers with the transonic entropy fix: rp1_burgers.f90 (apps/burgers/1d)
+struct RpBurgers {
+    static constexpr int ID = CLAW_RP_BURGERS;
+    static constexpr int MEQN = 1, MWAVES = 1, NROE = 1;
+    static constexpr int X_MINB = 6, Y_MINB = 6;
+    static constexpr int MAUX = 0;
+    static constexpr bool QCOR = false;
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &, const RpParams &, const double (&l)[1], const double (&r)[1],
+                                                 const AuxCell &, const AuxCell &, double (&wave)[1][1],
+                                                 double (&s)[1], double (&amdq)[1], double (&apdq)[1],
+                                                 double (&roe)[NROE])
+    {
+        wave[0][0] = r[0] - l[0];
+        s[0] = 0.5 * (l[0] + r[0]);
+        amdq[0] = dmin2(s[0], 0.0) * wave[0][0];
+        apdq[0] = dmax2(s[0], 0.0) * wave[0][0];
+        if (l[0] < 0.0 && r[0] > 0.0) {
+            amdq[0] = -0.5 * (l[0] * l[0]);
+            apdq[0] = 0.5 * (r[0] * r[0]);
+        }
+        roe[0] = 0.0;
+    }
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &, const RpParams &, const double (&)[NROE],
+                                                      const double (&)[1], const AuxCell &, const AuxCell &,
+                                                      const AuxCell &, const double (&)[1], double (&bm)[1],
+                                                      double (&bp)[1])
+    {
+        bm[0] = 0.0; bp[0] = 0.0;
+    }
+};
+
+// Colour equation q_t + u q_x (+ v q_y) = 0 with edge velocities in aux:
+// rp1_advection_color.f (NDIM = 1, apps/advection/1d/variable) and rpn2_vc_advection.f /
+// rpt2_vc_advection.f (NDIM = 2, apps/advection/2d/annulus).
+template <int NDIM, int IXY>
+struct RpColor {
+    static constexpr int ID = (NDIM == 1) ? CLAW_RP_ADVECTION_COLOR : CLAW_RP_VC_ADVECTION;
+    static constexpr int MEQN = 1, MWAVES = 1, NROE = 1;
+    static constexpr int X_MINB = 6, Y_MINB = 6;
+    static constexpr int MAUX = NDIM;
+    static constexpr bool QCOR = false;
+    static constexpr int MA = (IXY == 2) ? 1 : 0; // edge velocity of the sweep direction
+    static constexpr int KV = (IXY == 2) ? 0 : 1; // ... of the transverse direction
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &, const RpParams &, const double (&l)[1], const double (&r)[1],
+                                                 const AuxCell &axl, const AuxCell &axr, double (&wave)[1][1],
+                                                 double (&s)[1], double (&amdq)[1], double (&apdq)[1],
+                                                 double (&roe)[NROE])
+    {
+        const double u = axr(MA);
+        wave[0][0] = r[0] - l[0];
+        s[0] = u;
+        amdq[0] = dmin2(u, 0.0) * wave[0][0];
+        apdq[0] = dmax2(u, 0.0) * wave[0][0];
+        roe[0] = 0.0;
+    }
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &, const RpParams &, const double (&)[NROE],
+                                                      const double (&)[1], const AuxCell &ax1, const AuxCell &ax2,
+                                                      const AuxCell &ax3, const double (&asdq)[1], double (&bm)[1],
+                                                      double (&bp)[1])
+    {
+        bm[0] = dmin2(ax2(NDIM == 2 ? KV : 0), 0.0) * asdq[0];
+        bp[0] = dmax2(ax3(NDIM == 2 ? KV : 0), 0.0) * asdq[0];
+    }
+};
+
+// 1-D Euler, Roe solver with entropy fix: rp1_euler_with_efix.f (apps/euler/1d/wcblast);
+// the 1-D twin of RpEuler5.  cparam{gamma, gamma1}.
+struct RpEuler1D {
+    static constexpr int ID = CLAW_RP_EULER1D;
+    static constexpr int MEQN = 3, MWAVES = 3, NROE = 1;
+    static constexpr int X_MINB = 3, Y_MINB = 3;
+    static constexpr int MAUX = 0;
+    static constexpr bool QCOR = false;
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+    template <class AR>
+    __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[3], const double (&r)[3],
+                                                 const AuxCell &, const AuxCell &, double (&wave)[3][3],
+                                                 double (&s)[3], double (&amdq)[3], double (&apdq)[3],
+                                                 double (&roe)[NROE])
+    {
+        const double gamma1 = P.p[1];
+        const double rl = l[0], rr = r[0], ml = l[1], mr = r[1], el = l[2], er = r[2];
+        double rhsqrtl = ar.sqrt(rl), rhsqrtr = ar.sqrt(rr);
+        const Recip rrl = ar.rcp(rl), rrr = ar.rcp(rr);
+        double pl = gamma1 * (el - ar.div(0.5 * (ml * ml), rrl));
+        double pr = gamma1 * (er - ar.div(0.5 * (mr * mr), rrr));
+        double rhsq2 = rhsqrtl + rhsqrtr;
+        const Recip rsl = ar.rcp(rhsqrtl), rsr = ar.rcp(rhsqrtr), rs2 = ar.rcp(rhsq2);
+        double u = ar.div(ar.div(ml, rsl) + ar.div(mr, rsr), rs2);
+        double enth = ar.div((ar.div(el + pl, rsl) + ar.div(er + pr, rsr)), rs2);
+        double a2s = gamma1 * (enth - 0.5 * (u * u));
+        double a = ar.sqrt(a2s);
+        double d1 = rr - rl, d2 = mr - ml, d3 = er - el;
+        double a2 = ar.div(gamma1, a * a) * ((enth - u * u) * d1 + u * d2 - d3);
+        double a3 = ar.div(d2 + (a - u) * d1 - a * a2, 2.0 * a);
+        double a1 = d1 - a2 - a3;
+        wave[0][0] = a1; wave[1][0] = a1 * (u - a); wave[2][0] = a1 * (enth - u * a); s[0] = u - a;
+        wave[0][1] = a2; wave[1][1] = a2 * u;       wave[2][1] = a2 * 0.5 * (u * u);  s[1] = u;
+        wave[0][2] = a3; wave[1][2] = a3 * (u + a); wave[2][2] = a3 * (enth + u * a); s[2] = u + a;
+        bool done = false;
+        double ul = ar.div(ml, rrl);
+        double cl = ar.sqrt(gamma1 * (gamma1 + 1.0) * (ar.div(el, rrl) - 0.5 * (ul * ul)));
+        double s0 = ul - cl;
+        if (s0 >= 0.0 && s[0] > 0.0) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) amdq[m] = 0.0;
+            done = true;
+        }
+        if (!done) {
+            double rho1 = rl + wave[0][0], rhou1 = ml + wave[1][0], en1 = el + wave[2][0];
+            const Recip r1 = ar.rcp(rho1);
+            double p1 = gamma1 * (en1 - ar.div(0.5 * (rhou1 * rhou1), r1));
+            double c1 = ar.sqrt(ar.div((gamma1 + 1.0) * p1, r1));
+            double s1 = ar.div(rhou1, r1) - c1;
+            double sfract;
+            if (s0 < 0.0 && s1 > 0.0) sfract = ar.div(s0 * (s1 - s[0]), s1 - s0);
+            else if (s[0] < 0.0) sfract = s[0];
+            else sfract = 0.0;
+#pragma unroll
+            for (int m = 0; m < 3; m++) amdq[m] = sfract * wave[m][0];
+            if (s[1] >= 0.0) done = true;
+        }
+        if (!done) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) amdq[m] = amdq[m] + s[1] * wave[m][1];
+            double ur = ar.div(mr, rrr);
+            double cr = ar.sqrt(gamma1 * (gamma1 + 1.0) * (ar.div(er, rrr) - 0.5 * (ur * ur)));
+            double s3 = ur + cr;
+            double rho2 = rr - wave[0][2], rhou2 = mr - wave[1][2], en2 = er - wave[2][2];
+            const Recip r2 = ar.rcp(rho2);
+            double p2 = gamma1 * (en2 - ar.div(0.5 * (rhou2 * rhou2), r2));
+            double c2 = ar.sqrt(ar.div((gamma1 + 1.0) * p2, r2));
+            double s2 = ar.div(rhou2, r2) + c2;
+            double sfract = 0.0;
+            bool add = true;
+            if (s2 < 0.0 && s3 > 0.0) sfract = ar.div(s2 * (s3 - s[2]), s3 - s2);
+            else if (s[2] < 0.0) sfract = s[2];
+            else add = false;
+            if (add) {
+#pragma unroll
+                for (int m = 0; m < 3; m++) amdq[m] = amdq[m] + sfract * wave[m][2];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            double df = 0.0;
+#pragma unroll
+            for (int mw = 0; mw < 3; mw++) df = df + s[mw] * wave[m][mw];
+            apdq[m] = df - amdq[m];
+        }
+        roe[0] = 0.0;
+    }
+    template <class AR>
+    __device__ __forceinline__ static void transverse(AR &, const RpParams &, const double (&)[NROE],
+                                                      const double (&)[3], const AuxCell &, const AuxCell &,
+                                                      const AuxCell &, const double (&)[3], double (&bm)[3],
+                                                      double (&bp)[3])
+    {
+#pragma unroll
+        for (int m = 0; m < 3; m++) { bm[m] = 0.0; bp[m] = 0.0; }
     }
 };

@@ -7,7 +7,8 @@ these descriptors (or its name); if it is left unset the solver is inferred from
 keys of ``state.aux_global`` (the cparam common block the script fills).
 """
 from .._lib import (RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE, RP_NEL_FWAVE,
-                    RP_PSYSTEM, RP_ACOUSTICS3D_VC)
+                    RP_PSYSTEM, RP_ACOUSTICS3D_VC, RP_VC_ACOUSTICS, RP_BURGERS, RP_ADVECTION_COLOR,
+                    RP_VC_ADVECTION, RP_EULER1D)
 
 
 class RiemannSolver(object):
@@ -63,7 +64,15 @@ psystem = RiemannSolver("psystem", RP_PSYSTEM, 3, 2, [], (2,), fwave=True, maux=
 # 3-D acoustics in a heterogeneous medium (test/acoustics/3d): aux = {impedance, sound speed}
 vc_acoustics_3d = RiemannSolver("vc_acoustics_3d", RP_ACOUSTICS3D_VC, 4, 2, [], (3,), maux=2)
 
-_BY_NAME = {s.name: s for s in (vc_acoustics_3d, acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere,
+# further solvers of the reference's applications (set solver.rp to use them)
+vc_acoustics = RiemannSolver("vc_acoustics", RP_VC_ACOUSTICS, 3, 2, [], (2,), maux=2)          # aux {rho, c}
+burgers = RiemannSolver("burgers", RP_BURGERS, 1, 1, [], (1,))
+advection_color = RiemannSolver("advection_color", RP_ADVECTION_COLOR, 1, 1, [], (1,), maux=1)  # aux {u}
+vc_advection = RiemannSolver("vc_advection", RP_VC_ADVECTION, 1, 1, [], (2,), maux=2)           # aux {u, v[, capa]}
+euler_with_efix = RiemannSolver("euler_with_efix", RP_EULER1D, 3, 3, ["gamma", "gamma1"], (1,))
+
+_BY_NAME = {s.name: s for s in (vc_acoustics, burgers, advection_color, vc_advection, euler_with_efix,
+                                vc_acoustics_3d, acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere,
                                 nonlinear_elasticity_fwave, psystem)}
 _BY_NAME.update({"euler": euler_5wave, "shallow": shallow_roe_with_efix})
 
@@ -102,7 +111,7 @@ def resolve(rp, aux_global, ndim, fwave=False):
     if {"rho", "bulk", "cc", "zz"} <= keys:
         return acoustics
     if {"gamma", "gamma1"} <= keys:
-        return euler_5wave
+        return euler_with_efix if ndim == 1 else euler_5wave
     if "grav" in keys:
         return shallow_roe_with_efix
     if "u" in keys:

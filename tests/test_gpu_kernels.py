@@ -615,3 +615,110 @@ def test_sharpclaw_high_order_weno(order, rp, literals):
     q2 = np.zeros((3, 20 + 2 * mbc, 20 + 2 * mbc), order="F")
     with pytest.raises(_lib.ClawB200Error, match="1-D"):
         _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P2), _ptr(q2), _ptr(q2.copy("F")), None, 0.01, ctypes.byref(cfl_g))
+
+
+# ---------------------------------------------------------------------------
+# Further solvers of the reference's applications (external sources, parity unpinned):
+# variable-coefficient acoustics / colour equation, Burgers, 1-D Euler.
+# ---------------------------------------------------------------------------
+def _euler1d_data(n, seed, smooth):
+    q5 = (problems.smooth_state if smooth else problems.random_state)("euler", (n,), seed)   # rho, mx, my, E, tracer
+    rho, mom, e = q5[0], q5[1], q5[3] - 0.5 * q5[2] ** 2 / q5[0]
+    return np.asfortranarray(np.stack([rho, mom, e]))
+
+
+@pytest.mark.parametrize("rp", ["burgers", "color", "euler1d"])
+@pytest.mark.parametrize("mx", [7, 300, 1001])
+@pytest.mark.parametrize("order,limid", [(1, 0), (2, 4), (2, 2)])
+def test_step1_more_solvers(rp, mx, order, limid):
+    mbc = 2
+    dx, dt = 1.0 / mx, 0.15 / mx
+    rng = np.random.RandomState(mx)
+    aux, maux = None, 0
+    if rp == "burgers":
+        rp_id, params, meqn, mwaves = po.RP_BURGERS, [], 1, 1
+        q = np.asfortranarray(rng.uniform(-1.0, 1.0, (1, mx + 2 * mbc)))
+    elif rp == "color":
+        rp_id, params, meqn, mwaves = po.RP_ADVECTION_COLOR, [], 1, 1
+        q = np.asfortranarray(rng.uniform(0.0, 1.0, (1, mx + 2 * mbc)))
+        aux, maux = np.asfortranarray(rng.uniform(-1.5, 2.5, (1, mx + 2 * mbc))), 1
+    else:
+        rp_id, params, meqn, mwaves = po.RP_EULER1D, [1.4, 0.4], 3, 3
+        q = _euler1d_data(mx + 2 * mbc, mx, False)
+    lim = [limid] * mwaves
+    method = [1, order, 0, 0, 0, 0, maux]
+    P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, method, lim, maux=maux)
+    q_o = q.copy("F")
+    cfl_o = po.step1(rp_id, params, mbc, mx, q_o, aux, dx, dt, method, lim)
+    q_g = q.copy("F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_step1_host", ctypes.byref(P), _ptr(q_g), None if aux is None else _ptr(aux), dt,
+              ctypes.byref(cfl_g))
+    assert not np.isnan(q_o).any() and cfl_o > 0.01
+    assert np.array_equal(q_g[:, mbc:-mbc], q_o[:, mbc:-mbc]), np.abs(q_g - q_o)[:, mbc:-mbc].max()
+    assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["burgers", "euler1d"])
+@pytest.mark.parametrize("variant", [0, 2])
+def test_sharpclaw_dq1_more_solvers(rp, variant):
+    mbc = 3
+    for mx in (9, 400):
+        dx, dt = 1.0 / mx, 0.1 / mx
+        if rp == "burgers":
+            rp_id, params, meqn, mwaves = po.RP_BURGERS, [], 1, 1
+            q = np.asfortranarray(problems.smooth_state("advection", (mx + 2 * mbc,), seed=mx) * 2.0 - 1.0)
+        else:
+            rp_id, params, meqn, mwaves = po.RP_EULER1D, [1.4, 0.4], 3, 3
+            q = _euler1d_data(mx + 2 * mbc, mx, True)
+        P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, weno_variant=variant)
+        dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, variant)
+        dq_g = np.zeros_like(q, order="F")
+        cfl_g = ctypes.c_double()
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
+        assert not np.isnan(dq_o).any()
+        assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]) and cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("rp", ["vc_acoustics", "vc_advection", "vc_advection_capa"])
+@pytest.mark.parametrize("shape", [(37, 29), (130, 70)])
+@pytest.mark.parametrize("trans", [-1, 0, 1, 2])
+def test_step2_variable_coefficient_solvers(rp, shape, trans):
+    mx, my = shape
+    mbc = 2
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    rng = np.random.RandomState(mx + trans)
+    pad = (mx + 2 * mbc, my + 2 * mbc)
+    mcapa = 0
+    if rp == "vc_acoustics":
+        rp_id, meqn, mwaves, lim = po.RP_VC_ACOUSTICS, 3, 2, [4, 4]
+        q = _random_padded("acoustics", mx, my, mbc, seed=mx)
+        aux = np.asfortranarray(np.stack([rng.choice([1.0, 4.0], pad), rng.choice([1.0, 0.5, 2.0], pad)]))
+    else:
+        rp_id, meqn, mwaves, lim = po.RP_VC_ADVECTION, 1, 1, [4]
+        q = _random_padded("advection", mx, my, mbc, seed=mx)
+        comps = [rng.uniform(-1.0, 1.5, pad), rng.uniform(-1.2, 0.8, pad)]
+        if rp.endswith("capa"):
+            comps.append(rng.uniform(0.5, 1.5, pad))
+            mcapa = 3
+        aux = np.asfortranarray(np.stack(comps))
+    maux = aux.shape[0]
+    method = [1, 2, trans, 0, 0, mcapa, maux]
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, [], method, lim, maux=maux)
+    cfl_g = ctypes.c_double()
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    if trans < 0:
+        for ids in (1, 2):
+            qn_o = q.copy("F")
+            cfl_o = po.step2ds(rp_id, [], mbc, mx, my, q, qn_o, aux, dx, dy, dt, method, lim, ids)
+            qn_g = q.copy("F")
+            _lib.call("clawb200_step2ds_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), _ptr(aux), dt, ids, ctypes.byref(cfl_g))
+            assert np.array_equal(qn_g, qn_o), (ids, np.abs(qn_g - qn_o).max())
+            assert cfl_g.value == cfl_o
+    else:
+        qn_o = q.copy("F")
+        cfl_o = po.step2(rp_id, [], mbc, mx, my, q, qn_o, aux, dx, dy, dt, method, lim)
+        qn_g = q.copy("F")
+        _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), _ptr(aux), dt, ctypes.byref(cfl_g))
+        assert np.array_equal(qn_g[inner], qn_o[inner]), np.abs(qn_g[inner] - qn_o[inner]).max()
+        assert cfl_g.value == cfl_o and cfl_o > 0.01

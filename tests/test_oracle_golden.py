@@ -229,3 +229,38 @@ def test_acoustics1d_weno17_scalar():
     fr = s.run(pb["q"], None, pb["d"], 1.0, 5)
     err = pb["d"][0] * np.abs(fr[-1] - fr[0]).sum()
     assert abs(err - 0.000163221216565) < 1e-5, err
+
+
+def test_recalled_1d_solvers_against_exact_riemann_solutions():
+    """The 1-D Euler and shallow-water Roe solvers are external to the reference (un-vendored
+    clawpack/riemann) and have no golden data there; pin their restatement to physics instead:
+    Sod's shock tube and the 3:1 dam break have exact similarity solutions."""
+    mx, mbc, g = 400, 2, 1.4
+    x = (np.arange(-mbc, mx + mbc) + 0.5) / mx
+    rho = np.where(x < 0.5, 1.0, 0.125)
+    p = np.where(x < 0.5, 1.0, 0.1)
+    q = np.asfortranarray(np.stack([rho, 0 * rho, p / (g - 1)]))
+    t, dt = 0.0, 0.4 / mx / 2.2
+    while t < 0.2 - 1e-12:
+        q[:, :mbc] = q[:, mbc:mbc + 1]
+        q[:, -mbc:] = q[:, -mbc - 1:-mbc]
+        d = min(dt, 0.2 - t)
+        po.step1(po.RP_EULER1D, [g, g - 1], mbc, mx, q, None, 1.0 / mx, d, [1, 2, 0, 0, 0, 0, 0], [4, 4, 4])
+        t += d
+    r = q[0, mbc:-mbc]
+    u = q[1, mbc:-mbc] / r
+    pr = (g - 1) * (q[2, mbc:-mbc] - 0.5 * r * u * u)
+    xi = x[mbc:-mbc]
+    at = lambda a, x0: a[np.argmin(abs(xi - x0))]
+    assert abs(at(r, 0.6) - 0.42632) < 2e-4 and abs(at(r, 0.78) - 0.26557) < 2e-4
+    assert abs(at(pr, 0.7) - 0.30313) < 2e-4 and abs(at(u, 0.7) - 0.92745) < 2e-4
+    # dam break, g = 1, depths 3 : 1 -> middle state h = 1.848576
+    mx = 200
+    xs = (np.arange(-mbc, mx + mbc) + 0.5) / mx * 10 - 5
+    q = np.zeros((2, mx + 2 * mbc), order='F')
+    q[0] = np.where(xs < 0, 3.0, 1.0)
+    for _ in range(60):
+        q[:, :mbc] = q[:, mbc:mbc + 1]
+        q[:, -mbc:] = q[:, -mbc - 1:-mbc]
+        po.step1(po.RP_SHALLOW, [1.0], mbc, mx, q, None, 10.0 / mx, 0.01, [1, 2, 0, 0, 0, 0, 0], [4, 4])
+    assert abs(q[0, mbc + mx // 2] - 1.848576) < 2e-3
