@@ -4,7 +4,9 @@ Keeps the reference's Python API (src/pyclaw/__init__.py:22-43): Controller, Sol
 State, Grid, Dimension, CFL, BC, ClawSolver1D/2D, SharpClawSolver1D/2D, limiters, riemann.
 """
 from . import _lib, limiters, riemann, grid, state, solution, solver, clawpack, sharpclaw, controller, util
+from . import plot
 from .controller import Controller
+from .data import Data
 from .solution import Solution
 from .grid import Dimension, Grid
 from .state import State
@@ -14,6 +16,6 @@ from .sharpclaw import SharpClawSolver1D, SharpClawSolver2D
 from .solver import BC, CFLError
 from .limiters import tvd
 
-__all__ = ['Controller', 'Dimension', 'Grid', 'Solution', 'State', 'CFL', 'riemann',
+__all__ = ['Controller', 'Data', 'plot', 'Dimension', 'Grid', 'Solution', 'State', 'CFL', 'riemann',
            'ClawSolver1D', 'ClawSolver2D', 'ClawSolver3D', 'SharpClawSolver1D', 'SharpClawSolver2D',
            'limiters', 'tvd', 'BC']

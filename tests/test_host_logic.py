@@ -221,3 +221,22 @@ def test_controller_output_times_and_frames():
     assert status['numsteps'] >= 1
     # frames are snapshots, not views
     assert float(claw.frames[0].q[0, 0]) == 0.0 and float(claw.frames[-1].q[0, 0]) > 0.0
+
+
+def test_data_container_round_trip(tmp_path):
+    """pyclaw.Data (data.py:68-330): ``value =: name`` files."""
+    import pyclaw
+    f = tmp_path / "setprob.data"
+    f.write_text("   1.4d0   =: gamma   # ratio of specific heats\n  3 =: mthlim_count\n 1 2 4 =: mthlim\n T =: efix\n shock =: name\n")
+    d = pyclaw.Data(str(f))
+    assert d.gamma == 1.4 and d.mthlim_count == 3 and d.mthlim == [1, 2, 4] and d.efix is True and d.name == 'shock'
+    assert d.attributes == ['gamma', 'mthlim_count', 'mthlim', 'efix', 'name'] and d.get_owner('gamma') == str(f)
+    d.add_attribute('cfl', 0.9)
+    out = tmp_path / "out.data"
+    d.write(str(out))
+    e = pyclaw.Data(str(out))
+    assert e.gamma == 1.4 and e.cfl == 0.9 and e.mthlim == [1, 2, 4] and e.efix is True
+    d.remove_attributes('cfl')
+    assert not d.has_attribute('cfl')
+    with pytest.raises(NotImplementedError):
+        pyclaw.plot.interactive_plot()
