@@ -29,11 +29,20 @@ class _Module(object):
         self.cparam = _CParam()
         self.weno_variant = _lib.WENO_PYWENO_F32
 
-    def _problem(self, mbc, mx, my, q, dx, dy, method, mthlim):
-        params = [float(getattr(self.cparam, k, 0.0)) for k in self._rp.param_names]
-        return _lib.make_problem(self._ndim, q.shape[0], self._rp.mwaves, mbc, mx, my, dx, dy,
-                                 self._rp.rp_id, params, method=method, mthlim=mthlim,
+    def _problem(self, mbc, mx, my, q, dx, dy, method, mthlim, auxbc=None):
+        params = [float(getattr(self.cparam, k, self._rp.defaults.get(k, 0.0))) for k in self._rp.param_names]
+        maux = 0 if self._aux(auxbc) is None else auxbc.shape[0]
+        if method is None and maux:
+            method = [1, 2, 0, 0, 0, int(getattr(self, 'mcapa', 0)), maux]   # clawparams.mcapa (1-based)
+        return _lib.make_problem(self._ndim, q.shape[0], self._rp.nwaves(self._ndim), mbc, mx, my, dx, dy,
+                                 self._rp.rp_id, params, method=method, mthlim=mthlim, maux=maux,
                                  weno_variant=self.weno_variant)
+
+    def _aux(self, auxbc):
+        """f2py passes a dummy array when the application has no aux; None here."""
+        if auxbc is None or not isinstance(auxbc, np.ndarray) or auxbc.ndim != self._ndim + 1 or auxbc.shape[0] == 0:
+            return None
+        return self._check(auxbc)
 
     @staticmethod
     def _check(a):
@@ -47,8 +56,9 @@ class classic1(_Module):
         super().__init__(rp, 1)
 
     def step1(self, mbc, mx, qbc, auxbc, dx, dt, method, mthlim):
-        P, cfl = self._problem(mbc, mx, 1, qbc, dx, 1.0, list(method), list(mthlim)), ctypes.c_double()
-        _lib.call("clawb200_step1_host", ctypes.byref(P), self._check(qbc), None, float(dt), ctypes.byref(cfl))
+        P, cfl = self._problem(mbc, mx, 1, qbc, dx, 1.0, list(method), list(mthlim), auxbc), ctypes.c_double()
+        _lib.call("clawb200_step1_host", ctypes.byref(P), self._check(qbc), self._aux(auxbc), float(dt),
+                  ctypes.byref(cfl))
         return qbc, cfl.value
 
 
@@ -58,15 +68,15 @@ class classic2(_Module):
 
     def step2ds(self, maxm, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method, mthlim,
                 aux1=None, aux2=None, aux3=None, work=None, ids=1):
-        P, cfl = self._problem(mbc, mx, my, qold, dx, dy, list(method), list(mthlim)), ctypes.c_double()
-        _lib.call("clawb200_step2ds_host", ctypes.byref(P), self._check(qold), self._check(qnew), None,
+        P, cfl = self._problem(mbc, mx, my, qold, dx, dy, list(method), list(mthlim), auxbc), ctypes.c_double()
+        _lib.call("clawb200_step2ds_host", ctypes.byref(P), self._check(qold), self._check(qnew), self._aux(auxbc),
                   float(dt), int(ids), ctypes.byref(cfl))
         return qnew, cfl.value
 
     def step2(self, maxm, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method, mthlim,
               aux1=None, aux2=None, aux3=None, work=None):
-        P, cfl = self._problem(mbc, mx, my, qold, dx, dy, list(method), list(mthlim)), ctypes.c_double()
-        _lib.call("clawb200_step2_host", ctypes.byref(P), self._check(qold), self._check(qnew), None,
+        P, cfl = self._problem(mbc, mx, my, qold, dx, dy, list(method), list(mthlim), auxbc), ctypes.c_double()
+        _lib.call("clawb200_step2_host", ctypes.byref(P), self._check(qold), self._check(qnew), self._aux(auxbc),
                   float(dt), ctypes.byref(cfl))
         return qnew, cfl.value
 
@@ -77,8 +87,8 @@ class sharpclaw1(_Module):
 
     def flux1(self, q, auxbc, dt, t, ixy, mx, mbc, maxnx, dx=None):
         dq = np.zeros_like(q, order='F')
-        P, cfl = self._problem(mbc, mx, 1, q, dx, 1.0, None, None), ctypes.c_double()
-        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), self._check(q), self._check(dq), None,
+        P, cfl = self._problem(mbc, mx, 1, q, dx, 1.0, None, None, auxbc), ctypes.c_double()
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), self._check(q), self._check(dq), self._aux(auxbc),
                   float(dt), ctypes.byref(cfl))
         return dq, cfl.value
 
@@ -89,7 +99,23 @@ class sharpclaw2(_Module):
 
     def flux2(self, q, auxbc, dt, t, mbc, maxm, mx, my, dx=None, dy=None):
         dq = np.zeros_like(q, order='F')
-        P, cfl = self._problem(mbc, mx, my, q, dx, dy, None, None), ctypes.c_double()
-        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), self._check(q), self._check(dq), None,
+        P, cfl = self._problem(mbc, mx, my, q, dx, dy, None, None, auxbc), ctypes.c_double()
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), self._check(q), self._check(dq), self._aux(auxbc),
                   float(dt), ctypes.byref(cfl))
         return dq, cfl.value
+
+
+class classic3(_Module):
+    """classic3.step3ds (clawpack.py:656-676); only the dimensionally split routine exists."""
+
+    def __init__(self, rp='vc_acoustics_3d'):
+        super().__init__(rp, 3)
+
+    def step3ds(self, maxm, mbc, mx, my, mz, qold, qnew, auxbc, dx, dy, dz, dt, method, mthlim,
+                aux1=None, aux2=None, aux3=None, work=None, idir=1):
+        P, cfl = self._problem(mbc, mx, my, qold, dx, dy, list(method), list(mthlim), auxbc), ctypes.c_double()
+        # qold may be qnew (the reference's second and third calls pass the same array twice):
+        # the library uploads qold before it writes qnew
+        _lib.call("clawb200_step3ds_host", ctypes.byref(P), int(mz), float(dz), self._check(qold), self._check(qnew),
+                  self._aux(auxbc), float(dt), int(idir), ctypes.byref(cfl))
+        return qnew, cfl.value

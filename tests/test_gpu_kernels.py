@@ -186,6 +186,33 @@ def test_f2py_shaped_modules():
     assert np.array_equal(dq[:, 3:-3, 3:-3], dqo[:, 3:-3, 3:-3]) and cfl == cflo
     with pytest.raises(ValueError):
         classic2.step2(max(mx, my), mbc, mx, my, np.ascontiguousarray(q), qnew, None, dx, dy, dt, method, lim)
+    # an aux-dependent solver through the same signatures, and the three aliased classic3 calls
+    rng = np.random.RandomState(5)
+    pad = (mx + 2 * mbc, my + 2 * mbc)
+    qa = _random_padded("acoustics", mx, my, mbc, seed=4)
+    aux = np.asfortranarray(np.stack([rng.choice([1.0, 4.0], pad), rng.choice([1.0, 2.0], pad)]))
+    vc = f2py_shim.classic2('vc_acoustics')
+    m2 = [1, 2, 2, 0, 0, 0, 2]
+    qn = qa.copy('F')
+    _, cfl = vc.step2(max(mx, my), mbc, mx, my, qa, qn, aux, dx, dy, dt, m2, [4, 4])
+    qo = qa.copy('F')
+    cfl_o = po.step2(po.RP_VC_ACOUSTICS, [], mbc, mx, my, qa, qo, aux, dx, dy, dt, m2, [4, 4])
+    assert np.array_equal(qn[:, mbc:-mbc, mbc:-mbc], qo[:, mbc:-mbc, mbc:-mbc]) and cfl == cfl_o
+    mz, dz = 6, 0.02
+    pad3 = (mx + 2 * mbc, 9 + 2 * mbc, mz + 2 * mbc)
+    q3d = np.asfortranarray(rng.uniform(-1, 1, (4,) + pad3))
+    a3d = np.asfortranarray(np.stack([rng.choice([1.0, 2.0], pad3), rng.choice([1.0, 2.0], pad3)]))
+    classic3 = f2py_shim.classic3()
+    m3 = [1, 2, -1, 0, 0, 0, 2]
+    qg, qo = q3d.copy('F'), q3d.copy('F')
+    qg, c1 = classic3.step3ds(mx, mbc, mx, 9, mz, q3d, qg, a3d, dx, dy, dz, dt, m3, [4, 4], None, None, None, None, 1)
+    qg, c2 = classic3.step3ds(mx, mbc, mx, 9, mz, qg, qg, a3d, dx, dy, dz, dt, m3, [4, 4], None, None, None, None, 2)
+    qg, c3 = classic3.step3ds(mx, mbc, mx, 9, mz, qg, qg, a3d, dx, dy, dz, dt, m3, [4, 4], None, None, None, None, 3)
+    o = 0.0
+    for idir in (1, 2, 3):
+        qold = qo.copy('F')
+        o = max(o, po.step3ds(po.RP_ACOUSTICS3D_VC, [], mbc, mx, 9, mz, qold, qo, a3d, dx, dy, dz, dt, m3, [4, 4], idir))
+    assert np.array_equal(qg, qo) and max(c1, c2, c3) == o
 
 
 @pytest.mark.parametrize("rp", ["acoustics", "advection", "euler", "shallow"])
