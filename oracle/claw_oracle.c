@@ -1825,9 +1825,11 @@ static void workS_free(workS *w)
 
 static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double dt, double dxv,
                             int ixy, int meqn, int mwaves, int mx, int mbc, int weno_variant,
-                            int zero_dq, workS *w, const double *capa1d)
+                            int zero_dq, workS *w, const double *capa1d, const double *aux1d)
 {
     int n = mx + 2 * mbc;
+    const int maux = c->maux;
+    double *auxl2 = NULL, *auxr2 = NULL;
     double *ql = w->ql, *qr = w->qr, *wave = w->wave, *s = w->s;
     double *amdq = w->amdq, *apdq = w->apdq, *amdq2 = w->amdq2, *apdq2 = w->apdq2;
     double *dtdx = w->dtdx;
@@ -1843,7 +1845,8 @@ static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double d
     if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
     else if (weno_variant == WENO_TABLES) weno_tables(q1d, ql, qr, meqn, mx, mbc);
     else weno5_pyweno(q1d, ql, qr, meqn, mx, mbc, weno_variant == WENO_PYWENO_F32);
-    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, NULL, NULL, wave, s, amdq, apdq);
+    /* :128 rp(ql, qr, aux, aux) */
+    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, aux1d, aux1d, wave, s, amdq, apdq);
     double cfl = 0.0;
     for (int mw = 0; mw < mwaves; mw++)
         for (int i = 1; i <= mx + 1; i++)
@@ -1854,7 +1857,19 @@ static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double d
             Q2(qr, m, i - 1) = Q2(ql, m, i);
             Q2(ql, m, i) = Q2(qr, m, i);
         }
-    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, NULL, NULL, wave, s, amdq2, apdq2);
+    if (aux1d && maux > 0) { /* :177-184 auxr(i-1) = aux(i), auxl(i) = aux(i) */
+        auxl2 = (double *)calloc((size_t)n * maux, sizeof(double));
+        auxr2 = (double *)calloc((size_t)n * maux, sizeof(double));
+        memcpy(auxl2, aux1d, sizeof(double) * n * maux);
+        memcpy(auxr2, aux1d, sizeof(double) * n * maux);
+        for (int i = 1 - mbc + 1; i <= mx + mbc; i++)
+            for (int ma = 0; ma < maux; ma++) {
+                auxr2[ma + maux * IX(i - 1)] = aux1d[ma + maux * IX(i)];
+                auxl2[ma + maux * IX(i)] = aux1d[ma + maux * IX(i)];
+            }
+    }
+    rpn(c, ixy, meqn, mwaves, mbc, mx, ql, qr, auxl2, auxr2, wave, s, amdq2, apdq2);
+    free(auxl2); free(auxr2);
     for (int i = 1; i <= mx; i++)
         for (int m = 0; m < meqn; m++)
             Q2(dq1d, m, i) = Q2(dq1d, m, i) -
@@ -1867,7 +1882,7 @@ static double sc_flux1(rp_ctx *c, const double *q1d, double *dq1d, double dt, do
                        int ixy, int meqn, int mwaves, int mx, int mbc, int weno_variant,
                        int zero_dq, workS *w)
 {
-    return sc_flux1_capa(c, q1d, dq1d, dt, dxv, ixy, meqn, mwaves, mx, mbc, weno_variant, zero_dq, w, NULL);
+    return sc_flux1_capa(c, q1d, dq1d, dt, dxv, ixy, meqn, mwaves, mx, mbc, weno_variant, zero_dq, w, NULL, NULL);
 }
 
 /* 1-D entry: sharpclaw1.flux1(q,auxbc,dt,t,ixy,mx,mbc,maxnx) -> (dq1d, cfl); dq1d zero on entry */
@@ -1897,10 +1912,13 @@ double oracle_sc_flux1_capa(int rp_id, const double *rp_params, int meqn, int mw
     rp_ctx_init(&c, rp_id, rp_params, n);
     c.ndim = 1;
     workS w;
+    c.maux = maux;
     workS_alloc(&w, n, meqn, mwaves);
     double *capa = (double *)calloc(n, sizeof(double));
-    for (int k = 0; k < n; k++) capa[k] = aux[(mcapa - 1) + maux * k];
-    double cfl = sc_flux1_capa(&c, q, dq, dt, dx, 0, meqn, mwaves, mx, mbc, weno_variant, 0, &w, capa);
+    if (mcapa > 0)
+        for (int k = 0; k < n; k++) capa[k] = aux[(mcapa - 1) + maux * k];
+    double cfl = sc_flux1_capa(&c, q, dq, dt, dx, 0, meqn, mwaves, mx, mbc, weno_variant, 0, &w,
+                               mcapa > 0 ? capa : NULL, aux);
     free(capa);
     workS_free(&w);
     ctx_free(&c);
@@ -1916,16 +1934,20 @@ double oracle_sc_flux2_capa(int rp_id, const double *rp_params, int meqn, int mw
     rp_ctx c;
     rp_ctx_init(&c, rp_id, rp_params, n);
     workS w;
+    c.maux = maux;
     workS_alloc(&w, n, meqn, mwaves);
     double *capa = (double *)calloc(n, sizeof(double));
+    double *aux1d = (double *)calloc((size_t)n * maux, sizeof(double));
     double cfl = 0.0;
     double *q1d = w.q1d, *dq1d = w.dq1d;
     for (int j = 0; j <= my + 1; j++) {
         for (int i = 1 - mbc; i <= mx + mbc; i++) {
             for (int m = 0; m < meqn; m++) Q2(q1d, m, i) = Q3(q, m, i, j);
-            capa[IX(i)] = AUX3(mcapa - 1, i, j);
+            if (mcapa > 0) capa[IX(i)] = AUX3(mcapa - 1, i, j);
+            for (int ma = 0; ma < maux; ma++) aux1d[ma + maux * IX(i)] = AUX3(ma, i, j);
         }
-        double cfl1d = sc_flux1_capa(&c, q1d, dq1d, dt, dx, 1, meqn, mwaves, mx, mbc, weno_variant, 1, &w, capa);
+        double cfl1d = sc_flux1_capa(&c, q1d, dq1d, dt, dx, 1, meqn, mwaves, mx, mbc, weno_variant, 1, &w,
+                                     mcapa > 0 ? capa : NULL, aux1d);
         cfl = dmax2(cfl, cfl1d);
         for (int i = 1; i <= mx; i++)
             for (int m = 0; m < meqn; m++)
@@ -1934,15 +1956,18 @@ double oracle_sc_flux2_capa(int rp_id, const double *rp_params, int meqn, int mw
     for (int i = 0; i <= mx + 1; i++) {
         for (int j = 1 - mbc; j <= my + mbc; j++) {
             for (int m = 0; m < meqn; m++) Q2(q1d, m, j) = Q3(q, m, i, j);
-            capa[IX(j)] = AUX3(mcapa - 1, i, j);
+            if (mcapa > 0) capa[IX(j)] = AUX3(mcapa - 1, i, j);
+            for (int ma = 0; ma < maux; ma++) aux1d[ma + maux * IX(j)] = AUX3(ma, i, j);
         }
-        double cfl1d = sc_flux1_capa(&c, q1d, dq1d, dt, dy, 2, meqn, mwaves, my, mbc, weno_variant, 1, &w, capa);
+        double cfl1d = sc_flux1_capa(&c, q1d, dq1d, dt, dy, 2, meqn, mwaves, my, mbc, weno_variant, 1, &w,
+                                     mcapa > 0 ? capa : NULL, aux1d);
         cfl = dmax2(cfl, cfl1d);
         for (int j = 1; j <= my; j++)
             for (int m = 0; m < meqn; m++)
                 Q3(dq, m, i, j) = Q3(dq, m, i, j) + Q2(dq1d, m, j);
     }
     free(capa);
+    free(aux1d);
     workS_free(&w);
     ctx_free(&c);
     return cfl;

@@ -167,7 +167,7 @@ def set_weno_tables(tab):
 def sc_flux1(rp_id, rp_params, mwaves, mbc, mx, q, dx, dt, weno_variant, auxbc=None, mcapa=0):
     """sharpclaw1.flux1 (sharpclaw.py:385); mcapa is 1-based as in clawparams.mcapa (0 = none)."""
     dq = np.zeros_like(q, order="F")
-    if mcapa > 0:
+    if auxbc is not None:      # capacity function and / or a solver that reads aux
         cfl = lib().oracle_sc_flux1_capa(rp_id, _p(_params(rp_params)), q.shape[0], mwaves, mbc, mx,
                                          _p(q), _p(dq), dx, dt, weno_variant, _p(auxbc), auxbc.shape[0], mcapa)
         return dq, cfl
@@ -179,7 +179,7 @@ def sc_flux1(rp_id, rp_params, mwaves, mbc, mx, q, dx, dt, weno_variant, auxbc=N
 def sc_flux2(rp_id, rp_params, mwaves, mbc, mx, my, q, dx, dy, dt, weno_variant, nthreads=1,
              auxbc=None, mcapa=0):
     dq = np.zeros_like(q, order="F")
-    if mcapa > 0:
+    if auxbc is not None:
         cfl = lib().oracle_sc_flux2_capa(rp_id, _p(_params(rp_params)), q.shape[0], mwaves, mbc, mx, my,
                                          _p(q), _p(dq), dx, dy, dt, weno_variant, _p(auxbc),
                                          auxbc.shape[0], mcapa)

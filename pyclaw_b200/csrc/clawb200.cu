@@ -747,6 +747,8 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
     A.dtdy = (p->ndim > 1) ? dt / p->dy : 0.0;
     for (int i = 0; i < 8; i++) A.rp.p[i] = p->rp_params[i];
     weno_constants(A, p->weno_variant);
+    A.aux = aux;
+    A.amstride = p->mstride;
     A.mode = mode; A.ca = ca; A.cb = cb; A.div = div;
     A.cfl_bits = (unsigned long long *)cfl_dev;
     const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
@@ -798,6 +800,10 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
             return old ? sc_launch1<RpBurgers, true>(A, st) : sc_launch1<RpBurgers, false>(A, st);
         case CLAWB200_RP_EULER1D:
             return old ? sc_launch1<RpEuler1D, true>(A, st) : sc_launch1<RpEuler1D, false>(A, st);
+        case CLAWB200_RP_NEL_FWAVE: // with char_decomp = 0 an f-wave solver only contributes amdq / apdq
+            return old ? sc_launch1<RpElasticFwave<1, 1>, true>(A, st) : sc_launch1<RpElasticFwave<1, 1>, false>(A, st);
+        case CLAWB200_RP_ADVECTION_COLOR:
+            return old ? sc_launch1<RpColor1D, true>(A, st) : sc_launch1<RpColor1D, false>(A, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
     }
@@ -813,6 +819,12 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
                                         : sc_launch2<RpEuler5<1>, RpEuler5<2>, false>(A, st);
     case CLAWB200_RP_SHALLOW: return old ? sc_launch2<RpShallow<1>, RpShallow<2>, true>(A, st)
                                          : sc_launch2<RpShallow<1>, RpShallow<2>, false>(A, st);
+    case CLAWB200_RP_PSYSTEM: return old ? sc_launch2<RpElasticFwave<2, 1>, RpElasticFwave<2, 2>, true>(A, st)
+                                         : sc_launch2<RpElasticFwave<2, 1>, RpElasticFwave<2, 2>, false>(A, st);
+    case CLAWB200_RP_VC_ACOUSTICS: return old ? sc_launch2<RpVcAcoustics<1>, RpVcAcoustics<2>, true>(A, st)
+                                              : sc_launch2<RpVcAcoustics<1>, RpVcAcoustics<2>, false>(A, st);
+    case CLAWB200_RP_VC_ADVECTION: return old ? sc_launch2<RpColor<2, 1>, RpColor<2, 2>, true>(A, st)
+                                              : sc_launch2<RpColor<2, 1>, RpColor<2, 2>, false>(A, st);
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
 #undef SC2

@@ -36,7 +36,17 @@ struct ScArgs {
     // capacity function (flux1.f90:59-63): dtdx(i) = dt / (dx * aux(mcapa, i))
     const double *capa; // the capa component of aux, padded like q (or null)
     double dt, dx, dy;
+    // aux array for solvers that read it (flux1.f90:128,177-186): the interface solve sees
+    // aux(i-1), aux(i); the in-cell solve sees aux(i) on both sides
+    const double *aux;
+    long long amstride;
 };
+
+// aux of the cell at array offset `off` (row offset + clamped column)
+__device__ __forceinline__ AuxCell sc_aux(const ScArgs &A, long long off)
+{
+    return AuxCell{A.aux + off, A.amstride};
+}
 
 // dt / (d * capa) with one correctly rounded division, fast path first
 __device__ __forceinline__ double sc_dtd(double dt, double d, double capa)
@@ -185,12 +195,14 @@ template <class RP, int NT>
 __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql)[RP::MEQN],
                                               const double (&qr)[RP::MEQN], double *x1, double *x2,
                                               int t, bool iface_cfl, bool full, double &cfl,
-                                              double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l);
+                                              double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l,
+                                              const AuxCell &axl, const AuxCell &axc);
 
 template <class RP, bool OLD, int NT>
 __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, double *x1, double *x2,
                                         int t, bool iface_cfl, bool full, double &cfl,
-                                        double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l)
+                                        double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l,
+                                        const AuxCell &axl, const AuxCell &axc)
 {
     constexpr int MEQN = RP::MEQN;
     constexpr int QS = NT + 4;
@@ -202,14 +214,15 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
             weno5<OLD>(ar, A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m]);
         }
     });
-    sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, iface_cfl, full, cfl, dqx, dtdx_c, dtdx_l);
+    sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, iface_cfl, full, cfl, dqx, dtdx_c, dtdx_l, axl, axc);
 }
 
 template <class RP, int NT>
 __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql)[RP::MEQN],
                                               const double (&qr)[RP::MEQN], double *x1, double *x2,
                                               int t, bool iface_cfl, bool full, double &cfl,
-                                              double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l)
+                                              double (&dqx)[RP::MEQN], double dtdx_c, double dtdx_l,
+                                              const AuxCell &axl, const AuxCell &axc)
 {
     constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
 #pragma unroll
@@ -219,7 +232,7 @@ __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql
     double left[MEQN];
 #pragma unroll
     for (int m = 0; m < MEQN; m++) left[m] = x1[m * NT + (t > 0 ? t - 1 : 0)];
-    with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, left, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
+    with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, left, ql, axl, axc, wave, s, amdq, apdq, roe); });
     if (iface_cfl) {
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, dtdx_c * s[mw]), -dtdx_l * s[mw]);
@@ -229,7 +242,7 @@ __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql
     __syncthreads();
     if (full) {
         double amdq2[MEQN], apdq2[MEQN];
-        with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
+        with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, ql, qr, axc, axc, wave, s, amdq2, apdq2, roe); });
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             double an = x2[m * NT + (t < NT - 1 ? t + 1 : t)];
@@ -324,7 +337,11 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
                 dtdx_c = sc_dtd(A.dt, A.dx, __ldg(&A.capa[rowoff + icl]));
                 dtdx_l = sc_dtd(A.dt, A.dx, __ldg(&A.capa[rowoff + il]));
             }
-            sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1, dtdx_c, dtdx_l);
+            const AuxCell nocell{nullptr, 0};
+            const bool AUXRP = (RPX::MAUX > 0);
+            const int ilc = min(max(ic - 1, 1 - mbc), imax) + mbc - 1;
+            sc_xrow<RPX, OLD, NT>(A, qs, x1, x2, t, xiface, xfull, cfl, dx1, dtdx_c, dtdx_l,
+                                  AUXRP ? sc_aux(A, rowoff + ilc) : nocell, AUXRP ? sc_aux(A, rowoff + icl) : nocell);
         }
 
         // y-direction: reconstruct cell c = k-2 from rows k-4 .. k
@@ -345,14 +362,19 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
 #pragma unroll
             for (int m = 0; m < MEQN; m++) { amdq[m] = apdq[m] = amdq2[m] = apdq2[m] = 0.0; }
             if (c >= j0) {
-                with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq, apdq, roe); });
+                const AuxCell nocell{nullptr, 0};
+                const bool AUXRP = (RPY::MAUX > 0);
+                const long long offc = (long long)A.pitch * (c + mbc - 1) + icl;
+                const AuxCell ayc = AUXRP ? sc_aux(A, offc) : nocell;
+                const AuxCell aym = AUXRP ? sc_aux(A, offc - A.pitch) : nocell;
+                with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, aym, ayc, wave, s, amdq, apdq, roe); });
                 if (ycol && c >= 1 && c <= A.my + 1) {
 #pragma unroll
                     for (int mw = 0; mw < MW; mw++)
                         cfl = dmax2(dmax2(cfl, dtdy_c * s[mw]), -dtdy_p * s[mw]);
                 }
                 if (c < j1)
-                    with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, AuxCell{nullptr, 0}, AuxCell{nullptr, 0}, wave, s, amdq2, apdq2, roe); });
+                    with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, ayc, ayc, wave, s, amdq2, apdq2, roe); });
                 // cell c-1 = k-3 is complete
                 const int jc = c - 1;
                 if (jc >= j0 && jc < j1 && col_out) {
@@ -414,7 +436,11 @@ __global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
         dtdx_c = sc_dtd(A.dt, A.dx, __ldg(&A.capa[icl]));
         dtdx_l = sc_dtd(A.dt, A.dx, __ldg(&A.capa[il]));
     }
-    sc_xrow<RP, OLD, NT>(A, qs, x1, x2, t, xiface, true, cfl, dqx, dtdx_c, dtdx_l);
+    const AuxCell nocell{nullptr, 0};
+    const bool AUXRP = (RP::MAUX > 0);
+    const int ilc = min(max(ic - 1, 1 - mbc), imax) + mbc - 1;
+    sc_xrow<RP, OLD, NT>(A, qs, x1, x2, t, xiface, true, cfl, dqx, dtdx_c, dtdx_l,
+                         AUXRP ? sc_aux(A, ilc) : nocell, AUXRP ? sc_aux(A, icl) : nocell);
     if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
     sc_cfl_commit(cfl, A.cfl_bits);
 }
@@ -519,7 +545,11 @@ __global__ void __launch_bounds__(NT) sc1d_tab_kernel(const ScArgs A)
 #pragma unroll
         for (int m = 0; m < MEQN; m++) weno_tab(ar, qs + m * QS + t + H, ql[m], qr[m]);
     });
-    sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, xiface, true, cfl, dqx, A.dtdx, A.dtdx);
+    const AuxCell nocell{nullptr, 0};
+    const bool AUXRP = (RP::MAUX > 0);
+    const int ilc = min(max(ic - 1, 1 - mbc), imax) + mbc - 1;
+    sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, xiface, true, cfl, dqx, A.dtdx, A.dtdx,
+                          AUXRP ? sc_aux(A, ilc) : nocell, AUXRP ? sc_aux(A, icl) : nocell);
     if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
     sc_cfl_commit(cfl, A.cfl_bits);
 }

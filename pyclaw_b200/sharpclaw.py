@@ -224,8 +224,10 @@ class SharpClawSolver(Solver):
         else:
             raise NotImplementedError("lim_type=%s char_decomp=%s is not implemented"
                                       % (self.lim_type, self.char_decomp))
-        if self.tfluct_solver or self.fwave:
-            raise NotImplementedError("tfluct / f-wave SharpClaw solvers are not implemented")
+        if self.tfluct_solver:
+            raise NotImplementedError("tfluct (total fluctuation) solvers are not implemented")
+        # fwave = True with char_decomp = 0 (e.g. the stegoton script): flux1.f90 only uses the
+        # solver's amdq / apdq, so an f-wave solver works unchanged
         self.mbc = (self.weno_order + 1) // 2
         state = solution.state
         state.set_mbc(self.mbc)

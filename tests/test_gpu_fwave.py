@@ -31,11 +31,16 @@ def _stegoton_q(x, aux, law, xupper):
 
 
 @pytest.mark.parametrize("law", [1, 2])
-def test_stegoton_fwave_vs_oracle(law):
+@pytest.mark.parametrize("solver_type", ['classic', 'sharpclaw'])
+def test_stegoton_fwave_vs_oracle(law, solver_type):
     import pyclaw
     xupper, cellsperlayer = 60.0, 6
     mx = int(round(xupper)) * cellsperlayer
-    solver = pyclaw.ClawSolver1D()
+    if solver_type == 'classic':
+        solver = pyclaw.ClawSolver1D()
+    else:                                   # stegoton.py:85-86,137-139
+        solver = pyclaw.SharpClawSolver1D()
+        solver.lim_type, solver.char_decomp = 2, 0
     solver.kernel_language = 'Fortran'
     solver.bc_lower[0] = solver.bc_upper[0] = pyclaw.BC.periodic
     solver.aux_bc_lower[0] = solver.aux_bc_upper[0] = pyclaw.BC.periodic
@@ -55,7 +60,7 @@ def test_stegoton_fwave_vs_oracle(law):
     status = claw.run()
     qg = np.asarray(claw.frames[-1].q)
 
-    s = po.OracleSolver("classic", 1, po.RP_NEL_FWAVE, [float(law)], 2)
+    s = po.OracleSolver(solver_type, 1, po.RP_NEL_FWAVE, [float(law)], 2)
     s.bc_lower = s.bc_upper = [po.BC_PERIODIC]
     s.aux_bc_lower = s.aux_bc_upper = [po.BC_PERIODIC]
     qo = s.run(q0, aux, [grid.d[0]], 8.0, 2)[-1]

@@ -749,3 +749,59 @@ def test_step2_variable_coefficient_solvers(rp, shape, trans):
         _lib.call("clawb200_step2_host", ctypes.byref(P), _ptr(q), _ptr(qn_g), _ptr(aux), dt, ctypes.byref(cfl_g))
         assert np.array_equal(qn_g[inner], qn_o[inner]), np.abs(qn_g[inner] - qn_o[inner]).max()
         assert cfl_g.value == cfl_o and cfl_o > 0.01
+
+
+@pytest.mark.parametrize("rp", ["nel", "color1d", "psystem", "vc_acoustics", "vc_advection"])
+@pytest.mark.parametrize("variant", [0, 2])
+def test_sharpclaw_with_aux_dependent_solvers(rp, variant):
+    """flux1.f90:128,177-186: the interface solve sees aux(i-1), aux(i), the in-cell solve aux(i)
+    on both sides."""
+    mbc, dt = 3, 0.0011
+    rng = np.random.RandomState(17)
+    cfl_g = ctypes.c_double()
+    if rp in ("nel", "color1d"):
+        for mx in (9, 400):
+            dx = 1.0 / mx
+            n = mx + 2 * mbc
+            if rp == "nel":
+                rp_id, params, meqn, mwaves = po.RP_NEL_FWAVE, [1.0], 2, 2
+                q, aux = _elastic_data((n,), seed=mx, law=1, ndim=1)
+                q = np.asfortranarray(problems.smooth_state("acoustics", (n,), seed=mx) * 0.2)
+            else:
+                rp_id, params, meqn, mwaves = po.RP_ADVECTION_COLOR, [], 1, 1
+                q = problems.smooth_state("advection", (n,), seed=mx)
+                aux = np.asfortranarray(rng.uniform(-1.0, 2.0, (1, n)))
+            maux = aux.shape[0]
+            P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, method=[1, 2, 0, 0, 0, 0, maux],
+                                  maux=maux, weno_variant=variant)
+            dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, variant, auxbc=aux, mcapa=0)
+            dq_g = np.zeros_like(q, order="F")
+            _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), _ptr(aux), dt, ctypes.byref(cfl_g))
+            assert not np.isnan(dq_o).any() and np.abs(dq_o).max() > 1e-6
+            assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]) and cfl_g.value == cfl_o
+        return
+    for mx, my in ((37, 29), (130, 70)):
+        dx, dy = 0.01, 0.013
+        pad = (mx + 2 * mbc, my + 2 * mbc)
+        if rp == "psystem":
+            rp_id, meqn, mwaves = po.RP_PSYSTEM, 3, 2
+            _, aux = _elastic_data(pad, seed=mx, law=1, ndim=2)
+            q = np.asfortranarray(problems.smooth_state("acoustics", pad, seed=mx) * 0.2)
+        elif rp == "vc_acoustics":
+            rp_id, meqn, mwaves = po.RP_VC_ACOUSTICS, 3, 2
+            q = problems.smooth_state("acoustics", pad, seed=mx)
+            aux = np.asfortranarray(np.stack([rng.choice([1.0, 4.0], pad), rng.choice([1.0, 2.0], pad)]))
+        else:
+            rp_id, meqn, mwaves = po.RP_VC_ADVECTION, 1, 1
+            q = problems.smooth_state("advection", pad, seed=mx)
+            aux = np.asfortranarray(np.stack([rng.uniform(-1.0, 1.5, pad), rng.uniform(-1.2, 0.8, pad)]))
+        maux = aux.shape[0]
+        P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, [], method=[1, 2, 0, 0, 0, 0, maux],
+                              maux=maux, weno_variant=variant)
+        dq_o, cfl_o = po.sc_flux2(rp_id, [], mwaves, mbc, mx, my, q, dx, dy, dt, variant, auxbc=aux, mcapa=0)
+        dq_g = np.zeros_like(q, order="F")
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), _ptr(aux), dt, ctypes.byref(cfl_g))
+        inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+        assert not np.isnan(dq_o).any() and np.abs(dq_o).max() > 1e-6
+        assert np.array_equal(dq_g[inner], dq_o[inner]), np.abs(dq_g - dq_o)[inner].max()
+        assert cfl_g.value == cfl_o
