@@ -218,7 +218,7 @@ def psystem(cells_per_layer=20, petsc=False, tfinal=2.0, outdir=None):
     x, y = grid.x.center, grid.y.center
     yy, xx = np.meshgrid(y - np.floor(y), x - np.floor(x))
     same = (xx <= 0.5) * (yy <= 0.5) + (xx > 0.5) * (yy > 0.5)
-    aux = np.empty((4, n, n), order='F')
+    aux = np.empty((4, len(x), len(y)), order='F')
     aux[0] = 1. * same + 4. * (1 - same)
     aux[1] = 1. * same + 4. * (1 - same)
     aux[2] = 2.                                               # exponential stress law
@@ -252,9 +252,9 @@ def acoustics3d(mx=256, my=4, mz=4, petsc=False, tfinal=2.0, outdir=None):
     state = pyclaw.State(grid, 4, 2)
     grid.compute_c_center()
     X = grid._c_center[0]
-    state.aux = np.ones((2, mx, my, mz), order='F')
+    state.aux = np.ones((2,) + X.shape, order='F')
     r = np.abs(X + 0.5)
-    q0 = np.zeros((4, mx, my, mz), order='F')
+    q0 = np.zeros((4,) + X.shape, order='F')
     q0[0] = (r <= 0.2) * (1. + np.cos(np.pi * r / 0.2))
     state.q[...] = q0
     return _run(pyclaw, solver, state, tfinal, 10, outdir)

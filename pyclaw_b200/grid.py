@@ -50,13 +50,15 @@ class Dimension(object):
     @property
     def edge(self):
         if self._edge is None:
-            self._edge = np.array([self.lowerg + i * self.d for i in range(self.ng + 1)])
+            # global index arithmetic: the coordinates of a cell do not depend on how the
+            # dimension is partitioned (and equal the reference's lower + i*d in serial)
+            self._edge = np.array([self.lower + (self.nstart + i) * self.d for i in range(self.ng + 1)])
         return self._edge
 
     @property
     def center(self):
         if self._center is None:
-            self._center = np.array([self.lowerg + (i + 0.5) * self.d for i in range(self.ng)])
+            self._center = np.array([self.lower + (self.nstart + i + 0.5) * self.d for i in range(self.ng)])
         return self._center
 
     def _set_range(self, nstart, nend):

@@ -49,9 +49,12 @@ class SlabPartition(object):
         self._bufs = {}
 
     def _buffers(self, field, nrows):
-        key = (field.ncomp, nrows, field.pitch, field.cur.device)
+        # a "row" of the partitioned (last) dimension: a cell in 1-D, a padded row in 2-D, a
+        # padded plane in 3-D
+        tail = tuple(field.cur.shape[2:])
+        key = (field.ncomp, nrows, tail, field.cur.device)
         if key not in self._bufs:
-            shape = (field.ncomp, nrows, field.pitch)
+            shape = (field.ncomp, nrows) + tail
             mk = lambda: torch.empty(shape, dtype=torch.float64, device=field.cur.device)
             self._bufs[key] = dict(send_lo=mk(), send_hi=mk(), recv_lo=mk(), recv_hi=mk())
         return self._bufs[key]

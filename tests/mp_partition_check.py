@@ -113,6 +113,24 @@ def main():
         print("case sphere: %d ranks, %d steps, bit-identical=%s maxdiff=%g"
               % (world, nsteps, same, np.abs(qp - qser).max()), flush=True)
         ok &= same
+    # the reference's applications (examples/apps.py) on the slab partition
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import apps
+    for name, kw in (("shallow1d", dict(mx=200, tfinal=0.5)),
+                     ("stegoton", dict(layers=30, tfinal=5.0, solver_type='sharpclaw')),
+                     ("annulus", dict(mx=20, my=60, tfinal=0.2)),
+                     ("vc_acoustics2d", dict(mx=48, my=40, tfinal=0.1)),
+                     ("psystem", dict(cells_per_layer=8, tfinal=0.15)),
+                     ("acoustics3d", dict(mx=32, my=4, mz=8 * world, tfinal=0.3))):
+        cp = apps.APPS[name](petsc=True, **kw)
+        st = cp.frames[-1].state
+        qp = np.asarray(st._partition.gather_interior(st))
+        if rank == 0:
+            cs = apps.APPS[name](petsc=False, **kw)
+            qs = np.asarray(cs.frames[-1].q)
+            same = np.array_equal(qp, qs) and np.isfinite(qs).all()
+            print("app %s: %d ranks, bit-identical=%s maxdiff=%g" % (name, world, same, np.abs(qp - qs).max()), flush=True)
+            ok &= same
     flag = torch.tensor([1.0 if ok else 0.0], device='cuda')
     dist.broadcast(flag, 0)
     dist.barrier()

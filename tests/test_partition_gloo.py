@@ -127,3 +127,43 @@ def test_frames_written_and_restarted_on_two_ranks(tmp_path):
         out = mgr.dict()
         mp.spawn(_io_worker, args=(world, port, str(tmp_path), out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _nd_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import petclaw as pyclaw
+        ok = True
+        mbc = 2
+        # 1-D: the only dimension is partitioned; 3-D: z-slabs, halo "rows" are padded planes
+        for dims in ([('x', 13)], [('x', 5), ('y', 4), ('z', 9)]):
+            grid = pyclaw.Grid([pyclaw.Dimension(n, 0., 1., m) for n, m in dims])
+            state = pyclaw.State(grid, 2, device='cpu')
+            state.set_mbc(mbc)
+            last = grid.dimensions[-1]
+            k0, k1 = last.nstart, last.nend
+            glob = np.arange(2 * np.prod([m for _, m in dims]), dtype=float).reshape([2] + [m for _, m in dims])
+            state.q[...] = glob[..., k0:k1]
+            state._partition.exchange(state._q, 2, periodic=[False] * (len(dims) - 1) + [True])
+            qbc = np.asarray(state._q.padded())
+            nloc = k1 - k0
+            n = dims[-1][1]
+            inner = (slice(None),) + (slice(mbc, -mbc),) * (len(dims) - 1)
+            for g in range(mbc):
+                lo = (k0 - mbc + g) % n
+                hi = (k1 + g) % n
+                ok &= np.array_equal(qbc[inner + (g,)], glob[..., lo])
+                ok &= np.array_equal(qbc[inner + (mbc + nloc + g,)], glob[..., hi])
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_in_1d_and_3d():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_nd_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
