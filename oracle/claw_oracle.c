@@ -7,9 +7,14 @@
  * follows the reference's arithmetic order statement by statement.
  *
  * The reference's own Fortran cannot be built in this image (no Fortran compiler),
- * so this is a "port" oracle.  It is pinned against the reference's golden files
- * (tests/test_oracle_golden.py): test/sb_density, test/acoustics2D_solution,
- * test/ac_sc_solution and the two 1-D scalars of test/test_examples.py.
+ * so this is a "port" oracle.  It is pinned against every golden the reference holds for
+ * the path (tests/test_oracle_golden.py): test/sb_density, test/acoustics2D_solution,
+ * test/ac_sc_solution, test/swsphere_height, the 1-D scalars of test/test_examples.py
+ * (classic, WENO5, WENO17) and the 3-D dimension-split scalar.  PARITY UNPINNED (no golden in
+ * the reference; external solver sources): rpt2 acoustics / Euler results, advection,
+ * shallow Roe (1-D, 2-D), the f-wave elasticity / p-system solvers, variable-coefficient
+ * acoustics / colour equation, Burgers, 1-D Euler -- for those the 1-D Euler and shallow
+ * restatements are additionally checked against exact Riemann solutions.
  *
  * Layout follows the reference: Fortran order q(meqn, 1-mbc:mx+mbc, 1-mbc:my+mbc),
  * i.e. component fastest.  Strict IEEE double: compile with -ffp-contract=off.
@@ -20,6 +25,9 @@
  *   src/fortran/1d/sharpclaw/flux1.f90:2-195 (and the 2-D twin),
  *   src/fortran/1d/sharpclaw/reconstruct.f90:120-185 (old weno5), weno.f90:5-102
  *   src/fortran/2d/sharpclaw/flux2.f90:2-96
+ *   src/fortran/1d/classic/step1fw.f:135-136, src/fortran/2d/classic/flux2fw.f:151-152
+ *   src/fortran/3d/classic/step3ds.f:2-376, flux3.f:176-237 (dimensional splitting)
+ *   src/fortran/1d/sharpclaw/weno.f90:104-2425 (table driven; tables from the caller)
  *   development/rp_approaches/rpn2_euler_5wave.f:5-302, rpt2_euler_5wave.f:4-98
  * Riemann solvers that live in the external clawpack/riemann repository (un-vendored,
  * un-pinned) are restated from their published algorithm:

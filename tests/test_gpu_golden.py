@@ -548,3 +548,34 @@ def test_shallow1d_app_vs_oracle(solver_type, ic):
     assert np.array_equal(qg, qo)
     if ic == 'dam-break':       # exact middle state of the 3:1 dam break with g = 1
         assert abs(qg[0, mx // 2] - 1.848576) < 2e-3
+
+
+def test_baseline_config0_acoustics1d_800_cells():
+    """BASELINE.json configs[0]: 1-D acoustics, ClawSolver1D, MC limiter, 800 cells -- the
+    reference's CPU-runnable case; GPU through the pyclaw API vs the oracle driver, bit for bit."""
+    import pyclaw
+    mx = 800
+    solver = pyclaw.ClawSolver1D()
+    solver.mwaves, solver.limiters = 2, [4, 4]
+    solver.bc_lower[0] = solver.bc_upper[0] = pyclaw.BC.periodic
+    grid = pyclaw.Grid(pyclaw.Dimension('x', 0.0, 1.0, mx))
+    state = pyclaw.State(grid, 2)
+    state.aux_global.update(rho=1.0, bulk=1.0, zz=1.0, cc=1.0)
+    xc = grid.x.center
+    q0 = np.zeros((2, mx), order='F')
+    q0[0] = np.exp(-100 * (xc - 0.75) ** 2)
+    state.q[...] = q0
+    solver.dt_initial = grid.d[0] * 0.1
+    claw = pyclaw.Controller()
+    claw.keep_copy, claw.output_format, claw.tfinal, claw.nout = True, None, 1.0, 5
+    claw.solution, claw.solver = pyclaw.Solution(state), solver
+    claw.run()
+    s = po.OracleSolver("classic", 1, po.RP_ACOUSTICS, [1.0, 1.0, 1.0, 1.0], 2)
+    s.limiters = [4, 4]
+    s.bc_lower = s.bc_upper = [po.BC_PERIODIC]
+    s.dt_initial = grid.d[0] * 0.1
+    fr = s.run(q0, None, [grid.d[0]], 1.0, 5)
+    for k in range(6):
+        assert np.array_equal(np.asarray(claw.frames[k].q), fr[k]), k
+    # one period: the pulse is back where it started, second-order accurate
+    assert grid.d[0] * np.abs(fr[-1] - fr[0]).sum() < 2e-4
