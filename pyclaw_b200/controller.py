@@ -3,7 +3,6 @@
 ``output_format`` ('ascii', 'petsc', a list of those, or None) and/or kept in memory with
 ``keep_copy``.  Plotting is outside the hot-path scope."""
 import copy
-import logging
 import os
 
 import numpy as np

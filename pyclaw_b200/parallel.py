@@ -15,12 +15,8 @@ Results are bit-identical for any number of slabs: every cell update is a pure f
 of its neighbourhood and max is associative (the reference's own standard: its 6-rank
 run is compared with the serial golden file at 1e-14, test/test_examples.py:264-277).
 """
-import ctypes
-
 import torch
 import torch.distributed as dist
-
-from . import _lib
 
 
 def world():

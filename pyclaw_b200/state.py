@@ -12,7 +12,7 @@ import copy
 import numpy as np
 import torch
 
-from .array import ClawArray, as_claw, default_device
+from .array import as_claw, default_device
 from .grid import Grid
 
 
