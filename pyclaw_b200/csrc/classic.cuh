@@ -226,6 +226,12 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
     int qb = 0;
     for (int r = rbeg; r <= rend; r++) {
         const long long rowoff = (long long)A.pitch * (r + mbc - 1);
+        if (RP::MAUX >= 8) { // aux of row r+2 (first needed as the "row above" of iteration r+1)
+            const int jp = min(r + 2, A.my + mbc) + mbc - 1;
+            const double *ap = A.aux + (long long)A.pitch * jp + (min(max(ii, 1 - mbc), imax) + mbc - 1);
+#pragma unroll
+            for (int ma = 0; ma < RP::MAUX; ma++) prefetch_l1(ap + ma * A.amstride);
+        }
         cp_async_wait_all();
         __syncthreads();
         double *qs = qs0 + qb * (MEQN * QS);
@@ -504,6 +510,12 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     int par = 0;
     for (int k = j0 - 2; k <= j1 + 1; k++) {
         const long long rowoff = (long long)A.pitch * (k + mbc - 1);
+        if (RP::MAUX >= 8) { // aux of row k+2, a full iteration before its first use
+            const int jp = min(k + 2, A.my + mbc) + mbc - 1;
+            const double *ap = A.aux + (long long)A.pitch * jp + icl;
+#pragma unroll
+            for (int ma = 0; ma < RP::MAUX; ma++) prefetch_l1(ap + ma * A.amstride);
+        }
         cp_async_wait_all();
         double qk[MEQN];
 #pragma unroll
