@@ -168,6 +168,9 @@ int clawb200_ssp104_combine(const double *q, double *s1, double *s2, long long n
  * at reconstruct.f90:96-113.  Host pointers; the call returns after the upload. */
 int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
                              const double *WL, const double *WR, double eps, void *stream);
+/* Number of table uploads so far: the tables are one set per process (constant memory), a
+ * caller that remembers the value after its own upload can tell whether they are still its. */
+int clawb200_weno_generation(void);
 
 /* apps/shallow-sphere/src2.f:2-147 (the f2py `problem.src2` the reference script wraps as
  * solver.step_src): Coriolis source term with tangent-plane projection, in place on the

@@ -106,6 +106,7 @@ def load():
                 "pyclaw_b200 has no CPU fallback" % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
         L.clawb200_version.restype = ctypes.c_int
+        L.clawb200_weno_generation.restype = ctypes.c_int
         L.clawb200_last_error.restype = ctypes.c_char_p
         for name, args in SIGNATURES.items():
             f = getattr(L, name)

@@ -659,7 +659,10 @@ extern "C" int clawb200_halo_unpack(const clawb200_problem *p, double *q, int na
 // ---------------------------------------------------------------------------
 constexpr int SNT = 128;
 
-static int g_weno_k = 0; // stencils of the table-driven WENO currently in constant memory
+static int g_weno_k = 0;   // stencils of the table-driven WENO currently in constant memory
+static int g_weno_gen = 0; // bumped by every upload, so callers can tell whose tables are resident
+
+extern "C" int clawb200_weno_generation(void) { return g_weno_gen; }
 
 extern "C" int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
                                         const double *WL, const double *WR, double eps, void *stream)
@@ -681,6 +684,7 @@ extern "C" int clawb200_set_weno_tables(int k, const double *S, const double *CL
     CUDA_OK(cudaMemcpyToSymbolAsync(c_weno, &h, sizeof(h), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     g_weno_k = k;
+    g_weno_gen++;
     return 0;
 }
 

@@ -50,8 +50,24 @@ class SharpClawSolver(Solver):
     def _needs_backup_copy(self):
         return self.start_step is not start_step
 
+    # The table-driven WENO kernel reads its coefficients from constant memory, one table set
+    # per process: a solver uploads its own again when somebody else's upload came after it.
+    def _upload_weno_tables(self):
+        tab = getattr(self, '_weno_tab', None)
+        if tab is None:
+            return
+        L = _lib.load()
+        if getattr(self, '_weno_gen', None) == L.clawb200_weno_generation():
+            return
+        import numpy as np
+        arr = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('S', 'CL', 'CR', 'WL', 'WR')]
+        _lib.call("clawb200_set_weno_tables", int(tab['k']),
+                  *[ctypes.c_void_p(a.ctypes.data) for a in arr], float(tab['eps']), _stream())
+        self._weno_gen = L.clawb200_weno_generation()
+
     # ---- one dq evaluation fused with a stage update ----
     def _stage(self, q_buf, qa_buf, out_buf, mode, ca, cb, div, slot, dq_buf=None):
+        self._upload_weno_tables()
         _lib.call("clawb200_sharpclaw_stage", ctypes.byref(self._problem), _ptr(q_buf), _ptr(qa_buf),
                   _ptr(out_buf), _ptr(dq_buf), self._aux_ptr, float(self.dt), mode, float(ca), float(cb),
                   float(div), ctypes.c_void_p(self._cfl_dev.data_ptr() + 8 * slot), _stream())
@@ -236,10 +252,8 @@ class SharpClawSolver(Solver):
         # clawparams.mcapa = state.mcapa + 1 (sharpclaw.py:270)
         method = [int(self.dt_variable), 2, 0, 0, 0, state.mcapa + 1, state.maux]
         self._setup_device(state, method=method, weno_variant=variant)
-        if variant == _lib.WENO_TABLES:
-            arr = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('S', 'CL', 'CR', 'WL', 'WR')]
-            _lib.call("clawb200_set_weno_tables", int(tab['k']),
-                      *[ctypes.c_void_p(a.ctypes.data) for a in arr], float(tab['eps']), _stream())
+        self._weno_tab = tab if variant == _lib.WENO_TABLES else None
+        self._upload_weno_tables()
         self.allocate_bc_arrays(state)
         self._aux_ptr = _ptr(state._aux.cur if state._aux is not None else None)
         self._dq_field = None

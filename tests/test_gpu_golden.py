@@ -579,3 +579,36 @@ def test_baseline_config0_acoustics1d_800_cells():
         assert np.array_equal(np.asarray(claw.frames[k].q), fr[k]), k
     # one period: the pulse is back where it started, second-order accurate
     assert grid.d[0] * np.abs(fr[-1] - fr[0]).sum() < 2e-4
+
+
+def test_two_weno_orders_alive_at_once():
+    """The WENO tables are one set per process; interleaving solvers of different orders must
+    still give each its own (sharpclaw.py re-uploads when another upload came in between)."""
+    import pyclaw
+
+    def make(order):
+        solver = pyclaw.SharpClawSolver1D()
+        solver.weno_order = order
+        solver.mwaves = 2
+        solver.bc_lower[0] = solver.bc_upper[0] = pyclaw.BC.periodic
+        grid = pyclaw.Grid(pyclaw.Dimension('x', 0.0, 1.0, 100))
+        state = pyclaw.State(grid, 2)
+        state.aux_global.update(rho=1.0, bulk=1.0, zz=1.0, cc=1.0)
+        state.q[0, :] = np.exp(-100 * (grid.x.center - 0.75) ** 2)
+        state.q[1, :] = 0.
+        solver.dt_initial = 0.001
+        sol = pyclaw.Solution(state)
+        solver.setup(sol)
+        solver.dt = solver.dt_initial
+        return solver, sol
+
+    a, sa = make(9)
+    b, sb = make(13)
+    for _ in range(5):                      # interleaved
+        a.evolve_to_time(sa)
+        b.evolve_to_time(sb)
+    a2, sa2 = make(9)
+    for _ in range(5):                      # alone
+        a2.evolve_to_time(sa2)
+    assert np.array_equal(np.asarray(sa.q), np.asarray(sa2.q))
+    assert not np.array_equal(np.asarray(sa.q), np.asarray(sb.q))
