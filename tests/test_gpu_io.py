@@ -110,3 +110,30 @@ def test_compute_p_frames_and_functionals(tmp_path):
         assert abs(F[k, 0] - claw.frames[k].t) < 1e-15
         expect = np.abs(np.asarray(claw.frames[k].q)[0] * dxdy).sum()
         assert abs(F[k, 1] - expect) < 1e-13
+
+
+def test_gauges_record_every_step(tmp_path):
+    """grid.add_gauges / solver.write_gauge_values (grid.py:519-545, solver.py:731-741): one line
+    ``t p...`` per accepted step plus the initial one, values from compute_gauge_values(q, aux)."""
+    import pyclaw
+    solver, state = _setup(pyclaw)
+    dt = solver.dt_initial
+    grid = state.grid
+    grid.gauge_path = str(tmp_path / '_gauges') + os.sep
+    grid.add_gauges([[0.5, 0.25], [1.0, 1.0]])
+    solver.compute_gauge_values = lambda q, aux: [q[0], 10 * q[0] + q[1]]
+    claw = pyclaw.Controller()
+    claw.keep_copy, claw.output_format = True, None
+    claw.tfinal, claw.nout = 8 * dt, 2
+    claw.solution, claw.solver = pyclaw.Solution(state), solver
+    claw.run()
+    files = sorted(os.listdir(grid.gauge_path))
+    assert files == ['gauge0.5_0.25.txt', 'gauge1.0_1.0.txt']
+    g = np.loadtxt(os.path.join(grid.gauge_path, files[0]))
+    assert g.shape == (9, 3)                                   # initial line + 8 steps
+    np.testing.assert_allclose(g[:, 0], dt * np.arange(9), rtol=0, atol=1e-15)
+    # the gauge cell is floor(coordinate / d), as the reference computes it
+    i, j = int(np.floor(0.5 / grid.d[0])), int(np.floor(0.25 / grid.d[1]))
+    for k, row in ((0, 0), (1, 4), (2, 8)):
+        q = np.asarray(claw.frames[k].q)
+        assert g[row, 1] == q[0, i, j] and g[row, 2] == 10 * q[0, i, j] + q[1, i, j]
