@@ -699,6 +699,18 @@ static int sc_launch1_tab(const ScArgs &A, cudaStream_t st)
     return 0;
 }
 
+template <class RPX, class RPY>
+static int sc_launch2_tab(const ScArgs &A, cudaStream_t st)
+{
+    constexpr int NC = SNT - 2;
+    const int H = g_weno_k - 1;
+    size_t smem = sizeof(double) * (RPX::MEQN * (SNT + 2 * H) + 2 * RPX::MEQN * SNT);
+    dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);
+    sc2d_tab_kernel<RPX, RPY, SNT><<<grid, SNT, smem, st>>>(A);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static void weno_constants(ScArgs &A, int variant)
 {
     const bool f32 = (variant == CLAWB200_WENO_PYWENO_F32);
@@ -757,10 +769,20 @@ static int sharpclaw_launch(const clawb200_problem *p, const double *q, const do
     A.cfl_bits = (unsigned long long *)cfl_dev;
     const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
     if (p->weno_variant == CLAWB200_WENO_TABLES) {
-        if (p->ndim != 1) return fail(CLAWB200_ERR_UNSUPPORTED, "WENO orders above 5 are compiled for 1-D only");
         if (g_weno_k < 3) return fail(CLAWB200_ERR_INVALID, "call clawb200_set_weno_tables first");
         if (p->mbc < g_weno_k) return fail(CLAWB200_ERR_INVALID, "WENO of order 2k-1 needs mbc >= k");
         if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for WENO orders above 5");
+        if (p->ndim == 2) {
+            A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+            switch (p->rp_id) {
+            case CLAWB200_RP_ACOUSTICS: return sc_launch2_tab<RpAcoustics<2, 1>, RpAcoustics<2, 2>>(A, st);
+            case CLAWB200_RP_ADVECTION: return sc_launch2_tab<RpAdvection<2, 1>, RpAdvection<2, 2>>(A, st);
+            case CLAWB200_RP_EULER5: return sc_launch2_tab<RpEuler5<1>, RpEuler5<2>>(A, st);
+            case CLAWB200_RP_SHALLOW: return sc_launch2_tab<RpShallow<1>, RpShallow<2>>(A, st);
+            case CLAWB200_RP_VC_ACOUSTICS: return sc_launch2_tab<RpVcAcoustics<1>, RpVcAcoustics<2>>(A, st);
+            default: return fail(CLAWB200_ERR_UNSUPPORTED, "WENO orders above 5 are not compiled for this solver in 2-D");
+            }
+        }
         switch (p->rp_id) {
         case CLAWB200_RP_ACOUSTICS: return sc_launch1_tab<RpAcoustics<1, 1>>(A, st);
         case CLAWB200_RP_ADVECTION: return sc_launch1_tab<RpAdvection<1, 1>>(A, st);

@@ -553,3 +553,118 @@ __global__ void __launch_bounds__(NT) sc1d_tab_kernel(const ScArgs A)
     if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
     sc_cfl_commit(cfl, A.cfl_bits);
 }
+
+// ---------------------------------------------------------------------------
+// WENO of order 7 .. 17 in 2-D (flux2.f90:2-96 over the table-driven reconstruction).
+// Same decomposition as sc2d_kernel -- thread t <-> column ic, rows walked in order, the
+// x-direction of a row through shared memory -- but the y-stencil (2k-1 rows) is gathered
+// from global memory at every row instead of living in a rolling register window: these
+// orders are a capability (no application of the reference selects them), not a tuned path.
+// ---------------------------------------------------------------------------
+template <class RPX, class RPY, int NT>
+__global__ void __launch_bounds__(NT) sc2d_tab_kernel(const ScArgs A)
+{
+    constexpr int MEQN = RPX::MEQN, MW = RPX::MWAVES, NROE = RPX::NROE;
+    constexpr int NC = NT - 2;
+    const int kk = c_weno.k;
+    const int H = kk - 1;
+    const int QS = NT + 2 * H;
+    extern __shared__ double sm[];
+    double *qs = sm;                // [MEQN][NT + 2H], index e <-> column i0-1-H+e
+    double *x1 = qs + MEQN * QS;
+    double *x2 = x1 + MEQN * NT;
+    const int t = threadIdx.x;
+    const int mbc = A.mbc;
+    const int i0 = 1 + blockIdx.x * NC;
+    const int ic = i0 - 1 + t;
+    const int imax = A.mx + mbc;
+    const int icl = min(ic, imax) + mbc - 1;
+    const int ilc = min(max(ic - 1, 1 - mbc), imax) + mbc - 1;
+    const bool col_out = (t >= 1) && (t <= NC) && (ic <= A.mx);
+    const bool xiface = (t >= 1) && (ic >= 1) && (ic <= A.mx + 1);
+    const bool ycol = (ic >= 0) && (ic <= A.mx + 1);
+    const int j0 = 1 + blockIdx.y * A.rows_per_cta;
+    const int j1 = min(j0 + A.rows_per_cta, A.my + 1);
+    const AuxCell nocell{nullptr, 0};
+    constexpr bool AUXX = (RPX::MAUX > 0), AUXY = (RPY::MAUX > 0);
+
+    double cfl = 0.0;
+    double dqx_prev[MEQN], q_prev[MEQN];
+    double qr_prev[MEQN], apdq_prev[MEQN], amdq2_prev[MEQN], apdq2_prev[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        dqx_prev[m] = 0.0; q_prev[m] = 1.0;
+        qr_prev[m] = 1.0; apdq_prev[m] = amdq2_prev[m] = apdq2_prev[m] = 0.0;
+    }
+    for (int c = j0 - 1; c <= j1; c++) {
+        const long long rowoff = (long long)A.pitch * (c + mbc - 1);
+        // ---- x-direction of row c (rows 0 and my+1 only contribute to the CFL number)
+        const bool xfull = (c >= j0) && (c < j1);
+        const bool xcfl_only = (c == 0 && j0 == 1) || (c == A.my + 1 && j1 == A.my + 1);
+        double dqx[MEQN], qc[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) { dqx[m] = 0.0; qc[m] = A.q[m * A.mstride + rowoff + icl]; }
+        if (xfull || xcfl_only) { // uniform over the CTA
+            __syncthreads();
+            for (int e = t; e < QS; e += NT) {
+                const int col = min(max(i0 - 1 - H + e, 1 - mbc), imax) + mbc - 1;
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) qs[m * QS + e] = A.q[m * A.mstride + rowoff + col];
+            }
+            __syncthreads();
+            double ql[MEQN], qr[MEQN];
+            with_arith_fz([&](auto &ar) {
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) weno_tab(ar, qs + m * QS + t + H, ql[m], qr[m]);
+            });
+            sc_xrow_solve<RPX, NT>(A, ql, qr, x1, x2, t, xiface, xfull, cfl, dqx, A.dtdx, A.dtdx,
+                                   AUXX ? sc_aux(A, rowoff + ilc) : nocell, AUXX ? sc_aux(A, rowoff + icl) : nocell);
+        }
+        // ---- y-direction: reconstruct cell (ic, c) from rows c-H .. c+H
+        double ql[MEQN], qr[MEQN];
+        with_arith_fz([&](auto &ar) {
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                double col[17];
+                for (int e = 0; e <= 2 * H; e++) {
+                    const int row = min(max(c - H + e, 1 - mbc), A.my + mbc) + mbc - 1;
+                    col[e] = A.q[m * A.mstride + (long long)A.pitch * row + icl];
+                }
+                weno_tab(ar, col + H, ql[m], qr[m]);
+            }
+        });
+        double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+        double amdq2[MEQN], apdq2[MEQN];
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) { amdq[m] = apdq[m] = amdq2[m] = apdq2[m] = 0.0; }
+        if (c >= j0) {
+            const long long offc = rowoff + icl;
+            const AuxCell ayc = AUXY ? sc_aux(A, offc) : nocell;
+            const AuxCell aym = AUXY ? sc_aux(A, offc - A.pitch) : nocell;
+            with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, qr_prev, ql, aym, ayc, wave, s, amdq, apdq, roe); });
+            if (ycol && c >= 1 && c <= A.my + 1) {
+#pragma unroll
+                for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, A.dtdy * s[mw]), -A.dtdy * s[mw]);
+            }
+            if (c < j1)
+                with_arith_fz([&](auto &ar) { RPY::solve(ar, A.rp, ql, qr, ayc, ayc, wave, s, amdq2, apdq2, roe); });
+            const int jc = c - 1; // this row's lower interface completes cell row c-1
+            if (jc >= j0 && jc < j1 && col_out) {
+                double dq[MEQN];
+#pragma unroll
+                for (int m = 0; m < MEQN; m++) {
+                    double dqy = 0.0 - A.dtdy * (amdq[m] + apdq_prev[m] + amdq2_prev[m] + apdq2_prev[m]);
+                    dq[m] = (0.0 + dqx_prev[m]) + dqy;
+                }
+                stage_store<MEQN>(A, (long long)A.pitch * (jc + mbc - 1) + icl, q_prev, dq);
+            }
+        } // c == j0-1: only the reconstruction (its right-edge value feeds interface j0)
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            qr_prev[m] = qr[m]; apdq_prev[m] = apdq[m];
+            amdq2_prev[m] = amdq2[m]; apdq2_prev[m] = apdq2[m];
+            dqx_prev[m] = dqx[m]; q_prev[m] = qc[m];
+        }
+    }
+    sc_cfl_commit(cfl, A.cfl_bits);
+}

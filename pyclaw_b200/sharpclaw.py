@@ -225,10 +225,9 @@ class SharpClawSolver(Solver):
             # reconstruct.f90:111-113
             raise Exception("weno_order must be an odd number between 5 and 17 (inclusive).")
         if self.weno_order != 5:
-            # weno7 .. weno17 (weno.f90:104-2425): table-driven kernel, 1-D component-wise only
-            if self.ndim != 1 or self.lim_type != 2 or self.char_decomp != 0:
-                raise NotImplementedError("weno_order > 5 is implemented for SharpClawSolver1D with "
-                                          "lim_type=2, char_decomp=0")
+            # weno7 .. weno17 (weno.f90:104-2425): table-driven kernels, component-wise only
+            if self.lim_type != 2 or self.char_decomp != 0:
+                raise NotImplementedError("weno_order > 5 is implemented for lim_type=2, char_decomp=0")
             from .weno_tables import tables
             import numpy as np
             tab = tables((self.weno_order + 1) // 2, self.weno_literals)

@@ -612,3 +612,22 @@ def test_two_weno_orders_alive_at_once():
         a2.evolve_to_time(sa2)
     assert np.array_equal(np.asarray(sa.q), np.asarray(sa2.q))
     assert not np.array_equal(np.asarray(sa.q), np.asarray(sb.q))
+
+
+def test_acoustics2d_sharpclaw_weno7_vs_oracle():
+    """test/acoustics/2d/homogeneous with SharpClaw and weno_order = 7 (mbc = 4), SSP104."""
+    from pyclaw_b200.weno_tables import tables
+    p = np.asarray(_acoustics2d('sharpclaw', weno_order=7))
+    pb = problems.acoustics2d()
+    s = po.OracleSolver("sharpclaw", 2, po.RP_ACOUSTICS, pb["params"], 2)
+    s.cfl_max, s.cfl_desired = 0.5, 0.45
+    s.bc_lower = [po.BC_OUTFLOW] * 2
+    s.bc_upper = [po.BC_OUTFLOW] * 2
+    s.dt_initial = pb["dt_initial"]
+    s.weno_order, s.weno_tables = 7, tables(4, 'f32')
+    qo = s.run(pb["q"], None, pb["d"], 0.12, 10)[-1]
+    assert not np.isnan(qo).any()
+    assert np.array_equal(p, qo[0])
+    # close to, but not the same as, the fifth-order result
+    p5 = np.asarray(_acoustics2d('sharpclaw'))
+    assert 1e-8 < np.abs(p - p5).max() < 5e-2

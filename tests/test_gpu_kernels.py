@@ -637,11 +637,37 @@ def test_sharpclaw_high_order_weno(order, rp, literals):
         assert not np.isnan(dq_o).any()
         assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]), np.abs(dq_g - dq_o)[:, mbc:-mbc].max()
         assert cfl_g.value == cfl_o
-    # orders above 5 are refused in 2-D, and too few ghost cells are refused
-    P2 = _lib.make_problem(2, 3, 2, mbc, 20, 20, 0.1, 0.1, 1, [1.0, 4.0, 2.0, 2.0], weno_variant=_lib.WENO_TABLES)
-    q2 = np.zeros((3, 20 + 2 * mbc, 20 + 2 * mbc), order="F")
-    with pytest.raises(_lib.ClawB200Error, match="1-D"):
+    # too few ghost cells for the stencil are refused
+    P2 = _lib.make_problem(1, meqn, mwaves, mbc - 1, 20, 1, 0.1, 1.0, rp_id, params, weno_variant=_lib.WENO_TABLES)
+    q2 = np.zeros((meqn, 20 + 2 * (mbc - 1)), order="F")
+    with pytest.raises(_lib.ClawB200Error, match="mbc"):
         _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P2), _ptr(q2), _ptr(q2.copy("F")), None, 0.01, ctypes.byref(cfl_g))
+
+
+@pytest.mark.parametrize("order", [7, 11, 17])
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "shallow", "euler"])
+def test_sharpclaw_high_order_weno_2d(order, rp):
+    """flux2.f90 over weno7 .. weno17: 2-D, both sweep directions."""
+    from pyclaw_b200.weno_tables import tables
+    k = (order + 1) // 2
+    mbc = k
+    rp_id, params, meqn, mwaves, _ = RPS[rp]
+    tab = tables(k, 'f32')
+    po.set_weno_tables(tab)
+    arr = [np.ascontiguousarray(tab[n], dtype=np.float64) for n in ('S', 'CL', 'CR', 'WL', 'WR')]
+    _lib.call("clawb200_set_weno_tables", k, *[_ptr(a) for a in arr], float(tab['eps']), None)
+    cfl_g = ctypes.c_double()
+    for mx, my in ((37, 29), (130, 70), (5, 140)):
+        dx, dy, dt = 0.01, 0.013, 0.0011
+        q = _random_padded(rp, mx, my, mbc, seed=mx + order, smooth=True)
+        P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, weno_variant=_lib.WENO_TABLES)
+        dq_o, cfl_o = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, po.WENO_TABLES)
+        dq_g = np.zeros_like(q, order="F")
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
+        inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+        assert not np.isnan(dq_o).any()
+        assert np.array_equal(dq_g[inner], dq_o[inner]), np.abs(dq_g - dq_o)[inner].max()
+        assert cfl_g.value == cfl_o
 
 
 # ---------------------------------------------------------------------------
