@@ -584,18 +584,29 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
             }
             normk[mw] = n2; dotk[mw] = d;
         }
+        // Interface k-1's waves, fluctuations and Roe data are in registers now: put
+        // interface k's into the slots at once instead of at the end of the iteration, so that
+        // they are not live (32 doubles for Euler) across the limiter and the transverse solves.
+#pragma unroll
+        for (int m = 0; m < MEQN; m++)
+#pragma unroll
+            for (int mw = 0; mw < MW; mw++)
+                if (RP::nz(m, mw)) YS(SL::W + m * MW + mw) = wave[m][mw];
 
         // limit interface k-1, form its correction flux and split it transversely
         double cqxx[MEQN], F1[MEQN], amdq1[MEQN], apdq1[MEQN];
         double bmm[MEQN], bpm[MEQN], bmp1[MEQN], bpp1[MEQN];
 #pragma unroll
-        for (int m = 0; m < MEQN; m++) { amdq1[m] = YS(SL::AM1 + m); apdq1[m] = YS(SL::AP1 + m); }
+        for (int m = 0; m < MEQN; m++) {
+            amdq1[m] = YS(SL::AM1 + m); apdq1[m] = YS(SL::AP1 + m);
+            YS(SL::AM1 + m) = amdq[m]; YS(SL::AP1 + m) = apdq[m];
+        }
         {
             const bool lim = order2 && k >= j0 + 1;
             double roe1[NROE];
             if (TRANS) {
 #pragma unroll
-                for (int n = 0; n < NROE; n++) roe1[n] = YS(SL::ROE + n);
+                for (int n = 0; n < NROE; n++) { roe1[n] = YS(SL::ROE + n); YS(SL::ROE + n) = roe[n]; }
             }
             with_arith([&](auto &ar) {
                 double wlim[MEQN][MW];
@@ -705,19 +716,10 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
             qm2[m] = qm1[m]; qm1[m] = qk[m];
             YS(SL::AP2 + m) = apdq1[m];
             YS(SL::F2 + m) = F1[m];
-            YS(SL::AM1 + m) = amdq[m];
-            YS(SL::AP1 + m) = apdq[m];
             if (TRANS) { YS(SL::BMP2 + m) = bmp1[m]; YS(SL::BPP2 + m) = bpp1[m]; }
-#pragma unroll
-            for (int mw = 0; mw < MW; mw++)
-                if (RP::nz(m, mw)) YS(SL::W + m * MW + mw) = wave[m][mw];
         }
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) { sm1[mw] = s[mw]; norm1[mw] = normk[mw]; dot1[mw] = dotk[mw]; }
-        if (TRANS) {
-#pragma unroll
-            for (int n = 0; n < NROE; n++) YS(SL::ROE + n) = roe[n];
-        }
     }
 #undef YS
     if (ICFL) cfl = dtdy * __longlong_as_double((long long)smax);
