@@ -489,9 +489,8 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     double dy_k = dtdy, dy_1 = dtdy, dy_2 = dtdy, cap_1 = 1.0, cap_2 = 1.0;
 
     double cfl = 0.0;
-    // integer running maximum of |s| (see smax_update); the 255-register Euler y-sweep has no
-    // room for the extra pair of live registers (measured 4 % slower), it keeps the FP form
-    constexpr bool ICFL = !CAPA && (RP::MEQN < 5);
+    // integer running maximum of |s| (see smax_update)
+    constexpr bool ICFL = !CAPA;
     unsigned long long smax = 0ULL;
     double qm1[MEQN], qm2[MEQN], sm1[MW], norm1[MW], dot1[MW];
 #pragma unroll
