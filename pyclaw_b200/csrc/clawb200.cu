@@ -139,6 +139,22 @@ static cudaError_t set_smem(K kernel, size_t bytes)
     return cudaSuccess;
 }
 
+// Kernels that read many aux components per interface (the sphere) live on L1 hits: ask for
+// the smallest shared-memory carve-out that still holds the resident CTAs, the rest is L1.
+template <class K>
+static void hint_carveout(K kernel, size_t smem_per_cta, int ctas)
+{
+    static std::mutex mu;
+    static std::unordered_map<const void *, int> done;
+    std::lock_guard<std::mutex> lock(mu);
+    int &d = done[(const void *)kernel];
+    if (d) return;
+    int pct = (int)((smem_per_cta + 1024) * ctas * 100 / (228 * 1024)) + 1;
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    d = 1;
+}
+
 constexpr int XNT = 128; // threads per CTA of the x-engine
 constexpr int YNT = 128; // threads per CTA of the y-engine
 
@@ -149,6 +165,7 @@ static int launch_x(SweepArgs A, cudaStream_t st)
     size_t smem = sizeof(double) * (2 * RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
     auto k = xsweep_kernel<RP, TRANS, CAPA, XNT>;
     CUDA_OK(set_smem(k, smem));
+    if (RP::MAUX >= 8) hint_carveout(k, smem, RP::X_MINB);
     int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
     dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
     k<<<grid, XNT, smem, st>>>(A);
@@ -163,6 +180,7 @@ static int launch_y(SweepArgs A, cudaStream_t st)
     size_t smem = sizeof(double) * YNT * ((TRANS ? 4 * RP::MEQN : 0) + YSlots<RP, TRANS>::COUNT);
     auto k = ysweep_kernel<RP, TRANS, CAPA, YNT>;
     CUDA_OK(set_smem(k, smem));
+    if (RP::MAUX >= 8) hint_carveout(k, smem, RP::Y_MINB);
     int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
     dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
     k<<<grid, YNT, smem, st>>>(A);
