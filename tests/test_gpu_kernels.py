@@ -872,3 +872,31 @@ def test_boundary_fills_match_the_reference_order(ndim):
         torch.cuda.synchronize()
         got = dev.cpu().numpy().transpose([0] + list(range(ndim, 0, -1)))
         assert np.array_equal(got, ref), (ndim, lower, upper)
+
+
+def test_halo_pack_unpack_and_layout_converters():
+    """clawb200_halo_pack / unpack (DMDA globalToLocal's replacement for a C caller) and the
+    AoS <-> SoA converters of the host entry points."""
+    import torch
+    rng = np.random.RandomState(4)
+    meqn, mx, my, mbc = 3, 37, 21, 2
+    nx, ny = mx + 2 * mbc, my + 2 * mbc
+    P = _lib.make_problem(2, meqn, 2, mbc, mx, my, 0.1, 0.1, 1, [1.0, 4.0, 2.0, 2.0])
+    soa = torch.as_tensor(rng.uniform(-1, 1, (meqn, ny, nx)), device="cuda")
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    # rows mbc .. 2 mbc - 1 (what a lower neighbour needs) into a contiguous buffer and back
+    buf = torch.zeros((meqn, mbc, nx), dtype=torch.float64, device="cuda")
+    _lib.call("clawb200_halo_pack", ctypes.byref(P), ptr(soa), meqn, mbc, mbc, ptr(buf), None)
+    assert torch.equal(buf, soa[:, mbc:2 * mbc, :])
+    dst = torch.zeros_like(soa)
+    _lib.call("clawb200_halo_unpack", ctypes.byref(P), ptr(dst), meqn, ny - mbc, mbc, ptr(buf), None)
+    assert torch.equal(dst[:, ny - mbc:, :], soa[:, mbc:2 * mbc, :]) and float(dst[:, :ny - mbc].abs().max()) == 0.0
+    # Fortran-ordered q(m, i, j) (component fastest) <-> device [m][j][i]
+    host = np.asfortranarray(rng.uniform(-1, 1, (meqn, nx, ny)))
+    aos = torch.as_tensor(host.ravel(order="F").copy(), device="cuda")
+    out = torch.zeros((meqn, ny, nx), dtype=torch.float64, device="cuda")
+    _lib.call("clawb200_aos_to_soa", ptr(aos), ptr(out), meqn, nx, ny, nx * ny, nx, None)
+    assert np.array_equal(out.cpu().numpy(), host.transpose(0, 2, 1))
+    back = torch.zeros_like(aos)
+    _lib.call("clawb200_soa_to_aos", ptr(out), ptr(back), meqn, nx, ny, nx * ny, nx, None)
+    assert torch.equal(back, aos)
