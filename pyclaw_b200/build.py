@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libclawb200.so")
 SOURCES = ["clawb200.cu"]
-HEADERS = ["rp.cuh", "classic.cuh", "sharpclaw.cuh", os.path.join("..", "..", "include", "clawb200.h")]
+HEADERS = ["arith.cuh", "rp.cuh", "classic.cuh", "sharpclaw.cuh", os.path.join("..", "..", "include", "clawb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
