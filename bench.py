@@ -534,6 +534,10 @@ def main():
         v, k, el = time_cpu(args.workload, ncpu, ncores, 12.0)
         cpu = {"value": v, "unit": "cell-updates/s", "cores": ncores, "kind": "port",
                "sample": "%d steps on a %dx%d sample of the workload in %.1f s, y-slab threads over the oracle C port" % (k, ncpu, ncpu, el)}
+        # the reference's Fortran is serial: the same port on one core
+        v1, k1, el1 = time_cpu(args.workload, 512, 1, 4.0)
+        cpu["single_core"] = {"value": v1, "unit": "cell-updates/s", "cores": 1,
+                              "sample": "%d steps on a 512x512 sample in %.1f s" % (k1, el1)}
 
     bc_launches = sum(1 for b in solver.bc_lower + solver.bc_upper if b in (1, 2, 3))
     # kernels of libclawb200.so per accepted step: boundary fills + sweeps (classic), or
