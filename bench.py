@@ -309,6 +309,10 @@ def run_reference(args, rank):
         fn()
     el = time.perf_counter() - t0
     value = cells * args.steps / el
+    # the reference's Fortran is serial: the same port on ONE core, bounded sample
+    v1, k1, el1 = time_cpu(args.workload, 512, 1, 4.0)
+    single = {"value": v1, "unit": "cell-updates/s", "cores": 1,
+              "sample": "%d steps on a 512x512 sample in %.1f s" % (k1, el1)}
     sample = "%dx%d sample of the workload, %d host threads (y-slabs), oracle C port of step2/flux2/rpn2/rpt2" % (n, n, ncores)
     line = {
         "impl": "reference", "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s",
@@ -317,10 +321,37 @@ def run_reference(args, rank):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": ncores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "single_core": single},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def check_partition_parity(rank, world, torch, dist):
+    """Strong-scaling comparison on a small grid: the same global problem on `world` slabs and on
+    one GPU (rank 0), np.array_equal on q and equal step counts.  Returns a dict on rank 0."""
+    import mp_partition_check as mp
+    import problems
+    import petclaw
+    import pyclaw
+    mx, my = 160, 16 * world
+    pb = problems.shockbubble(mx, my)
+    qs = problems.smooth_state("shallow", (mx, my), seed=5)
+    cases = [("euler_unsplit", "euler", pb["q"], dict(dim_split=False, order_trans=2)),
+             ("euler_dimsplit", "euler", pb["q"], dict(dim_split=True)),
+             ("shallow_sharpclaw_ssp33", "shallow", qs, dict(time_integrator="SSP33"))]
+    res = {"ranks": world, "grid": [mx, my], "cases": {}}
+    ok = True
+    for name, kind, q0, opts in cases:
+        qp, nsteps = mp.run(petclaw, kind, q0, None, mx, my, opts)
+        if rank == 0:
+            qser, nser = mp.run(pyclaw, kind, q0, None, mx, my, opts)
+            same = bool(np.array_equal(qp, qser) and nsteps == nser and np.isfinite(qser).all())
+            res["cases"][name] = {"bit_identical": same, "steps": int(nsteps)}
+            ok = ok and same
+        dist.barrier()
+    res["ok"] = ok
+    return res if rank == 0 else None
 
 
 # --------------------------------------------------------------------------------------
@@ -332,8 +363,12 @@ def main():
     ap.add_argument("--workload", default="euler", choices=sorted(WORKLOADS))  # sphere: no --impl reference arm
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override the per-GPU grid size (debug)")
-    ap.add_argument("--perturb", action="store_true",
-                    help="add a smooth non-zero velocity field (SURVEY 8(d): branch behaviour differs)")
+    ap.add_argument("--perturb", action="store_true", help="(default now) time the developed field")
+    ap.add_argument("--quiescent", action="store_true",
+                    help="time the application's own initial data only (mostly at rest) instead of the developed field")
+    ap.add_argument("--arithmetic", default="strict", choices=["strict", "fma"],
+                    help="library build: strict IEEE (parity) or with FMA contraction")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 partition-parity check")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
     args = ap.parse_args()
@@ -359,20 +394,6 @@ def main():
 
     wl = WORKLOADS[args.workload]
     n = args.n or wl["n"]
-    state, solver = build_problem(pyclaw, args.workload, n, world, torch)
-    if args.perturb and args.workload in ("euler", "shallow"):
-        xc = torch.as_tensor(state.grid.x.center, device=state.device)
-        yc = torch.as_tensor(state.grid.y.center, device=state.device)
-        bump = torch.sin(2 * np.pi * xc)[:, None] * torch.sin(2 * np.pi * yc)[None, :]
-        rho = state.q[0].clone()
-        state.q[1] = rho * 0.3 * bump
-        state.q[2] = -rho * 0.2 * bump
-        if args.workload == "euler":
-            state.q[3] = state.q[3] + 0.5 * (state.q[1] ** 2 + state.q[2] ** 2) / rho
-    solution = pyclaw.Solution(state)
-    solver.setup(solution)
-    solver.dt = solver.dt_initial
-    solver.max_steps = 10 ** 9
     cells_per_rank = n * n if args.workload != "sphere" else 2 * n * n
 
     def barrier():
@@ -380,33 +401,113 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: lets dt settle at cfl_desired -------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        solver.evolve_to_time(solution)
+    # ---- partition parity (N > 1): the slab-partitioned run against the single-GPU run, bit for
+    # bit, on a small grid, before anything is timed (the reference compares its 6-rank run with
+    # the serial golden file, test/test_examples.py:264-277) ------------------------------------
+    partition_parity = None
+    if world > 1 and not args.no_parity:
+        partition_parity = check_partition_parity(rank, world, torch, dist)
 
-    # ---- timed region ---------------------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    accepted = 0
-    ev0.record()
-    for _ in range(args.steps):
-        st = solver.evolve_to_time(solution)
-        accepted += st['numsteps']
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-        acc = torch.tensor([accepted], dtype=torch.float64, device="cuda")
-        dist.all_reduce(acc, op=dist.ReduceOp.MIN)
-        accepted = int(acc.item())
-    value = cells_per_rank * world * accepted / (ms * 1e-3)
+    def timed_run(field, steps, warmup, sample_clocks):
+        """Set the problem up, let dt settle, time `steps` calls of solver.evolve_to_time."""
+        state, solver = build_problem(pyclaw, args.workload, n, world, torch)
+        solver.arithmetic = args.arithmetic
+        if field == "developed" and args.workload in ("euler", "shallow"):
+            # A smooth velocity field over the whole domain (SURVEY 8(d)): every interface has
+            # non-zero jumps in every wave family, so the limiter, the entropy fix and the
+            # transverse solves do their full work everywhere.  The initial data of the reference's
+            # application alone leaves > 99 % of an 8192^2 grid at rest for the first few hundred
+            # steps (zero waves: the limiter is skipped, the entropy fix exits early).
+            xc = torch.as_tensor(state.grid.x.center, device=state.device)
+            yc = torch.as_tensor(state.grid.y.center, device=state.device)
+            bump = torch.sin(2 * np.pi * xc)[:, None] * torch.sin(2 * np.pi * yc)[None, :]
+            rho = state.q[0].clone()
+            state.q[1] = rho * 0.3 * bump
+            state.q[2] = -rho * 0.2 * bump
+            if args.workload == "euler":
+                state.q[3] = state.q[3] + 0.5 * (state.q[1] ** 2 + state.q[2] ** 2) / rho
+        solution = pyclaw.Solution(state)
+        solver.setup(solution)
+        solver.dt = solver.dt_initial
+        solver.max_steps = 10 ** 9
+        for _ in range(warmup):
+            solver.evolve_to_time(solution)
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        accepted = 0
+        ev0.record()
+        for _ in range(steps):
+            st = solver.evolve_to_time(solution)
+            accepted += st['numsteps']
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+            acc = torch.tensor([accepted], dtype=torch.float64, device="cuda")
+            dist.all_reduce(acc, op=dist.ReduceOp.MIN)
+            accepted = int(acc.item())
+        value = cells_per_rank * world * accepted / (ms * 1e-3)
+        return dict(value=value, ms=ms, accepted=accepted, clocks=clocks, state=state, solver=solver,
+                    solution=solution)
+
+    # The headline field: for the workloads whose application data is mostly at rest (Euler
+    # shock-bubble, shallow-water dam break) the timed field is the developed one; the
+    # application's own initial data is timed next to it and reported as config.quiescent_value.
+    has_quiescent = args.workload in ("euler", "shallow")
+    field = "developed" if (has_quiescent and not args.quiescent) else "application"
+    quiescent = None
+    if has_quiescent and field == "developed":
+        rq = timed_run("application", min(args.steps, 10), max(args.warmup, 3), False)
+        quiescent = {"value": rq["value"], "ms_per_step": rq["ms"] / min(args.steps, 10),
+                     "what": "the application's own initial data (>99% of the cells at rest)"}
+        del rq
+        torch.cuda.empty_cache()
+    run = timed_run(field, args.steps, max(args.warmup, 3), True)
+    value, ms, accepted, clocks = run["value"], run["ms"], run["accepted"], run["clocks"]
+    state, solver, solution = run["state"], run["solver"], run["solution"]
+
+    # ---- e2e at N > 1: every rank uploads its slab from pinned host memory, takes one step
+    # through the petclaw API (halo exchange + CFL all-reduce included) and downloads the result
+    e2e_multi = None
+    if world > 1 and not args.no_e2e:
+        F = state._q
+        host_in = torch.empty(F.cur.shape, dtype=torch.float64).pin_memory()
+        host_out = torch.empty(F.cur.shape, dtype=torch.float64).pin_memory()
+        host_in.copy_(F.cur)
+        k = 3
+        for it in range(k + 1):
+            if it == 1:
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                acc_e = 0
+            state._q.cur.copy_(host_in, non_blocking=True)
+            st = solver.evolve_to_time(solution)
+            host_out.copy_(state._q.cur, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if it >= 1:
+                acc_e += st['numsteps']
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        acc_t = torch.tensor([acc_e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(acc_t, op=dist.ReduceOp.MIN)
+        nbytes = host_in.numel() * 8
+        e2e_multi = {"value": cells_per_rank * world * float(acc_t.item()) / (float(ems.item()) * 1e-3),
+                     "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes * world,
+                     "d2h_bytes_per_step": (nbytes + 8) * world, "steps": k,
+                     "what": "per rank and step: pinned host slab -> H2D -> solver.evolve_to_time through the "
+                             "petclaw API (NCCL halo exchange, CFL all-reduce) -> D2H of the new slab; "
+                             "device-timed, max over ranks"}
+        del host_in, host_out
 
     if rank != 0:
         if world > 1:
@@ -488,12 +589,7 @@ def main():
     # ---- e2e: the f2py-shaped C ABI call with HOST buffers (H2D + kernels + D2H timed) ----
     e2e = None
     if not args.no_e2e and world > 1:
-        # the host-buffer C-ABI call is a single-process path; at N > 1 the end-to-end
-        # figure is the whole-job API number (q resident, dt in / 8-byte CFL out per step)
-        e2e = {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 8 * world,
-               "d2h_bytes_per_step": 8 * world,
-               "what": "solver.evolve_to_time through the petclaw API on %d ranks (q resident in HBM; "
-                       "dt in, 8-byte CFL out per rank per step)" % world}
+        e2e = e2e_multi
     elif not args.no_e2e and args.workload in ("euler", "acoustics"):
         mbc = solver.mbc
         nx = n + 2 * mbc
@@ -523,8 +619,28 @@ def main():
                                         "8-byte CFL read back per step"}}
         del host_in, host_out
     elif not args.no_e2e:
-        e2e = {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8 * 3,
-               "what": "solver.evolve_to_time through the pyclaw API (q resident in HBM; dt in, per-stage CFL out)"}
+        # no f2py-shaped host entry point exists for a whole SharpClaw / sphere step: upload the
+        # padded field from pinned host memory, one step through the API, download the result
+        host_in = torch.empty(F.cur.shape, dtype=torch.float64).pin_memory()
+        host_out = torch.empty(F.cur.shape, dtype=torch.float64).pin_memory()
+        host_in.copy_(F.cur)
+        k, acc_e = 3, 0
+        for it in range(k + 1):
+            if it == 1:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            state._q.cur.copy_(host_in, non_blocking=True)
+            st = solver.evolve_to_time(solution)
+            host_out.copy_(state._q.cur, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if it >= 1:
+                acc_e += st['numsteps']
+        el = time.perf_counter() - t0
+        nbytes = host_in.numel() * 8
+        e2e = {"value": cells_per_rank * acc_e / el, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes + 8 * 3, "steps": k,
+               "what": "pinned host q -> H2D -> solver.evolve_to_time through the pyclaw API -> D2H of the new q, every step"}
+        del host_in, host_out
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------
     cpu = None
@@ -556,13 +672,20 @@ def main():
         "data": "synthetic",
         "config": {"workload": wl["label"], "cells_per_gpu": cells_per_rank, "accepted_steps": accepted,
                    "l2": "inputs larger than L2 (%.1f GB per field)" % (cells_per_rank * wl["meqn"] * 8 / 1e9),
-                   "parallelism": "y-slabs x%d" % world, "arithmetic": "strict IEEE, -fmad=false (bit-exact vs oracle)"},
+                   "parallelism": "y-slabs x%d" % world,
+                   "arithmetic": ("strict IEEE, -fmad=false (bit-exact vs oracle)" if args.arithmetic == "strict"
+                                  else "fma: -fmad=true build (round-off-level differences, profiles/README.md)"),
+                   "field": field, "quiescent_value": quiescent["value"] if quiescent else None,
+                   "quiescent": quiescent},
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": args.steps * per_step_launches,
     }
+    if world > 1:
+        line["partition_parity"] = partition_parity
+        line["ranks"] = world
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -210,6 +210,28 @@ int clawb200_halo_pack(const clawb200_problem *p, const double *q, int narr, int
 int clawb200_halo_unpack(const clawb200_problem *p, double *q, int narr, int row0,
                          int nrows, const double *buf, void *stream);
 
+/* ---- Riemann solvers as pointwise operators --------------------------------------------
+ * The reference's plugin contract for a Riemann solver (doc/rp.rst:7-62, src/pyclaw/clawpack.py:349
+ * `wave,s,amdq,apdq = self.rp(q_l,q_r,aux_l,aux_r,aux_global)`; Fortran rpn2 / rpt2,
+ * src/fortran/2d/classic/flux2.f:99-100,167-168,180-181) on arrays of n interfaces, evaluated by
+ * the very device functions that are inlined into the sweeps.  Solvers without aux data only.
+ * Structure of arrays: ql[m][n], qr[m][n] (left / right state of each interface),
+ * wave[m*mwaves+mw][n], s[mw][n], amdq[m][n], apdq[m][n].  ixy = 1 | 2 (ignored in 1-D).
+ * clawb200_rp_transverse: rpt2 with the Roe data of the interface (ql, qr); imp = 1 splits asdq
+ * moving into the left cell, imp = 2 into the right cell. */
+int clawb200_rp_solve(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                      const double *qr, double *wave, double *s, double *amdq, double *apdq,
+                      void *stream);
+int clawb200_rp_transverse(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                           const double *qr, int imp, const double *asdq, double *bmasdq,
+                           double *bpasdq, void *stream);
+/* the same on HOST arrays */
+int clawb200_rp_solve_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                           const double *qr, double *wave, double *s, double *amdq, double *apdq);
+int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                                const double *qr, int imp, const double *asdq, double *bmasdq,
+                                double *bpasdq);
+
 /* ---- host-pointer entry points (the f2py signatures) -----------------------------
  * As the Fortran documents (step2.f:8-9), qold and qnew are taken to be identical on entry:
  * only qold is uploaded, qnew receives the result (untouched cells = qold).  Large 2-D

@@ -2126,3 +2126,59 @@ double oracle_sc_flux2_slabs(int rp_id, const double *rp_params, int meqn, int m
     jb.qold = q; jb.qnew = dq; jb.dx = dx; jb.dy = dy; jb.dt = dt; jb.weno_variant = weno_variant;
     return run_slabs(&jb, nslabs);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Pointwise access to the Riemann solvers (test infrastructure for the      */
+/* solver property tests): n independent interfaces, left state ql[m][k],    */
+/* right state qr[m][k] (structure of arrays, like clawb200_rp_solve).       */
+/* Each pair is presented to rpn / rpt as a 3-cell slice (mbc = 1, mx = 1):   */
+/* cells 0 | 1 | 2 = left | right | right, the interface of interest is i=1. */
+/* ixy = 0 for a 1-D solver.  asdq == NULL: normal solve only.               */
+/* ------------------------------------------------------------------------- */
+void oracle_rp_point(int rp_id, const double *rp_params, int ixy, int meqn, int mwaves, long long n,
+                     const double *ql, const double *qr, double *wave_o, double *s_o, double *amdq_o,
+                     double *apdq_o, int imp, const double *asdq_i, double *bm_o, double *bp_o)
+{
+    const int mbc = 1, mx = 1, nc = 3;
+    rp_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.rp_id = rp_id; c.ndim = (ixy == 0) ? 1 : 2;
+    memcpy(c.p, rp_params, 8 * sizeof(double));
+    ctx_alloc(&c, nc);
+    double *q = (double *)calloc((size_t)meqn * nc, sizeof(double));
+    double *wave = (double *)calloc((size_t)meqn * mwaves * nc, sizeof(double));
+    double *s = (double *)calloc((size_t)mwaves * nc, sizeof(double));
+    double *amdq = (double *)calloc((size_t)meqn * nc, sizeof(double));
+    double *apdq = (double *)calloc((size_t)meqn * nc, sizeof(double));
+    double *asdq = (double *)calloc((size_t)meqn * nc, sizeof(double));
+    double *bm = (double *)calloc((size_t)meqn * nc, sizeof(double));
+    double *bp = (double *)calloc((size_t)meqn * nc, sizeof(double));
+    double aux[8] = {0};
+    for (long long k = 0; k < n; k++) {
+        for (int m = 0; m < meqn; m++) {
+            Q2(q, m, 0) = ql[m * n + k];
+            Q2(q, m, 1) = qr[m * n + k];
+            Q2(q, m, 2) = qr[m * n + k];
+        }
+        rpn(&c, ixy, meqn, mwaves, mbc, mx, q, q, aux, aux, wave, s, amdq, apdq);
+        if (wave_o) {
+            for (int m = 0; m < meqn; m++) {
+                for (int mw = 0; mw < mwaves; mw++) wave_o[(m * mwaves + mw) * n + k] = WV(m, mw, 1);
+                amdq_o[m * n + k] = Q2(amdq, m, 1);
+                apdq_o[m * n + k] = Q2(apdq, m, 1);
+            }
+            for (int mw = 0; mw < mwaves; mw++) s_o[mw * n + k] = SP(mw, 1);
+        }
+        if (asdq_i) {
+            for (int m = 0; m < meqn; m++)
+                for (int i = 0; i <= 2; i++) Q2(asdq, m, i) = asdq_i[m * n + k];
+            rpt(&c, ixy, meqn, mwaves, mbc, mx, q, aux, aux, aux, imp, asdq, bm, bp);
+            for (int m = 0; m < meqn; m++) {
+                bm_o[m * n + k] = Q2(bm, m, 1);
+                bp_o[m * n + k] = Q2(bp, m, 1);
+            }
+        }
+    }
+    free(q); free(wave); free(s); free(amdq); free(apdq); free(asdq); free(bm); free(bp);
+    ctx_free(&c);
+}

@@ -74,6 +74,9 @@ def lib():
         L.oracle_sphere_qinit.argtypes = [i, i, i, d, d, d, d, _dp, d]
         L.oracle_sphere_src2.restype = None
         L.oracle_sphere_src2.argtypes = [i, i, d, d, d, d, _dp, _dp, d, d]
+        L.oracle_rp_point.restype = None
+        L.oracle_rp_point.argtypes = [i, _dp, i, i, i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp,
+                                      i, _dp, _dp, _dp]
         _LIB = L
     return _LIB
 
@@ -105,6 +108,28 @@ def step1(rp_id, rp_params, mbc, mx, qbc, auxbc, dx, dt, method, mthlim):
     assert qbc.flags["F_CONTIGUOUS"]
     return lib().oracle_step1(rp_id, _p(_params(rp_params)), meqn, len(mthlim), mbc, maux, mx,
                               _p(qbc), _p(aux), dx, dt, _pi(method), _pi(mthlim))
+
+
+def rp_point(rp_id, rp_params, ixy, mwaves, ql, qr, imp=0, asdq=None):
+    """The restated Riemann solvers on n independent interfaces: ql, qr are [meqn, n] arrays
+    (left / right state).  Returns (wave[meqn, mwaves, n], s[mwaves, n], amdq, apdq), or
+    (bmasdq, bpasdq) of the transverse solver when ``asdq`` is given.  ixy = 0: 1-D solver."""
+    ql = np.ascontiguousarray(ql, dtype=np.float64)
+    qr = np.ascontiguousarray(qr, dtype=np.float64)
+    meqn, n = ql.shape
+    null = ctypes.cast(None, _dp)
+    if asdq is None:
+        wave = np.zeros((meqn, mwaves, n))
+        s = np.zeros((mwaves, n))
+        amdq, apdq = np.zeros((meqn, n)), np.zeros((meqn, n))
+        lib().oracle_rp_point(rp_id, _p(_params(rp_params)), ixy, meqn, mwaves, n, _p(ql), _p(qr), _p(wave), _p(s),
+                              _p(amdq), _p(apdq), 0, null, null, null)
+        return wave, s, amdq, apdq
+    asdq = np.ascontiguousarray(asdq, dtype=np.float64)
+    bm, bp = np.zeros((meqn, n)), np.zeros((meqn, n))
+    lib().oracle_rp_point(rp_id, _p(_params(rp_params)), ixy, meqn, mwaves, n, _p(ql), _p(qr), null, null, null,
+                          null, imp, _p(asdq), _p(bm), _p(bp))
+    return bm, bp
 
 
 def step2ds(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method, mthlim, ids):

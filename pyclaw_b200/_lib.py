@@ -9,6 +9,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CLAWB200_LIB selects another build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("CLAWB200_LIB") or os.path.join(_HERE, "csrc", "libclawb200.so")
+# Arithmetic variants: two builds of the same sources (pyclaw_b200/build.py).  'strict' is the
+# parity build (-fmad=false, bit for bit against the oracle); 'fma' lets nvcc contract a*b+c.
+LIB_PATHS = {"strict": LIB_PATH, "fma": os.path.join(_HERE, "csrc", "libclawb200_fma.so")}
 
 MAXWAVES = 8
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
@@ -64,7 +67,8 @@ def make_problem(ndim, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, rp_params, meth
     return p
 
 
-_lib = None
+_libs = {}
+_active = "strict"
 _vp, _dp, _i, _d = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double
 _pp = ctypes.POINTER(Problem)
 _dref = ctypes.POINTER(ctypes.c_double)
@@ -93,18 +97,34 @@ SIGNATURES = {
     "clawb200_step3ds": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dp, _vp],
     "clawb200_bc_fill3": [_pp, _i, _dp, _i, _i, _i, _i, _i, _vp],
     "clawb200_step3ds_host": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dref],
+    "clawb200_rp_solve": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp, _vp],
+    "clawb200_rp_transverse": [_pp, _i, ctypes.c_longlong, _dp, _dp, _i, _dp, _dp, _dp, _vp],
+    "clawb200_rp_solve_host": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp],
+    "clawb200_rp_transverse_host": [_pp, _i, ctypes.c_longlong, _dp, _dp, _i, _dp, _dp, _dp],
 }
 
 
-def load():
+def set_variant(name):
+    """Select the build that `call` dispatches to ('strict' | 'fma'); returns the previous one.
+    Solvers set it from ``solver.arithmetic`` at the start of every step."""
+    global _active
+    if name not in LIB_PATHS:
+        raise ClawB200Error("unknown arithmetic variant %r (expected one of %s)" % (name, sorted(LIB_PATHS)))
+    prev, _active = _active, name
+    return prev
+
+
+def load(variant=None):
     """Load the CUDA library; raises if it has not been built (no CPU fallback)."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+    variant = variant or _active
+    if variant not in _libs:
+        path = LIB_PATHS[variant]
+        if not os.path.exists(path):
             raise ClawB200Error(
-                "libclawb200.so is missing (%s): build it with `python -m pyclaw_b200.build`; "
-                "pyclaw_b200 has no CPU fallback" % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
+                "%s is missing (%s): build it with `python -m pyclaw_b200.build%s`; "
+                "pyclaw_b200 has no CPU fallback" % (os.path.basename(path), path,
+                                                     " --fma" if variant == "fma" else ""))
+        L = ctypes.CDLL(path)
         L.clawb200_version.restype = ctypes.c_int
         L.clawb200_weno_generation.restype = ctypes.c_int
         L.clawb200_last_error.restype = ctypes.c_char_p
@@ -112,8 +132,8 @@ def load():
             f = getattr(L, name)
             f.restype = ctypes.c_int
             f.argtypes = args
-        _lib = L
-    return _lib
+        _libs[variant] = L
+    return _libs[variant]
 
 
 def check(rc):

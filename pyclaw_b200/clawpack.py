@@ -30,6 +30,7 @@ class ClawSolver(Solver):
 
     # ---- clawpack.py:114-165 ----
     def step(self, solution):
+        _lib.set_variant(self.arithmetic)
         if self.start_step is not None:
             self.start_step(self, solution)
         if self.src_split == 2 and self.step_src is not None:
@@ -87,7 +88,11 @@ class ClawSolver(Solver):
             self._cfl_host.copy_(self._cfl_dev, non_blocking=True)
 
         self._dt_pin[0] = float(self.dt)
-        key = self._graph_key
+        # everything a captured sequence depends on besides dt: the buffers, the aux array and
+        # the boundary-condition types (the problem itself is covered by _setup_device)
+        key = tuple(self._graph_key) + (
+            state._aux.cur.data_ptr() if state._aux is not None else 0,
+            tuple(self.bc_lower), tuple(self.bc_upper))
         g = self._graphs.get(key)
         if g is None:
             sequence()                               # this step, eagerly

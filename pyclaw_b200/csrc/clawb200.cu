@@ -1,39 +1,23 @@
 // clawb200.cu -- C ABI (include/clawb200.h) over the sm_100a kernels in classic.cuh and
-// sharpclaw.cuh.  Built in-tree with
+// sharpclaw.cuh (instantiated in the sweep_*.cu / step1.cu / sharpclaw.cu translation units,
+// see launch.cuh).  Built in-tree with
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared ...
 // -fmad=false is part of the contract: the reference's Fortran is compiled without FMA
 // contraction and results must match it bit for bit ("hard parts").
-#include <cuda_runtime.h>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <unordered_map>
-
-#include "../../include/clawb200.h"
-#include "classic.cuh"
-#include "sharpclaw.cuh"
-
-using RpColor1D = RpColor<1, 1>; // (a template-id with a comma cannot be a macro argument)
+#include "launch.cuh"
 
 static thread_local std::string g_err;
 
-static int fail(int code, const char *msg)
+int fail(int code, const char *msg)
 {
     g_err = msg;
     return code;
 }
-static int cuda_fail(cudaError_t e, const char *where)
+int cuda_fail(cudaError_t e, const char *where)
 {
     g_err = std::string(where) + ": " + cudaGetErrorString(e);
     return CLAWB200_ERR_CUDA;
 }
-#define CUDA_OK(call)                                             \
-    do {                                                          \
-        cudaError_t e__ = (call);                                 \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
-    } while (0)
 
 extern "C" int clawb200_version(void) { return 100; }
 extern "C" const char *clawb200_last_error(void) { return g_err.c_str(); }
@@ -122,131 +106,20 @@ static SweepArgs make_args(const clawb200_problem *p, const double *qin, double 
     return A;
 }
 
-// opt in to > 48 KB of dynamic shared memory, once per kernel
-template <class K>
-static cudaError_t set_smem(K kernel, size_t bytes)
-{
-    static std::mutex mu;
-    static std::unordered_map<const void *, size_t> granted;
-    if (bytes <= 48 * 1024) return cudaSuccess;
-    std::lock_guard<std::mutex> lock(mu);
-    size_t &g = granted[(const void *)kernel];
-    if (bytes > g) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        g = bytes;
-    }
-    return cudaSuccess;
-}
-
-// Kernels that read many aux components per interface (the sphere) live on L1 hits: ask for
-// the smallest shared-memory carve-out that still holds the resident CTAs, the rest is L1.
-template <class K>
-static void hint_carveout(K kernel, size_t smem_per_cta, int ctas)
-{
-    static std::mutex mu;
-    static std::unordered_map<const void *, int> done;
-    std::lock_guard<std::mutex> lock(mu);
-    int &d = done[(const void *)kernel];
-    if (d) return;
-    int pct = (int)((smem_per_cta + 1024) * ctas * 100 / (228 * 1024)) + 1;
-    if (pct > 100) pct = 100;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    d = 1;
-}
-
-constexpr int XNT = 128; // threads per CTA of the x-engine
-constexpr int YNT = 128; // threads per CTA of the y-engine
-
-template <class RP, bool TRANS, bool CAPA = false>
-static int launch_x(SweepArgs A, cudaStream_t st)
-{
-    constexpr int NC = XNT - 3;
-    size_t smem = sizeof(double) * (2 * RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
-    auto k = xsweep_kernel<RP, TRANS, CAPA, XNT>;
-    CUDA_OK(set_smem(k, smem));
-    if (RP::MAUX >= 8) hint_carveout(k, smem, RP::X_MINB);
-    int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
-    dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
-    k<<<grid, XNT, smem, st>>>(A);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-template <class RP, bool TRANS, bool CAPA = false>
-static int launch_y(SweepArgs A, cudaStream_t st)
-{
-    constexpr int NC = TRANS ? YNT - 2 : YNT;
-    size_t smem = sizeof(double) * YNT * ((TRANS ? 4 * RP::MEQN : 0) + YSlots<RP, TRANS>::COUNT);
-    auto k = ysweep_kernel<RP, TRANS, CAPA, YNT>;
-    CUDA_OK(set_smem(k, smem));
-    if (RP::MAUX >= 8) hint_carveout(k, smem, RP::Y_MINB);
-    int ncols = A.ihi - A.ilo + 1, nrows = A.jhi - A.jlo + 1;
-    dim3 grid((ncols + NC - 1) / NC, (nrows + A.rows_per_cta - 1) / A.rows_per_cta);
-    k<<<grid, YNT, smem, st>>>(A);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-static int pick_rows(int nrows, int ncol_ctas)
-{
-    // enough CTAs to fill 148 SMs a few times over, but strips tall enough that the
-    // start-up rows of the streaming engines stay a small fraction of the work
-    int h = 64;
-    while (h > 8 && (long long)ncol_ctas * ((nrows + h - 1) / h) < 148 * 4) h /= 2;
-    return h;
-}
-
-// dispatch on the Riemann solver (the sweep direction is a template parameter of the solver)
+// dispatch on the Riemann-solver family (one translation unit each, launch.cuh)
 template <bool TRANS>
 static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
 {
-    if (A.mcapa > 0) {
-        switch (rp_id) {
-        case CLAWB200_RP_ACOUSTICS: return launch_x<RpAcoustics<2, 1>, TRANS, true>(A, st);
-        case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS, true>(A, st);
-        case CLAWB200_RP_SPHERE: return launch_x<RpSphere<1>, TRANS, true>(A, st);
-        case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS, true>(A, st);
-        case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS, true>(A, st);
-        case CLAWB200_RP_VC_ADVECTION: return launch_x<RpColor<2, 1>, TRANS, true>(A, st);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
-        }
-    }
-    switch (rp_id) {
-    case CLAWB200_RP_ACOUSTICS: return launch_x<RpAcoustics<2, 1>, TRANS>(A, st);
-    case CLAWB200_RP_ADVECTION: return launch_x<RpAdvection<2, 1>, TRANS>(A, st);
-    case CLAWB200_RP_EULER5: return launch_x<RpEuler5<1>, TRANS>(A, st);
-    case CLAWB200_RP_SHALLOW: return launch_x<RpShallow<1>, TRANS>(A, st);
-    case CLAWB200_RP_PSYSTEM: return launch_x<RpElasticFwave<2, 1>, TRANS>(A, st);
-    case CLAWB200_RP_VC_ACOUSTICS: return launch_x<RpVcAcoustics<1>, TRANS>(A, st);
-    case CLAWB200_RP_VC_ADVECTION: return launch_x<RpColor<2, 1>, TRANS>(A, st);
-    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
-    }
+    if (rp_id == CLAWB200_RP_EULER5) return claw_x_euler(TRANS, A, st);
+    if (rp_id == CLAWB200_RP_SPHERE) return claw_x_sphere(TRANS, A, st);
+    return claw_x_misc(rp_id, TRANS, A, st);
 }
 template <bool TRANS>
 static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
 {
-    if (A.mcapa > 0) {
-        switch (rp_id) {
-        case CLAWB200_RP_ACOUSTICS: return launch_y<RpAcoustics<2, 2>, TRANS, true>(A, st);
-        case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS, true>(A, st);
-        case CLAWB200_RP_SPHERE: return launch_y<RpSphere<2>, TRANS, true>(A, st);
-        case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS, true>(A, st);
-        case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS, true>(A, st);
-        case CLAWB200_RP_VC_ADVECTION: return launch_y<RpColor<2, 2>, TRANS, true>(A, st);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
-        }
-    }
-    switch (rp_id) {
-    case CLAWB200_RP_ACOUSTICS: return launch_y<RpAcoustics<2, 2>, TRANS>(A, st);
-    case CLAWB200_RP_ADVECTION: return launch_y<RpAdvection<2, 2>, TRANS>(A, st);
-    case CLAWB200_RP_EULER5: return launch_y<RpEuler5<2>, TRANS>(A, st);
-    case CLAWB200_RP_SHALLOW: return launch_y<RpShallow<2>, TRANS>(A, st);
-    case CLAWB200_RP_PSYSTEM: return launch_y<RpElasticFwave<2, 2>, TRANS>(A, st);
-    case CLAWB200_RP_VC_ACOUSTICS: return launch_y<RpVcAcoustics<2>, TRANS>(A, st);
-    case CLAWB200_RP_VC_ADVECTION: return launch_y<RpColor<2, 2>, TRANS>(A, st);
-    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
-    }
+    if (rp_id == CLAWB200_RP_EULER5) return claw_y_euler(TRANS, A, st);
+    if (rp_id == CLAWB200_RP_SPHERE) return claw_y_sphere(TRANS, A, st);
+    return claw_y_misc(rp_id, TRANS, A, st);
 }
 
 static int check_rp_shape(const clawb200_problem *p)
@@ -289,49 +162,7 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
     if ((rc = check_aux(p, aux, false))) return rc;
     SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev, aux);
     cudaStream_t st = (cudaStream_t)stream;
-    constexpr int NT = 128, NC = NT - 3;
-    dim3 grid((p->mx + NC - 1) / NC);
-    const bool capa = A.mcapa > 0;
-    switch (p->rp_id) {
-    case CLAWB200_RP_ACOUSTICS: {
-        using RP = RpAcoustics<1, 1>;
-        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
-        if (capa) step1_kernel<RP, NT, true><<<grid, NT, smem, st>>>(A);
-        else step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
-    } break;
-    case CLAWB200_RP_ADVECTION: {
-        using RP = RpAdvection<1, 1>;
-        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
-        if (capa) step1_kernel<RP, NT, true><<<grid, NT, smem, st>>>(A);
-        else step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
-    } break;
-    case CLAWB200_RP_SHALLOW: {
-        using RP = RpShallow1D;
-        if (capa) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
-        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
-        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
-    } break;
-    case CLAWB200_RP_NEL_FWAVE: {
-        using RP = RpElasticFwave<1, 1>;
-        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT);
-        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);
-    } break;
-#define STEP1_PLAIN(RPT)                                                                                     \
-    {                                                                                                        \
-        using RP = RPT;                                                                                      \
-        if (capa) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");               \
-        size_t smem = sizeof(double) * (RP::MEQN * (NT + 1) + RP::MEQN * RP::MWAVES * NT + 2 * RP::MEQN * NT); \
-        step1_kernel<RP, NT><<<grid, NT, smem, st>>>(A);                                                     \
-    }                                                                                                        \
-    break
-    case CLAWB200_RP_BURGERS: STEP1_PLAIN(RpBurgers);
-    case CLAWB200_RP_ADVECTION_COLOR: STEP1_PLAIN(RpColor1D);
-    case CLAWB200_RP_EULER1D: STEP1_PLAIN(RpEuler1D);
-#undef STEP1_PLAIN
-    default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
-    }
-    CUDA_OK(cudaGetLastError());
-    return 0;
+    return claw_step1(p->rp_id, A, p->mx, st);
 }
 
 extern "C" int clawb200_step2ds(const clawb200_problem *p, const double *q_in, double *q_out,
@@ -402,11 +233,11 @@ extern "C" int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, co
             if (idir == 1) {
                 A.ilo = 1; A.ihi = p->mx; A.jlo = 0; A.jhi = p->my + 1;
                 A.rows_per_cta = pick_rows(A.jhi - A.jlo + 1, (p->mx + XNT - 4) / (XNT - 3));
-                if ((rc = launch_x<RpAcoustics3D<1>, false>(A, st))) return rc;
+                if ((rc = claw_x_ac3d(A, st))) return rc;
             } else {
                 A.ilo = 0; A.ihi = p->mx + 1; A.jlo = 1; A.jhi = p->my;
                 A.rows_per_cta = pick_rows(p->my, (p->mx + 2 + YNT - 1) / YNT);
-                if ((rc = launch_y<RpAcoustics3D<2>, false>(A, st))) return rc;
+                if ((rc = claw_y_ac3d(2, A, st))) return rc;
             }
         }
     } else {
@@ -420,7 +251,7 @@ extern "C" int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, co
             A.trans = -1;
             A.ilo = 0; A.ihi = p->mx + 1; A.jlo = 1; A.jhi = mz;
             A.rows_per_cta = pick_rows(mz, (p->mx + 2 + YNT - 1) / YNT);
-            if ((rc = launch_y<RpAcoustics3D<3>, false>(A, st))) return rc;
+            if ((rc = claw_y_ac3d(3, A, st))) return rc;
         }
     }
     return 0;
@@ -670,208 +501,6 @@ extern "C" int clawb200_halo_unpack(const clawb200_problem *p, double *q, int na
                                                                  nx, narr, row0, nrows);
     CUDA_OK(cudaGetLastError());
     return 0;
-}
-
-// ---------------------------------------------------------------------------
-// SharpClaw
-// ---------------------------------------------------------------------------
-constexpr int SNT = 128;
-
-static int g_weno_k = 0;   // stencils of the table-driven WENO currently in constant memory
-static int g_weno_gen = 0; // bumped by every upload, so callers can tell whose tables are resident
-
-extern "C" int clawb200_weno_generation(void) { return g_weno_gen; }
-
-extern "C" int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
-                                        const double *WL, const double *WR, double eps, void *stream)
-{
-    if (k < 3 || k > 9) return fail(CLAWB200_ERR_INVALID, "weno_order must be an odd number between 5 and 17");
-    if (!S || !CL || !CR || !WL || !WR) return fail(CLAWB200_ERR_INVALID, "null table");
-    static WenoTab h; // staging copy: must outlive the asynchronous upload
-    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    memset(&h, 0, sizeof(h));
-    const int npair = k * (k + 1) / 2;
-    h.k = k;
-    h.eps = eps;
-    for (int r = 0; r < k; r++) {
-        for (int n = 0; n < npair; n++) h.S[r][n] = S[r * npair + n];
-        for (int j = 0; j < k; j++) { h.CL[r][j] = CL[r * k + j]; h.CR[r][j] = CR[r * k + j]; }
-        h.WL[r] = WL[r];
-        h.WR[r] = WR[r];
-    }
-    CUDA_OK(cudaMemcpyToSymbolAsync(c_weno, &h, sizeof(h), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    g_weno_k = k;
-    g_weno_gen++;
-    return 0;
-}
-
-template <class RP>
-static int sc_launch1_tab(const ScArgs &A, cudaStream_t st)
-{
-    constexpr int NC = SNT - 2;
-    const int H = g_weno_k - 1;
-    size_t smem = sizeof(double) * (RP::MEQN * (SNT + 2 * H) + 2 * RP::MEQN * SNT);
-    sc1d_tab_kernel<RP, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-template <class RPX, class RPY>
-static int sc_launch2_tab(const ScArgs &A, cudaStream_t st)
-{
-    constexpr int NC = SNT - 2;
-    const int H = g_weno_k - 1;
-    size_t smem = sizeof(double) * (RPX::MEQN * (SNT + 2 * H) + 2 * RPX::MEQN * SNT);
-    dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);
-    sc2d_tab_kernel<RPX, RPY, SNT><<<grid, SNT, smem, st>>>(A);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-static void weno_constants(ScArgs &A, int variant)
-{
-    const bool f32 = (variant == CLAWB200_WENO_PYWENO_F32);
-#define LIT(x) (f32 ? (double)(x##f) : (double)(x))
-    A.c333 = LIT(3.33333333333333); A.c1033 = LIT(10.3333333333333);
-    A.c366 = LIT(3.66666666666667); A.c833 = LIT(8.33333333333333);
-    A.c633 = LIT(6.33333333333333); A.c133 = LIT(1.33333333333333);
-    A.c433 = LIT(4.33333333333333); A.c166 = LIT(1.66666666666667);
-    A.d01 = LIT(0.1); A.d06 = LIT(0.6); A.d03 = LIT(0.3); A.eps = LIT(1.0e-36);
-    A.r183 = LIT(1.83333333333333); A.r116 = LIT(1.16666666666667);
-    A.r0333 = LIT(0.333333333333333); A.r0833 = LIT(0.833333333333333);
-    A.r0166 = LIT(0.166666666666667);
-#undef LIT
-    A.epweno = (double)1.e-36f; // reconstruct.f90:7, a REAL(4) literal
-}
-
-template <class RPX, class RPY, bool OLD, bool CAPA = false>
-static int sc_launch2(const ScArgs &A, cudaStream_t st)
-{
-    constexpr int NC = SNT - 2;
-    size_t smem = sizeof(double) * (2 * RPX::MEQN * (SNT + 4) + 2 * RPX::MEQN * SNT);
-    auto k = sc2d_kernel<RPX, RPY, OLD, SNT, CAPA>;
-    CUDA_OK(set_smem(k, smem));
-    dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);
-    k<<<grid, SNT, smem, st>>>(A);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-template <class RP, bool OLD, bool CAPA = false>
-static int sc_launch1(const ScArgs &A, cudaStream_t st)
-{
-    constexpr int NC = SNT - 2;
-    size_t smem = sizeof(double) * (RP::MEQN * (SNT + 4) + 2 * RP::MEQN * SNT);
-    sc1d_kernel<RP, OLD, SNT, CAPA><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-static int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *qa, double *out,
-                            double *dq_out, double dt, int mode, double ca, double cb, double div,
-                            double *cfl_dev, cudaStream_t st, const double *aux = nullptr)
-{
-    ScArgs A;
-    memset(&A, 0, sizeof(A));
-    A.q = q; A.qa = qa; A.out = out; A.dq_out = dq_out;
-    A.mstride = p->mstride; A.pitch = p->pitch;
-    A.mx = p->mx; A.my = p->my; A.mbc = p->mbc;
-    A.dtdx = dt / p->dx;
-    A.dtdy = (p->ndim > 1) ? dt / p->dy : 0.0;
-    for (int i = 0; i < 8; i++) A.rp.p[i] = p->rp_params[i];
-    weno_constants(A, p->weno_variant);
-    A.aux = aux;
-    A.amstride = p->mstride;
-    A.mode = mode; A.ca = ca; A.cb = cb; A.div = div;
-    A.cfl_bits = (unsigned long long *)cfl_dev;
-    const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
-    if (p->weno_variant == CLAWB200_WENO_TABLES) {
-        if (g_weno_k < 3) return fail(CLAWB200_ERR_INVALID, "call clawb200_set_weno_tables first");
-        if (p->mbc < g_weno_k) return fail(CLAWB200_ERR_INVALID, "WENO of order 2k-1 needs mbc >= k");
-        if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for WENO orders above 5");
-        if (p->ndim == 2) {
-            A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
-            switch (p->rp_id) {
-            case CLAWB200_RP_ACOUSTICS: return sc_launch2_tab<RpAcoustics<2, 1>, RpAcoustics<2, 2>>(A, st);
-            case CLAWB200_RP_ADVECTION: return sc_launch2_tab<RpAdvection<2, 1>, RpAdvection<2, 2>>(A, st);
-            case CLAWB200_RP_EULER5: return sc_launch2_tab<RpEuler5<1>, RpEuler5<2>>(A, st);
-            case CLAWB200_RP_SHALLOW: return sc_launch2_tab<RpShallow<1>, RpShallow<2>>(A, st);
-            case CLAWB200_RP_VC_ACOUSTICS: return sc_launch2_tab<RpVcAcoustics<1>, RpVcAcoustics<2>>(A, st);
-            default: return fail(CLAWB200_ERR_UNSUPPORTED, "WENO orders above 5 are not compiled for this solver in 2-D");
-            }
-        }
-        switch (p->rp_id) {
-        case CLAWB200_RP_ACOUSTICS: return sc_launch1_tab<RpAcoustics<1, 1>>(A, st);
-        case CLAWB200_RP_ADVECTION: return sc_launch1_tab<RpAdvection<1, 1>>(A, st);
-        case CLAWB200_RP_SHALLOW: return sc_launch1_tab<RpShallow1D>(A, st);
-        case CLAWB200_RP_BURGERS: return sc_launch1_tab<RpBurgers>(A, st);
-        case CLAWB200_RP_EULER1D: return sc_launch1_tab<RpEuler1D>(A, st);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
-        }
-    }
-    if (p->method[5] > 0) {
-        // capacity function (flux1.f90:59-63): compiled for the acoustics and advection solvers
-        A.capa = aux + (long long)(p->method[5] - 1) * p->mstride;
-        A.dt = dt; A.dx = p->dx; A.dy = (p->ndim > 1) ? p->dy : 1.0;
-        if (p->ndim == 1) {
-            switch (p->rp_id) {
-            case CLAWB200_RP_ACOUSTICS:
-                return old ? sc_launch1<RpAcoustics<1, 1>, true, true>(A, st) : sc_launch1<RpAcoustics<1, 1>, false, true>(A, st);
-            case CLAWB200_RP_ADVECTION:
-                return old ? sc_launch1<RpAdvection<1, 1>, true, true>(A, st) : sc_launch1<RpAdvection<1, 1>, false, true>(A, st);
-            default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
-            }
-        }
-        A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
-        switch (p->rp_id) {
-        case CLAWB200_RP_ACOUSTICS: return old ? sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, true, true>(A, st)
-                                               : sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, false, true>(A, st);
-        case CLAWB200_RP_ADVECTION: return old ? sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, true, true>(A, st)
-                                               : sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, false, true>(A, st);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
-        }
-    }
-    if (p->ndim == 1) {
-        switch (p->rp_id) {
-        case CLAWB200_RP_ACOUSTICS:
-            return old ? sc_launch1<RpAcoustics<1, 1>, true>(A, st) : sc_launch1<RpAcoustics<1, 1>, false>(A, st);
-        case CLAWB200_RP_ADVECTION:
-            return old ? sc_launch1<RpAdvection<1, 1>, true>(A, st) : sc_launch1<RpAdvection<1, 1>, false>(A, st);
-        case CLAWB200_RP_SHALLOW:
-            return old ? sc_launch1<RpShallow1D, true>(A, st) : sc_launch1<RpShallow1D, false>(A, st);
-        case CLAWB200_RP_BURGERS:
-            return old ? sc_launch1<RpBurgers, true>(A, st) : sc_launch1<RpBurgers, false>(A, st);
-        case CLAWB200_RP_EULER1D:
-            return old ? sc_launch1<RpEuler1D, true>(A, st) : sc_launch1<RpEuler1D, false>(A, st);
-        case CLAWB200_RP_NEL_FWAVE: // with char_decomp = 0 an f-wave solver only contributes amdq / apdq
-            return old ? sc_launch1<RpElasticFwave<1, 1>, true>(A, st) : sc_launch1<RpElasticFwave<1, 1>, false>(A, st);
-        case CLAWB200_RP_ADVECTION_COLOR:
-            return old ? sc_launch1<RpColor1D, true>(A, st) : sc_launch1<RpColor1D, false>(A, st);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
-        }
-    }
-    A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
-#define SC2(RPT)                                                                         \
-    return old ? sc_launch2<RPT, true>(A, st) : sc_launch2<RPT, false>(A, st)
-    switch (p->rp_id) {
-    case CLAWB200_RP_ACOUSTICS: return old ? sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, true>(A, st)
-                                           : sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, false>(A, st);
-    case CLAWB200_RP_ADVECTION: return old ? sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, true>(A, st)
-                                           : sc_launch2<RpAdvection<2, 1>, RpAdvection<2, 2>, false>(A, st);
-    case CLAWB200_RP_EULER5: return old ? sc_launch2<RpEuler5<1>, RpEuler5<2>, true>(A, st)
-                                        : sc_launch2<RpEuler5<1>, RpEuler5<2>, false>(A, st);
-    case CLAWB200_RP_SHALLOW: return old ? sc_launch2<RpShallow<1>, RpShallow<2>, true>(A, st)
-                                         : sc_launch2<RpShallow<1>, RpShallow<2>, false>(A, st);
-    case CLAWB200_RP_PSYSTEM: return old ? sc_launch2<RpElasticFwave<2, 1>, RpElasticFwave<2, 2>, true>(A, st)
-                                         : sc_launch2<RpElasticFwave<2, 1>, RpElasticFwave<2, 2>, false>(A, st);
-    case CLAWB200_RP_VC_ACOUSTICS: return old ? sc_launch2<RpVcAcoustics<1>, RpVcAcoustics<2>, true>(A, st)
-                                              : sc_launch2<RpVcAcoustics<1>, RpVcAcoustics<2>, false>(A, st);
-    case CLAWB200_RP_VC_ADVECTION: return old ? sc_launch2<RpColor<2, 1>, RpColor<2, 2>, true>(A, st)
-                                              : sc_launch2<RpColor<2, 1>, RpColor<2, 2>, false>(A, st);
-    default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
-    }
-#undef SC2
 }
 
 extern "C" int clawb200_sharpclaw_stage(const clawb200_problem *p, const double *q, const double *qa,
@@ -1303,6 +932,101 @@ extern "C" int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const doubl
         return rc;
     if ((rc = host_download(P, g_hs.d_b, dq))) return rc;
     return host_finish(cfl);
+}
+
+// ---------------------------------------------------------------------------
+// Riemann solvers as pointwise operators (rp_point.cu)
+// ---------------------------------------------------------------------------
+static int check_rp_point(const clawb200_problem *p, int ixy, long long n)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    if (n < 0) return fail(CLAWB200_ERR_INVALID, "negative n");
+    if (p->ndim == 2 && ixy != 1 && ixy != 2) return fail(CLAWB200_ERR_INVALID, "ixy must be 1 or 2");
+    if (p->ndim != 1 && p->ndim != 2) return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: 1-D and 2-D solvers");
+    return check_rp_shape(p);
+}
+
+extern "C" int clawb200_rp_solve(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                                 const double *qr, double *wave, double *s, double *amdq, double *apdq,
+                                 void *stream)
+{
+    int rc = check_rp_point(p, ixy, n);
+    if (rc) return rc;
+    if (!ql || !qr || !wave || !s || !amdq || !apdq) return fail(CLAWB200_ERR_INVALID, "null argument");
+    return claw_rp_point(p, ixy, n, ql, qr, wave, s, amdq, apdq, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int clawb200_rp_transverse(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                                      const double *qr, int imp, const double *asdq, double *bmasdq,
+                                      double *bpasdq, void *stream)
+{
+    int rc = check_rp_point(p, ixy, n);
+    if (rc) return rc;
+    if (!ql || !qr || !asdq || !bmasdq || !bpasdq) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (imp != 1 && imp != 2) return fail(CLAWB200_ERR_INVALID, "imp must be 1 or 2");
+    if (p->ndim != 2) return fail(CLAWB200_ERR_INVALID, "transverse solves exist in 2-D only");
+    return claw_rp_point(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq, bpasdq,
+                         (cudaStream_t)stream);
+}
+
+static int rp_point_host(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
+                         double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
+                         double *bm, double *bp)
+{
+    int rc = check_rp_point(p, ixy, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    const size_t me = (size_t)p->meqn * n, mw = (size_t)p->mwaves * n;
+    // one device block: ql, qr, asdq | wave, s, amdq, apdq, bm, bp
+    const size_t total = 3 * me + me * p->mwaves + mw + 4 * me;
+    if ((rc = g_hs.ensure(16))) return rc;
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, total * sizeof(double)));
+    double *d_ql = d, *d_qr = d + me, *d_as = d + 2 * me, *d_w = d + 3 * me, *d_s = d_w + me * p->mwaves,
+           *d_am = d_s + mw, *d_ap = d_am + me, *d_bm = d_ap + me, *d_bp = d_bm + me;
+    cudaStream_t st = g_hs.st;
+    auto done = [&](int code) { cudaStreamSynchronize(st); cudaFree(d); return code; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_ql, ql, me * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_qr, qr, me * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return done(cuda_fail(e, "upload"));
+    if (asdq) {
+        if ((e = cudaMemcpyAsync(d_as, asdq, me * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return done(cuda_fail(e, "upload"));
+        if ((rc = claw_rp_point(p, ixy, n, d_ql, d_qr, nullptr, nullptr, nullptr, nullptr, imp, d_as, d_bm, d_bp, st)))
+            return done(rc);
+        if ((e = cudaMemcpyAsync(bm, d_bm, me * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(bp, d_bp, me * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return done(cuda_fail(e, "download"));
+    } else {
+        if ((rc = claw_rp_point(p, ixy, n, d_ql, d_qr, d_w, d_s, d_am, d_ap, 0, nullptr, nullptr, nullptr, st)))
+            return done(rc);
+        if ((e = cudaMemcpyAsync(wave, d_w, me * p->mwaves * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(s, d_s, mw * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(amdq, d_am, me * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(apdq, d_ap, me * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return done(cuda_fail(e, "download"));
+    }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "sync"));
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int clawb200_rp_solve_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                                      const double *qr, double *wave, double *s, double *amdq, double *apdq)
+{
+    if (!ql || !qr || !wave || !s || !amdq || !apdq) return fail(CLAWB200_ERR_INVALID, "null argument");
+    return rp_point_host(p, ixy, n, ql, qr, wave, s, amdq, apdq, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
+                                           const double *qr, int imp, const double *asdq, double *bmasdq,
+                                           double *bpasdq)
+{
+    if (!ql || !qr || !asdq || !bmasdq || !bpasdq) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (imp != 1 && imp != 2) return fail(CLAWB200_ERR_INVALID, "imp must be 1 or 2");
+    if (p && p->ndim != 2) return fail(CLAWB200_ERR_INVALID, "transverse solves exist in 2-D only");
+    return rp_point_host(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq, bpasdq);
 }
 
 // classic3.step3ds with host arrays q(meqn, mx+2mbc, my+2mbc, mz+2mbc) (clawpack.py:656-676)

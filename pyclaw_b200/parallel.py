@@ -37,12 +37,21 @@ class SlabPartition(object):
         self.dim_index = grid.ndim - 1
         dim = grid.dimensions[self.dim_index]
         nstart, nend = slab_range(dim.n, self.rank, self.size)
-        if nend - nstart < 3:
-            raise Exception("slab of %d cells is thinner than the ghost width" % (nend - nstart))
+        if nend - nstart < 1:
+            raise Exception("more ranks (%d) than cells (%d) along the partitioned dimension"
+                            % (self.size, dim.n))
         dim._set_range(nstart, nend)
+        self.nloc = nend - nstart
         self.lower_nbr = self.rank - 1
         self.upper_nbr = self.rank + 1
         self._bufs = {}
+
+    def check_thickness(self, mbc):
+        """The exchange sends the ``mbc`` interior rows next to each slab face: a slab thinner
+        than the ghost width would send ghost rows.  Called once the solver knows ``mbc``."""
+        if self.size > 1 and self.nloc < mbc:
+            raise Exception("slab of %d cells is thinner than the ghost width mbc = %d"
+                            % (self.nloc, mbc))
 
     def _buffers(self, field, nrows):
         # a "row" of the partitioned (last) dimension: a cell in 1-D, a padded row in 2-D, a
@@ -69,6 +78,8 @@ class SlabPartition(object):
         mbc = field.mbc
         t = field.cur
         nloc = t.shape[1] - 2 * mbc
+        if nloc < mbc:
+            raise Exception("slab of %d cells is thinner than the ghost width mbc = %d" % (nloc, mbc))
         wrap = bool(periodic[self.dim_index])
         lo = self.lower_nbr if self.lower_nbr >= 0 else (self.size - 1 if wrap else None)
         hi = self.upper_nbr if self.upper_nbr < self.size else (0 if wrap else None)

@@ -102,6 +102,18 @@ def resolve(rp, aux_global, ndim, fwave=False):
     if rp is not None:
         raise NotImplementedError("Python Riemann solvers are not supported: there is no CPU "
                                   "path; set solver.rp to a pyclaw.riemann descriptor")
+    found = _infer(aux_global, ndim, fwave)
+    # The reference binds the solver at link time (RP_SOURCE in the application's Makefile); a
+    # guess from the cparam names must be visible, so that a script whose aux_global happens to
+    # match another physics does not run the wrong solver silently.
+    import logging
+    logging.getLogger('evolve').warning(
+        "solver.rp is not set: using Riemann solver %r inferred from aux_global keys %s "
+        "(set solver.rp = pyclaw.riemann.<name> to choose explicitly)", found.name, sorted(aux_global.keys()))
+    return found
+
+
+def _infer(aux_global, ndim, fwave):
     if ndim == 3:
         return vc_acoustics_3d       # the only 3-D solver the reference's applications link
     if fwave:

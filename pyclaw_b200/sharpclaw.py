@@ -57,13 +57,13 @@ class SharpClawSolver(Solver):
         if tab is None:
             return
         L = _lib.load()
-        if getattr(self, '_weno_gen', None) == L.clawb200_weno_generation():
+        if getattr(self, '_weno_gen', None) == (_lib._active, L.clawb200_weno_generation()):
             return
         import numpy as np
         arr = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('S', 'CL', 'CR', 'WL', 'WR')]
         _lib.call("clawb200_set_weno_tables", int(tab['k']),
                   *[ctypes.c_void_p(a.ctypes.data) for a in arr], float(tab['eps']), _stream())
-        self._weno_gen = L.clawb200_weno_generation()
+        self._weno_gen = (_lib._active, L.clawb200_weno_generation())
 
     # ---- one dq evaluation fused with a stage update ----
     def _stage(self, q_buf, qa_buf, out_buf, mode, ca, cb, div, slot, dq_buf=None):
@@ -91,6 +91,7 @@ class SharpClawSolver(Solver):
         The stages are launched back to back and their Courant numbers are read once at
         the end; the result is committed only if no stage exceeded cfl_max, which is the
         state the reference is left in when CFLError interrupts it (q untouched)."""
+        _lib.set_variant(self.arithmetic)
         state = solution.states[0]
         self.start_step(self, solution)
         if self.dq_src is not None:

@@ -74,6 +74,9 @@ class Solver(object):
         self._cfl_dev = None
         self._cfl_host = None
         self._halo = None  # set by the slab partition (pyclaw_b200.parallel)
+        # 'strict': -fmad=false build, bit for bit against the reference's arithmetic (default);
+        # 'fma': the same kernels with mul+add contraction (profiles/README.md has the error table)
+        self.arithmetic = 'strict'
 
     def _make_cfl(self, v):
         return CFL(v)
@@ -124,6 +127,7 @@ class Solver(object):
         if state.device.type != 'cuda':
             raise _lib.ClawB200Error("pyclaw_b200 computes on CUDA devices only (no CPU fallback); "
                                      "state lives on %s" % state.device)
+        _lib.set_variant(self.arithmetic)
         _lib.load()
         grid = state.grid
         fwave = bool(getattr(self, 'fwave', False))
@@ -152,6 +156,13 @@ class Solver(object):
             method=method, mthlim=mthlim, maux=state.maux, pitch=state._q.pitch,
             mstride=state._q.mstride, weno_variant=weno_variant)
         self._halo = state._partition
+        if self._halo is not None:
+            self._halo.check_thickness(self.mbc)
+        # a new problem invalidates every captured launch sequence (clawpack.py: the graphs hold
+        # a byte copy of the previous problem and the previous buffers' addresses)
+        self._dt_dev = None
+        self._gproblem = None
+        self._graphs = {}
         self._cfl_dev = torch.zeros(16, dtype=torch.float64, device=state.device)
         self._cfl_host = torch.zeros(16, dtype=torch.float64).pin_memory()
 
@@ -221,6 +232,7 @@ class Solver(object):
         return True
 
     def evolve_to_time(self, solution, tend=None):
+        _lib.set_variant(self.arithmetic)
         take_one_step = tend is None
         tstart = solution.t
         self.status['cflmax'] = self.cfl.get_cached_max()
@@ -259,9 +271,9 @@ class Solver(object):
                 self.status['cflmax'] = max(cfl, self.status['cflmax'])
                 if self.dt_variable:
                     solution.t += self.dt
-                    state._accept_step()
                 else:
                     solution.t = tstart + (n + 1) * self.dt
+                state._accept_step()
                 self.logger.debug("Step %i  CFL = %f   dt = %f   t = %f" % (n, cfl, self.dt, solution.t))
                 self.write_gauge_values(solution)
                 self.status['numsteps'] += 1

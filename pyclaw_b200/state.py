@@ -32,7 +32,8 @@ class _Field(object):
         return self.spare.pop() if self.spare else self._alloc()
 
     def put_spare(self, t):
-        if len(self.spare) < 3:
+        # buffers of another padded shape (a previous ghost-cell width) are dropped, never reused
+        if t.shape == self.cur.shape and len(self.spare) < 3:
             self.spare.append(t)
 
     @staticmethod
@@ -171,6 +172,10 @@ class State(object):
     def set_mbc(self, mbc):
         """Re-allocate the padded storage for ``mbc`` ghost cells (the PetClaw State
         re-creates its DMDA with the real stencil width here, petclaw/state.py:271-290)."""
+        if mbc != self._q.mbc:
+            # ping-pong buffers of the old padded shape must not come back as spares
+            self._backup = None
+            self._explicit = None
         self._q.set_mbc(mbc)
         if self._aux is not None:
             self._aux.set_mbc(mbc)

@@ -212,3 +212,57 @@ def sphere_qbc_upper_y(idim, t, qbc, mbc):
     for j in range(mbc):
         qbc1D = qbc[:, :, my + mbc - 1 - j].copy()
         qbc[:, :, my + mbc + j] = qbc1D[:, ::-1]
+
+
+# ---------------------------------------------------------------------------
+# BASELINE-size inputs: separable (outer-product) fields, cheap to build at 8192^2
+# ---------------------------------------------------------------------------
+def big_state(rp, shape, seed=0):
+    """Seeded smooth-plus-jump data built from 1-D profiles, f(i, j) = a(i) + b(j) + c(i) d(j):
+    a 67-M-cell field costs a few outer products instead of a meshgrid of transcendentals.
+    Velocities span both signs and exceed the sound speed in places, so every entropy-fix
+    branch, both limiter branches (s > 0, s < 0) and zero / non-zero jumps are exercised."""
+    rng = np.random.RandomState(seed)
+    nx, ny = shape
+    x = np.linspace(0.0, 1.0, nx)
+    y = np.linspace(0.0, 1.0, ny)
+
+    def prof(t):
+        p = np.zeros_like(t)
+        for _ in range(3):
+            p += np.sin(2 * np.pi * rng.randint(1, 6) * t + rng.uniform(0, 2 * np.pi)) / 3.0
+        p += 0.6 * (t > rng.uniform(0.2, 0.8)) - 0.3      # one jump
+        k = rng.randint(0, len(t) - 8)
+        p[k:k + 8] = p[k]                                 # a flat patch: zero jumps
+        return p
+
+    def field(lo, hi):
+        f = np.add.outer(prof(x), prof(y)) + np.multiply.outer(prof(x), prof(y))
+        fmin, fmax = f.min(), f.max()
+        f -= fmin
+        f *= (hi - lo) / (fmax - fmin)
+        f += lo
+        return f
+
+    if rp == "acoustics":
+        q = np.empty((3, nx, ny), order="F")
+        for m in range(3):
+            q[m] = field(-1, 1)
+    elif rp == "euler":
+        q = np.empty((5, nx, ny), order="F")
+        rho, u, v, p = field(0.6, 1.6), field(-1.6, 1.6), field(-1.6, 1.6), field(0.6, 1.6)
+        q[0] = rho
+        q[1] = rho * u
+        q[2] = rho * v
+        q[3] = p / GAMMA1 + 0.5 * rho * (u * u + v * v)
+        del u, v, p
+        q[4] = field(0, 1)
+    elif rp == "shallow":
+        q = np.empty((3, nx, ny), order="F")
+        h = field(0.6, 1.6)
+        q[0] = h
+        q[1] = h * field(-1.6, 1.6)
+        q[2] = h * field(-1.6, 1.6)
+    else:
+        raise ValueError(rp)
+    return q

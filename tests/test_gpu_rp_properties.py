@@ -1,0 +1,79 @@
+"""The CUDA Riemann solvers (the device functions inlined into the sweeps), called through
+`clawb200_rp_solve_host` / `clawb200_rp_transverse_host`: (1) against oracle-independent
+properties (tests/rp_properties.py), (2) bit for bit against the oracle's solvers."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import rp_properties as rpp
+import test_rp_properties as cpu
+from oracle import pyclaw_oracle as po
+from pyclaw_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+MEQN = {po.RP_EULER5: 5, po.RP_SHALLOW: 3, po.RP_ACOUSTICS: 3, po.RP_ADVECTION: 1}
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _problem(name):
+    rp_id, params, mw = cpu._spec(name)
+    return _lib.make_problem(2, MEQN[rp_id], mw, 2, 8, 8, 1.0, 1.0, rp_id, params), mw
+
+
+def _solve_for(name):
+    P, mw = _problem(name)
+
+    def solve(ixy, ql, qr):
+        ql, qr = np.ascontiguousarray(ql), np.ascontiguousarray(qr)
+        meqn, n = ql.shape
+        wave, s = np.zeros((meqn, mw, n)), np.zeros((mw, n))
+        amdq, apdq = np.zeros((meqn, n)), np.zeros((meqn, n))
+        _lib.call("clawb200_rp_solve_host", ctypes.byref(P), ixy, n, _ptr(ql), _ptr(qr), _ptr(wave), _ptr(s),
+                  _ptr(amdq), _ptr(apdq))
+        return wave, s, amdq, apdq
+    return solve
+
+
+def _transverse_for(name):
+    P, mw = _problem(name)
+
+    def transverse(ixy, ql, qr, imp, asdq):
+        ql, qr, asdq = np.ascontiguousarray(ql), np.ascontiguousarray(qr), np.ascontiguousarray(asdq)
+        meqn, n = ql.shape
+        bm, bp = np.zeros((meqn, n)), np.zeros((meqn, n))
+        _lib.call("clawb200_rp_transverse_host", ctypes.byref(P), ixy, n, _ptr(ql), _ptr(qr), imp, _ptr(asdq),
+                  _ptr(bm), _ptr(bp))
+        return bm, bp
+    return transverse
+
+
+def test_cuda_riemann_solvers_satisfy_their_defining_properties():
+    rpp.run_all(_solve_for, _transverse_for, n=8192)
+
+
+@pytest.mark.parametrize("name", ["euler", "shallow", "acoustics", ("advection", (0.7, -0.4))])
+@pytest.mark.parametrize("ixy", [1, 2])
+def test_cuda_riemann_solvers_equal_the_oracle_bit_for_bit(name, ixy):
+    n = 4096
+    if name == "euler":
+        ql, qr, _ = rpp.euler_states(n, 11)
+    elif name == "shallow":
+        ql, qr = rpp.shallow_states(n, 12)
+    else:
+        rng = np.random.RandomState(13)
+        m = 3 if name == "acoustics" else 1
+        ql, qr = rng.uniform(-1, 1, (m, n)), rng.uniform(-1, 1, (m, n))
+    got = _solve_for(name)(ixy, ql, qr)
+    want = cpu._solve_for(name)(ixy, ql, qr)
+    for g, w, what in zip(got, want, ("wave", "s", "amdq", "apdq")):
+        assert np.array_equal(g, w), (name, ixy, what, np.abs(g - w).max())
+    asdq = np.random.RandomState(14).uniform(-1, 1, ql.shape)
+    for imp in (1, 2):
+        gb = _transverse_for(name)(ixy, ql, qr, imp, asdq)
+        wb = cpu._transverse_for(name)(ixy, ql, qr, imp, asdq)
+        assert np.array_equal(gb[0], wb[0]) and np.array_equal(gb[1], wb[1]), (name, ixy, imp)
