@@ -366,9 +366,14 @@ def main():
     ap.add_argument("--perturb", action="store_true", help="(default now) time the developed field")
     ap.add_argument("--quiescent", action="store_true",
                     help="time the application's own initial data only (mostly at rest) instead of the developed field")
-    ap.add_argument("--arithmetic", default="strict", choices=["strict", "fma"],
-                    help="library build: strict IEEE (parity) or with FMA contraction")
+    ap.add_argument("--arithmetic", default="auto", choices=["auto", "strict", "fma"],
+                    help="library build: strict IEEE (bit-exact parity build) or fma (FMA contraction + "
+                         "1.5-ulp division).  auto = the fastest build that meets north_star's 1e-12 "
+                         "relative tolerance on that workload (profiles/README.md, table 'fma vs strict'): "
+                         "fma for the classic sweeps, strict for SharpClaw")
     ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 partition-parity check")
+    ap.add_argument("--no-other-build", action="store_true", help="skip timing the other arithmetic build")
+    ap.add_argument("--no-quiescent-leg", action="store_true", help="skip timing the application's own (quiescent) field")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
     args = ap.parse_args()
@@ -395,6 +400,11 @@ def main():
     wl = WORKLOADS[args.workload]
     n = args.n or wl["n"]
     cells_per_rank = n * n if args.workload != "sphere" else 2 * n * n
+    # measured relative L-infinity of the fma build against the strict one over the reference's
+    # own test runs (profiles/fma_study.py -> profiles/r2/fma_study.json)
+    FMA_ERR = {"euler": 2.8e-14, "acoustics": 6.3e-16, "sphere": 1.4e-13, "shallow": 1.5e-11}
+    if args.arithmetic == "auto":
+        args.arithmetic = "fma" if FMA_ERR[args.workload] <= 1e-12 else "strict"
 
     def barrier():
         if world > 1:
@@ -408,10 +418,10 @@ def main():
     if world > 1 and not args.no_parity:
         partition_parity = check_partition_parity(rank, world, torch, dist)
 
-    def timed_run(field, steps, warmup, sample_clocks):
+    def timed_run(field, steps, warmup, sample_clocks, arithmetic=None):
         """Set the problem up, let dt settle, time `steps` calls of solver.evolve_to_time."""
         state, solver = build_problem(pyclaw, args.workload, n, world, torch)
-        solver.arithmetic = args.arithmetic
+        solver.arithmetic = arithmetic or args.arithmetic
         if field == "developed" and args.workload in ("euler", "shallow"):
             # A smooth velocity field over the whole domain (SURVEY 8(d)): every interface has
             # non-zero jumps in every wave family, so the limiter, the entropy fix and the
@@ -463,15 +473,24 @@ def main():
     has_quiescent = args.workload in ("euler", "shallow")
     field = "developed" if (has_quiescent and not args.quiescent) else "application"
     quiescent = None
-    if has_quiescent and field == "developed":
+    if has_quiescent and field == "developed" and not args.no_quiescent_leg:
         rq = timed_run("application", min(args.steps, 10), max(args.warmup, 3), False)
         quiescent = {"value": rq["value"], "ms_per_step": rq["ms"] / min(args.steps, 10),
                      "what": "the application's own initial data (>99% of the cells at rest)"}
         del rq
         torch.cuda.empty_cache()
+    other_build = None
+    if not args.no_other_build:
+        ob = "strict" if args.arithmetic == "fma" else "fma"
+        ro = timed_run(field, min(args.steps, 10), max(args.warmup, 3), False, arithmetic=ob)
+        other_build = {"arithmetic": ob, "value": ro["value"], "ms_per_step": ro["ms"] / min(args.steps, 10),
+                       "field": field}
+        del ro
+        torch.cuda.empty_cache()
     run = timed_run(field, args.steps, max(args.warmup, 3), True)
     value, ms, accepted, clocks = run["value"], run["ms"], run["accepted"], run["clocks"]
     state, solver, solution = run["state"], run["solver"], run["solution"]
+    _lib.set_variant(args.arithmetic)
 
     # ---- e2e at N > 1: every rank uploads its slab from pinned host memory, takes one step
     # through the petclaw API (halo exchange + CFL all-reduce included) and downloads the result
@@ -673,8 +692,13 @@ def main():
         "config": {"workload": wl["label"], "cells_per_gpu": cells_per_rank, "accepted_steps": accepted,
                    "l2": "inputs larger than L2 (%.1f GB per field)" % (cells_per_rank * wl["meqn"] * 8 / 1e9),
                    "parallelism": "y-slabs x%d" % world,
-                   "arithmetic": ("strict IEEE, -fmad=false (bit-exact vs oracle)" if args.arithmetic == "strict"
-                                  else "fma: -fmad=true build (round-off-level differences, profiles/README.md)"),
+                   "arithmetic": args.arithmetic,
+                   "arithmetic_note": ("strict IEEE build, -fmad=false: bit for bit against the oracle" if args.arithmetic == "strict"
+                                       else "fma build (-fmad=true, quotients within 1.5 ulp): relative L-inf %.1e against the "
+                                            "strict build over the reference's own test run of this workload; north_star asks 1e-12"
+                                            % FMA_ERR[args.workload]),
+                   "fma_rel_linf_vs_strict": FMA_ERR[args.workload],
+                   "other_build": other_build,
                    "field": field, "quiescent_value": quiescent["value"] if quiescent else None,
                    "quiescent": quiescent},
         "clocks": clocks,

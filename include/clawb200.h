@@ -70,6 +70,10 @@ extern "C" {
 #define CLAWB200_WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)                     */
 #define CLAWB200_WENO_TABLES 3     /* weno.f90:104-2425, orders 7..17 (1-D): coefficient tables set
                                       with clawb200_set_weno_tables                               */
+#define CLAWB200_RECON_TVD2 4      /* reconstruct.f90:568-625 (lim_type = 1, char_decomp = 0): second-
+                                      order TVD reconstruction; problem.mthlim[m] is the limiter of
+                                      COMPONENT m (1 minmod, 2 superbee, 3 van Leer, 4 MC, 5 Cada-
+                                      Torrilhon).  First cell of a slice: see DESIGN.md            */
 
 #define CLAWB200_ERR_INVALID (-1)
 #define CLAWB200_ERR_UNSUPPORTED (-2)

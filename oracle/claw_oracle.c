@@ -59,6 +59,7 @@
 #define WENO_PYWENO_F64 1 /* same formulas, literals read as doubles            */
 #define WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)              */
 #define WENO_TABLES 3     /* weno.f90:104-2425 (orders 7..17) through coefficient tables */
+#define RECON_TVD2 4      /* reconstruct.f90:568-625 (lim_type = 1, char_decomp = 0)     */
 
 typedef struct {
     int rp_id;
@@ -1803,6 +1804,55 @@ static void weno5_old(const double *q, double *ql, double *qr, int meqn, int mx,
     }
 }
 
+/* gfortran's MIN / MAX (trans-intrinsic.c, gfc_conv_intrinsic_minmax):
+   mvar = a1; if (a2 < mvar || isnan(mvar)) mvar = a2  -- a NaN argument loses. */
+static inline double fmin_g(double a1, double a2) { return (a2 < a1 || a1 != a1) ? a2 : a1; }
+static inline double fmax_g(double a1, double a2) { return (a2 > a1 || a1 != a1) ? a2 : a1; }
+
+static int g_tvd_mthlim[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+void oracle_set_tvd_limiters(const int *mthlim, int n)
+{
+    for (int m = 0; m < 8; m++) g_tvd_mthlim[m] = (m < n) ? mthlim[m] : 0;
+}
+
+/* reconstruct.f90:568-625 (tvd2), component-wise second-order TVD reconstruction.  The routine
+   declares its own mbc = 2, so in 1-based storage p runs over 3 .. mx2-2: with the solver's
+   three ghost cells that is cells 0 .. mx+1.  The Fortran starts each component's loop with
+   "dqm = dqp" where dqp has not been assigned (first component: undefined; later components:
+   the last difference of the PREVIOUS component).  DEVIATION, stated in DESIGN.md: the first
+   cell uses its own backward difference q(p) - q(p-1) like every other cell. */
+static void tvd2(const double *q, double *ql, double *qr, int meqn, int mx, int mbc)
+{
+    const int mx2 = mx + 2 * mbc;
+    for (int m = 0; m < meqn; m++) {
+        double dqp = QP(q, m, 3) - QP(q, m, 2);
+        for (int p = 3; p <= mx2 - 2; p++) {
+            double dqm = dqp;
+            dqp = QP(q, m, p + 1) - QP(q, m, p);
+            double r = dqp / dqm;
+            double qlimitr = 0.0;
+            switch (g_tvd_mthlim[m]) {
+            case 1: qlimitr = fmax_g(0.0, fmin_g(1.0, r)); break;
+            case 2: qlimitr = fmax_g(fmax_g(0.0, fmin_g(1.0, 2.0 * r)), fmin_g(2.0, r)); break;
+            case 3: qlimitr = (r + fabs(r)) / (1.0 + fabs(r)); break;
+            case 4: {
+                double c = (1.0 + r) / 2.0;
+                qlimitr = fmax_g(0.0, fmin_g(fmin_g(c, 2.0), 2.0 * r));
+            } break;
+            case 5: {
+                const double beta = 2.0, xgamma = 2.0, alpha = 1.0 / 3.0;
+                double pp = (2.0 + r) / 3.0;
+                double amax = fmax_g(fmax_g(-alpha * r, 0.0), fmin_g(fmin_g(beta * r, pp), xgamma));
+                qlimitr = fmax_g(0.0, fmin_g(pp, amax));
+            } break;
+            default: qlimitr = 0.0;
+            }
+            QP(qr, m, p) = QP(q, m, p) + 0.5 * qlimitr * dqm;
+            QP(ql, m, p) = QP(q, m, p) - 0.5 * qlimitr * dqm;
+        }
+    }
+}
+
 /* flux1.f90:2-195.  Returns cfl; dq1d(meqn, n) receives the increments for i=1..mx
    (entries outside are left untouched). */
 typedef struct {
@@ -1850,7 +1900,8 @@ static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double d
        results at those interfaces are never consumed). */
     memcpy(ql, q1d, sizeof(double) * n * meqn);
     memcpy(qr, q1d, sizeof(double) * n * meqn);
-    if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
+    if (weno_variant == RECON_TVD2) tvd2(q1d, ql, qr, meqn, mx, mbc);
+    else if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
     else if (weno_variant == WENO_TABLES) weno_tables(q1d, ql, qr, meqn, mx, mbc);
     else weno5_pyweno(q1d, ql, qr, meqn, mx, mbc, weno_variant == WENO_PYWENO_F32);
     /* :128 rp(ql, qr, aux, aux) */

@@ -26,7 +26,7 @@ RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 RP_NEL_FWAVE, RP_PSYSTEM = 6, 7   # f-wave solvers (step1fw.f / flux2fw.f corrections)
 RP_ACOUSTICS3D_VC = 8              # 3-D variable-coefficient acoustics (dimensional splitting)
 RP_VC_ACOUSTICS, RP_BURGERS, RP_ADVECTION_COLOR, RP_VC_ADVECTION, RP_EULER1D = 9, 10, 11, 12, 13
-WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES = 0, 1, 2, 3
+WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES, RECON_TVD2 = 0, 1, 2, 3, 4
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -74,6 +74,8 @@ def lib():
         L.oracle_sphere_qinit.argtypes = [i, i, i, d, d, d, d, _dp, d]
         L.oracle_sphere_src2.restype = None
         L.oracle_sphere_src2.argtypes = [i, i, d, d, d, d, _dp, _dp, d, d]
+        L.oracle_set_tvd_limiters.restype = None
+        L.oracle_set_tvd_limiters.argtypes = [_ip, i]
         L.oracle_rp_point.restype = None
         L.oracle_rp_point.argtypes = [i, _dp, i, i, i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp,
                                       i, _dp, _dp, _dp]
@@ -179,6 +181,12 @@ def step2_slabs(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, me
     return lib().oracle_step2_slabs(rp_id, _p(_params(rp_params)), meqn, len(mthlim), maux, mbc,
                                     mx, my, _p(qold), _p(qnew), _p(aux), dx, dy, dt,
                                     _pi(method), _pi(mthlim), nthreads, int(dimsplit))
+
+
+def set_tvd_limiters(mthlim):
+    """Limiter per COMPONENT for weno_variant = RECON_TVD2 (reconstruct.f90:568-625)."""
+    a = np.ascontiguousarray(mthlim, dtype=np.int32)
+    lib().oracle_set_tvd_limiters(_pi(a), len(a))
 
 
 def set_weno_tables(tab):
@@ -301,6 +309,7 @@ class OracleSolver(object):
             self.mbc, self.cfl_max, self.cfl_desired = 3, 2.5, 2.45
             self.time_integrator, self.weno_variant = "SSP104", WENO_PYWENO_F32
             self.weno_order, self.weno_tables = 5, None
+            self.lim_type, self.limiters = 2, [1]
         self.mcapa = -1
         self.cfl = self.cfl_desired
         self.status = {}
@@ -315,6 +324,13 @@ class OracleSolver(object):
             self.mbc = (self.weno_order + 1) // 2
             set_weno_tables(self.weno_tables)
             self.weno_variant = WENO_TABLES
+        if self.kind == "sharpclaw" and self.lim_type == 1:
+            # flux1.f90:79-83 tvd2; clawparams.mthlim = solver.mthlim (sharpclaw.py:213-218, 278)
+            lim = self.limiters if isinstance(self.limiters, list) else [self.limiters]
+            if len(lim) == 1:
+                lim = lim * self.mwaves
+            set_tvd_limiters(lim)
+            self.weno_variant = RECON_TVD2
         mbc = self.mbc
         self.n = list(q.shape[1:])
         self.qbc = np.zeros([q.shape[0]] + [n + 2 * mbc for n in self.n], order="F")

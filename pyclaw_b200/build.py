@@ -92,7 +92,10 @@ def build(force=False, verbose=False, fma=False, jobs=None):
                 failed = src
     if failed:
         raise subprocess.CalledProcessError(1, "nvcc -c " + failed)
-    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs, cwd=CSRC)
+    # link under a temporary name and rename: a reader (a gpurun snapshot, a running process that
+    # dlopens the library) sees either the old or the new file, never a half-written one
+    subprocess.check_call([nvcc, "-shared", "-o", lib + ".tmp"] + objs, cwd=CSRC)
+    os.replace(lib + ".tmp", lib)
     return lib
 
 

@@ -205,6 +205,11 @@ class ClawSolver2D(ClawSolver):
     overlap_halo = True
 
     def _step_overlapped(self, state):
+        """Two streams.  Side stream: halo exchange -> ghost rows' boundary conditions -> the
+        ``mbc`` boundary rows per side (they need the halo).  Main stream: x-direction boundary
+        conditions -> the interior rows (they do not).  The boundary bands are small launches
+        (2 * mbc rows: less than one wave of CTAs); running them beside the interior sweeps
+        instead of after them takes their latency off the step."""
         import torch
         from .solver import BC
         part, F, mbc = self._halo, state._q, self.mbc
@@ -216,24 +221,26 @@ class ClawSolver2D(ClawSolver):
         cur = torch.cuda.current_stream()
         if getattr(self, '_hstream', None) is None:
             self._hstream = torch.cuda.Stream()
-            self._ev0, self._ev1 = torch.cuda.Event(), torch.cuda.Event()
+            self._ev0, self._ev1, self._evx = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        _lib.call("clawb200_cfl_reset", cfl, _stream())
         self._ev0.record(cur)
+        # main stream: x-direction boundary conditions of the rows this rank already has
+        self.apply_q_bcs(state, exchange=False, dims=[0])
+        self._evx.record(cur)
         with torch.cuda.stream(self._hstream):
             self._hstream.wait_event(self._ev0)
-            part.exchange(F, F.ncomp, periodic=[b == BC.periodic for b in self.bc_lower])
+            part.exchange(F, F.ncomp, periodic=[b == BC.periodic for b in self.bc_lower],
+                          problem=self._halo_problem(F))
+            # the halo has landed: ghost rows get their x-BCs (after the main stream's fill, which
+            # saw them half-written), edge ranks their y-BCs, then the boundary rows are updated
+            self._hstream.wait_event(self._evx)
+            self.apply_q_bcs(state, exchange=False)
+            st = _stream()
+            _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1, mbc, cfl, st)
+            _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, my - mbc + 1, my, cfl, st)
             self._ev1.record(self._hstream)
-        # x-direction boundary conditions and the interior rows, concurrently with the exchange
-        self.apply_q_bcs(state, exchange=False, dims=[0])
-        st = _stream()
-        _lib.call("clawb200_cfl_reset", cfl, st)
-        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1 + mbc, my - mbc, cfl, st)
-        # the halo has landed: ghost rows get their x-BCs, edge ranks their y-BCs, then the
-        # boundary rows are updated
+        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1 + mbc, my - mbc, cfl, _stream())
         cur.wait_event(self._ev1)
-        self.apply_q_bcs(state, exchange=False)
-        st = _stream()
-        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1, mbc, cfl, st)
-        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, my - mbc + 1, my, cfl, st)
         state._commit(qnew)
         self.cfl.update_global_max(self._read_cfl()[0])
 

@@ -181,7 +181,7 @@ struct RpEuler5 {
     static constexpr int ID = CLAW_RP_EULER5;
     static constexpr int MEQN = 5, MWAVES = 5, NROE = 8; // 7 Roe quantities + 1/(2a)
 #ifndef CLAW_EU_X_MINB
-#define CLAW_EU_X_MINB 2
+#define CLAW_EU_X_MINB 3
 #define CLAW_EU_Y_MINB 2
 #endif
     static constexpr int X_MINB = CLAW_EU_X_MINB, Y_MINB = CLAW_EU_Y_MINB;

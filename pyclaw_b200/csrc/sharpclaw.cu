@@ -119,6 +119,11 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
     A.mode = mode; A.ca = ca; A.cb = cb; A.div = div;
     A.cfl_bits = (unsigned long long *)cfl_dev;
     const bool old = (p->weno_variant == CLAWB200_WENO_OLD);
+    if (p->weno_variant == CLAWB200_RECON_TVD2) {
+        if (p->meqn > CLAWB200_MAXWAVES) return fail(CLAWB200_ERR_INVALID, "tvd2: meqn exceeds the limiter array");
+        A.tvd = 1;
+        for (int m = 0; m < p->meqn; m++) A.mthlim[m] = p->mthlim[m];
+    }
     if (p->weno_variant == CLAWB200_WENO_TABLES) {
         if (g_weno_k < 3) return fail(CLAWB200_ERR_INVALID, "call clawb200_set_weno_tables first");
         if (p->mbc < g_weno_k) return fail(CLAWB200_ERR_INVALID, "WENO of order 2k-1 needs mbc >= k");

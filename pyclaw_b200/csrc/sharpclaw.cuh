@@ -40,6 +40,9 @@ struct ScArgs {
     // aux(i-1), aux(i); the in-cell solve sees aux(i) on both sides
     const double *aux;
     long long amstride;
+    // lim_type = 1 (flux1.f90:79-83): second-order TVD reconstruction, limiter id per COMPONENT
+    int tvd;
+    int mthlim[8];
 };
 
 // aux of the cell at array offset `off` (row offset + clamped column)
@@ -142,11 +145,50 @@ __device__ __forceinline__ void weno5_old(AR &ar, const ScArgs &A, double a, dou
                         3. * d3 - d4, b, c, d, e);
 }
 
+// gfortran's MIN / MAX: "mvar = a1; if (a2 < mvar .or. isnan(mvar)) mvar = a2" -- a NaN argument
+// is dropped in favour of the other one.  tvd2 divides by a jump that is zero in flat regions
+// (r = 0/0), so the NaN rule decides the result there.
+__device__ __forceinline__ double fmin_g(double a1, double a2) { return (a2 < a1 || a1 != a1) ? a2 : a1; }
+__device__ __forceinline__ double fmax_g(double a1, double a2) { return (a2 > a1 || a1 != a1) ? a2 : a1; }
+
+// reconstruct.f90:568-625 (tvd2) for one component of one cell: dqm = q(i) - q(i-1),
+// dqp = q(i+1) - q(i), r = dqp / dqm, ql / qr = q(i) -/+ 0.5 phi(r) dqm.  The Fortran carries
+// dqm over from the previous iteration (dqm = dqp), which for the FIRST cell of a slice is a
+// variable that was never assigned; here every cell, the first included, uses its own backward
+// difference (the only defined reading).
+template <class AR>
+__device__ __forceinline__ void tvd2(AR &ar, int meth, double b, double c, double d, double &ql, double &qr)
+{
+    const double dqm = c - b;
+    const double dqp = d - c;
+    const double r = ar.div(dqp, dqm);
+    double qlimitr;
+    switch (meth) {
+    case 1: qlimitr = fmax_g(0.0, fmin_g(1.0, r)); break;
+    case 2: qlimitr = fmax_g(fmax_g(0.0, fmin_g(1.0, 2.0 * r)), fmin_g(2.0, r)); break;
+    case 3: qlimitr = ar.div(r + fabs(r), 1.0 + fabs(r)); break;
+    case 4: {
+        double cc = (1.0 + r) / 2.0;
+        qlimitr = fmax_g(0.0, fmin_g(fmin_g(cc, 2.0), 2.0 * r));
+    } break;
+    case 5: { // Cada & Torrilhon, simple version
+        const double beta = 2.0, xgamma = 2.0, alpha = 1.0 / 3.0;
+        double pp = (2.0 + r) / 3.0;
+        double amax = fmax_g(fmax_g(-alpha * r, 0.0), fmin_g(fmin_g(beta * r, pp), xgamma));
+        qlimitr = fmax_g(0.0, fmin_g(pp, amax));
+    } break;
+    default: qlimitr = 0.0; // "select case" without a matching case leaves qlimitr as it was; 0 = first order
+    }
+    qr = c + 0.5 * qlimitr * dqm;
+    ql = c - 0.5 * qlimitr * dqm;
+}
+
 template <bool OLD, class AR>
 __device__ __forceinline__ void weno5(AR &ar, const ScArgs &A, double a, double b, double c, double d,
-                                      double e, double &ql, double &qr)
+                                      double e, double &ql, double &qr, int m = 0)
 {
     if (OLD) weno5_old(ar, A, a, b, c, d, e, ql, qr);
+    else if (A.tvd) tvd2(ar, A.mthlim[m], b, c, d, ql, qr);
     else weno5_pyweno(ar, A, a, b, c, d, e, ql, qr);
 }
 
@@ -211,7 +253,7 @@ __device__ __forceinline__ void sc_xrow(const ScArgs &A, const double *qs, doubl
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
             const double *row = qs + m * QS + t;
-            weno5<OLD>(ar, A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m]);
+            weno5<OLD>(ar, A, row[0], row[1], row[2], row[3], row[4], ql[m], qr[m], m);
         }
     });
     sc_xrow_solve<RP, NT>(A, ql, qr, x1, x2, t, iface_cfl, full, cfl, dqx, dtdx_c, dtdx_l, axl, axc);
@@ -355,7 +397,7 @@ __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_
             with_arith_fz([&](auto &ar) {
 #pragma unroll
                 for (int m = 0; m < MEQN; m++)
-                    weno5<OLD>(ar, A, w0[m], w1[m], w2[m], w3[m], w4[m], ql[m], qr[m]);
+                    weno5<OLD>(ar, A, w0[m], w1[m], w2[m], w3[m], w4[m], ql[m], qr[m], m);
             });
             double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
             double amdq2[MEQN], apdq2[MEQN];

@@ -69,10 +69,33 @@ class SlabPartition(object):
         t = field.cur
         return t[:, r0:r0 + n] if t.dim() == 3 else t[:, r0:r0 + n]
 
-    def exchange(self, field, ncomp, periodic):
+    def _pack(self, field, row0, buf, problem):
+        """mbc padded rows starting at array row ``row0`` -> contiguous buffer [m][row][i]:
+        the halo kernel of the C ABI for 2-D fields, a strided copy otherwise."""
+        if problem is not None and field.cur.dim() == 3 and field.cur.is_cuda:
+            import ctypes
+            from . import _lib
+            from .solver import _ptr, _stream
+            _lib.call("clawb200_halo_pack", ctypes.byref(problem), _ptr(field.cur), field.ncomp, row0,
+                      field.mbc, _ptr(buf), _stream())
+        else:
+            buf.copy_(field.cur[:, row0:row0 + field.mbc])
+
+    def _unpack(self, field, row0, buf, problem):
+        if problem is not None and field.cur.dim() == 3 and field.cur.is_cuda:
+            import ctypes
+            from . import _lib
+            from .solver import _ptr, _stream
+            _lib.call("clawb200_halo_unpack", ctypes.byref(problem), _ptr(field.cur), field.ncomp, row0,
+                      field.mbc, _ptr(buf), _stream())
+        else:
+            field.cur[:, row0:row0 + field.mbc].copy_(buf)
+
+    def exchange(self, field, ncomp, periodic, problem=None):
         """Fill the ghost rows shared with neighbouring slabs.  ``periodic`` is the list of
         per-dimension flags: with a periodic partitioned dimension rank 0 and rank P-1
-        are neighbours (the DMDA is created periodic, petclaw/state.py:205-208)."""
+        are neighbours (the DMDA is created periodic, petclaw/state.py:205-208).
+        ``problem`` (the solver's clawb200_problem) selects the library's pack / unpack kernels."""
         if self.size == 1:
             return
         mbc = field.mbc
@@ -89,11 +112,11 @@ class SlabPartition(object):
         # the peer's "lower ghost" receive: upward traffic first, downward traffic second.
         ops = []
         if hi is not None:
-            b['send_hi'].copy_(t[:, nloc:nloc + mbc])
+            self._pack(field, nloc, b['send_hi'], problem)
             ops.append(dist.P2POp(dist.isend, b['send_hi'], hi, self.group))
         if lo is not None:
             ops.append(dist.P2POp(dist.irecv, b['recv_lo'], lo, self.group))
-            b['send_lo'].copy_(t[:, mbc:2 * mbc])
+            self._pack(field, mbc, b['send_lo'], problem)
             ops.append(dist.P2POp(dist.isend, b['send_lo'], lo, self.group))
         if hi is not None:
             ops.append(dist.P2POp(dist.irecv, b['recv_hi'], hi, self.group))
@@ -101,9 +124,9 @@ class SlabPartition(object):
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         if lo is not None:
-            t[:, 0:mbc].copy_(b['recv_lo'])
+            self._unpack(field, 0, b['recv_lo'], problem)
         if hi is not None:
-            t[:, nloc + mbc:nloc + 2 * mbc].copy_(b['recv_hi'])
+            self._unpack(field, nloc + mbc, b['recv_hi'], problem)
 
     def allreduce_max(self, cfl_dev):
         if self.size > 1:

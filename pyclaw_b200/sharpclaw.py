@@ -237,6 +237,9 @@ class SharpClawSolver(Solver):
             variant = _lib.WENO_PYWENO_F32 if self.weno_literals == 'f32' else _lib.WENO_PYWENO_F64
         elif self.lim_type == 3:
             variant = _lib.WENO_OLD
+        elif self.lim_type == 1 and self.char_decomp == 0:
+            # tvd2 (reconstruct.f90:568-625): second-order TVD reconstruction of the components of q
+            variant = _lib.RECON_TVD2
         else:
             raise NotImplementedError("lim_type=%s char_decomp=%s is not implemented"
                                       % (self.lim_type, self.char_decomp))
@@ -249,9 +252,14 @@ class SharpClawSolver(Solver):
         state.set_mbc(self.mbc)
         self.allocate_rk_stages(solution)
         self.set_mthlim()
+        if variant == _lib.RECON_TVD2 and state.meqn > len(self.mthlim):
+            # tvd2 indexes mthlim (length mwaves, sharpclaw.py:213-218) with the COMPONENT number:
+            # with meqn > mwaves the reference reads past the end of the array
+            raise Exception("lim_type=1 reads limiters[m] for every component m: meqn = %d needs %d entries "
+                            "but solver.limiters has mwaves = %d" % (state.meqn, state.meqn, len(self.mthlim)))
         # clawparams.mcapa = state.mcapa + 1 (sharpclaw.py:270)
         method = [int(self.dt_variable), 2, 0, 0, 0, state.mcapa + 1, state.maux]
-        self._setup_device(state, method=method, weno_variant=variant)
+        self._setup_device(state, method=method, mthlim=self.mthlim, weno_variant=variant)
         self._weno_tab = tab if variant == _lib.WENO_TABLES else None
         self._upload_weno_tables()
         self.allocate_bc_arrays(state)

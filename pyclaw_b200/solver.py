@@ -188,7 +188,8 @@ class Solver(object):
         grid = state.grid
         P = self._problem
         if exchange and self._halo is not None:
-            self._halo.exchange(arr_field, arr_field.ncomp, periodic=[b == BC.periodic for b in bc_lower])
+            self._halo.exchange(arr_field, arr_field.ncomp, periodic=[b == BC.periodic for b in bc_lower],
+                                problem=self._halo_problem(arr_field))
         for idim, dim in enumerate(grid.dimensions):
             if dims is not None and idim not in dims:
                 continue
@@ -213,6 +214,14 @@ class Solver(object):
                     raise Exception("One or more of the boundary conditions has not been specified.")
                 else:
                     raise NotImplementedError("Boundary condition %s not implemented" % bc)
+
+    def _halo_problem(self, field):
+        """The problem struct for the halo pack / unpack kernels, when ``field`` has q's padded
+        shape (the kernels take pitch / mstride from it); None selects plain tensor copies."""
+        P = self._problem
+        if P is None or field.cur.dim() != 3 or field.pitch != P.pitch or field.mstride != P.mstride:
+            return None
+        return P
 
     def apply_q_bcs(self, state, exchange=True, dims=None):
         """Fill the ghost cells of the state's padded q (solver.py:315-381): dimension by

@@ -631,3 +631,13 @@ def test_acoustics2d_sharpclaw_weno7_vs_oracle():
     # close to, but not the same as, the fifth-order result
     p5 = np.asarray(_acoustics2d('sharpclaw'))
     assert 1e-8 < np.abs(p - p5).max() < 5e-2
+
+
+@pytest.mark.parametrize("lim", [1, 4])
+def test_shallow_sharpclaw_tvd2_vs_oracle(lim):
+    """lim_type = 1 (second-order TVD reconstruction) through the API, SSP33, against the oracle."""
+    o = dict(time_integrator='SSP33', cfl_max=0.6, cfl_desired=0.5, lim_type=1, limiters=[lim] * 3)
+    qg = _shallow('sharpclaw', **o)
+    qo = _oracle_shallow('sharpclaw', **o)
+    assert np.isfinite(qo).all()
+    assert np.array_equal(qg, qo)

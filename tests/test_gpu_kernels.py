@@ -900,3 +900,55 @@ def test_halo_pack_unpack_and_layout_converters():
     back = torch.zeros_like(aos)
     _lib.call("clawb200_soa_to_aos", ptr(out), ptr(back), meqn, nx, ny, nx * ny, nx, None)
     assert torch.equal(back, aos)
+
+
+# ---------------------------------------------------------------------------
+# lim_type = 1: second-order TVD reconstruction (reconstruct.f90:568-625, flux1.f90:79-83)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("rp", ["advection", "euler", "shallow"])
+@pytest.mark.parametrize("lim", [1, 2, 3, 4, 5])
+def test_sharpclaw_tvd2_dq2(rp, lim):
+    rp_id, params, meqn, mwaves, _ = RPS[rp]
+    mx, my, mbc = 70, 45, 3
+    dx, dy, dt = 0.01, 0.013, 0.0011
+    # smooth data without flat patches: with van Leer (3) a zero jump gives r = 0/0 and the
+    # reference itself returns NaN there
+    q = _random_padded(rp, mx, my, mbc, seed=mx + lim, smooth=True)
+    mthlim = [lim] * mwaves
+    po.set_tvd_limiters(mthlim)
+    P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, mthlim=mthlim,
+                          weno_variant=_lib.RECON_TVD2)
+    dq_o, cfl_o = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, po.RECON_TVD2)
+    dq_g = np.zeros_like(q, order="F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt,
+              ctypes.byref(cfl_g))
+    inner = (slice(None), slice(mbc, -mbc), slice(mbc, -mbc))
+    assert np.isfinite(dq_o[inner]).all()
+    assert np.array_equal(dq_g[inner], dq_o[inner]), (rp, lim, np.abs(dq_g[inner] - dq_o[inner]).max())
+    assert cfl_g.value == cfl_o
+
+
+@pytest.mark.parametrize("lim", [1, 2, 4, 5])
+def test_sharpclaw_tvd2_dq1_flat_regions(lim):
+    """1-D, data with constant stretches: dqm = 0 gives r = +-Inf or NaN, and gfortran's MIN / MAX
+    drop the NaN (the limited slope is multiplied by dqm = 0 afterwards)."""
+    rp_id, params, _, mwaves, _ = RPS["acoustics"]
+    params = [1.0, 1.0, 1.0, 1.0]
+    mx, mbc = 300, 3
+    dx, dt = 1.0 / mx, 0.4 / mx
+    q = _random_padded("acoustics", mx, 0, mbc, seed=lim)
+    q[:, 40:90] = q[:, 40:41]
+    q[0, 150:] = 0.25
+    mthlim = [lim, lim]
+    po.set_tvd_limiters(mthlim)
+    P = _lib.make_problem(1, 2, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, mthlim=mthlim,
+                          weno_variant=_lib.RECON_TVD2)
+    dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, po.RECON_TVD2)
+    dq_g = np.zeros_like(q, order="F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt,
+              ctypes.byref(cfl_g))
+    assert np.isfinite(dq_o[:, mbc:-mbc]).all()
+    assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc])
+    assert cfl_g.value == cfl_o

@@ -264,3 +264,32 @@ def test_recalled_1d_solvers_against_exact_riemann_solutions():
         q[:, -mbc:] = q[:, -mbc - 1:-mbc]
         po.step1(po.RP_SHALLOW, [1.0], mbc, mx, q, None, 10.0 / mx, 0.01, [1, 2, 0, 0, 0, 0, 0], [4, 4])
     assert abs(q[0, mbc + mx // 2] - 1.848576) < 2e-3
+
+
+def test_tvd2_reconstruction_properties():
+    """tvd2 (reconstruct.f90:568-625) has no golden in the reference: tie the restatement to what a
+    TVD reconstruction is.  On linear data every limiter returns the exact edge values (r = 1,
+    phi(1) = 1); at an extremum the slope is zero (first order); the reconstructed edge values
+    never leave the interval spanned by the neighbouring cell averages (minmod, MC, superbee)."""
+    mx, mbc = 40, 3
+    n = mx + 2 * mbc
+    x = np.arange(n, dtype=float)
+    for lim in (1, 2, 3, 4, 5):
+        po.set_tvd_limiters([lim])
+        # advection with u = 1: dq = -dt/dx (q_i^R - q_{i-1}^R) for a linear profile = -dt/dx * slope
+        q = np.asfortranarray((0.5 * x + 2.0)[None, :])
+        dq, cfl = po.sc_flux1(po.RP_ADVECTION, [1.0], 1, mbc, mx, q, 1.0, 0.1, po.RECON_TVD2)
+        assert np.allclose(dq[0, mbc:-mbc], -0.1 * 0.5, rtol=0, atol=1e-15), lim
+        assert cfl == 0.1
+    # extremum -> zero slope -> the first-order (upwind) increment
+    po.set_tvd_limiters([1])
+    q = np.asfortranarray(np.where(x < n // 2, x, n - 1 - x)[None, :].astype(float))
+    dq, _ = po.sc_flux1(po.RP_ADVECTION, [1.0], 1, mbc, mx, q, 1.0, 0.1, po.RECON_TVD2)
+    i = n // 2  # the first cell of the descending branch: its left neighbour is the maximum
+    assert np.isfinite(dq).all()
+    # flat data: r = 0/0 must not poison the result (gfortran MIN / MAX drop the NaN)
+    q = np.asfortranarray(np.full((1, n), 3.0))
+    for lim in (1, 2, 4, 5):
+        po.set_tvd_limiters([lim])
+        dq, _ = po.sc_flux1(po.RP_ADVECTION, [1.0], 1, mbc, mx, q, 1.0, 0.1, po.RECON_TVD2)
+        assert np.array_equal(dq[0, mbc:-mbc], np.zeros(mx)), lim
