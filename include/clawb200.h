@@ -55,6 +55,10 @@ extern "C" {
 #define CLAWB200_RP_ADVECTION_COLOR 11 /* rp1_advection_color (apps/advection/1d/variable); aux {u}        */
 #define CLAWB200_RP_VC_ADVECTION 12   /* rpn2/rpt2_vc_advection (apps/advection/2d/annulus); aux {u, v[, capa]} */
 #define CLAWB200_RP_EULER1D 13        /* rp1_euler_with_efix (apps/euler/1d/wcblast); params {gamma,gamma1} */
+/* A Riemann solver supplied by the user as a header and compiled into a variant of the library
+ * (pyclaw_b200/csrc/sweep_user.cu, `python -m pyclaw_b200.build --user-rp header.cuh`): the
+ * reference's link-time RP_SOURCE seam (Makefile.rules:1-26).  meqn / mwaves / maux come from it. */
+#define CLAWB200_RP_USER 100
 #define CLAWB200_RP_ACOUSTICS3D_VC 8 /* rpn3_vc_acoustics (test/acoustics/3d); aux {impedance, c};
                                         3-D, dimensional splitting only */
 
@@ -68,8 +72,8 @@ extern "C" {
 #define CLAWB200_WENO_PYWENO_F32 0 /* weno.f90:35-98 with its kind-less literals read as REAL(4) */
 #define CLAWB200_WENO_PYWENO_F64 1 /* same formulas, literals read as doubles                    */
 #define CLAWB200_WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)                     */
-#define CLAWB200_WENO_TABLES 3     /* weno.f90:104-2425, orders 7..17 (1-D): coefficient tables set
-                                      with clawb200_set_weno_tables                               */
+#define CLAWB200_WENO_TABLES 3     /* weno.f90:104-2425, orders 7..17 (1-D): coefficient tables in
+                                      problem.weno_tab (clawb200_pack_weno_tables)                               */
 #define CLAWB200_RECON_TVD2 4      /* reconstruct.f90:568-625 (lim_type = 1, char_decomp = 0): second-
                                       order TVD reconstruction; problem.mthlim[m] is the limiter of
                                       COMPONENT m (1 minmod, 2 superbee, 3 van Leer, 4 MC, 5 Cada-
@@ -99,6 +103,11 @@ typedef struct clawb200_problem {
        the time step from there and ignore their `dt` argument, so that the launch sequence of
        a step does not depend on dt and can be replayed as a CUDA graph. */
     const double *dt_dev;
+    /* weno_variant = CLAWB200_WENO_TABLES only: k = (weno_order+1)/2 and the coefficient table
+       packed by clawb200_pack_weno_tables -- caller-owned, DEVICE memory for the device entry
+       points, host memory for the *_host entry points.  The library keeps no table state. */
+    int weno_k;
+    const double *weno_tab;
 } clawb200_problem;
 
 int clawb200_version(void);
@@ -169,12 +178,13 @@ int clawb200_ssp104_combine(const double *q, double *s1, double *s2, long long n
  * stencils; S[k][k(k+1)/2] smoothness quadratic forms (pairs a <= b in stencil order),
  * CL/CR[k][k] left / right edge reconstruction, WL/WR[k] ideal weights, eps (the 1e-36 of the
  * generated code).  Replaces the literals of weno7 .. weno17 (weno.f90:104-2425), selected
- * at reconstruct.f90:96-113.  Host pointers; the call returns after the upload. */
-int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
-                             const double *WL, const double *WR, double eps, void *stream);
-/* Number of table uploads so far: the tables are one set per process (constant memory), a
- * caller that remembers the value after its own upload can tell whether they are still its. */
-int clawb200_weno_generation(void);
+ * at reconstruct.f90:96-113.  clawb200_pack_weno_tables lays them out in a caller-provided HOST
+ * buffer of clawb200_weno_table_doubles() doubles; the caller copies that buffer to the device
+ * and points problem.weno_tab at it (no state is kept in the library, any number of solvers
+ * with different orders can be alive at once). */
+int clawb200_weno_table_doubles(void);
+int clawb200_pack_weno_tables(int k, const double *S, const double *CL, const double *CR,
+                              const double *WL, const double *WR, double eps, double *packed);
 
 /* apps/shallow-sphere/src2.f:2-147 (the f2py `problem.src2` the reference script wraps as
  * solver.step_src): Coriolis source term with tangent-plane projection, in place on the

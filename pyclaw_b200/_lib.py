@@ -17,6 +17,7 @@ MAXWAVES = 8
 RP_ACOUSTICS, RP_ADVECTION, RP_EULER5, RP_SHALLOW, RP_SPHERE = 1, 2, 3, 4, 5
 RP_NEL_FWAVE, RP_PSYSTEM, RP_ACOUSTICS3D_VC = 6, 7, 8
 RP_VC_ACOUSTICS, RP_BURGERS, RP_ADVECTION_COLOR, RP_VC_ADVECTION, RP_EULER1D = 9, 10, 11, 12, 13
+RP_USER = 100   # a solver compiled in from a user header (riemann.from_header)
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES, RECON_TVD2 = 0, 1, 2, 3, 4
 STAGE_AXPY, STAGE_CONVEX, STAGE_FINAL104, STAGE_DQ_ONLY = 0, 1, 2, 3
 
@@ -40,6 +41,8 @@ class Problem(ctypes.Structure):
         ("pitch", ctypes.c_int),
         ("weno_variant", ctypes.c_int),
         ("dt_dev", ctypes.c_void_p),
+        ("weno_k", ctypes.c_int),
+        ("weno_tab", ctypes.c_void_p),
     ]
 
 
@@ -64,7 +67,21 @@ def make_problem(ndim, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, rp_params, meth
     p.mstride = p.pitch * ny if mstride is None else mstride
     p.weno_variant = weno_variant
     p.dt_dev = None
+    p.weno_k = 0
+    p.weno_tab = None
     return p
+
+
+def pack_weno_tables(tab):
+    """Coefficient tables of pyclaw_b200.weno_tables.tables() in the layout the kernels read
+    (clawb200_pack_weno_tables): a float64 numpy array the caller keeps alive / uploads."""
+    import numpy as np
+    L = load()
+    out = np.zeros(L.clawb200_weno_table_doubles(), dtype=np.float64)
+    arr = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('S', 'CL', 'CR', 'WL', 'WR')]
+    call("clawb200_pack_weno_tables", int(tab['k']), *[ctypes.c_void_p(a.ctypes.data) for a in arr],
+         float(tab['eps']), ctypes.c_void_p(out.ctypes.data))
+    return out
 
 
 _libs = {}
@@ -93,7 +110,7 @@ SIGNATURES = {
     "clawb200_step2ds_host": [_pp, _dp, _dp, _dp, _d, _i, _dref],
     "clawb200_step2_host": [_pp, _dp, _dp, _dp, _d, _dref],
     "clawb200_sharpclaw_dq_host": [_pp, _dp, _dp, _dp, _d, _dref],
-    "clawb200_set_weno_tables": [_i, _dp, _dp, _dp, _dp, _dp, _d, _vp],
+    "clawb200_pack_weno_tables": [_i, _dp, _dp, _dp, _dp, _dp, _d, _dp],
     "clawb200_step3ds": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dp, _vp],
     "clawb200_bc_fill3": [_pp, _i, _dp, _i, _i, _i, _i, _i, _vp],
     "clawb200_step3ds_host": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dref],
@@ -109,7 +126,7 @@ def set_variant(name):
     Solvers set it from ``solver.arithmetic`` at the start of every step."""
     global _active
     if name not in LIB_PATHS:
-        raise ClawB200Error("unknown arithmetic variant %r (expected one of %s)" % (name, sorted(LIB_PATHS)))
+        raise ClawB200Error("unknown arithmetic variant %r (expected 'strict' or 'fma')" % (name,))
     prev, _active = _active, name
     return prev
 
@@ -126,7 +143,7 @@ def load(variant=None):
                                                      " --fma" if variant == "fma" else ""))
         L = ctypes.CDLL(path)
         L.clawb200_version.restype = ctypes.c_int
-        L.clawb200_weno_generation.restype = ctypes.c_int
+        L.clawb200_weno_table_doubles.restype = ctypes.c_int
         L.clawb200_last_error.restype = ctypes.c_char_p
         for name, args in SIGNATURES.items():
             f = getattr(L, name)

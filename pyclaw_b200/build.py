@@ -1,6 +1,7 @@
 """Builds the CUDA library in-tree with nvcc for sm_100a.
 
     python -m pyclaw_b200.build [--force] [-v] [--fma | --all]
+    python -m pyclaw_b200.build --user-rp my_rp.cuh [--name mine] [--fma]     (plugin seam, see below)
 
 Two builds of the same sources:
   libclawb200.so      -fmad=false : strict IEEE, bit-for-bit agreement with the reference's
@@ -10,6 +11,11 @@ Two builds of the same sources:
                       instructions); results differ from the strict build at round-off level
                       (measured in profiles/README.md), selected with solver.arithmetic = 'fma'.
 -lineinfo keeps the ncu source page usable.
+
+Riemann-solver plugin seam: `--user-rp header.cuh` compiles a user-supplied solver (a header with
+`template <int IXY> struct RpUser`, see examples/user_rp/rp_kpp.cuh) into
+libclawb200_user_<name>.so -- the reference does the same at link time with RP_SOURCE in each
+application's Makefile (Makefile.rules:1-26).  pyclaw.riemann.from_header() builds and binds it.
 """
 import os
 import subprocess
@@ -30,6 +36,7 @@ UNITS = {
     "step1.cu": _COMMON,
     "rp_point.cu": _COMMON,
     "sharpclaw.cu": _COMMON + ["sharpclaw.cuh"],
+    "sweep_user.cu": _COMMON + ["sharpclaw.cuh"],   # the user-supplied Riemann solver (a stub without one)
 }
 SOURCES = list(UNITS)
 HEADERS = sorted({h for hs in UNITS.values() for h in hs})
@@ -99,6 +106,40 @@ def build(force=False, verbose=False, fma=False, jobs=None):
     return lib
 
 
+def user_lib_path(name, fma=False):
+    return os.path.join(CSRC, "libclawb200_user_%s%s.so" % (name, "_fma" if fma else ""))
+
+
+def build_user(header, name=None, fma=False, force=False, verbose=False):
+    """A variant of the library with a user-supplied Riemann solver (csrc/sweep_user.cu): the
+    header defines `template <int IXY> struct RpUser` with the interface of the solvers in
+    rp.cuh.  Only sweep_user.cu is compiled; every other object comes from the base build.
+    Returns the path of libclawb200_user_<name>[_fma].so."""
+    header = os.path.abspath(header)
+    if not os.path.exists(header):
+        raise FileNotFoundError(header)
+    name = name or os.path.splitext(os.path.basename(header))[0]
+    build(fma=fma)  # base objects
+    lib = user_lib_path(name, fma)
+    deps = [header] + [os.path.join(CSRC, f) for f in ["sweep_user.cu"] + UNITS["sweep_user.cu"]]
+    base_lib = LIB_FMA if fma else LIB
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps + [base_lib]):
+        return lib
+    nvcc = os.environ.get("NVCC", "nvcc")
+    flags = NVCC_FLAGS + (["-fmad=true", "-DCLAWB200_FMA=1"] if fma else ["-fmad=false"])
+    objdir = os.path.join(CSRC, "_obj", "user_%s%s" % (name, "_fma" if fma else ""))
+    os.makedirs(objdir, exist_ok=True)
+    obj = os.path.join(objdir, "sweep_user.o")
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + \
+        ['-DCLAWB200_USER_RP_HEADER="%s"' % header, "-c", "-o", obj, "sweep_user.cu"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    base = os.path.join(CSRC, "_obj", "fma" if fma else "strict")
+    objs = [obj] + [os.path.join(base, s[:-3] + ".o") for s in SOURCES if s != "sweep_user.cu"]
+    subprocess.check_call([nvcc, "-shared", "-o", lib + ".tmp"] + objs, cwd=CSRC)
+    os.replace(lib + ".tmp", lib)
+    return lib
+
+
 def build_all(force=False):
     """Both builds, side by side (two nvcc processes)."""
     import threading
@@ -110,7 +151,11 @@ def build_all(force=False):
 
 
 if __name__ == "__main__":
-    if "--all" in sys.argv:
+    if "--user-rp" in sys.argv:
+        hdr = sys.argv[sys.argv.index("--user-rp") + 1]
+        nm = sys.argv[sys.argv.index("--name") + 1] if "--name" in sys.argv else None
+        print(build_user(hdr, nm, fma="--fma" in sys.argv, force="--force" in sys.argv, verbose="-v" in sys.argv))
+    elif "--all" in sys.argv:
         print(*build_all(force="--force" in sys.argv))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, fma="--fma" in sys.argv))

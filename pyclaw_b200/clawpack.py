@@ -30,7 +30,7 @@ class ClawSolver(Solver):
 
     # ---- clawpack.py:114-165 ----
     def step(self, solution):
-        _lib.set_variant(self.arithmetic)
+        _lib.set_variant(getattr(self, '_variant', None) or self.arithmetic)
         if self.start_step is not None:
             self.start_step(self, solution)
         if self.src_split == 2 and self.step_src is not None:
@@ -220,7 +220,8 @@ class ClawSolver2D(ClawSolver):
         P, cfl = ctypes.byref(self._problem), _ptr(self._cfl_dev)
         cur = torch.cuda.current_stream()
         if getattr(self, '_hstream', None) is None:
-            self._hstream = torch.cuda.Stream()
+            # high priority: the small boundary launches must not queue behind the interior sweeps' CTAs
+            self._hstream = torch.cuda.Stream(priority=-1)
             self._ev0, self._ev1, self._evx = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         _lib.call("clawb200_cfl_reset", cfl, _stream())
         self._ev0.record(cur)

@@ -287,21 +287,23 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
 #pragma unroll
         for (int m = 0; m < MEQN; m++) cqxx[m] = 0.0;
         double bmp[MEQN], bpp[MEQN], bmm[MEQN], bpm[MEQN];
-        double wnorm2[MW], dotl[MW], dotr[MW];
+        // limiter.f:35-43 takes the dot product with the UPWIND neighbour's wave: only that one
+        // is formed (a * b == b * a bit for bit, so the product order of dotl / dotr is immaterial)
+        double wnorm2[MW], dotu[MW];
         if (order2 && t >= 1 && t <= NT - 2) {
 #pragma unroll
             for (int mw = 0; mw < MW; mw++) {
-                double n2 = 0.0, dl = 0.0, dr = 0.0;
+                const int nb = (s[mw] > 0.0) ? t - 1 : t + 1;
+                double n2 = 0.0, du = 0.0;
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {
                     if (RP::nz(m, mw)) {
                         double w = wave[m][mw];
                         n2 = n2 + w * w;
-                        dl = dl + ws[(m * MW + mw) * NT + t - 1] * w;
-                        dr = dr + w * ws[(m * MW + mw) * NT + t + 1];
+                        du = du + ws[(m * MW + mw) * NT + nb] * w;
                     }
                 }
-                wnorm2[mw] = n2; dotl[mw] = dl; dotr[mw] = dr;
+                wnorm2[mw] = n2; dotu[mw] = du;
             }
         }
         // limiter, second-order correction and the two transverse solves: one block of
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                             if (RP::nz(m, mw)) wave[m][mw] = ws[(m * MW + mw) * NT + t];
                 }
                 if (lim) {
-                    limit_waves<RP>(ar, wave, s, wnorm2, dotl, dotr, A.mthlim);
+                    limit_waves<RP>(ar, wave, s, wnorm2, dotu, dotu, A.mthlim);
                     double dtdxave = 0.5 * (dtdx_l + dtdx_c);
                     second_order<RP>(wave, s, dtdxave, cqxx);
                 }
@@ -792,20 +794,20 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
 #pragma unroll
     for (int m = 0; m < MEQN; m++) f[m] = 0.0;
     if (order2 && t >= 1 && t <= NT - 2) {
-        double wnorm2[MW], dotl[MW], dotr[MW];
+        double wnorm2[MW], dotu[MW]; // dot product with the upwind neighbour only (see the x-engine)
 #pragma unroll
         for (int mw = 0; mw < MW; mw++) {
-            double n2 = 0.0, dl = 0.0, dr = 0.0;
+            const int nb = (s[mw] > 0.0) ? t - 1 : t + 1;
+            double n2 = 0.0, du = 0.0;
 #pragma unroll
             for (int m = 0; m < MEQN; m++) {
                 if (RP::nz(m, mw)) {
                     double w = wave[m][mw];
                     n2 = n2 + w * w;
-                    dl = dl + ws[(m * MW + mw) * NT + t - 1] * w;
-                    dr = dr + w * ws[(m * MW + mw) * NT + t + 1];
+                    du = du + ws[(m * MW + mw) * NT + nb] * w;
                 }
             }
-            wnorm2[mw] = n2; dotl[mw] = dl; dotr[mw] = dr;
+            wnorm2[mw] = n2; dotu[mw] = du;
         }
         with_arith([&](auto &ar) {
             if (!ar.FAST) {
@@ -815,7 +817,7 @@ __global__ void __launch_bounds__(NT) step1_kernel(const SweepArgs A)
                     for (int mw = 0; mw < MW; mw++)
                         if (RP::nz(m, mw)) wave[m][mw] = ws[(m * MW + mw) * NT + t];
             }
-            limit_waves<RP>(ar, wave, s, wnorm2, dotl, dotr, A.mthlim);
+            limit_waves<RP>(ar, wave, s, wnorm2, dotu, dotu, A.mthlim);
         });
         // step1.f:121-128
         double dtdxave = 0.5 * (dtdx_l + dtdx);

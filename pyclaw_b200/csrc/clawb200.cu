@@ -112,6 +112,7 @@ static int dispatch_x(int rp_id, const SweepArgs &A, cudaStream_t st)
 {
     if (rp_id == CLAWB200_RP_EULER5) return claw_x_euler(TRANS, A, st);
     if (rp_id == CLAWB200_RP_SPHERE) return claw_x_sphere(TRANS, A, st);
+    if (rp_id == CLAWB200_RP_USER) return claw_x_user(TRANS, A, st);
     return claw_x_misc(rp_id, TRANS, A, st);
 }
 template <bool TRANS>
@@ -119,6 +120,7 @@ static int dispatch_y(int rp_id, const SweepArgs &A, cudaStream_t st)
 {
     if (rp_id == CLAWB200_RP_EULER5) return claw_y_euler(TRANS, A, st);
     if (rp_id == CLAWB200_RP_SPHERE) return claw_y_sphere(TRANS, A, st);
+    if (rp_id == CLAWB200_RP_USER) return claw_y_user(TRANS, A, st);
     return claw_y_misc(rp_id, TRANS, A, st);
 }
 
@@ -138,6 +140,12 @@ static int check_rp_shape(const clawb200_problem *p)
     case CLAWB200_RP_ADVECTION_COLOR: meqn = 1; mwaves = 1; break;
     case CLAWB200_RP_VC_ADVECTION: meqn = 1; mwaves = 1; break;
     case CLAWB200_RP_EULER1D: meqn = 3; mwaves = 3; break;
+    case CLAWB200_RP_USER: {
+        int maux = 0;
+        int rc = claw_user_shape(p->ndim, &meqn, &mwaves, &maux);
+        if (rc) return rc;
+        if (p->maux < maux) return fail(CLAWB200_ERR_INVALID, "the user Riemann solver reads more aux components than maux");
+    } break;
     default: return fail(CLAWB200_ERR_UNSUPPORTED, "unknown rp_id");
     }
     if (p->meqn != meqn || p->mwaves != mwaves)
@@ -162,6 +170,7 @@ extern "C" int clawb200_step1(const clawb200_problem *p, const double *q_in, dou
     if ((rc = check_aux(p, aux, false))) return rc;
     SweepArgs A = make_args(p, q_in, q_out, dt, cfl_dev, aux);
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->rp_id == CLAWB200_RP_USER) return claw_step1_user(A, p->mx, st);
     return claw_step1(p->rp_id, A, p->mx, st);
 }
 
@@ -604,6 +613,7 @@ extern "C" int clawb200_ssp104_combine(const double *q, double *s1, double *s2, 
 struct HostScratch {
     double *d_aos = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_cfl = nullptr;
     double *d_aux = nullptr;
+    double *d_tab = nullptr; // WENO coefficient table of the current host call
     size_t aux_cap = 0;
     int ensure_aux(size_t n)
     {
@@ -927,6 +937,12 @@ extern "C" int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const doubl
     if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
     CUDA_OK(cudaMemsetAsync(g_hs.d_b, 0, n * sizeof(double), g_hs.st));
     if ((rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st))) return rc;
+    if (P.weno_variant == CLAWB200_WENO_TABLES && P.weno_tab) { // host table -> device scratch
+        const size_t nb = (size_t)clawb200_weno_table_doubles() * sizeof(double);
+        if (!g_hs.d_tab) CUDA_OK(cudaMalloc(&g_hs.d_tab, nb));
+        CUDA_OK(cudaMemcpyAsync(g_hs.d_tab, P.weno_tab, nb, cudaMemcpyHostToDevice, g_hs.st));
+        P.weno_tab = g_hs.d_tab;
+    }
     if ((rc = clawb200_sharpclaw_stage(&P, g_hs.d_a, nullptr, nullptr, g_hs.d_b, d_aux, dt,
                                        CLAWB200_STAGE_DQ_ONLY, 0.0, 0.0, 1.0, g_hs.d_cfl, g_hs.st)))
         return rc;

@@ -4,7 +4,8 @@
 // The library is built from several translation units (pyclaw_b200/build.py compiles them in
 // parallel): clawb200.cu (C ABI, boundary fills, layout / halo kernels, host entry points),
 // sweep_euler_x.cu / sweep_euler_y.cu, sweep_sphere.cu, sweep_misc.cu (instantiations of the
-// classic sweeps per Riemann-solver family), step1.cu, sharpclaw.cu.
+// classic sweeps per Riemann-solver family), sweep_user.cu (the user-supplied solver), step1.cu,
+// rp_point.cu, sharpclaw.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -110,6 +111,16 @@ int claw_x_misc(int rp_id, bool trans, const SweepArgs &A, cudaStream_t st);
 int claw_y_misc(int rp_id, bool trans, const SweepArgs &A, cudaStream_t st);
 int claw_x_ac3d(const SweepArgs &A, cudaStream_t st);           // 3-D acoustics, x-engine (idir = 1)
 int claw_y_ac3d(int idir, const SweepArgs &A, cudaStream_t st); // 3-D acoustics, y-engine (idir = 2, 3)
+// the user-supplied solver (sweep_user.cu), id CLAWB200_RP_USER
+struct ScArgs;
+int claw_user_shape(int ndim, int *meqn, int *mwaves, int *maux);
+int claw_x_user(bool trans, const SweepArgs &A, cudaStream_t st);
+int claw_y_user(bool trans, const SweepArgs &A, cudaStream_t st);
+int claw_step1_user(const SweepArgs &A, int mx, cudaStream_t st);
+int claw_sc_user(int ndim, bool old, const ScArgs &A, cudaStream_t st);
+int claw_rp_point_user(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
+                       double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
+                       double *bm, double *bp, cudaStream_t st);
 int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
                   double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
                   double *bm, double *bp, cudaStream_t st);

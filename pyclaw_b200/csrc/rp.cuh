@@ -35,6 +35,7 @@
 #define CLAW_RP_ADVECTION_COLOR 11
 #define CLAW_RP_VC_ADVECTION 12
 #define CLAW_RP_EULER1D 13
+#define CLAW_RP_USER 100 // a solver compiled in from a user header (sweep_user.cu)
 
 // Solvers that return f-waves (jumps in the flux) instead of waves: the sweeps then use the
 // second-order correction of step1fw.f:135-136 / flux2fw.f:151-152.  A member FWAVE = true

@@ -64,6 +64,8 @@ int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double 
                   double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
                   double *bm, double *bp, cudaStream_t st)
 {
+    if (p->rp_id == CLAWB200_RP_USER)
+        return claw_rp_point_user(p, ixy, n, ql, qr, wave, s, amdq, apdq, imp, asdq, bm, bp, st);
     RpParams P;
     for (int i = 0; i < 8; i++) P.p[i] = p->rp_params[i];
 #define GO(RPT) return rp_point_launch<RPT>(n, P, ql, qr, wave, s, amdq, apdq, imp, asdq, bm, bp, st)

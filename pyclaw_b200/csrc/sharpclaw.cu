@@ -1,5 +1,5 @@
-// sharpclaw.cu -- SharpClaw stage kernels (sharpclaw.cuh): launch dispatch and the WENO
-// coefficient tables in constant memory.
+// sharpclaw.cu -- SharpClaw stage kernels (sharpclaw.cuh): launch dispatch and the packing of the WENO
+// coefficient tables (caller-owned, no state in the library).
 #include "launch.cuh"
 #include "sharpclaw.cuh"
 
@@ -10,21 +10,17 @@ using RpColor1D = RpColor<1, 1>;
 // ---------------------------------------------------------------------------
 constexpr int SNT = 128;
 
-static int g_weno_k = 0;   // stencils of the table-driven WENO currently in constant memory
-static int g_weno_gen = 0; // bumped by every upload, so callers can tell whose tables are resident
+extern "C" int clawb200_weno_table_doubles(void) { return (int)(sizeof(WenoTab) / sizeof(double)); }
 
-extern "C" int clawb200_weno_generation(void) { return g_weno_gen; }
-
-extern "C" int clawb200_set_weno_tables(int k, const double *S, const double *CL, const double *CR,
-                                        const double *WL, const double *WR, double eps, void *stream)
+extern "C" int clawb200_pack_weno_tables(int k, const double *S, const double *CL, const double *CR,
+                                         const double *WL, const double *WR, double eps, double *packed)
 {
     if (k < 3 || k > 9) return fail(CLAWB200_ERR_INVALID, "weno_order must be an odd number between 5 and 17");
-    if (!S || !CL || !CR || !WL || !WR) return fail(CLAWB200_ERR_INVALID, "null table");
-    static WenoTab h; // staging copy: must outlive the asynchronous upload
-    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (!S || !CL || !CR || !WL || !WR || !packed) return fail(CLAWB200_ERR_INVALID, "null table");
+    WenoTab &h = *reinterpret_cast<WenoTab *>(packed);
     memset(&h, 0, sizeof(h));
     const int npair = k * (k + 1) / 2;
-    h.k = k;
+    h.k = (double)k;
     h.eps = eps;
     for (int r = 0; r < k; r++) {
         for (int n = 0; n < npair; n++) h.S[r][n] = S[r * npair + n];
@@ -32,18 +28,14 @@ extern "C" int clawb200_set_weno_tables(int k, const double *S, const double *CL
         h.WL[r] = WL[r];
         h.WR[r] = WR[r];
     }
-    CUDA_OK(cudaMemcpyToSymbolAsync(c_weno, &h, sizeof(h), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    g_weno_k = k;
-    g_weno_gen++;
     return 0;
 }
 
 template <class RP>
-static int sc_launch1_tab(const ScArgs &A, cudaStream_t st)
+static int sc_launch1_tab(const ScArgs &A, int weno_k, cudaStream_t st)
 {
     constexpr int NC = SNT - 2;
-    const int H = g_weno_k - 1;
+    const int H = weno_k - 1;
     size_t smem = sizeof(double) * (RP::MEQN * (SNT + 2 * H) + 2 * RP::MEQN * SNT);
     sc1d_tab_kernel<RP, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);
     CUDA_OK(cudaGetLastError());
@@ -51,10 +43,10 @@ static int sc_launch1_tab(const ScArgs &A, cudaStream_t st)
 }
 
 template <class RPX, class RPY>
-static int sc_launch2_tab(const ScArgs &A, cudaStream_t st)
+static int sc_launch2_tab(const ScArgs &A, int weno_k, cudaStream_t st)
 {
     constexpr int NC = SNT - 2;
-    const int H = g_weno_k - 1;
+    const int H = weno_k - 1;
     size_t smem = sizeof(double) * (RPX::MEQN * (SNT + 2 * H) + 2 * RPX::MEQN * SNT);
     dim3 grid((A.mx + NC - 1) / NC, (A.my + A.rows_per_cta - 1) / A.rows_per_cta);
     sc2d_tab_kernel<RPX, RPY, SNT><<<grid, SNT, smem, st>>>(A);
@@ -125,28 +117,37 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
         for (int m = 0; m < p->meqn; m++) A.mthlim[m] = p->mthlim[m];
     }
     if (p->weno_variant == CLAWB200_WENO_TABLES) {
-        if (g_weno_k < 3) return fail(CLAWB200_ERR_INVALID, "call clawb200_set_weno_tables first");
-        if (p->mbc < g_weno_k) return fail(CLAWB200_ERR_INVALID, "WENO of order 2k-1 needs mbc >= k");
+        const int wk = p->weno_k;
+        if (wk < 3 || wk > 9 || !p->weno_tab)
+            return fail(CLAWB200_ERR_INVALID, "weno_variant = tables needs problem.weno_k in 3..9 and problem.weno_tab "
+                                              "(clawb200_pack_weno_tables)");
+        if (p->mbc < wk) return fail(CLAWB200_ERR_INVALID, "WENO of order 2k-1 needs mbc >= k");
+        A.tab = reinterpret_cast<const WenoTab *>(p->weno_tab);
         if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for WENO orders above 5");
         if (p->ndim == 2) {
             A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
             switch (p->rp_id) {
-            case CLAWB200_RP_ACOUSTICS: return sc_launch2_tab<RpAcoustics<2, 1>, RpAcoustics<2, 2>>(A, st);
-            case CLAWB200_RP_ADVECTION: return sc_launch2_tab<RpAdvection<2, 1>, RpAdvection<2, 2>>(A, st);
-            case CLAWB200_RP_EULER5: return sc_launch2_tab<RpEuler5<1>, RpEuler5<2>>(A, st);
-            case CLAWB200_RP_SHALLOW: return sc_launch2_tab<RpShallow<1>, RpShallow<2>>(A, st);
-            case CLAWB200_RP_VC_ACOUSTICS: return sc_launch2_tab<RpVcAcoustics<1>, RpVcAcoustics<2>>(A, st);
+            case CLAWB200_RP_ACOUSTICS: return sc_launch2_tab<RpAcoustics<2, 1>, RpAcoustics<2, 2>>(A, wk, st);
+            case CLAWB200_RP_ADVECTION: return sc_launch2_tab<RpAdvection<2, 1>, RpAdvection<2, 2>>(A, wk, st);
+            case CLAWB200_RP_EULER5: return sc_launch2_tab<RpEuler5<1>, RpEuler5<2>>(A, wk, st);
+            case CLAWB200_RP_SHALLOW: return sc_launch2_tab<RpShallow<1>, RpShallow<2>>(A, wk, st);
+            case CLAWB200_RP_VC_ACOUSTICS: return sc_launch2_tab<RpVcAcoustics<1>, RpVcAcoustics<2>>(A, wk, st);
             default: return fail(CLAWB200_ERR_UNSUPPORTED, "WENO orders above 5 are not compiled for this solver in 2-D");
             }
         }
         switch (p->rp_id) {
-        case CLAWB200_RP_ACOUSTICS: return sc_launch1_tab<RpAcoustics<1, 1>>(A, st);
-        case CLAWB200_RP_ADVECTION: return sc_launch1_tab<RpAdvection<1, 1>>(A, st);
-        case CLAWB200_RP_SHALLOW: return sc_launch1_tab<RpShallow1D>(A, st);
-        case CLAWB200_RP_BURGERS: return sc_launch1_tab<RpBurgers>(A, st);
-        case CLAWB200_RP_EULER1D: return sc_launch1_tab<RpEuler1D>(A, st);
+        case CLAWB200_RP_ACOUSTICS: return sc_launch1_tab<RpAcoustics<1, 1>>(A, wk, st);
+        case CLAWB200_RP_ADVECTION: return sc_launch1_tab<RpAdvection<1, 1>>(A, wk, st);
+        case CLAWB200_RP_SHALLOW: return sc_launch1_tab<RpShallow1D>(A, wk, st);
+        case CLAWB200_RP_BURGERS: return sc_launch1_tab<RpBurgers>(A, wk, st);
+        case CLAWB200_RP_EULER1D: return sc_launch1_tab<RpEuler1D>(A, wk, st);
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
+    }
+    if (p->rp_id == CLAWB200_RP_USER) {
+        if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa is not compiled for the user solver in SharpClaw");
+        if (p->ndim == 2) A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+        return claw_sc_user(p->ndim, old, A, st);
     }
     if (p->method[5] > 0) {
         // capacity function (flux1.f90:59-63): compiled for the acoustics and advection solvers

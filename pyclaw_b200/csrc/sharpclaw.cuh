@@ -13,6 +13,7 @@
 #pragma once
 #include "rp.cuh"
 
+struct WenoTab;
 struct ScArgs {
     const double *q;  // stage state, ghost cells filled
     const double *qa; // second register of the RK combination (or null)
@@ -40,6 +41,7 @@ struct ScArgs {
     // aux(i-1), aux(i); the in-cell solve sees aux(i) on both sides
     const double *aux;
     long long amstride;
+    const struct WenoTab *tab; // weno_variant = tables: device memory owned by the caller
     // lim_type = 1 (flux1.f90:79-83): second-order TVD reconstruction, limiter id per COMPONENT
     int tvd;
     int mthlim[8];
@@ -492,19 +494,19 @@ __global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
 // ---------------------------------------------------------------------------
 // WENO of order 7 .. 17 (weno.f90:104-2425), 1-D.  The generated subroutines all have the
 // shape of weno5 with k = (order+1)/2 stencils; the kernel walks coefficient tables held in
-// constant memory (regenerated on the host from the formulas' definition,
+// caller-owned device memory (ScArgs::tab; regenerated on the host from the formulas' definition,
 // pyclaw_b200/weno_tables.py) in the order the generated code evaluates its terms.
 // ---------------------------------------------------------------------------
-struct WenoTab {
-    int k;
-    double S[9][45], CL[9][9], CR[9][9], WL[9], WR[9], eps;
+struct WenoTab { // all doubles: the packed buffer of clawb200_pack_weno_tables
+    double k, eps;
+    double S[9][45], CL[9][9], CR[9][9], WL[9], WR[9];
 };
-__constant__ WenoTab c_weno;
 
 template <class AR>
-__device__ __forceinline__ void weno_tab(AR &ar, const double *row /* cell i at row[0] */, double &ql, double &qr)
+__device__ __forceinline__ void weno_tab(AR &ar, const WenoTab &c_weno, const double *row /* cell i at row[0] */,
+                                         double &ql, double &qr)
 {
-    const int k = c_weno.k;
+    const int k = (int)c_weno.k;
     const double eps = c_weno.eps;
     double sigma[9], omega[18];
     for (int r = 0; r < k; r++) {
@@ -558,7 +560,8 @@ __global__ void __launch_bounds__(NT) sc1d_tab_kernel(const ScArgs A)
 {
     constexpr int MEQN = RP::MEQN;
     constexpr int NC = NT - 2;
-    const int k = c_weno.k;
+    const WenoTab &c_weno = *A.tab;
+    const int k = (int)c_weno.k;
     const int H = k - 1;            // halo cells of the stencil on each side
     const int QS = NT + 2 * H;
     extern __shared__ double sm[];
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(NT) sc1d_tab_kernel(const ScArgs A)
     for (int m = 0; m < MEQN; m++) { q0[m] = qs[m * QS + t + H]; dqx[m] = 0.0; }
     with_arith_fz([&](auto &ar) {
 #pragma unroll
-        for (int m = 0; m < MEQN; m++) weno_tab(ar, qs + m * QS + t + H, ql[m], qr[m]);
+        for (int m = 0; m < MEQN; m++) weno_tab(ar, c_weno, qs + m * QS + t + H, ql[m], qr[m]);
     });
     const AuxCell nocell{nullptr, 0};
     const bool AUXRP = (RP::MAUX > 0);
@@ -608,7 +611,8 @@ __global__ void __launch_bounds__(NT) sc2d_tab_kernel(const ScArgs A)
 {
     constexpr int MEQN = RPX::MEQN, MW = RPX::MWAVES, NROE = RPX::NROE;
     constexpr int NC = NT - 2;
-    const int kk = c_weno.k;
+    const WenoTab &c_weno = *A.tab;
+    const int kk = (int)c_weno.k;
     const int H = kk - 1;
     const int QS = NT + 2 * H;
     extern __shared__ double sm[];
@@ -657,7 +661,7 @@ __global__ void __launch_bounds__(NT) sc2d_tab_kernel(const ScArgs A)
             double ql[MEQN], qr[MEQN];
             with_arith_fz([&](auto &ar) {
 #pragma unroll
-                for (int m = 0; m < MEQN; m++) weno_tab(ar, qs + m * QS + t + H, ql[m], qr[m]);
+                for (int m = 0; m < MEQN; m++) weno_tab(ar, c_weno, qs + m * QS + t + H, ql[m], qr[m]);
             });
             sc_xrow_solve<RPX, NT>(A, ql, qr, x1, x2, t, xiface, xfull, cfl, dqx, A.dtdx, A.dtdx,
                                    AUXX ? sc_aux(A, rowoff + ilc) : nocell, AUXX ? sc_aux(A, rowoff + icl) : nocell);
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(NT) sc2d_tab_kernel(const ScArgs A)
                     const int row = min(max(c - H + e, 1 - mbc), A.my + mbc) + mbc - 1;
                     col[e] = A.q[m * A.mstride + (long long)A.pitch * row + icl];
                 }
-                weno_tab(ar, col + H, ql[m], qr[m]);
+                weno_tab(ar, c_weno, col + H, ql[m], qr[m]);
             }
         });
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];

@@ -22,6 +22,48 @@ class RiemannSolver(object):
         self.defaults = dict(defaults or {})
         self.fwave = fwave      # returns f-waves: pairs with the classic*fw modules (clawpack.py:222)
         self.maux = maux        # aux components the solver reads
+        self.lib = None         # user-supplied solvers: {arithmetic: path of the library variant}
+
+    def __call__(self, q_l, q_r, aux_l=None, aux_r=None, aux_global=None, ixy=1):
+        """The reference's Python Riemann-solver contract (doc/rp.rst:7-62, clawpack.py:349):
+        ``wave, s, amdq, apdq = rp(q_l, q_r, aux_l, aux_r, aux_global)`` on arrays of interfaces,
+        evaluated by the CUDA solver that the sweeps inline.  q_l, q_r: [meqn, n] CUDA tensors
+        (left / right state of each interface); returns CUDA tensors wave[meqn, mwaves, n],
+        s[mwaves, n], amdq[meqn, n], apdq[meqn, n].  Solvers without aux data only."""
+        import ctypes
+        import torch
+        from .. import _lib
+        if aux_l is not None or aux_r is not None:
+            raise NotImplementedError("pointwise evaluation is built for solvers that read no aux array")
+        ndim = 2 if 2 in self.ndims else 1
+        q_l = q_l.contiguous().to(torch.float64)
+        q_r = q_r.contiguous().to(torch.float64)
+        meqn, n = q_l.shape
+        mw = self.nwaves(ndim)
+        P = _lib.make_problem(ndim, meqn, mw, 2, 8, 8, 1.0, 1.0, self.rp_id, self.params(aux_global or {}))
+        wave = torch.empty((meqn, mw, n), dtype=torch.float64, device=q_l.device)
+        s = torch.empty((mw, n), dtype=torch.float64, device=q_l.device)
+        amdq, apdq = torch.empty_like(q_l), torch.empty_like(q_l)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        prev = _lib.set_variant(self._variant()) if self.lib else None
+        try:
+            _lib.call("clawb200_rp_solve", ctypes.byref(P), ixy, n, ptr(q_l), ptr(q_r), ptr(wave), ptr(s),
+                      ptr(amdq), ptr(apdq), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        finally:
+            if prev is not None:
+                _lib.set_variant(prev)
+        return wave, s, amdq, apdq
+
+    def _variant(self, arithmetic='strict'):
+        """Name under which the library variant holding a user-supplied solver is registered."""
+        from .. import _lib
+        base = 'fma' if arithmetic == 'fma' else 'strict'
+        if base not in self.lib:
+            from ..build import build_user
+            self.lib[base] = build_user(self.header, self.name, fma=(base == 'fma'))
+        key = 'user:%s:%s' % (self.name, base)
+        _lib.LIB_PATHS[key] = self.lib[base]
+        return key
 
     def meqn(self, ndim):
         return self._meqn(ndim) if callable(self._meqn) else self._meqn
@@ -70,6 +112,36 @@ burgers = RiemannSolver("burgers", RP_BURGERS, 1, 1, [], (1,))
 advection_color = RiemannSolver("advection_color", RP_ADVECTION_COLOR, 1, 1, [], (1,), maux=1)  # aux {u}
 vc_advection = RiemannSolver("vc_advection", RP_VC_ADVECTION, 1, 1, [], (2,), maux=2)           # aux {u, v[, capa]}
 euler_with_efix = RiemannSolver("euler_with_efix", RP_EULER1D, 3, 3, ["gamma", "gamma1"], (1,))
+
+def from_header(header, name=None, meqn=1, mwaves=1, ndims=(2,), param_names=(), optional=(), defaults=None,
+                fwave=False, maux=0, build=True):
+    """A user-supplied Riemann solver: ``header`` defines ``template <int IXY> struct RpUser`` with the
+    interface of the solvers in pyclaw_b200/csrc/rp.cuh (examples/user_rp/rp_kpp.cuh).  It is
+    compiled into a variant of the library (pyclaw_b200.build.build_user; nvcc must be on PATH
+    unless the variant was built before) and returned as a descriptor for ``solver.rp``.
+
+    This is the reference's plugin seam -- the rpn2 / rpt2 Fortran files an application's Makefile
+    names in RP_SOURCE (Makefile.rules:1-26) -- with the solver named in Python instead of in a
+    Makefile.  ``param_names``: the aux_global entries handed to the solver as P.p[0..7] (the
+    cparam common block); meqn / mwaves / maux must agree with the header's constants (the
+    library checks them at the first call)."""
+    import os
+    from .. import _lib
+    from ..build import build_user, user_lib_path
+    header = os.path.abspath(header)
+    name = name or os.path.splitext(os.path.basename(header))[0]
+    rs = RiemannSolver(name, _lib.RP_USER, meqn, mwaves, list(param_names), tuple(ndims), optional=optional,
+                       defaults=defaults, fwave=fwave, maux=maux)
+    rs.header = header
+    rs.lib = {}
+    if build:
+        rs.lib['strict'] = build_user(header, name)
+    elif os.path.exists(user_lib_path(name)):
+        rs.lib['strict'] = user_lib_path(name)
+    else:
+        raise Exception("library variant %s has not been built" % user_lib_path(name))
+    return rs
+
 
 _BY_NAME = {s.name: s for s in (vc_acoustics, burgers, advection_color, vc_advection, euler_with_efix,
                                 vc_acoustics_3d, acoustics, advection, euler_5wave, shallow_roe_with_efix, shallow_sphere,

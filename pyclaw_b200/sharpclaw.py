@@ -50,24 +50,21 @@ class SharpClawSolver(Solver):
     def _needs_backup_copy(self):
         return self.start_step is not start_step
 
-    # The table-driven WENO kernel reads its coefficients from constant memory, one table set
-    # per process: a solver uploads its own again when somebody else's upload came after it.
+    # The table-driven WENO kernels (orders 7-17) read their coefficients from a device buffer
+    # this solver owns; the problem struct points at it.  No table state lives in the library, so
+    # solvers of different orders can be alive side by side.
     def _upload_weno_tables(self):
         tab = getattr(self, '_weno_tab', None)
         if tab is None:
             return
-        L = _lib.load()
-        if getattr(self, '_weno_gen', None) == (_lib._active, L.clawb200_weno_generation()):
-            return
-        import numpy as np
-        arr = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ('S', 'CL', 'CR', 'WL', 'WR')]
-        _lib.call("clawb200_set_weno_tables", int(tab['k']),
-                  *[ctypes.c_void_p(a.ctypes.data) for a in arr], float(tab['eps']), _stream())
-        self._weno_gen = (_lib._active, L.clawb200_weno_generation())
+        import torch
+        packed = _lib.pack_weno_tables(tab)
+        self._weno_dev = torch.as_tensor(packed, device=self._cfl_dev.device)
+        self._problem.weno_k = int(tab['k'])
+        self._problem.weno_tab = self._weno_dev.data_ptr()
 
     # ---- one dq evaluation fused with a stage update ----
     def _stage(self, q_buf, qa_buf, out_buf, mode, ca, cb, div, slot, dq_buf=None):
-        self._upload_weno_tables()
         _lib.call("clawb200_sharpclaw_stage", ctypes.byref(self._problem), _ptr(q_buf), _ptr(qa_buf),
                   _ptr(out_buf), _ptr(dq_buf), self._aux_ptr, float(self.dt), mode, float(ca), float(cb),
                   float(div), ctypes.c_void_p(self._cfl_dev.data_ptr() + 8 * slot), _stream())
@@ -91,7 +88,7 @@ class SharpClawSolver(Solver):
         The stages are launched back to back and their Courant numbers are read once at
         the end; the result is committed only if no stage exceeded cfl_max, which is the
         state the reference is left in when CFLError interrupts it (q untouched)."""
-        _lib.set_variant(self.arithmetic)
+        _lib.set_variant(getattr(self, '_variant', None) or self.arithmetic)
         state = solution.states[0]
         self.start_step(self, solution)
         if self.dq_src is not None:

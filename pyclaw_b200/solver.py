@@ -127,11 +127,17 @@ class Solver(object):
         if state.device.type != 'cuda':
             raise _lib.ClawB200Error("pyclaw_b200 computes on CUDA devices only (no CPU fallback); "
                                      "state lives on %s" % state.device)
-        _lib.set_variant(self.arithmetic)
-        _lib.load()
         grid = state.grid
         fwave = bool(getattr(self, 'fwave', False))
         self._rp = riemann.resolve(self.rp, state.aux_global, grid.ndim, fwave=fwave)
+        self._variant = self.arithmetic
+        if self._rp.lib is not None:
+            # a user-supplied solver lives in its own variant of the library (riemann.from_header)
+            if self.arithmetic not in ('strict', 'fma'):
+                raise _lib.ClawB200Error("solver.arithmetic must be 'strict' or 'fma'")
+            self._variant = self._rp._variant(self.arithmetic)
+        _lib.set_variant(self._variant)
+        _lib.load()
         if self._rp.fwave != fwave:
             # the reference links an f-wave solver into classic*fw.so and a wave solver into
             # classic*.so (clawpack.py:221-222); mixing them gives wrong second-order terms
@@ -241,7 +247,7 @@ class Solver(object):
         return True
 
     def evolve_to_time(self, solution, tend=None):
-        _lib.set_variant(self.arithmetic)
+        _lib.set_variant(getattr(self, '_variant', None) or self.arithmetic)
         take_one_step = tend is None
         tstart = solution.t
         self.status['cflmax'] = self.cfl.get_cached_max()

@@ -25,3 +25,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _strict_library_variant():
+    """Kernel-level tests call the C ABI directly and mean the strict (parity) build: a test that
+    selected another build through ``solver.arithmetic`` must not leak it into the next test."""
+    try:
+        from pyclaw_b200 import _lib
+        _lib.set_variant("strict")
+    except Exception:
+        pass
+    yield

@@ -623,13 +623,13 @@ def test_sharpclaw_high_order_weno(order, rp, literals):
     params = [1.0, 1.0, 1.0, 1.0] if rp == "acoustics" else params
     tab = tables(k, literals)
     po.set_weno_tables(tab)
-    arr = [np.ascontiguousarray(tab[n], dtype=np.float64) for n in ('S', 'CL', 'CR', 'WL', 'WR')]
-    _lib.call("clawb200_set_weno_tables", k, *[_ptr(a) for a in arr], float(tab['eps']), None)
+    packed = _lib.pack_weno_tables(tab)   # host table: the *_host entry point uploads it
     for mx in (11, 300):
         dx, dt = 1.0 / mx, 0.1 / mx
         q = _shallow1d_data(mx, mbc, mx + order, True) if rp == "shallow" else \
             _random_padded(rp, mx, 0, mbc, seed=mx + order, smooth=True)
         P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, weno_variant=_lib.WENO_TABLES)
+        P.weno_k, P.weno_tab = k, packed.ctypes.data
         dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, po.WENO_TABLES)
         dq_g = np.zeros_like(q, order="F")
         cfl_g = ctypes.c_double()
@@ -639,6 +639,7 @@ def test_sharpclaw_high_order_weno(order, rp, literals):
         assert cfl_g.value == cfl_o
     # too few ghost cells for the stencil are refused
     P2 = _lib.make_problem(1, meqn, mwaves, mbc - 1, 20, 1, 0.1, 1.0, rp_id, params, weno_variant=_lib.WENO_TABLES)
+    P2.weno_k, P2.weno_tab = k, packed.ctypes.data
     q2 = np.zeros((meqn, 20 + 2 * (mbc - 1)), order="F")
     with pytest.raises(_lib.ClawB200Error, match="mbc"):
         _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P2), _ptr(q2), _ptr(q2.copy("F")), None, 0.01, ctypes.byref(cfl_g))
@@ -654,13 +655,13 @@ def test_sharpclaw_high_order_weno_2d(order, rp):
     rp_id, params, meqn, mwaves, _ = RPS[rp]
     tab = tables(k, 'f32')
     po.set_weno_tables(tab)
-    arr = [np.ascontiguousarray(tab[n], dtype=np.float64) for n in ('S', 'CL', 'CR', 'WL', 'WR')]
-    _lib.call("clawb200_set_weno_tables", k, *[_ptr(a) for a in arr], float(tab['eps']), None)
+    packed = _lib.pack_weno_tables(tab)   # host table: the *_host entry point uploads it
     cfl_g = ctypes.c_double()
     for mx, my in ((37, 29), (130, 70), (5, 140)):
         dx, dy, dt = 0.01, 0.013, 0.0011
         q = _random_padded(rp, mx, my, mbc, seed=mx + order, smooth=True)
         P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, weno_variant=_lib.WENO_TABLES)
+        P.weno_k, P.weno_tab = k, packed.ctypes.data
         dq_o, cfl_o = po.sc_flux2(rp_id, params, mwaves, mbc, mx, my, q, dx, dy, dt, po.WENO_TABLES)
         dq_g = np.zeros_like(q, order="F")
         _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g), None, dt, ctypes.byref(cfl_g))
