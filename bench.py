@@ -373,6 +373,8 @@ def main():
                          "fma for the classic sweeps, strict for SharpClaw")
     ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 partition-parity check")
     ap.add_argument("--no-other-build", action="store_true", help="skip timing the other arithmetic build")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--no-quiescent-leg", action="store_true", help="skip timing the application's own (quiescent) field")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
@@ -418,11 +420,14 @@ def main():
     if world > 1 and not args.no_parity:
         partition_parity = check_partition_parity(rank, world, torch, dist)
 
-    def timed_run(field, steps, warmup, sample_clocks, arithmetic=None):
+    def timed_run(field, steps, warmup, sample_clocks, arithmetic=None, workload=None):
         """Set the problem up, let dt settle, time `steps` calls of solver.evolve_to_time."""
-        state, solver = build_problem(pyclaw, args.workload, n, world, torch)
+        workload = workload or args.workload
+        wn = (args.n if workload == args.workload and args.n else WORKLOADS[workload]["n"])
+        wcells = wn * wn if workload != "sphere" else 2 * wn * wn
+        state, solver = build_problem(pyclaw, workload, wn, world, torch)
         solver.arithmetic = arithmetic or args.arithmetic
-        if field == "developed" and args.workload in ("euler", "shallow"):
+        if field == "developed" and workload in ("euler", "shallow"):
             # A smooth velocity field over the whole domain (SURVEY 8(d)): every interface has
             # non-zero jumps in every wave family, so the limiter, the entropy fix and the
             # transverse solves do their full work everywhere.  The initial data of the reference's
@@ -434,7 +439,7 @@ def main():
             rho = state.q[0].clone()
             state.q[1] = rho * 0.3 * bump
             state.q[2] = -rho * 0.2 * bump
-            if args.workload == "euler":
+            if workload == "euler":
                 state.q[3] = state.q[3] + 0.5 * (state.q[1] ** 2 + state.q[2] ** 2) / rho
         solution = pyclaw.Solution(state)
         solver.setup(solution)
@@ -463,7 +468,7 @@ def main():
             acc = torch.tensor([accepted], dtype=torch.float64, device="cuda")
             dist.all_reduce(acc, op=dist.ReduceOp.MIN)
             accepted = int(acc.item())
-        value = cells_per_rank * world * accepted / (ms * 1e-3)
+        value = wcells * world * accepted / (ms * 1e-3)
         return dict(value=value, ms=ms, accepted=accepted, clocks=clocks, state=state, solver=solver,
                     solution=solution)
 
@@ -479,6 +484,23 @@ def main():
                      "what": "the application's own initial data (>99% of the cells at rest)"}
         del rq
         torch.cuda.empty_cache()
+    # ---- the other BASELINE configurations, short runs, so that the driver's one line carries a
+    # measured number for every config (configs[1] acoustics is a 1-GPU configuration) ----------
+    others = None
+    if args.workload == "euler" and not args.no_other_workloads and not args.n:
+        others = {}
+        for w in ("acoustics", "shallow", "sphere"):
+            if w == "acoustics" and world > 1:
+                continue
+            ar = "fma" if FMA_ERR[w] <= 1e-12 else "strict"
+            ksteps = 10 if w == "acoustics" else 5
+            r = timed_run("developed" if w == "shallow" else "application", ksteps, 3, False, arithmetic=ar, workload=w)
+            others[w] = {"workload": WORKLOADS[w]["label"], "value": r["value"], "unit": "cell-updates/s",
+                         "ms_per_step": r["ms"] / ksteps, "steps": ksteps, "arithmetic": ar,
+                         "field": "developed" if w == "shallow" else "application",
+                         "step_frac_of_hbm_roofline": r["value"] / world * WORKLOADS[w]["balg"] / 1e9 / peaks()[0]}
+            del r
+            torch.cuda.empty_cache()
     other_build = None
     if not args.no_other_build:
         ob = "strict" if args.arithmetic == "fma" else "fma"
@@ -706,6 +728,7 @@ def main():
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": args.steps * per_step_launches,
+        "other_workloads": others,
     }
     if world > 1:
         line["partition_parity"] = partition_parity

@@ -2,7 +2,7 @@
 # usage: scratch/sweep_variants.sh lib1.so lib2.so ...   (files under pyclaw_b200/csrc)
 # Euler 4096^2, developed field (value) and the application's quiescent field, per-kernel times.
 for lib in "$@"; do
-  CLAWB200_LIB=$PWD/pyclaw_b200/csrc/$lib python bench.py --n 4096 --steps 6 --warmup 3 --no-cpu --no-e2e --no-other-build --arithmetic strict ${VARIANT_ARGS} 2>/dev/null | python -c "
+  CLAWB200_LIB=$PWD/pyclaw_b200/csrc/$lib python bench.py --n 4096 --steps 6 --warmup 3 --no-cpu --no-e2e --no-other-build --no-other-workloads --arithmetic strict ${VARIANT_ARGS} 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
