@@ -78,6 +78,8 @@ extern "C" {
                                       order TVD reconstruction; problem.mthlim[m] is the limiter of
                                       COMPONENT m (1 minmod, 2 superbee, 3 van Leer, 4 MC, 5 Cada-
                                       Torrilhon).  First cell of a slice: see DESIGN.md            */
+#define CLAWB200_RECON_WENO_WAVE 5  /* reconstruct.f90:393-471 weno5_wave (lim_type 2, char_decomp 1), 1-D */
+#define CLAWB200_RECON_WENO_FWAVE 6 /* reconstruct.f90:474-565 weno5_fwave (the same with solver.fwave), 1-D */
 
 #define CLAWB200_ERR_INVALID (-1)
 #define CLAWB200_ERR_UNSUPPORTED (-2)

@@ -60,6 +60,8 @@
 #define WENO_OLD 2        /* reconstruct.f90:120-185 (lim_type = 3)              */
 #define WENO_TABLES 3     /* weno.f90:104-2425 (orders 7..17) through coefficient tables */
 #define RECON_TVD2 4      /* reconstruct.f90:568-625 (lim_type = 1, char_decomp = 0)     */
+#define RECON_WENO_WAVE 5  /* reconstruct.f90:393-471 weno5_wave  (lim_type 2, char_decomp 1)  */
+#define RECON_WENO_FWAVE 6 /* reconstruct.f90:474-565 weno5_fwave (same, solver.fwave = True)  */
 
 typedef struct {
     int rp_id;
@@ -1853,6 +1855,81 @@ static void tvd2(const double *q, double *ql, double *qr, int meqn, int mx, int 
     }
 }
 
+/* reconstruct.f90:393-471 (weno5_wave) and :474-565 (weno5_fwave): fifth-order WENO in which the
+   smoothness is measured on the WAVES of a Riemann solve between cell averages (flux1.f90:95-105,
+   char_decomp = 1).  1-based storage index p <-> interface between cells p-1 and p.  The Fortran
+   loop runs p = 2 .. mx2 and reads waves at p-2 .. p+2 and q at p-2 .. p+1, i.e. out of bounds
+   at both ends; only p = 3 .. mx2-2 is in bounds, and with mbc = 3 that covers every interface
+   whose edge values flux1 consumes (1 .. mx+1 <-> p = 4 .. mx+4). */
+#define WVP(m, mw, p) wave[(m) + meqn * ((mw) + mwaves * ((p)-1))]
+static void weno5_wave(const double *q, double *ql, double *qr, double *wave, const double *s,
+                       int meqn, int mwaves, int mx, int mbc, int fw)
+{
+    const int mx2 = mx + 2 * mbc;
+    const double epweno = (double)1.e-36f;  /* reconstruct.f90:7, REAL(4) literal */
+    const double tiny = (double)1.e-14f;    /* "1.e-14": REAL(4) literal          */
+    if (fw) /* :495-497 forall: fwave = fwave / s, in place */
+        for (int p = 1; p <= mx2; p++)
+            for (int mw = 0; mw < mwaves; mw++)
+                for (int m = 0; m < meqn; m++)
+                    WVP(m, mw, p) = WVP(m, mw, p) / s[mw + mwaves * (p - 1)];
+    for (int p = 3; p <= mx2 - 2; p++) {
+        for (int m = 0; m < meqn; m++) {
+            if (fw) {
+                QP(qr, m, p - 1) = QP(q, m, p - 1);
+                QP(ql, m, p) = QP(q, m, p);
+            } else {
+                QP(qr, m, p - 1) = (-QP(q, m, p - 2) + 7. * (QP(q, m, p - 1) + QP(q, m, p)) - QP(q, m, p + 1)) / 12.;
+                QP(ql, m, p) = QP(qr, m, p - 1);
+            }
+        }
+        for (int mw = 0; mw < mwaves; mw++) {
+            double u[2], wn = 0.0;
+            for (int m1 = 1; m1 <= 2; m1++) {
+                const int im = (m1 == 1) ? 1 : -1;
+                const int ione = im, inone = -im, intwo = -2 * im;
+                double wnorm2 = WVP(0, mw, p) * WVP(0, mw, p);
+                double theta1 = WVP(0, mw, p + intwo) * WVP(0, mw, p);
+                double theta2 = WVP(0, mw, p + inone) * WVP(0, mw, p);
+                double theta3 = WVP(0, mw, p + ione) * WVP(0, mw, p);
+                for (int m = 1; m < meqn; m++) {
+                    wnorm2 = wnorm2 + WVP(m, mw, p) * WVP(m, mw, p);
+                    theta1 = theta1 + WVP(m, mw, p + intwo) * WVP(m, mw, p);
+                    theta2 = theta2 + WVP(m, mw, p + inone) * WVP(m, mw, p);
+                    theta3 = theta3 + WVP(m, mw, p + ione) * WVP(m, mw, p);
+                }
+                double t1 = im * (theta1 - theta2);
+                double t2 = im * (theta2 - wnorm2);
+                double t3 = im * (wnorm2 - theta3);
+                double tt1 = 13. * (t1 * t1) + 3. * ((theta1 - 3. * theta2) * (theta1 - 3. * theta2));
+                double tt2 = 13. * (t2 * t2) + 3. * ((theta2 + wnorm2) * (theta2 + wnorm2));
+                double tt3 = 13. * (t3 * t3) + 3. * ((3. * wnorm2 - theta3) * (3. * wnorm2 - theta3));
+                tt1 = (epweno + tt1) * (epweno + tt1);
+                tt2 = (epweno + tt2) * (epweno + tt2);
+                tt3 = (epweno + tt3) * (epweno + tt3);
+                double s1 = tt2 * tt3;
+                double s2 = 6. * tt1 * tt3;
+                double s3 = 3. * tt1 * tt2;
+                double t0 = 1. / (s1 + s2 + s3);
+                s1 = s1 * t0;
+                s3 = s3 * t0;
+                if (wnorm2 > tiny) {
+                    u[m1 - 1] = (s1 * (t2 - t1) + (0.5 * s3 - 0.25) * (t3 - t2)) / 3.;
+                    if (fw) u[m1 - 1] = u[m1 - 1] + im * (theta2 + 6.0 * wnorm2 - theta3) / 12.0;
+                    wn = 1.0 / wnorm2;
+                } else {
+                    u[m1 - 1] = 0.0;
+                    wn = 0.0;
+                }
+            }
+            for (int m = 0; m < meqn; m++) {
+                QP(qr, m, p - 1) = QP(qr, m, p - 1) + u[0] * WVP(m, mw, p) * wn;
+                QP(ql, m, p) = QP(ql, m, p) + u[1] * WVP(m, mw, p) * wn;
+            }
+        }
+    }
+}
+
 /* flux1.f90:2-195.  Returns cfl; dq1d(meqn, n) receives the increments for i=1..mx
    (entries outside are left untouched). */
 typedef struct {
@@ -1900,7 +1977,11 @@ static double sc_flux1_capa(rp_ctx *c, const double *q1d, double *dq1d, double d
        results at those interfaces are never consumed). */
     memcpy(ql, q1d, sizeof(double) * n * meqn);
     memcpy(qr, q1d, sizeof(double) * n * meqn);
-    if (weno_variant == RECON_TVD2) tvd2(q1d, ql, qr, meqn, mx, mbc);
+    if (weno_variant == RECON_WENO_WAVE || weno_variant == RECON_WENO_FWAVE) {
+        /* flux1.f90:95-105: rp1(q1d, q1d, aux, aux) on the cell averages, then the wave-based WENO */
+        rpn(c, ixy, meqn, mwaves, mbc, mx, q1d, q1d, aux1d, aux1d, wave, s, amdq, apdq);
+        weno5_wave(q1d, ql, qr, wave, s, meqn, mwaves, mx, mbc, weno_variant == RECON_WENO_FWAVE);
+    } else if (weno_variant == RECON_TVD2) tvd2(q1d, ql, qr, meqn, mx, mbc);
     else if (weno_variant == WENO_OLD) weno5_old(q1d, ql, qr, meqn, mx, mbc, w->dq1m, w->uu);
     else if (weno_variant == WENO_TABLES) weno_tables(q1d, ql, qr, meqn, mx, mbc);
     else weno5_pyweno(q1d, ql, qr, meqn, mx, mbc, weno_variant == WENO_PYWENO_F32);

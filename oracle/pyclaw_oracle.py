@@ -27,6 +27,7 @@ RP_NEL_FWAVE, RP_PSYSTEM = 6, 7   # f-wave solvers (step1fw.f / flux2fw.f correc
 RP_ACOUSTICS3D_VC = 8              # 3-D variable-coefficient acoustics (dimensional splitting)
 RP_VC_ACOUSTICS, RP_BURGERS, RP_ADVECTION_COLOR, RP_VC_ADVECTION, RP_EULER1D = 9, 10, 11, 12, 13
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES, RECON_TVD2 = 0, 1, 2, 3, 4
+RECON_WENO_WAVE, RECON_WENO_FWAVE = 5, 6
 BC_CUSTOM, BC_OUTFLOW, BC_PERIODIC, BC_REFLECTING = 0, 1, 2, 3
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -310,6 +311,7 @@ class OracleSolver(object):
             self.time_integrator, self.weno_variant = "SSP104", WENO_PYWENO_F32
             self.weno_order, self.weno_tables = 5, None
             self.lim_type, self.limiters = 2, [1]
+            self.char_decomp, self.fwave = 0, False
         self.mcapa = -1
         self.cfl = self.cfl_desired
         self.status = {}
@@ -324,6 +326,9 @@ class OracleSolver(object):
             self.mbc = (self.weno_order + 1) // 2
             set_weno_tables(self.weno_tables)
             self.weno_variant = WENO_TABLES
+        if self.kind == "sharpclaw" and self.lim_type == 2 and self.char_decomp == 1:
+            assert self.ndim == 1  # the reference's 2-D flux1 cannot run this branch (wrong rpn2 argument list)
+            self.weno_variant = RECON_WENO_FWAVE if self.fwave else RECON_WENO_WAVE
         if self.kind == "sharpclaw" and self.lim_type == 1:
             # flux1.f90:79-83 tvd2; clawparams.mthlim = solver.mthlim (sharpclaw.py:213-218, 278)
             lim = self.limiters if isinstance(self.limiters, list) else [self.limiters]

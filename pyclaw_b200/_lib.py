@@ -19,6 +19,7 @@ RP_NEL_FWAVE, RP_PSYSTEM, RP_ACOUSTICS3D_VC = 6, 7, 8
 RP_VC_ACOUSTICS, RP_BURGERS, RP_ADVECTION_COLOR, RP_VC_ADVECTION, RP_EULER1D = 9, 10, 11, 12, 13
 RP_USER = 100   # a solver compiled in from a user header (riemann.from_header)
 WENO_PYWENO_F32, WENO_PYWENO_F64, WENO_OLD, WENO_TABLES, RECON_TVD2 = 0, 1, 2, 3, 4
+RECON_WENO_WAVE, RECON_WENO_FWAVE = 5, 6
 STAGE_AXPY, STAGE_CONVEX, STAGE_FINAL104, STAGE_DQ_ONLY = 0, 1, 2, 3
 
 

@@ -473,7 +473,13 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     double *ys = sm + (TRANS ? 4 * MEQN * NT : 0);     // [SL::COUNT][NT] rolling window
 
     const int t = threadIdx.x;
-#define YS(slot) ys[(slot) * NT + t]
+#define YQ(slot) ys[(slot) * NT + t]
+    // Light solvers (RP::Y_REGS) keep the rolling window in registers: they have the registers to
+    // spare, and the window traffic (~50 LDS / STS per row for acoustics) competes with the
+    // arithmetic for issue slots.  Every window index is a compile-time constant after unrolling.
+    constexpr bool YREGS = rp_y_regs<RP>::value;
+    double yr[YREGS ? SL::STATE_END : 1];
+#define YS(slot) (*(YREGS ? &yr[YREGS ? (slot) : 0] : &ys[(slot) * NT + t]))
     const int mbc = A.mbc;
     const int i0 = A.ilo + blockIdx.x * NC;
     const int ic = TRANS ? i0 - 1 + t : i0 + t;      // this thread's column (Fortran index)
@@ -499,6 +505,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     for (int m = 0; m < MEQN; m++) { qm1[m] = 1.0; qm2[m] = 1.0; }
 #pragma unroll
     for (int mw = 0; mw < MW; mw++) { sm1[mw] = 0.0; norm1[mw] = 0.0; dot1[mw] = 0.0; }
+#pragma unroll
     for (int sl = 0; sl < SL::STATE_END; sl++) YS(sl) = (TRANS && sl >= SL::ROE && sl < SL::ROE + NROE) ? 1.0 : 0.0;
 
     int buf = 0;
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     // thread-private slots, double buffered on the parity of k
 #pragma unroll
     for (int m = 0; m < MEQN; m++)
-        cp_async8(&YS(SL::QN + m), &A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl]);
+        cp_async8(&YQ(SL::QN + m), &A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl]);
     cp_async_commit();
     int par = 0;
     for (int k = j0 - 2; k <= j1 + 1; k++) {
@@ -520,19 +527,19 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
         cp_async_wait_all();
         double qk[MEQN];
 #pragma unroll
-        for (int m = 0; m < MEQN; m++) qk[m] = YS(SL::QN + par * MEQN + m);
+        for (int m = 0; m < MEQN; m++) qk[m] = YQ(SL::QN + par * MEQN + m);
         const int qxslot = SL::QX + par * MEQN; // x-sweep result of row k-2, requested last iteration
         if (k <= j1) {
 #pragma unroll
             for (int m = 0; m < MEQN; m++)
-                cp_async8(&YS(SL::QN + (par ^ 1) * MEQN + m), &A.qin[m * A.mstride + rowoff + A.pitch + icl]);
+                cp_async8(&YQ(SL::QN + (par ^ 1) * MEQN + m), &A.qin[m * A.mstride + rowoff + A.pitch + icl]);
         }
         if (TRANS) {
             const bool need = (k - 1 >= j0) && (k - 1 < j1) && col_out;
             if (need) {
 #pragma unroll
                 for (int m = 0; m < MEQN; m++)
-                    cp_async8(&YS(SL::QX + (par ^ 1) * MEQN + m),
+                    cp_async8(&YQ(SL::QX + (par ^ 1) * MEQN + m),
                               &A.qout[m * A.mstride + (long long)A.pitch * (k - 1 + mbc - 1) + icl]);
             }
         }
@@ -693,7 +700,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
                 for (int m = 0; m < MEQN; m++) {
                     double G2l = gs[(buf * 2 * MEQN + MEQN + m) * NT + t - 1];
                     double G1r = gs[(buf * 2 * MEQN + m) * NT + t + 1];
-                    double q = YS(qxslot + m);
+                    double q = YQ(qxslot + m);
                     if (!CAPA) {
                         q = q + dtdx * G2l;
                         q = q + mainE[m];
@@ -723,6 +730,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
         for (int mw = 0; mw < MW; mw++) { sm1[mw] = s[mw]; norm1[mw] = normk[mw]; dot1[mw] = dotk[mw]; }
     }
 #undef YS
+#undef YQ
     if (ICFL) cfl = dtdy * __longlong_as_double((long long)smax);
     cfl_commit(cfl, A.cfl_bits);
 }

@@ -45,6 +45,12 @@ struct rp_is_fwave { static constexpr bool value = false; };
 template <class RP>
 struct rp_is_fwave<RP, decltype((void)RP::FWAVE)> { static constexpr bool value = RP::FWAVE; };
 
+// Solvers whose y-sweep window fits in registers declare Y_REGS = true (classic.cuh, y-engine).
+template <class RP, class = void>
+struct rp_y_regs { static constexpr bool value = false; };
+template <class RP>
+struct rp_y_regs<RP, decltype((void)RP::Y_REGS)> { static constexpr bool value = RP::Y_REGS; };
+
 struct RpParams {
     double p[8];
 };
@@ -71,9 +77,13 @@ struct RpAcoustics {
     static constexpr int MEQN = NDIM + 1, MWAVES = 2, NROE = 1;
 #ifndef CLAW_AC_X_MINB
 #define CLAW_AC_X_MINB 5
-#define CLAW_AC_Y_MINB 4
+#define CLAW_AC_Y_MINB 3
 #endif
     static constexpr int X_MINB = CLAW_AC_X_MINB, Y_MINB = CLAW_AC_Y_MINB;
+#ifndef CLAW_AC_Y_REGS
+#define CLAW_AC_Y_REGS 1
+#endif
+    static constexpr bool Y_REGS = CLAW_AC_Y_REGS;
     static constexpr int MAUX = 0; // aux components read by the solver
     static constexpr bool QCOR = false; // CTAs/SM the sweeps are compiled for
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;

@@ -144,6 +144,37 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
     }
+    if (p->weno_variant == CLAWB200_RECON_WENO_WAVE || p->weno_variant == CLAWB200_RECON_WENO_FWAVE) {
+        // char_decomp = 1 (flux1.f90:95-105).  1-D only: the reference's 2-D flux1.f90:102-106 calls
+        // rpn2 with a wrong argument list and then both reconstructions, it cannot run
+        if (p->ndim != 1) return fail(CLAWB200_ERR_UNSUPPORTED, "wave-based reconstruction (char_decomp = 1) exists in 1-D only");
+        if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa is not compiled for the wave-based reconstruction");
+        const bool fw = (p->weno_variant == CLAWB200_RECON_WENO_FWAVE);
+#define WAVE1(RPT)                                                                                          \
+    {                                                                                                       \
+        using RP = RPT;                                                                                     \
+        constexpr int NC = SNT - 6;                                                                         \
+        size_t smem = sizeof(double) * (RP::MEQN * (SNT + 1) + RP::MEQN * RP::MWAVES * SNT + 2 * RP::MEQN * SNT); \
+        if (fw) sc1d_wave_kernel<RP, true, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);               \
+        else sc1d_wave_kernel<RP, false, SNT><<<(A.mx + NC - 1) / NC, SNT, smem, st>>>(A);                 \
+        CUDA_OK(cudaGetLastError());                                                                        \
+        return 0;                                                                                           \
+    }
+        using Ac1 = RpAcoustics<1, 1>;
+        using Ad1 = RpAdvection<1, 1>;
+        using El1 = RpElasticFwave<1, 1>;
+        switch (p->rp_id) {
+        case CLAWB200_RP_ACOUSTICS: WAVE1(Ac1)
+        case CLAWB200_RP_ADVECTION: WAVE1(Ad1)
+        case CLAWB200_RP_SHALLOW: WAVE1(RpShallow1D)
+        case CLAWB200_RP_BURGERS: WAVE1(RpBurgers)
+        case CLAWB200_RP_EULER1D: WAVE1(RpEuler1D)
+        case CLAWB200_RP_NEL_FWAVE: WAVE1(El1)
+        case CLAWB200_RP_ADVECTION_COLOR: WAVE1(RpColor1D)
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
+        }
+#undef WAVE1
+    }
     if (p->rp_id == CLAWB200_RP_USER) {
         if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa is not compiled for the user solver in SharpClaw");
         if (p->ndim == 2) A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));

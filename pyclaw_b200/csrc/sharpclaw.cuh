@@ -492,6 +492,163 @@ __global__ void __launch_bounds__(NT) sc1d_kernel(const ScArgs A)
 
 
 // ---------------------------------------------------------------------------
+// 1-D, char_decomp = 1 (flux1.f90:95-105): wave-based WENO5, reconstruct.f90:393-471 (weno5_wave)
+// and :474-565 (weno5_fwave, solver.fwave = True).  A Riemann solve between CELL AVERAGES gives
+// the waves of every interface; the smoothness indicators are built from the projections of the
+// neighbouring interfaces' waves (i-2 .. i+2) onto this interface's wave, family by family, and
+// the reconstructed jump is added along the wave.  Thread t <-> cell / interface ic = i0-3+t;
+// the waves travel through shared memory, both edge values of an interface (the right edge of
+// cell t-1, the left edge of cell t) are produced by thread t itself.  Cells t = 3 .. NT-4 are
+// output.  (The reference's 2-D flux1.f90 cannot run this branch: it calls rpn2 without ixy and
+// then both reconstructions, src/fortran/2d/sharpclaw/flux1.f90:102-106.)
+// ---------------------------------------------------------------------------
+template <class RP, bool FW, int NT>
+__global__ void __launch_bounds__(NT) sc1d_wave_kernel(const ScArgs A)
+{
+    constexpr int MEQN = RP::MEQN, MW = RP::MWAVES, NROE = RP::NROE;
+    constexpr int NC = NT - 6;
+    constexpr int QS = NT + 1;
+    constexpr bool AUXRP = (RP::MAUX > 0);
+    extern __shared__ double sm[];
+    double *qs = sm;                   // [MEQN][NT+1], index k <-> cell i0-4+k
+    double *wsm = qs + MEQN * QS;      // [MEQN*MW][NT] waves (f-waves / s) of interface t
+    double *x1 = wsm + MEQN * MW * NT; // [MEQN][NT] right-edge value of cell t-1
+    double *x2 = x1 + MEQN * NT;       // [MEQN][NT] amdq of interface t
+    const int t = threadIdx.x;
+    const int mbc = A.mbc;
+    const int i0 = 1 + blockIdx.x * NC;
+    const int ic = i0 - 3 + t;
+    const int imax = A.mx + mbc;
+    auto col = [&](int i) { return min(max(i, 1 - mbc), imax) + mbc - 1; };
+    const int icl = col(ic), ill = col(ic - 1);
+    const bool col_out = (t >= 3) && (t <= NT - 4) && (ic >= 1) && (ic <= A.mx);
+    const bool xiface = (t >= 2) && (t <= NT - 3) && (ic >= 1) && (ic <= A.mx + 1);
+    const double epweno = A.epweno, tiny = (double)1.e-14f;
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) {
+        qs[m * QS + t] = A.q[m * A.mstride + col(i0 - 4 + t)];
+        if (t == 0) qs[m * QS + NT] = A.q[m * A.mstride + col(i0 - 4 + NT)];
+    }
+    __syncthreads();
+    const AuxCell nocell{nullptr, 0};
+    const AuxCell axl = AUXRP ? sc_aux(A, ill) : nocell, axc = AUXRP ? sc_aux(A, icl) : nocell;
+    double qm[MEQN], q0[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) { qm[m] = qs[m * QS + t]; q0[m] = qs[m * QS + t + 1]; }
+    // ---- waves between the cell averages (rp1(q1d, q1d, aux, aux)) ----
+    double wv[MEQN][MW];
+    {
+        double s[MW], am[MEQN], ap[MEQN], roe[NROE];
+        with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, qm, q0, axl, axc, wv, s, am, ap, roe); });
+        if (FW) { // weno5_fwave: fwave / s, plain IEEE division (s = 0 gives Inf / NaN as in the Fortran)
+#pragma unroll
+            for (int m = 0; m < MEQN; m++)
+#pragma unroll
+                for (int mw = 0; mw < MW; mw++) wv[m][mw] = wv[m][mw] / s[mw];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MEQN; m++)
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) wsm[(m * MW + mw) * NT + t] = wv[m][mw];
+    __syncthreads();
+    // ---- reconstruction at interface t: qrl = right edge of cell t-1, qll = left edge of cell t ----
+    double qrl[MEQN], qll[MEQN];
+    const int tm2 = max(t - 2, 0), tm1 = max(t - 1, 0), tp1 = min(t + 1, NT - 1), tp2 = min(t + 2, NT - 1);
+    with_arith_fz([&](auto &ar) {
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            if (FW) {
+                qrl[m] = qm[m];
+                qll[m] = q0[m];
+            } else {
+                const double a = qs[m * QS + tm1], d = qs[m * QS + min(t + 2, NT)];
+                qrl[m] = ar.div(-a + 7. * (qm[m] + q0[m]) - d, 12.);
+                qll[m] = qrl[m];
+            }
+        }
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) {
+            // projections of the neighbouring interfaces' waves on this one
+            double wnorm2 = 0.0, dm2 = 0.0, dm1 = 0.0, dp1 = 0.0, dp2 = 0.0;
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                const double w = wv[m][mw];
+                const double *row = wsm + (m * MW + mw) * NT;
+                if (m == 0) {
+                    wnorm2 = w * w; dm2 = row[tm2] * w; dm1 = row[tm1] * w; dp1 = row[tp1] * w; dp2 = row[tp2] * w;
+                } else {
+                    wnorm2 = wnorm2 + w * w; dm2 = dm2 + row[tm2] * w; dm1 = dm1 + row[tm1] * w;
+                    dp1 = dp1 + row[tp1] * w; dp2 = dp2 + row[tp2] * w;
+                }
+            }
+            double u[2], wn = 0.0;
+#pragma unroll
+            for (int m1 = 0; m1 < 2; m1++) {
+                const double im = (m1 == 0) ? 1.0 : -1.0;
+                const double theta1 = (m1 == 0) ? dm2 : dp2; // i + intwo
+                const double theta2 = (m1 == 0) ? dm1 : dp1; // i + inone
+                const double theta3 = (m1 == 0) ? dp1 : dm1; // i + ione
+                const double t1 = im * (theta1 - theta2);
+                const double t2 = im * (theta2 - wnorm2);
+                const double t3 = im * (wnorm2 - theta3);
+                double tt1 = 13. * (t1 * t1) + 3. * ((theta1 - 3. * theta2) * (theta1 - 3. * theta2));
+                double tt2 = 13. * (t2 * t2) + 3. * ((theta2 + wnorm2) * (theta2 + wnorm2));
+                double tt3 = 13. * (t3 * t3) + 3. * ((3. * wnorm2 - theta3) * (3. * wnorm2 - theta3));
+                tt1 = (epweno + tt1) * (epweno + tt1);
+                tt2 = (epweno + tt2) * (epweno + tt2);
+                tt3 = (epweno + tt3) * (epweno + tt3);
+                double s1 = tt2 * tt3;
+                const double s2 = 6. * tt1 * tt3;
+                double s3 = 3. * tt1 * tt2;
+                const double t0 = ar.div(1., s1 + s2 + s3);
+                s1 = s1 * t0;
+                s3 = s3 * t0;
+                if (wnorm2 > tiny) {
+                    double uu = ar.div(s1 * (t2 - t1) + (0.5 * s3 - 0.25) * (t3 - t2), 3.);
+                    if (FW) uu = uu + ar.div(im * (theta2 + 6.0 * wnorm2 - theta3), 12.0);
+                    u[m1] = uu;
+                    wn = ar.div(1.0, wnorm2);
+                } else {
+                    u[m1] = 0.0;
+                    wn = 0.0;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MEQN; m++) {
+                qrl[m] = qrl[m] + u[0] * wv[m][mw] * wn;
+                qll[m] = qll[m] + u[1] * wv[m][mw] * wn;
+            }
+        }
+    });
+    // ---- flux1.f90:129-192: interface solve, CFL, in-cell solve, fluctuation sum ----
+    double cfl = 0.0;
+    double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
+    with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, qrl, qll, axl, axc, wave, s, amdq, apdq, roe); });
+    if (xiface) {
+#pragma unroll
+        for (int mw = 0; mw < MW; mw++) cfl = dmax2(dmax2(cfl, A.dtdx * s[mw]), -A.dtdx * s[mw]);
+    }
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) { x1[m * NT + t] = qrl[m]; x2[m * NT + t] = amdq[m]; }
+    __syncthreads();
+    double qrc[MEQN], dqx[MEQN];
+#pragma unroll
+    for (int m = 0; m < MEQN; m++) qrc[m] = x1[m * NT + tp1]; // right edge of this cell
+    {
+        double amdq2[MEQN], apdq2[MEQN];
+        with_arith_fz([&](auto &ar) { RP::solve(ar, A.rp, qll, qrc, axc, axc, wave, s, amdq2, apdq2, roe); });
+#pragma unroll
+        for (int m = 0; m < MEQN; m++) {
+            const double an = x2[m * NT + tp1];
+            dqx[m] = 0.0 - A.dtdx * (an + apdq[m] + amdq2[m] + apdq2[m]);
+        }
+    }
+    if (col_out) stage_store<MEQN>(A, icl, q0, dqx);
+    sc_cfl_commit(cfl, A.cfl_bits);
+}
+
+// ---------------------------------------------------------------------------
 // WENO of order 7 .. 17 (weno.f90:104-2425), 1-D.  The generated subroutines all have the
 // shape of weno5 with k = (order+1)/2 stencils; the kernel walks coefficient tables held in
 // caller-owned device memory (ScArgs::tab; regenerated on the host from the formulas' definition,

@@ -234,14 +234,27 @@ class SharpClawSolver(Solver):
             variant = _lib.WENO_PYWENO_F32 if self.weno_literals == 'f32' else _lib.WENO_PYWENO_F64
         elif self.lim_type == 3:
             variant = _lib.WENO_OLD
+        elif self.lim_type == 2 and self.char_decomp == 1:
+            # wave-based WENO (flux1.f90:95-105; weno5_wave / weno5_fwave).  The reference's 2-D
+            # flux1.f90:102-106 calls rpn2 without ixy and then BOTH reconstructions: it cannot run
+            if self.ndim != 1:
+                raise NotImplementedError("char_decomp=1 (wave-based reconstruction) exists in 1-D only: the "
+                                          "reference's 2-D flux1.f90 cannot execute this branch")
+            variant = _lib.RECON_WENO_FWAVE if self.fwave else _lib.RECON_WENO_WAVE
         elif self.lim_type == 1 and self.char_decomp == 0:
             # tvd2 (reconstruct.f90:568-625): second-order TVD reconstruction of the components of q
             variant = _lib.RECON_TVD2
         else:
-            raise NotImplementedError("lim_type=%s char_decomp=%s is not implemented"
+            # char_decomp = 2 / 3 call evec(), which the reference ships as a stub that stops
+            # (src/fortran/1d/sharpclaw/evec.f90:11-13: "subroutine evec() has not been provided")
+            raise NotImplementedError("lim_type=%s char_decomp=%s is not implemented (char_decomp 2 and 3 need a "
+                                      "user-supplied evec(); the reference's own evec.f90 stops)"
                                       % (self.lim_type, self.char_decomp))
         if self.tfluct_solver:
-            raise NotImplementedError("tfluct (total fluctuation) solvers are not implemented")
+            # the reference's own tfluct is a stub that stops the interpreter
+            # (src/fortran/1d/sharpclaw/tfluct.f90:11-13: "you have not defined a function tfluct")
+            raise NotImplementedError("tfluct_solver=True: the reference ships no total-fluctuation solver "
+                                      "(tfluct.f90 prints an error and stops); none is provided here either")
         # fwave = True with char_decomp = 0 (e.g. the stegoton script): flux1.f90 only uses the
         # solver's amdq / apdq, so an f-wave solver works unchanged
         self.mbc = (self.weno_order + 1) // 2

@@ -641,3 +641,18 @@ def test_shallow_sharpclaw_tvd2_vs_oracle(lim):
     qo = _oracle_shallow('sharpclaw', **o)
     assert np.isfinite(qo).all()
     assert np.array_equal(qg, qo)
+
+
+@pytest.mark.parametrize("ti", ['SSP33', 'SSP104'])
+def test_acoustics1d_sharpclaw_wave_based_vs_oracle(ti):
+    """char_decomp = 1 through the API (1-D acoustics, the reference's test problem) against the
+    oracle; the wave-based scheme converges like the component-wise one on this smooth problem."""
+    err, claw = _acoustics1d('sharpclaw', char_decomp=1, time_integrator=ti)
+    pb = problems.acoustics1d(100)
+    s = po.OracleSolver("sharpclaw", 1, po.RP_ACOUSTICS, pb["params"], 2)
+    s.char_decomp, s.time_integrator = 1, ti
+    s.bc_lower = s.bc_upper = [po.BC_PERIODIC]
+    s.dt_initial = pb["dt_initial"]
+    frames = s.run(pb["q"], None, pb["d"], pb["tfinal"], pb["nout"])
+    assert np.array_equal(np.asarray(claw.frames[-1].q), frames[-1])
+    assert err < 2e-3

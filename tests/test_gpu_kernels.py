@@ -953,3 +953,57 @@ def test_sharpclaw_tvd2_dq1_flat_regions(lim):
     assert np.isfinite(dq_o[:, mbc:-mbc]).all()
     assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc])
     assert cfl_g.value == cfl_o
+
+
+# ---------------------------------------------------------------------------
+# char_decomp = 1: wave-based WENO5 (reconstruct.f90:393-565, flux1.f90:95-105), 1-D
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("rp", ["acoustics", "advection", "shallow", "burgers", "euler1d", "elastic_fwave"])
+@pytest.mark.parametrize("mx", [9, 130, 1001])
+def test_sharpclaw_wave_based_weno_dq1(rp, mx):
+    mbc = 3
+    dx, dt = 1.0 / mx, 0.1 / mx
+    aux, maux = None, 0
+    variant = _lib.RECON_WENO_WAVE
+    rng = np.random.RandomState(mx)
+    if rp == "acoustics":
+        rp_id, params, meqn, mwaves = 1, [1.0, 1.0, 1.0, 1.0], 2, 2
+        q = _random_padded(rp, mx, 0, mbc, seed=mx, smooth=True)
+    elif rp == "advection":
+        rp_id, params, meqn, mwaves = 2, [0.7, -0.4], 1, 1
+        q = _random_padded(rp, mx, 0, mbc, seed=mx, smooth=True)
+        q[:, mx // 2:mx // 2 + 9] = q[:, mx // 2:mx // 2 + 1]    # a flat patch: wnorm2 <= 1e-14 branch
+    elif rp == "shallow":
+        rp_id, params, meqn, mwaves = 4, [1.0], 2, 2
+        q = _shallow1d_data(mx, mbc, mx, True)
+    elif rp == "burgers":
+        rp_id, params, meqn, mwaves = po.RP_BURGERS, [], 1, 1
+        q = _random_padded("advection", mx, 0, mbc, seed=mx, smooth=True) - 0.4
+    elif rp == "euler1d":
+        rp_id, params, meqn, mwaves = po.RP_EULER1D, [1.4, 0.4], 3, 3
+        q = _euler1d_data(mx + 2 * mbc, mx, True)
+    else:  # the stegoton's f-wave solver with the linear stress law: weno5_fwave
+        rp_id, params, meqn, mwaves = po.RP_NEL_FWAVE, [1.0], 2, 2
+        variant = _lib.RECON_WENO_FWAVE
+        q = np.asfortranarray(0.1 * _random_padded("acoustics", mx, 0, mbc, seed=mx, smooth=True))
+        aux, maux = np.asfortranarray(np.stack([rng.uniform(1.0, 4.0, mx + 2 * mbc), rng.uniform(1.0, 4.0, mx + 2 * mbc),
+                                                np.zeros(mx + 2 * mbc)])), 3
+    method = [1, 2, 0, 0, 0, 0, maux]
+    P = _lib.make_problem(1, meqn, mwaves, mbc, mx, 1, dx, 1.0, rp_id, params, method=method, maux=maux,
+                          weno_variant=variant)
+    dq_o, cfl_o = po.sc_flux1(rp_id, params, mwaves, mbc, mx, q, dx, dt, variant, auxbc=aux)
+    dq_g = np.zeros_like(q, order="F")
+    cfl_g = ctypes.c_double()
+    _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(dq_g),
+              _ptr(aux) if aux is not None else None, dt, ctypes.byref(cfl_g))
+    assert np.isfinite(dq_o[:, mbc:-mbc]).all()
+    assert np.array_equal(dq_g[:, mbc:-mbc], dq_o[:, mbc:-mbc]), np.abs(dq_g - dq_o)[:, mbc:-mbc].max()
+    assert cfl_g.value == cfl_o
+
+
+def test_sharpclaw_wave_based_weno_is_1d_only():
+    P = _lib.make_problem(2, 3, 2, 3, 16, 16, 0.1, 0.1, 1, [1.0, 4.0, 2.0, 2.0], weno_variant=_lib.RECON_WENO_WAVE)
+    q = np.zeros((3, 22, 22), order="F")
+    with pytest.raises(_lib.ClawB200Error, match="1-D only"):
+        _lib.call("clawb200_sharpclaw_dq_host", ctypes.byref(P), _ptr(q), _ptr(q.copy("F")), None, 0.01,
+                  ctypes.byref(ctypes.c_double()))
