@@ -655,4 +655,4 @@ def test_acoustics1d_sharpclaw_wave_based_vs_oracle(ti):
     s.dt_initial = pb["dt_initial"]
     frames = s.run(pb["q"], None, pb["d"], pb["tfinal"], pb["nout"])
     assert np.array_equal(np.asarray(claw.frames[-1].q), frames[-1])
-    assert err < 2e-3
+    assert err < 4e-4   # component-wise WENO5 gives 2.99e-4 on this problem, the wave-based form 2.82e-4
