@@ -225,9 +225,12 @@ class ClawSolver2D(ClawSolver):
             self._ev0, self._ev1, self._evx = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         _lib.call("clawb200_cfl_reset", cfl, _stream())
         self._ev0.record(cur)
-        # main stream: x-direction boundary conditions of the rows this rank already has
+        # main stream: x-direction boundary conditions of the rows this rank already has, then the
+        # interior sweeps -- enqueued BEFORE the side stream's ~30 small operations, so that the
+        # GPU is not idle while the host is busy issuing them
         self.apply_q_bcs(state, exchange=False, dims=[0])
         self._evx.record(cur)
+        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1 + mbc, my - mbc, cfl, _stream())
         with torch.cuda.stream(self._hstream):
             self._hstream.wait_event(self._ev0)
             part.exchange(F, F.ncomp, periodic=[b == BC.periodic for b in self.bc_lower],
@@ -240,7 +243,6 @@ class ClawSolver2D(ClawSolver):
             _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1, mbc, cfl, st)
             _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, my - mbc + 1, my, cfl, st)
             self._ev1.record(self._hstream)
-        _lib.call("clawb200_step2_rows", P, _ptr(qold), _ptr(qnew), aux, dt, 1 + mbc, my - mbc, cfl, _stream())
         cur.wait_event(self._ev1)
         state._commit(qnew)
         self.cfl.update_global_max(self._read_cfl()[0])
