@@ -230,20 +230,22 @@ int clawb200_halo_unpack(const clawb200_problem *p, double *q, int narr, int row
  * The reference's plugin contract for a Riemann solver (doc/rp.rst:7-62, src/pyclaw/clawpack.py:349
  * `wave,s,amdq,apdq = self.rp(q_l,q_r,aux_l,aux_r,aux_global)`; Fortran rpn2 / rpt2,
  * src/fortran/2d/classic/flux2.f:99-100,167-168,180-181) on arrays of n interfaces, evaluated by
- * the very device functions that are inlined into the sweeps.  Solvers without aux data only.
- * Structure of arrays: ql[m][n], qr[m][n] (left / right state of each interface),
+ * the very device functions that are inlined into the sweeps.
+ * Structure of arrays: ql[m][n], qr[m][n] (left / right state of each interface), auxl[ma][n],
+ * auxr[ma][n] (aux of the cell on either side; NULL for solvers that read none),
  * wave[m*mwaves+mw][n], s[mw][n], amdq[m][n], apdq[m][n].  ixy = 1 | 2 (ignored in 1-D).
  * clawb200_rp_transverse: rpt2 with the Roe data of the interface (ql, qr); imp = 1 splits asdq
  * moving into the left cell, imp = 2 into the right cell. */
 int clawb200_rp_solve(const clawb200_problem *p, int ixy, long long n, const double *ql,
-                      const double *qr, double *wave, double *s, double *amdq, double *apdq,
-                      void *stream);
+                      const double *qr, const double *auxl, const double *auxr, double *wave, double *s,
+                      double *amdq, double *apdq, void *stream);
 int clawb200_rp_transverse(const clawb200_problem *p, int ixy, long long n, const double *ql,
                            const double *qr, int imp, const double *asdq, double *bmasdq,
                            double *bpasdq, void *stream);
 /* the same on HOST arrays */
 int clawb200_rp_solve_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
-                           const double *qr, double *wave, double *s, double *amdq, double *apdq);
+                           const double *qr, const double *auxl, const double *auxr, double *wave,
+                           double *s, double *amdq, double *apdq);
 int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
                                 const double *qr, int imp, const double *asdq, double *bmasdq,
                                 double *bpasdq);
@@ -253,6 +255,13 @@ int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, long long n,
  * only qold is uploaded, qnew receives the result (untouched cells = qold).  Large 2-D
  * problems are processed as a pipeline of row slabs so that the upload of one slab, the
  * sweeps of the previous one and the download of the one before overlap. */
+
+/* The *_host entry points keep device scratch (staging buffers, three streams, events) per
+ * calling thread between calls -- the f2py modules' module-level work arrays, which the
+ * reference frees with dealloc_workspace at teardown (sharpclaw.py:328-340).  This frees it;
+ * the device entry points hold no state at all (q, aux, WENO tables, the CFL word and the
+ * stream are the caller's). */
+int clawb200_release_host_scratch(void);
 
 /* (q, cfl) = classic1.step1(mbc, mx, qbc, auxbc, dx, dt, method, mthlim); q updated in place */
 int clawb200_step1_host(const clawb200_problem *p, double *q, const double *aux, double dt,

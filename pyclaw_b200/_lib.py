@@ -115,9 +115,10 @@ SIGNATURES = {
     "clawb200_step3ds": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dp, _vp],
     "clawb200_bc_fill3": [_pp, _i, _dp, _i, _i, _i, _i, _i, _vp],
     "clawb200_step3ds_host": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dref],
-    "clawb200_rp_solve": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp, _vp],
+    "clawb200_release_host_scratch": [],
+    "clawb200_rp_solve": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp],
     "clawb200_rp_transverse": [_pp, _i, ctypes.c_longlong, _dp, _dp, _i, _dp, _dp, _dp, _vp],
-    "clawb200_rp_solve_host": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp],
+    "clawb200_rp_solve_host": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp],
     "clawb200_rp_transverse_host": [_pp, _i, ctypes.c_longlong, _dp, _dp, _i, _dp, _dp, _dp],
 }
 

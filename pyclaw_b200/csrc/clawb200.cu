@@ -855,6 +855,30 @@ static int host_pipeline(const clawb200_problem *p, const double *qold, double *
     return 0;
 }
 
+// The host entry points keep device scratch (buffers, streams, events) per calling thread and
+// reuse it from call to call; this releases all of it (the next host call allocates afresh).
+extern "C" int clawb200_release_host_scratch(void)
+{
+    HostScratch &h = g_hs;
+    if (h.st) cudaStreamSynchronize(h.st);
+    cudaFree(h.d_aos); cudaFree(h.d_a); cudaFree(h.d_b); cudaFree(h.d_c); cudaFree(h.d_cfl);
+    cudaFree(h.d_aux); cudaFree(h.d_tab);
+    if (h.h_cfl) cudaFreeHost(h.h_cfl);
+    if (h.st) cudaStreamDestroy(h.st);
+    h = HostScratch();
+    SlabPipe &S = g_pipe;
+    if (S.s_in) {
+        cudaStreamSynchronize(S.s_in); cudaStreamSynchronize(S.s_cmp); cudaStreamSynchronize(S.s_out);
+        for (int b = 0; b < SlabPipe::NBUF; b++) {
+            cudaFree(S.d_in_aos[b]); cudaFree(S.d_in[b]); cudaFree(S.d_out[b]); cudaFree(S.d_out_aos[b]);
+            cudaEventDestroy(S.e_in[b]); cudaEventDestroy(S.e_cmp[b]); cudaEventDestroy(S.e_out[b]);
+        }
+        cudaStreamDestroy(S.s_in); cudaStreamDestroy(S.s_cmp); cudaStreamDestroy(S.s_out);
+    }
+    S = SlabPipe();
+    return 0;
+}
+
 extern "C" int clawb200_step1_host(const clawb200_problem *p, double *q, const double *aux,
                                    double dt, double *cfl)
 {
@@ -963,13 +987,14 @@ static int check_rp_point(const clawb200_problem *p, int ixy, long long n)
 }
 
 extern "C" int clawb200_rp_solve(const clawb200_problem *p, int ixy, long long n, const double *ql,
-                                 const double *qr, double *wave, double *s, double *amdq, double *apdq,
-                                 void *stream)
+                                 const double *qr, const double *auxl, const double *auxr, double *wave,
+                                 double *s, double *amdq, double *apdq, void *stream)
 {
     int rc = check_rp_point(p, ixy, n);
     if (rc) return rc;
     if (!ql || !qr || !wave || !s || !amdq || !apdq) return fail(CLAWB200_ERR_INVALID, "null argument");
-    return claw_rp_point(p, ixy, n, ql, qr, wave, s, amdq, apdq, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    return claw_rp_point(p, ixy, n, ql, qr, auxl, auxr, wave, s, amdq, apdq, 0, nullptr, nullptr, nullptr,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int clawb200_rp_transverse(const clawb200_problem *p, int ixy, long long n, const double *ql,
@@ -981,41 +1006,47 @@ extern "C" int clawb200_rp_transverse(const clawb200_problem *p, int ixy, long l
     if (!ql || !qr || !asdq || !bmasdq || !bpasdq) return fail(CLAWB200_ERR_INVALID, "null argument");
     if (imp != 1 && imp != 2) return fail(CLAWB200_ERR_INVALID, "imp must be 1 or 2");
     if (p->ndim != 2) return fail(CLAWB200_ERR_INVALID, "transverse solves exist in 2-D only");
-    return claw_rp_point(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq, bpasdq,
-                         (cudaStream_t)stream);
+    return claw_rp_point(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq,
+                         bpasdq, (cudaStream_t)stream);
 }
 
 static int rp_point_host(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
-                         double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
+                         const double *auxl, const double *auxr, double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
                          double *bm, double *bp)
 {
     int rc = check_rp_point(p, ixy, n);
     if (rc) return rc;
     if (n == 0) return 0;
     const size_t me = (size_t)p->meqn * n, mw = (size_t)p->mwaves * n;
-    // one device block: ql, qr, asdq | wave, s, amdq, apdq, bm, bp
-    const size_t total = 3 * me + me * p->mwaves + mw + 4 * me;
+    const size_t ma = (auxl && auxr && p->maux > 0) ? (size_t)p->maux * n : 0;
+    // one device block: ql, qr, asdq | wave, s, amdq, apdq, bm, bp | auxl, auxr
+    const size_t total = 3 * me + me * p->mwaves + mw + 4 * me + 2 * ma;
     if ((rc = g_hs.ensure(16))) return rc;
     double *d = nullptr;
     CUDA_OK(cudaMalloc(&d, total * sizeof(double)));
     double *d_ql = d, *d_qr = d + me, *d_as = d + 2 * me, *d_w = d + 3 * me, *d_s = d_w + me * p->mwaves,
            *d_am = d_s + mw, *d_ap = d_am + me, *d_bm = d_ap + me, *d_bp = d_bm + me;
+    double *d_al = ma ? d_bp + me : nullptr, *d_ar = ma ? d_bp + me + ma : nullptr;
     cudaStream_t st = g_hs.st;
     auto done = [&](int code) { cudaStreamSynchronize(st); cudaFree(d); return code; };
     cudaError_t e;
     if ((e = cudaMemcpyAsync(d_ql, ql, me * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_qr, qr, me * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess)
         return done(cuda_fail(e, "upload"));
+    if (ma && ((e = cudaMemcpyAsync(d_al, auxl, ma * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+               (e = cudaMemcpyAsync(d_ar, auxr, ma * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess))
+        return done(cuda_fail(e, "upload"));
     if (asdq) {
         if ((e = cudaMemcpyAsync(d_as, asdq, me * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess)
             return done(cuda_fail(e, "upload"));
-        if ((rc = claw_rp_point(p, ixy, n, d_ql, d_qr, nullptr, nullptr, nullptr, nullptr, imp, d_as, d_bm, d_bp, st)))
+        if ((rc = claw_rp_point(p, ixy, n, d_ql, d_qr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, imp, d_as,
+                                d_bm, d_bp, st)))
             return done(rc);
         if ((e = cudaMemcpyAsync(bm, d_bm, me * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
             (e = cudaMemcpyAsync(bp, d_bp, me * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
             return done(cuda_fail(e, "download"));
     } else {
-        if ((rc = claw_rp_point(p, ixy, n, d_ql, d_qr, d_w, d_s, d_am, d_ap, 0, nullptr, nullptr, nullptr, st)))
+        if ((rc = claw_rp_point(p, ixy, n, d_ql, d_qr, d_al, d_ar, d_w, d_s, d_am, d_ap, 0, nullptr, nullptr, nullptr, st)))
             return done(rc);
         if ((e = cudaMemcpyAsync(wave, d_w, me * p->mwaves * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
             (e = cudaMemcpyAsync(s, d_s, mw * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
@@ -1029,10 +1060,11 @@ static int rp_point_host(const clawb200_problem *p, int ixy, long long n, const 
 }
 
 extern "C" int clawb200_rp_solve_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
-                                      const double *qr, double *wave, double *s, double *amdq, double *apdq)
+                                      const double *qr, const double *auxl, const double *auxr, double *wave,
+                                      double *s, double *amdq, double *apdq)
 {
     if (!ql || !qr || !wave || !s || !amdq || !apdq) return fail(CLAWB200_ERR_INVALID, "null argument");
-    return rp_point_host(p, ixy, n, ql, qr, wave, s, amdq, apdq, 0, nullptr, nullptr, nullptr);
+    return rp_point_host(p, ixy, n, ql, qr, auxl, auxr, wave, s, amdq, apdq, 0, nullptr, nullptr, nullptr);
 }
 
 extern "C" int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, long long n, const double *ql,
@@ -1042,7 +1074,7 @@ extern "C" int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, l
     if (!ql || !qr || !asdq || !bmasdq || !bpasdq) return fail(CLAWB200_ERR_INVALID, "null argument");
     if (imp != 1 && imp != 2) return fail(CLAWB200_ERR_INVALID, "imp must be 1 or 2");
     if (p && p->ndim != 2) return fail(CLAWB200_ERR_INVALID, "transverse solves exist in 2-D only");
-    return rp_point_host(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq, bpasdq);
+    return rp_point_host(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq, bpasdq);
 }
 
 // classic3.step3ds with host arrays q(meqn, mx+2mbc, my+2mbc, mz+2mbc) (clawpack.py:656-676)

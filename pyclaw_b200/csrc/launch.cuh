@@ -119,11 +119,11 @@ int claw_y_user(bool trans, const SweepArgs &A, cudaStream_t st);
 int claw_step1_user(const SweepArgs &A, int mx, cudaStream_t st);
 int claw_sc_user(int ndim, bool old, const ScArgs &A, cudaStream_t st);
 int claw_rp_point_user(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
-                       double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
-                       double *bm, double *bp, cudaStream_t st);
+                       const double *auxl, const double *auxr, double *wave, double *s, double *amdq,
+                       double *apdq, int imp, const double *asdq, double *bm, double *bp, cudaStream_t st);
 int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
-                  double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
-                  double *bm, double *bp, cudaStream_t st);
+                  const double *auxl, const double *auxr, double *wave, double *s, double *amdq, double *apdq,
+                  int imp, const double *asdq, double *bm, double *bp, cudaStream_t st);
 int claw_step1(int rp_id, const SweepArgs &A, int mx, cudaStream_t st);
 int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *qa, double *out,
                      double *dq_out, double dt, int mode, double ca, double cb, double div,

@@ -13,7 +13,8 @@
 
 template <class RP>
 __global__ void rp_point_kernel(long long n, RpParams P, const double *__restrict__ ql,
-                                const double *__restrict__ qr, double *__restrict__ wave,
+                                const double *__restrict__ qr, const double *__restrict__ auxl,
+                                const double *__restrict__ auxr, double *__restrict__ wave,
                                 double *__restrict__ s, double *__restrict__ amdq,
                                 double *__restrict__ apdq, int imp, const double *__restrict__ asdq,
                                 double *__restrict__ bm, double *__restrict__ bp)
@@ -25,7 +26,9 @@ __global__ void rp_point_kernel(long long n, RpParams P, const double *__restric
 #pragma unroll
     for (int m = 0; m < MEQN; m++) { l[m] = ql[m * n + i]; r[m] = qr[m * n + i]; }
     const AuxCell nocell{nullptr, 0};
-    with_arith([&](auto &ar) { RP::solve(ar, P, l, r, nocell, nocell, w, sp, am, ap, roe); });
+    // aux_l / aux_r of the reference's contract: [maux][n], the cell on either side of interface i
+    const AuxCell axl = auxl ? AuxCell{auxl + i, n} : nocell, axr = auxr ? AuxCell{auxr + i, n} : nocell;
+    with_arith([&](auto &ar) { RP::solve(ar, P, l, r, axl, axr, w, sp, am, ap, roe); });
     if (wave) {
 #pragma unroll
         for (int m = 0; m < MEQN; m++) {
@@ -48,27 +51,30 @@ __global__ void rp_point_kernel(long long n, RpParams P, const double *__restric
 }
 
 template <class RP>
-static int rp_point_launch(long long n, const RpParams &P, const double *ql, const double *qr, double *wave,
+static int rp_point_launch(long long n, const RpParams &P, const double *ql, const double *qr, const double *auxl,
+                           const double *auxr, double *wave,
                            double *s, double *amdq, double *apdq, int imp, const double *asdq, double *bm,
                            double *bp, cudaStream_t st)
 {
     if (n <= 0) return 0;
-    rp_point_kernel<RP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, P, ql, qr, wave, s, amdq, apdq, imp,
-                                                                    asdq, bm, bp);
+    if (RP::MAUX > 0 && (!auxl || !auxr)) return fail(CLAWB200_ERR_INVALID, "this Riemann solver reads aux_l / aux_r");
+    if (RP::MAUX > 0 && asdq) return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise transverse solves: solvers without aux only");
+    rp_point_kernel<RP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, P, ql, qr, auxl, auxr, wave, s, amdq, apdq,
+                                                                    imp, asdq, bm, bp);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// solvers that read no aux array; ixy = 1 | 2 selects the sweep direction of a 2-D solver
+// ixy = 1 | 2 selects the sweep direction of a 2-D solver; auxl / auxr may be null for solvers without aux
 int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
-                  double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
+                  const double *auxl, const double *auxr, double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
                   double *bm, double *bp, cudaStream_t st)
 {
     if (p->rp_id == CLAWB200_RP_USER)
-        return claw_rp_point_user(p, ixy, n, ql, qr, wave, s, amdq, apdq, imp, asdq, bm, bp, st);
+        return claw_rp_point_user(p, ixy, n, ql, qr, auxl, auxr, wave, s, amdq, apdq, imp, asdq, bm, bp, st);
     RpParams P;
     for (int i = 0; i < 8; i++) P.p[i] = p->rp_params[i];
-#define GO(RPT) return rp_point_launch<RPT>(n, P, ql, qr, wave, s, amdq, apdq, imp, asdq, bm, bp, st)
+#define GO(RPT) return rp_point_launch<RPT>(n, P, ql, qr, auxl, auxr, wave, s, amdq, apdq, imp, asdq, bm, bp, st)
     if (p->ndim == 1) {
         if (asdq) return fail(CLAWB200_ERR_INVALID, "1-D solvers have no transverse solve");
         switch (p->rp_id) {
@@ -77,7 +83,9 @@ int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double 
         case CLAWB200_RP_SHALLOW: GO(RpShallow1D);
         case CLAWB200_RP_BURGERS: GO(RpBurgers);
         case CLAWB200_RP_EULER1D: GO(RpEuler1D);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: solver reads aux or has no 1-D version");
+        case CLAWB200_RP_NEL_FWAVE: { using R = RpElasticFwave<1, 1>; GO(R); }
+        case CLAWB200_RP_ADVECTION_COLOR: { using R = RpColor<1, 1>; GO(R); }
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: no 1-D version of this solver");
         }
     }
     if (ixy == 1) {
@@ -86,7 +94,9 @@ int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double 
         case CLAWB200_RP_ADVECTION: { using R = RpAdvection<2, 1>; GO(R); }
         case CLAWB200_RP_EULER5: GO(RpEuler5<1>);
         case CLAWB200_RP_SHALLOW: GO(RpShallow<1>);
-        default: return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: solver reads aux or has no 2-D version");
+        case CLAWB200_RP_PSYSTEM: { using R = RpElasticFwave<2, 1>; GO(R); }
+        case CLAWB200_RP_VC_ACOUSTICS: GO(RpVcAcoustics<1>);
+        default: return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: not compiled for this solver");
         }
     }
     switch (p->rp_id) {
@@ -94,7 +104,9 @@ int claw_rp_point(const clawb200_problem *p, int ixy, long long n, const double 
     case CLAWB200_RP_ADVECTION: { using R = RpAdvection<2, 2>; GO(R); }
     case CLAWB200_RP_EULER5: GO(RpEuler5<2>);
     case CLAWB200_RP_SHALLOW: GO(RpShallow<2>);
-    default: return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: solver reads aux or has no 2-D version");
+    case CLAWB200_RP_PSYSTEM: { using R = RpElasticFwave<2, 2>; GO(R); }
+    case CLAWB200_RP_VC_ACOUSTICS: GO(RpVcAcoustics<2>);
+    default: return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: not compiled for this solver");
     }
 #undef GO
 }

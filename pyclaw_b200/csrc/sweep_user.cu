@@ -78,7 +78,8 @@ int claw_sc_user(int ndim, bool old, const ScArgs &A, cudaStream_t st)
 
 template <class RP>
 __global__ void rp_user_point_kernel(long long n, RpParams P, const double *__restrict__ ql,
-                                     const double *__restrict__ qr, double *__restrict__ wave,
+                                     const double *__restrict__ qr, const double *__restrict__ auxl,
+                                     const double *__restrict__ auxr, double *__restrict__ wave,
                                      double *__restrict__ s, double *__restrict__ amdq,
                                      double *__restrict__ apdq, int imp, const double *__restrict__ asdq,
                                      double *__restrict__ bm, double *__restrict__ bp)
@@ -89,7 +90,8 @@ __global__ void rp_user_point_kernel(long long n, RpParams P, const double *__re
     double l[MEQN], r[MEQN], w[MEQN][MW], sp[MW], am[MEQN], ap[MEQN], roe[NROE];
     for (int m = 0; m < MEQN; m++) { l[m] = ql[m * n + i]; r[m] = qr[m * n + i]; }
     const AuxCell nocell{nullptr, 0};
-    with_arith([&](auto &ar) { RP::solve(ar, P, l, r, nocell, nocell, w, sp, am, ap, roe); });
+    const AuxCell axl = auxl ? AuxCell{auxl + i, n} : nocell, axr = auxr ? AuxCell{auxr + i, n} : nocell;
+    with_arith([&](auto &ar) { RP::solve(ar, P, l, r, axl, axr, w, sp, am, ap, roe); });
     if (wave) {
         for (int m = 0; m < MEQN; m++) {
             for (int mw = 0; mw < MW; mw++) wave[(m * MW + mw) * n + i] = w[m][mw];
@@ -107,16 +109,17 @@ __global__ void rp_user_point_kernel(long long n, RpParams P, const double *__re
 }
 
 int claw_rp_point_user(const clawb200_problem *p, int ixy, long long n, const double *ql, const double *qr,
-                       double *wave, double *s, double *amdq, double *apdq, int imp, const double *asdq,
-                       double *bm, double *bp, cudaStream_t st)
+                       const double *auxl, const double *auxr, double *wave, double *s, double *amdq,
+                       double *apdq, int imp, const double *asdq, double *bm, double *bp, cudaStream_t st)
 {
-    if (RpUser<1>::MAUX > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise entry: the user solver reads aux");
+    if (RpUser<1>::MAUX > 0 && (!auxl || !auxr)) return fail(CLAWB200_ERR_INVALID, "the user solver reads aux_l / aux_r");
+    if (RpUser<1>::MAUX > 0 && asdq) return fail(CLAWB200_ERR_UNSUPPORTED, "pointwise transverse solves: solvers without aux only");
     if (n <= 0) return 0;
     RpParams P;
     for (int i = 0; i < 8; i++) P.p[i] = p->rp_params[i];
     const unsigned nb = (unsigned)((n + 127) / 128);
-    if (ixy == 2) rp_user_point_kernel<RpUser<2>><<<nb, 128, 0, st>>>(n, P, ql, qr, wave, s, amdq, apdq, imp, asdq, bm, bp);
-    else rp_user_point_kernel<RpUser<1>><<<nb, 128, 0, st>>>(n, P, ql, qr, wave, s, amdq, apdq, imp, asdq, bm, bp);
+    if (ixy == 2) rp_user_point_kernel<RpUser<2>><<<nb, 128, 0, st>>>(n, P, ql, qr, auxl, auxr, wave, s, amdq, apdq, imp, asdq, bm, bp);
+    else rp_user_point_kernel<RpUser<1>><<<nb, 128, 0, st>>>(n, P, ql, qr, auxl, auxr, wave, s, amdq, apdq, imp, asdq, bm, bp);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -131,6 +134,7 @@ int claw_x_user(bool, const SweepArgs &, cudaStream_t) { return none(); }
 int claw_y_user(bool, const SweepArgs &, cudaStream_t) { return none(); }
 int claw_step1_user(const SweepArgs &, int, cudaStream_t) { return none(); }
 int claw_sc_user(int, bool, const ScArgs &, cudaStream_t) { return none(); }
-int claw_rp_point_user(const clawb200_problem *, int, long long, const double *, const double *, double *, double *,
-                       double *, double *, int, const double *, double *, double *, cudaStream_t) { return none(); }
+int claw_rp_point_user(const clawb200_problem *, int, long long, const double *, const double *, const double *,
+                       const double *, double *, double *, double *, double *, int, const double *, double *, double *,
+                       cudaStream_t) { return none(); }
 #endif

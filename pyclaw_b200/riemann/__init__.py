@@ -29,25 +29,27 @@ class RiemannSolver(object):
         ``wave, s, amdq, apdq = rp(q_l, q_r, aux_l, aux_r, aux_global)`` on arrays of interfaces,
         evaluated by the CUDA solver that the sweeps inline.  q_l, q_r: [meqn, n] CUDA tensors
         (left / right state of each interface); returns CUDA tensors wave[meqn, mwaves, n],
-        s[mwaves, n], amdq[meqn, n], apdq[meqn, n].  Solvers without aux data only."""
+        s[mwaves, n], amdq[meqn, n], apdq[meqn, n].  aux_l, aux_r: [maux, n] or None."""
         import ctypes
         import torch
         from .. import _lib
-        if aux_l is not None or aux_r is not None:
-            raise NotImplementedError("pointwise evaluation is built for solvers that read no aux array")
         ndim = 2 if 2 in self.ndims else 1
         q_l = q_l.contiguous().to(torch.float64)
         q_r = q_r.contiguous().to(torch.float64)
         meqn, n = q_l.shape
         mw = self.nwaves(ndim)
-        P = _lib.make_problem(ndim, meqn, mw, 2, 8, 8, 1.0, 1.0, self.rp_id, self.params(aux_global or {}))
+        maux = 0 if aux_l is None else aux_l.shape[0]
+        if aux_l is not None:
+            aux_l, aux_r = aux_l.contiguous().to(torch.float64), aux_r.contiguous().to(torch.float64)
+        P = _lib.make_problem(ndim, meqn, mw, 2, 8, 8, 1.0, 1.0, self.rp_id, self.params(aux_global or {}), maux=maux)
         wave = torch.empty((meqn, mw, n), dtype=torch.float64, device=q_l.device)
         s = torch.empty((mw, n), dtype=torch.float64, device=q_l.device)
         amdq, apdq = torch.empty_like(q_l), torch.empty_like(q_l)
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
         prev = _lib.set_variant(self._variant()) if self.lib else None
         try:
-            _lib.call("clawb200_rp_solve", ctypes.byref(P), ixy, n, ptr(q_l), ptr(q_r), ptr(wave), ptr(s),
+            _lib.call("clawb200_rp_solve", ctypes.byref(P), ixy, n, ptr(q_l), ptr(q_r),
+                      ptr(aux_l) if aux_l is not None else None, ptr(aux_r) if aux_r is not None else None, ptr(wave), ptr(s),
                       ptr(amdq), ptr(apdq), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         finally:
             if prev is not None:
