@@ -571,10 +571,15 @@ def main():
     if args.workload in ("euler", "acoustics", "sphere"):
         scratch.copy_(F.cur)
         auxp = ptr(state._aux.cur) if state._aux is not None else None
-        launches_per_step = 2
         auxb = 16 * 8 if args.workload == "sphere" else 0   # each launch also streams the aux array once
-        for name, part, bytes_per_cell in (("xsweep_kernel<TRANS>", 1, 2 * wl["meqn"] * 8 + auxb),
-                                           ("ysweep_kernel<TRANS>", 2, 3 * wl["meqn"] * 8 + auxb)):
+        launches_per_step = _lib.load().clawb200_step2_launches(P)
+        if launches_per_step == 1:
+            # single-pass kernel (fused.cuh): both sweep families in one walk, q read once, written once
+            parts = (("fused_step2_kernel", 3, 2 * wl["meqn"] * 8 + auxb),)
+        else:
+            parts = (("xsweep_kernel<TRANS>", 1, 2 * wl["meqn"] * 8 + auxb),
+                     ("ysweep_kernel<TRANS>", 2, 3 * wl["meqn"] * 8 + auxb))
+        for name, part, bytes_per_cell in parts:
             for rep in range(2):
                 _lib.call("clawb200_step2_parts", P, ptr(F.cur), ptr(scratch), auxp, float(solver.dt), part,
                           ptr(solver._cfl_dev), stream)

@@ -110,6 +110,13 @@ typedef struct clawb200_problem {
        points, host memory for the *_host entry points.  The library keeps no table state. */
     int weno_k;
     const double *weno_tab;
+    /* Unsplit classic step (clawb200_step2 / _rows / _host) only: which kernels run it.
+       0 = the single-pass kernel (x- and y-sweeps in one walk over q: read once, written once)
+           where one is compiled for the solver, otherwise the two sweep kernels;
+       1 = always the two sweep kernels (one launch per family, qnew re-read by the second);
+       2 = the single-pass kernel or CLAWB200_ERR_UNSUPPORTED.
+       Results are bit-identical in every mode. */
+    int step2_mode;
 } clawb200_problem;
 
 int clawb200_version(void);
@@ -142,6 +149,10 @@ int clawb200_step2(const clawb200_problem *p, const double *qold, double *qnew,
  * in place), 3 both (= clawb200_step2). */
 int clawb200_step2_parts(const clawb200_problem *p, const double *qold, double *qnew,
                          const double *aux, double dt, int parts, double *cfl_dev, void *stream);
+
+/* Number of sweep kernels one clawb200_step2 call launches for this problem: 1 when the
+ * single-pass kernel runs it (problem.step2_mode, solver, capa), otherwise 2; negative on error. */
+int clawb200_step2_launches(const clawb200_problem *p);
 
 /* The same step for output rows jlo..jhi only (1-based interior rows, inclusive).  Lets the
  * caller update the rows that do not depend on a neighbour's halo while the halo exchange is

@@ -44,6 +44,7 @@ class Problem(ctypes.Structure):
         ("dt_dev", ctypes.c_void_p),
         ("weno_k", ctypes.c_int),
         ("weno_tab", ctypes.c_void_p),
+        ("step2_mode", ctypes.c_int),
     ]
 
 
@@ -70,6 +71,7 @@ def make_problem(ndim, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, rp_params, meth
     p.dt_dev = None
     p.weno_k = 0
     p.weno_tab = None
+    p.step2_mode = 0
     return p
 
 
@@ -146,6 +148,8 @@ def load(variant=None):
         L = ctypes.CDLL(path)
         L.clawb200_version.restype = ctypes.c_int
         L.clawb200_weno_table_doubles.restype = ctypes.c_int
+        L.clawb200_step2_launches.restype = ctypes.c_int
+        L.clawb200_step2_launches.argtypes = [_pp]
         L.clawb200_last_error.restype = ctypes.c_char_p
         for name, args in SIGNATURES.items():
             f = getattr(L, name)

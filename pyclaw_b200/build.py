@@ -33,6 +33,7 @@ UNITS = {
     "sweep_euler_y.cu": _COMMON,
     "sweep_sphere.cu": _COMMON,
     "sweep_misc.cu": _COMMON,
+    "sweep_fused.cu": _COMMON + ["fused.cuh"],
     "step1.cu": _COMMON,
     "rp_point.cu": _COMMON,
     "sharpclaw.cu": _COMMON + ["sharpclaw.cuh"],

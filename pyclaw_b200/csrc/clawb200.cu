@@ -313,6 +313,15 @@ static int step2_impl(const clawb200_problem *p, const double *qold, double *qne
     SweepArgs A = make_args(p, qold, qnew, dt, cfl_dev, aux);
     A.ilo = 1; A.ihi = p->mx; A.jlo = jlo; A.jhi = jhi;
     const int nrows = jhi - jlo + 1;
+    // both sweeps in one walk over q where a single-pass kernel exists (fused.cuh): q read once,
+    // written once.  problem.step2_mode = 1 (or CLAWB200_TWO_PASS=1 in the environment, for A/B
+    // measurements) keeps the two sweep kernels.
+    static const bool env_two_pass = [] { const char *e = getenv("CLAWB200_TWO_PASS"); return e && atoi(e) != 0; }();
+    if (p->step2_mode < 0 || p->step2_mode > 2) return fail(CLAWB200_ERR_INVALID, "step2_mode must be 0, 1 or 2");
+    if (parts == 3 && p->step2_mode != 1 && !(env_two_pass && p->step2_mode == 0)) {
+        if (claw_fused_available(p->rp_id, A)) return claw_fused(p->rp_id, A, st);
+        if (p->step2_mode == 2) return fail(CLAWB200_ERR_UNSUPPORTED, "no single-pass kernel for this solver / problem (step2_mode = 2)");
+    }
     if (parts & 1) {
         A.rows_per_cta = pick_rows(nrows, (p->mx + XNT - 4) / (XNT - 3));
         if ((rc = dispatch_x<true>(p->rp_id, A, st))) return rc;
@@ -330,6 +339,17 @@ extern "C" int clawb200_step2_parts(const clawb200_problem *p, const double *qol
 {
     if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
     return step2_impl(p, qold, qnew, aux, dt, parts, 1, p->my, cfl_dev, stream);
+}
+
+extern "C" int clawb200_step2_launches(const clawb200_problem *p)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    int rc = check_problem(p, 2);
+    if (rc) return rc;
+    static const bool env_two_pass = [] { const char *e = getenv("CLAWB200_TWO_PASS"); return e && atoi(e) != 0; }();
+    if (p->step2_mode == 1 || (env_two_pass && p->step2_mode == 0)) return 2;
+    SweepArgs A = make_args(p, nullptr, nullptr, 0.0, nullptr, nullptr);
+    return claw_fused_available(p->rp_id, A) ? 1 : 2;
 }
 
 extern "C" int clawb200_step2_rows(const clawb200_problem *p, const double *qold, double *qnew,

@@ -111,6 +111,9 @@ int claw_x_misc(int rp_id, bool trans, const SweepArgs &A, cudaStream_t st);
 int claw_y_misc(int rp_id, bool trans, const SweepArgs &A, cudaStream_t st);
 int claw_x_ac3d(const SweepArgs &A, cudaStream_t st);           // 3-D acoustics, x-engine (idir = 1)
 int claw_y_ac3d(int idir, const SweepArgs &A, cudaStream_t st); // 3-D acoustics, y-engine (idir = 2, 3)
+// single-pass unsplit step (sweep_fused.cu): solvers without aux / capa whose windows fit in registers
+bool claw_fused_available(int rp_id, const SweepArgs &A);
+int claw_fused(int rp_id, const SweepArgs &A, cudaStream_t st);
 // the user-supplied solver (sweep_user.cu), id CLAWB200_RP_USER
 struct ScArgs;
 int claw_user_shape(int ndim, int *meqn, int *mwaves, int *maux);

@@ -51,6 +51,12 @@ struct rp_y_regs { static constexpr bool value = false; };
 template <class RP>
 struct rp_y_regs<RP, decltype((void)RP::Y_REGS)> { static constexpr bool value = RP::Y_REGS; };
 
+// CTAs per SM the single-pass kernel (fused.cuh) is compiled for; solvers may override F_MINB.
+template <class RP, class = void>
+struct rp_f_minb { static constexpr int value = 3; };
+template <class RP>
+struct rp_f_minb<RP, decltype((void)RP::F_MINB)> { static constexpr int value = RP::F_MINB; };
+
 struct RpParams {
     double p[8];
 };
@@ -418,6 +424,7 @@ struct RpShallow {
 #define CLAW_SW_Y_MINB 3
 #endif
     static constexpr int X_MINB = CLAW_SW_X_MINB, Y_MINB = CLAW_SW_Y_MINB;
+    static constexpr int F_MINB = 2; // single-pass kernel: 3 CTAs/SM (168 registers) spills
     static constexpr int MAUX = 0;
     static constexpr bool QCOR = false;
     static constexpr int MU = (IXY == 2) ? 2 : 1, MV = (IXY == 2) ? 1 : 2;

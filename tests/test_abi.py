@@ -32,7 +32,8 @@ def test_every_declared_symbol_is_exported():
 
 
 def test_ctypes_signatures_cover_the_header():
-    declared = set(_declared_symbols()) - {"clawb200_version", "clawb200_last_error", "clawb200_weno_table_doubles"}
+    declared = set(_declared_symbols()) - {"clawb200_version", "clawb200_last_error", "clawb200_weno_table_doubles",
+                                                "clawb200_step2_launches"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
@@ -43,7 +44,17 @@ def test_problem_struct_matches_header_layout():
     assert P.method.offset == 48 and P.mthlim.offset == 76 and P.rp_id.offset == 108
     assert P.rp_params.offset == 112 and P.mstride.offset == 176 and P.pitch.offset == 184
     assert P.dt_dev.offset == 192 and P.weno_k.offset == 200 and P.weno_tab.offset == 208
-    assert ctypes.sizeof(P) == 216
+    assert P.step2_mode.offset == 216 and ctypes.sizeof(P) == 224
+
+
+def test_step2_launches_reports_the_single_pass_kernel():
+    L = _lib.load()
+    ac = _lib.make_problem(2, 3, 2, 2, 16, 16, 0.1, 0.1, _lib.RP_ACOUSTICS, [1.0, 4.0, 2.0, 2.0], [1, 2, 2, 0, 0, 0, 0], [4, 4])
+    eu = _lib.make_problem(2, 5, 5, 2, 16, 16, 0.1, 0.1, _lib.RP_EULER5, [1.4, 0.4], [1, 2, 2, 0, 0, 0, 0], [4] * 5)
+    assert L.clawb200_step2_launches(ctypes.byref(ac)) == 1
+    assert L.clawb200_step2_launches(ctypes.byref(eu)) == 2
+    ac.step2_mode = 1
+    assert L.clawb200_step2_launches(ctypes.byref(ac)) == 2
 
 
 def test_invalid_arguments_return_errors_without_a_gpu():

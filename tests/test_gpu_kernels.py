@@ -59,7 +59,10 @@ def test_step2ds(rp, shape, order):
 @pytest.mark.parametrize("rp", ["acoustics", "advection", "euler", "shallow"])
 @pytest.mark.parametrize("shape", [(37, 29), (130, 70), (9, 251)])
 @pytest.mark.parametrize("order,trans", [(2, 2), (2, 1), (1, 1), (2, 0)])
-def test_step2_unsplit(rp, shape, order, trans):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_step2_unsplit(rp, shape, order, trans, mode):
+    """mode 0: the single-pass kernel (fused.cuh) for acoustics / advection / shallow water, the
+    two sweep kernels for Euler; mode 1: the two sweep kernels for every solver."""
     rp_id, params, meqn, mwaves, lim = RPS[rp]
     mx, my = shape
     mbc = 2
@@ -67,6 +70,7 @@ def test_step2_unsplit(rp, shape, order, trans):
     method = [1, order, trans, 0, 0, 0, 0]
     q = _random_padded(rp, mx, my, mbc, seed=my + trans)
     P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, dx, dy, rp_id, params, method, lim)
+    P.step2_mode = mode
     qn_o = q.copy("F")
     cfl_o = po.step2(rp_id, params, mbc, mx, my, q, qn_o, None, dx, dy, dt, method, lim)
     qn_g = q.copy("F")
