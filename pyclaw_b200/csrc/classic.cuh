@@ -23,6 +23,16 @@
 //     columns i-1 / i+1) are exchanged through shared memory.
 // The arithmetic order of every cell update is the reference's.
 #pragma once
+// tuning switches (scratch/build_variant.py builds variants with other values)
+#ifndef CLAW_Y_UNROLL
+#define CLAW_Y_UNROLL 1
+#endif
+#ifndef CLAW_F_UNROLL
+#define CLAW_F_UNROLL 1
+#endif
+#ifndef CLAW_Y_PEEL
+#define CLAW_Y_PEEL 1
+#endif
 #include "rp.cuh"
 
 #define CLAW_MAXWAVES 8
@@ -509,14 +519,30 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
     for (int sl = 0; sl < SL::STATE_END; sl++) YS(sl) = (TRANS && sl >= SL::ROE && sl < SL::ROE + NROE) ? 1.0 : 0.0;
 
     int buf = 0;
+    // Row j0-2 only enters as the left state of interface j0-1: with CLAW_Y_PEEL it is loaded
+    // straight into the window and the walk starts at k = j0-1, so that every iteration solves an
+    // interface (the start-up iteration with its zero-filled alternative to the solve -- a register
+    // move per solver output where the two paths merge -- is gone).
+    const int kbeg = CLAW_Y_PEEL ? j0 - 1 : j0 - 2;
+    if (CLAW_Y_PEEL) {
+#pragma unroll
+        for (int m = 0; m < MEQN; m++)
+            qm1[m] = __ldg(&A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl]);
+        if (CAPA) {
+            cap_1 = aux_cell(A, ic, j0 - 2)(A.mcapa - 1);
+            dy_1 = div1(dtdy, cap_1);
+        }
+    }
     // cp.async staging of row k+1 (and, TRANS, of the x-sweep result of row k-1) into
     // thread-private slots, double buffered on the parity of k
 #pragma unroll
     for (int m = 0; m < MEQN; m++)
-        cp_async8(&YQ(SL::QN + m), &A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl]);
+        cp_async8(&YQ(SL::QN + m), &A.qin[m * A.mstride + (long long)A.pitch * (kbeg + mbc - 1) + icl]);
     cp_async_commit();
     int par = 0;
-    for (int k = j0 - 2; k <= j1 + 1; k++) {
+    constexpr int kUnroll = CLAW_Y_UNROLL;
+#pragma unroll kUnroll
+    for (int k = kbeg; k <= j1 + 1; k++) {
         const long long rowoff = (long long)A.pitch * (k + mbc - 1);
         if (RP::MAUX >= 8) { // aux of row k+2, a full iteration before its first use
             const int jp = min(k + 2, A.my + mbc) + mbc - 1;
@@ -553,7 +579,7 @@ __global__ void __launch_bounds__(NT, RP::Y_MINB) ysweep_kernel(const SweepArgs 
             cap_k = aux_cell(A, ic, k)(A.mcapa - 1);
             dy_k = div1(dtdy, cap_k);
         }
-        if (k >= j0 - 1) {
+        if (CLAW_Y_PEEL || k >= j0 - 1) {
             with_arith([&](auto &ar) {
                 RP::solve(ar, A.rp, qm1, qk, AUXRP ? aux_cell(A, ic, k - 1) : nocell,
                           AUXRP ? aux_cell(A, ic, k) : nocell, wave, s, amdq, apdq, roe);

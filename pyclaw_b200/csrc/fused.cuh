@@ -72,7 +72,13 @@ __global__ void __launch_bounds__(NT, rp_f_minb<RPX>::value) fused_step2_kernel(
 #pragma unroll
     for (int n = 0; n < NROE; n++) roe1[n] = 1.0;
 
-    const int rbeg = j0 - 2, rend = j1 + 1;
+    // CLAW_Y_PEEL (classic.cuh): row j0-2 goes straight into the y-window, the walk starts at j0-1
+    const int rbeg = CLAW_Y_PEEL ? j0 - 1 : j0 - 2, rend = j1 + 1;
+    if (CLAW_Y_PEEL) {
+#pragma unroll
+        for (int m = 0; m < MEQN; m++)
+            qm1[m] = __ldg(&A.qin[m * A.mstride + (long long)A.pitch * (j0 - 2 + mbc - 1) + icl]);
+    }
     {
         const long long ro = (long long)A.pitch * (rbeg + mbc - 1);
 #pragma unroll
@@ -83,6 +89,8 @@ __global__ void __launch_bounds__(NT, rp_f_minb<RPX>::value) fused_step2_kernel(
         cp_async_commit();
     }
     int qb = 0, buf = 0;
+    constexpr int kUnroll = CLAW_F_UNROLL;
+#pragma unroll kUnroll
     for (int r = rbeg; r <= rend; r++) {
         const long long rowoff = (long long)A.pitch * (r + mbc - 1);
         cp_async_wait_all();
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(NT, rp_f_minb<RPX>::value) fused_step2_kernel(
         for (int m = 0; m < MEQN; m++) { l[m] = qs[m * QS + t]; qk[m] = qs[m * QS + t + 1]; }
 
         // ================= x-sweep of row r (flux2.f, ixy = 1), slices j0-1 .. j1 =================
-        const bool xrow = (r >= j0 - 1) && (r <= j1);   // block-uniform
+        const bool xrow = (CLAW_Y_PEEL || r >= j0 - 1) && (r <= j1);   // block-uniform
         if (xrow) {
             double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
             with_arith([&](auto &ar) { RPX::solve(ar, A.rp, l, qk, nocell, nocell, wave, s, amdq, apdq, roe); });
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(NT, rp_f_minb<RPX>::value) fused_step2_kernel(
 
         // ================= y-sweep: interface r (rows r-1 | r) of this column ======================
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
-        if (r >= j0 - 1) {
+        if (CLAW_Y_PEEL || r >= j0 - 1) {
             with_arith([&](auto &ar) { RPY::solve(ar, A.rp, qm1, qk, nocell, nocell, wave, s, amdq, apdq, roe); });
             if (ycol_cfl && r >= 1 && r <= A.my + 1) {
 #pragma unroll

@@ -63,6 +63,10 @@ __device__ __forceinline__ double sc_dtd(double dt, double d, double capa)
     return v;
 }
 
+// a product / a sum that nvcc never contracts into an FMA, whatever -fmad says
+__device__ __forceinline__ double xm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xa(double a, double b) { return __dadd_rn(a, b); }
+
 // weno.f90:35-98 for one component of one cell: ql = value at the left edge, qr at the right.
 // The six weights are quotients over three denominators and two normalisations, i.e. five
 // reciprocals for twelve divisions.
@@ -70,12 +74,17 @@ template <class AR>
 __device__ __forceinline__ void weno5_pyweno(AR &ar, const ScArgs &A, double qm2, double qm1, double q0,
                                              double qp1, double qp2, double &ql, double &qr)
 {
-    double sigma0 = ((A.c333) * q0) * q0 + ((-A.c1033) * q0) * qp1 + ((A.c366) * q0) * qp2 +
-                    ((A.c833) * qp1) * qp1 + ((-A.c633) * qp1) * qp2 + ((A.c133) * qp2) * qp2;
-    double sigma1 = ((A.c133) * qm1) * qm1 + ((-A.c433) * qm1) * q0 + ((A.c166) * qm1) * qp1 +
-                    ((A.c433) * q0) * q0 + ((-A.c433) * q0) * qp1 + ((A.c133) * qp1) * qp1;
-    double sigma2 = ((A.c133) * qm2) * qm2 + ((-A.c633) * qm2) * qm1 + ((A.c366) * qm2) * q0 +
-                    ((A.c833) * qm1) * qm1 + ((-A.c1033) * qm1) * q0 + ((A.c333) * q0) * q0;
+    // Smoothness indicators: sums of products that cancel to (nearly) zero wherever q is smooth,
+    // over an eps of 1e-36 -- the non-linear weights are ill-conditioned in their rounding.  They
+    // are therefore evaluated product by product and sum by sum in every build (xm / xa are never
+    // contracted into an FMA): with contraction allowed here the fma build drifts from the strict
+    // one by 1.5e-11 over the shallow-water test run, without it by round-off (profiles/README.md).
+    double sigma0 = xa(xa(xa(xa(xa(xm(xm(A.c333, q0), q0), xm(xm(-A.c1033, q0), qp1)), xm(xm(A.c366, q0), qp2)),
+                             xm(xm(A.c833, qp1), qp1)), xm(xm(-A.c633, qp1), qp2)), xm(xm(A.c133, qp2), qp2));
+    double sigma1 = xa(xa(xa(xa(xa(xm(xm(A.c133, qm1), qm1), xm(xm(-A.c433, qm1), q0)), xm(xm(A.c166, qm1), qp1)),
+                             xm(xm(A.c433, q0), q0)), xm(xm(-A.c433, q0), qp1)), xm(xm(A.c133, qp1), qp1));
+    double sigma2 = xa(xa(xa(xa(xa(xm(xm(A.c133, qm2), qm2), xm(xm(-A.c633, qm2), qm1)), xm(xm(A.c366, qm2), q0)),
+                             xm(xm(A.c833, qm1), qm1)), xm(xm(-A.c1033, qm1), q0)), xm(xm(A.c333, q0), q0));
     const Recip e0 = ar.rcp((sigma0 + A.eps) * (sigma0 + A.eps));
     const Recip e1 = ar.rcp((sigma1 + A.eps) * (sigma1 + A.eps));
     const Recip e2 = ar.rcp((sigma2 + A.eps) * (sigma2 + A.eps));
@@ -671,8 +680,8 @@ __device__ __forceinline__ void weno_tab(AR &ar, const WenoTab &c_weno, const do
         int n = 0;
         for (int a = 0; a < k; a++)
             for (int b = a; b < k; b++) {
-                double tt = ((c_weno.S[r][n]) * row[a - r]) * row[b - r];
-                sg = (n == 0) ? tt : sg + tt;
+                double tt = xm(xm(c_weno.S[r][n], row[a - r]), row[b - r]); // never contracted (see weno5_pyweno)
+                sg = (n == 0) ? tt : xa(sg, tt);
                 n++;
             }
         sigma[r] = sg;

@@ -1,8 +1,7 @@
+set -x
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -q -m gpu 2>&1 | tail -6
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --no-other-workloads > gpurun_out/bench_euler_n2_r2b.json 2> gpurun_out/bench_euler_n2_r2b.err
-python bench.py --steps 20 --warmup 5 --no-cpu --no-other-workloads > gpurun_out/bench_euler_n1_r2b.json 2>/dev/null; python -c "
-import json
-for f in ('gpurun_out/bench_euler_n1_r2b.json','gpurun_out/bench_euler_n2_r2b.json'):
-    d=json.loads(open(f).read().strip().split('\n')[-1]); print(f, d['n_gpus'], '%.4e'%d['value'], d['ms_per_step'], (d.get('partition_parity') or {}).get('ok'), '%.3e'%d['e2e']['value'], d['config']['other_build'])
-"
+B="python bench.py --workload acoustics --steps 2 --warmup 3 --no-cpu --no-e2e --no-other-build"
+$B > gpurun_out/plain_ac7.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:fused_step2 -s 6 -c 1 -o gpurun_out/prof_r02_acoustics4096_fused $B > gpurun_out/ncu_ac7.log 2>&1
+CLAWB200_TWO_PASS=1 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 6 -c 2 -o gpurun_out/prof_r02_acoustics4096_twopass $B > gpurun_out/ncu_ac7b.log 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -3
