@@ -617,14 +617,15 @@ def main():
             tr = prof.get(args.workload, {}).get(dom)
             if tr:  # measured DRAM bytes per cell per launch (ncu), scaled to this launch's cells
                 traffic = tr["bytes_per_cell"] * cells_per_rank
-            if tr and "fp64_inst_per_cell" in tr:
+            ipc = (tr or {}).get("fp64_inst_per_cell", {}).get(args.arithmetic)
+            if ipc:
                 # the resource that actually binds: FP64-pipe instructions the
-                # kernel executes (ncu count, -fmad=false so one instruction = one flop) per second,
+                # kernel executes (ncu count for this arithmetic build, developed field) per second,
                 # against the FP64 issue rate measured on this GPU type by scratch/fp64_peak.cu
-                rate = tr["fp64_inst_per_cell"] * cells_per_rank / (kms * 1e-3)
+                rate = ipc * cells_per_rank / (kms * 1e-3)
                 fp64 = {"achieved": rate / 1e12, "peak": prof["_fp64_peak_inst_per_s"] / 1e12,
                         "unit": "T FP64 inst/s", "frac": rate / prof["_fp64_peak_inst_per_s"],
-                        "inst_per_cell_per_launch": tr["fp64_inst_per_cell"]}
+                        "inst_per_cell_per_launch": ipc}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "kernel_ms": kms, "algorithmic_bytes_per_cell_per_launch": bpc,
