@@ -215,9 +215,18 @@ int clawb200_bc_fill(const clawb200_problem *p, double *q, int narr, int idim, i
  * algorithm, idir = 1, 2, 3.  p->ndim = 3; p->mx, my, dx, dy as usual, the third dimension
  * travels as (mz, dz); the field is q[m][k][j][i] with p->pitch = padded row length and
  * p->mstride >= pitch*(my+2mbc)*(mz+2mbc).  q_out receives qold in cells the sweep does not
- * touch; q_in != q_out.  Unsplit 3-D (step3.f / flux3.f with rpt3, rptt3) is not built. */
+ * touch; q_in != q_out. */
 int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, const double *q_in, double *q_out,
                      const double *aux, double dt, int idir, double *cfl_dev, void *stream);
+/* classic3.step3 (src/fortran/3d/classic/step3.f:2-594 with flux3.f:5-595 and the rpt3 / rptt3
+ * transverse solvers; called at clawpack.py:680-682): the unsplit 3-D step, same layout as
+ * clawb200_step3ds.  p->method[2] = 0, 10, 11, 20, 21 or 22 (flux3.f:42-68; ClawSolver3D.no_trans
+ * = 0, trans_inc = 11, trans_cor = 22).  qold has its ghost cells filled; the interior of qnew is
+ * the result (qnew receives qold elsewhere); qold != qnew.  `scratch` is caller-owned device memory
+ * of clawb200_step3_scratch_doubles(p) doubles (the per-cell flux increments of one sweep family). */
+long long clawb200_step3_scratch_doubles(const clawb200_problem *p);
+int clawb200_step3(const clawb200_problem *p, int mz, double dz, const double *qold, double *qnew,
+                   const double *aux, double dt, double *scratch, double *cfl_dev, void *stream);
 /* qbc_lower / qbc_upper for a 3-D field (idim = 0, 1, 2). */
 int clawb200_bc_fill3(const clawb200_problem *p, int mz, double *q, int narr, int idim, int side,
                       int bctype, int negate, void *stream);
@@ -294,6 +303,10 @@ int clawb200_sharpclaw_dq_host(const clawb200_problem *p, const double *q, doubl
  *                                mthlim, aux1, aux2, aux3, work, idir) */
 int clawb200_step3ds_host(const clawb200_problem *p, int mz, double dz, const double *qold,
                           double *qnew, const double *aux, double dt, int idir, double *cfl);
+/* (qnew, cfl) = classic3.step3(maxm, mbc, mx, my, mz, qold, qnew, auxbc, dx, dy, dz, dt, method, mthlim,
+ *                              aux1, aux2, aux3, work)                      (clawpack.py:680-682) */
+int clawb200_step3_host(const clawb200_problem *p, int mz, double dz, const double *qold,
+                        double *qnew, const double *aux, double dt, double *cfl);
 
 #ifdef __cplusplus
 }

@@ -1510,6 +1510,370 @@ double oracle_step3ds(int rp_id, const double *rp_params, int meqn, int mwaves, 
 }
 
 /* ------------------------------------------------------------------------- */
+/* Unsplit 3-D: step3.f:2-594 with flux3.f:5-595 (method(3) = 0, 10, 11, 20, 21, 22; no capa). */
+/* The transverse solvers are external (clawpack/riemann rpt3_vc_acoustics.f90 and             */
+/* rptt3_vc_acoustics.f90, linked by test/acoustics/3d/Makefile:3; un-vendored, no pinned       */
+/* version): restated from the published algorithm.  The reference's golden for this path is   */
+/* test/pressure_3D.txt (test/test_examples.py:497-514, heterogeneous medium, 30^3).            */
+/* ------------------------------------------------------------------------- */
+/* aux1 / aux2 / aux3 (maux, 1-mbc:maxm+mbc, 3): k = 1..3 */
+#define AUXN3(arr, ma, i, k) arr[(ma) + maux * (IX(i) + n1d * ((k) - 1))]
+/* gadd / hadd (meqn, 2, -1:1, 1-mbc:maxm+mbc): k = 1..2, j = -1..1 */
+#define GH(arr, m, k, j, i) arr[(m) + meqn * (((k) - 1) + 2 * (((j) + 1) + 3 * IX(i)))]
+
+/* rpt3: asdq (a fluctuation of the slice direction ixyz) split in the y-like (icoor = 2) or z-like
+   (icoor = 3) direction.  aux(1) = impedance, aux(2) = sound speed.  auxN(:,:,2) with N = 1,2,3 are
+   the rows below / at / above in the y-like direction, aux2(:,:,k) with k = 1,2,3 the planes
+   below / at / above in the z-like direction. */
+static void rpt3_vc_acoustics(int ixyz, int icoor, int meqn, int mbc, int mx, int maux, int n1d,
+                              const double *aux1, const double *aux2, const double *aux3, int imp,
+                              const double *asdq, double *bmasdq, double *bpasdq)
+{
+    int iuvw = ixyz + icoor - 1;
+    if (iuvw > 3) iuvw = iuvw - 3;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int i1 = (imp == 1) ? i - 1 : i;
+        double zm, zz, zp, cm, cp;
+        if (icoor == 2) {
+            zm = AUXN3(aux1, 0, i1, 2); zz = AUXN3(aux2, 0, i1, 2); zp = AUXN3(aux3, 0, i1, 2);
+            cm = AUXN3(aux1, 1, i1, 2); cp = AUXN3(aux3, 1, i1, 2);
+        } else {
+            zm = AUXN3(aux2, 0, i1, 1); zz = AUXN3(aux2, 0, i1, 2); zp = AUXN3(aux2, 0, i1, 3);
+            cm = AUXN3(aux2, 1, i1, 1); cp = AUXN3(aux2, 1, i1, 3);
+        }
+        double a1 = (-Q2(asdq, 0, i) + Q2(asdq, iuvw, i) * zz) / (zm + zz);
+        double a2 = (Q2(asdq, 0, i) + Q2(asdq, iuvw, i) * zz) / (zz + zp);
+        for (int m = 0; m < meqn; m++) { Q2(bmasdq, m, i) = 0.0; Q2(bpasdq, m, i) = 0.0; }
+        Q2(bmasdq, 0, i) = cm * a1 * zm;
+        Q2(bpasdq, 0, i) = cp * a2 * zp;
+        Q2(bmasdq, iuvw, i) = -cm * a1;
+        Q2(bpasdq, iuvw, i) = cp * a2;
+    }
+}
+
+/* rptt3: bsasdq (already split once, in the OTHER transverse direction; impt = 1 / 2: its down- /
+   up-going part) split in direction icoor.  The material of the row (or plane) the first split
+   moved into is used: auxN(:,:,1 or 3) for icoor = 2, aux1 / aux3(:,:,N) for icoor = 3. */
+static void rptt3_vc_acoustics(int ixyz, int icoor, int meqn, int mbc, int mx, int maux, int n1d,
+                               const double *aux1, const double *aux2, const double *aux3, int imp,
+                               int impt, const double *bsasdq, double *cmbsasdq, double *cpbsasdq)
+{
+    int iuvw = ixyz + icoor - 1;
+    if (iuvw > 3) iuvw = iuvw - 3;
+    for (int i = 2 - mbc; i <= mx + mbc; i++) {
+        int i1 = (imp == 1) ? i - 1 : i;
+        double zm, zz, zp, cm, cp;
+        if (icoor == 2) {
+            const int k = (impt == 1) ? 1 : 3;
+            zm = AUXN3(aux1, 0, i1, k); zz = AUXN3(aux2, 0, i1, k); zp = AUXN3(aux3, 0, i1, k);
+            cm = AUXN3(aux1, 1, i1, k); cp = AUXN3(aux3, 1, i1, k);
+        } else {
+            const double *ax = (impt == 1) ? aux1 : aux3;
+            zm = AUXN3(ax, 0, i1, 1); zz = AUXN3(ax, 0, i1, 2); zp = AUXN3(ax, 0, i1, 3);
+            cm = AUXN3(ax, 1, i1, 1); cp = AUXN3(ax, 1, i1, 3);
+        }
+        double a1 = (-Q2(bsasdq, 0, i) + Q2(bsasdq, iuvw, i) * zz) / (zm + zz);
+        double a2 = (Q2(bsasdq, 0, i) + Q2(bsasdq, iuvw, i) * zz) / (zz + zp);
+        for (int m = 0; m < meqn; m++) { Q2(cmbsasdq, m, i) = 0.0; Q2(cpbsasdq, m, i) = 0.0; }
+        Q2(cmbsasdq, 0, i) = cm * a1 * zm;
+        Q2(cpbsasdq, 0, i) = cp * a2 * zp;
+        Q2(cmbsasdq, iuvw, i) = -cm * a1;
+        Q2(cpbsasdq, iuvw, i) = cp * a2;
+    }
+}
+
+typedef struct {
+    int n1d;
+    double *q1d, *dtdx1d, *aux1, *aux2, *aux3, *qadd, *fadd, *gadd, *hadd, *wave, *s;
+    double *v[30]; /* amdq, apdq, cqxx and the 27 transverse arrays of flux3.f:5-14 */
+} work3;
+
+static void work3_alloc(work3 *w, int n, int meqn, int mwaves, int maux)
+{
+    const size_t nm = (size_t)n * meqn;
+    w->n1d = n;
+    w->q1d = (double *)calloc(nm, sizeof(double));
+    w->dtdx1d = (double *)calloc(n, sizeof(double));
+    w->aux1 = (double *)calloc((size_t)n * (maux > 0 ? maux : 1) * 3, sizeof(double));
+    w->aux2 = (double *)calloc((size_t)n * (maux > 0 ? maux : 1) * 3, sizeof(double));
+    w->aux3 = (double *)calloc((size_t)n * (maux > 0 ? maux : 1) * 3, sizeof(double));
+    w->qadd = (double *)calloc(nm, sizeof(double));
+    w->fadd = (double *)calloc(nm, sizeof(double));
+    w->gadd = (double *)calloc(nm * 6, sizeof(double));
+    w->hadd = (double *)calloc(nm * 6, sizeof(double));
+    w->wave = (double *)calloc(nm * mwaves, sizeof(double));
+    w->s = (double *)calloc((size_t)n * mwaves, sizeof(double));
+    for (int a = 0; a < 30; a++) w->v[a] = (double *)calloc(nm, sizeof(double));
+}
+static void work3_free(work3 *w)
+{
+    free(w->q1d); free(w->dtdx1d); free(w->aux1); free(w->aux2); free(w->aux3); free(w->qadd);
+    free(w->fadd); free(w->gadd); free(w->hadd); free(w->wave); free(w->s);
+    for (int a = 0; a < 30; a++) free(w->v[a]);
+}
+
+/* flux3.f:5-595 */
+static double flux3(rp_ctx *c, int ixyz, int meqn, int mwaves, int mbc, int mx, int maux,
+                    double dtdy, double dtdz, const int *method, const int *mthlim, work3 *w)
+{
+    const int n1d = w->n1d;
+    const double *q1d = w->q1d, *dtdx1d = w->dtdx1d, *aux1 = w->aux1, *aux2 = w->aux2, *aux3 = w->aux3;
+    double *qadd = w->qadd, *fadd = w->fadd, *gadd = w->gadd, *hadd = w->hadd, *wave = w->wave, *s = w->s;
+    double *amdq = w->v[0], *apdq = w->v[1], *cqxx = w->v[2];
+    double *bmamdq = w->v[3], *bmapdq = w->v[4], *bpamdq = w->v[5], *bpapdq = w->v[6];
+    double *cmamdq = w->v[7], *cmapdq = w->v[8], *cpamdq = w->v[9], *cpapdq = w->v[10];
+    double *cmamdq2 = w->v[11], *cmapdq2 = w->v[12], *cpamdq2 = w->v[13], *cpapdq2 = w->v[14];
+    double *bmcqxxp = w->v[15], *bpcqxxp = w->v[16], *bmcqxxm = w->v[17], *bpcqxxm = w->v[18];
+    double *cmcqxxp = w->v[19], *cpcqxxp = w->v[20], *cmcqxxm = w->v[21], *cpcqxxm = w->v[22];
+    double *bmcmamdq = w->v[23], *bmcmapdq = w->v[24], *bpcmamdq = w->v[25], *bpcmapdq = w->v[26];
+    double *bmcpamdq = w->v[27], *bmcpapdq = w->v[28], *bpcpamdq = w->v[29];
+    /* flux3.f keeps 32 arrays; bpcpapdq shares nothing, take it from the spare wave-sized block */
+    static __thread double *bpcpapdq_buf = NULL;
+    static __thread size_t bpcpapdq_n = 0;
+    if (bpcpapdq_n < (size_t)n1d * meqn) {
+        free(bpcpapdq_buf);
+        bpcpapdq_n = (size_t)n1d * meqn;
+        bpcpapdq_buf = (double *)calloc(bpcpapdq_n, sizeof(double));
+    }
+    double *bpcpapdq = bpcpapdq_buf;
+
+    int limit = 0;
+    for (int mw = 0; mw < mwaves; mw++) if (mthlim[mw] > 0) limit = 1;
+    for (int i = 1 - mbc; i <= mx + mbc; i++)
+        for (int m = 0; m < meqn; m++) {
+            Q2(qadd, m, i) = 0.0; Q2(fadd, m, i) = 0.0;
+            for (int k = 1; k <= 2; k++)
+                for (int j = -1; j <= 1; j++) { GH(gadd, m, k, j, i) = 0.0; GH(hadd, m, k, j, i) = 0.0; }
+        }
+    int m3, m4;
+    if (method[2] < 0) { m3 = -1; m4 = 0; }
+    else { m3 = method[2] / 10; m4 = method[2] - 10 * m3; }
+
+    /* :194-196  aux2(1,1-mbc,2) is the 1-d aux array rpn3 sees */
+    const double *auxn = aux2 + (size_t)maux * n1d; /* plane k = 2 */
+    rpn(c, ixyz, meqn, mwaves, mbc, mx, q1d, q1d, auxn, auxn, wave, s, amdq, apdq);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++) Q2(qadd, m, i) = Q2(qadd, m, i) - dtdx1d[IX(i)] * Q2(apdq, m, i);
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++)
+            Q2(qadd, m, i - 1) = Q2(qadd, m, i - 1) - dtdx1d[IX(i - 1)] * Q2(amdq, m, i);
+    double cfl1d = 0.0;
+    for (int i = 1; i <= mx + 1; i++)
+        for (int mw = 0; mw < mwaves; mw++)
+            cfl1d = dmax2(dmax2(cfl1d, dtdx1d[IX(i)] * SP(mw, i)), -dtdx1d[IX(i - 1)] * SP(mw, i));
+    if (method[1] != 1) {
+        if (limit) limiter(mx, meqn, mwaves, mbc, mx, wave, s, mthlim);
+        for (int i = 2 - mbc; i <= mx + mbc; i++) {
+            double dtdxave = 0.5 * (dtdx1d[IX(i - 1)] + dtdx1d[IX(i)]);
+            for (int m = 0; m < meqn; m++) Q2(cqxx, m, i) = 0.0;
+            for (int mw = 0; mw < mwaves; mw++)
+                for (int m = 0; m < meqn; m++)
+                    Q2(cqxx, m, i) = Q2(cqxx, m, i) + 0.5 * fabs(SP(mw, i)) *
+                                     (1.0 - fabs(SP(mw, i)) * dtdxave) * WV(m, mw, i);
+            for (int m = 0; m < meqn; m++) Q2(fadd, m, i) = Q2(fadd, m, i) + Q2(cqxx, m, i);
+        }
+    }
+    if (m3 <= 0) return cfl1d;
+
+#define RPT3(icoor, imp, as, bm, bp) rpt3_vc_acoustics(ixyz, icoor, meqn, mbc, mx, maux, n1d, aux1, aux2, aux3, imp, as, bm, bp)
+#define RPTT3(icoor, imp, impt, bs, cm, cp) rptt3_vc_acoustics(ixyz, icoor, meqn, mbc, mx, maux, n1d, aux1, aux2, aux3, imp, impt, bs, cm, cp)
+    RPT3(2, 1, amdq, bmamdq, bpamdq);
+    RPT3(2, 2, apdq, bmapdq, bpapdq);
+    RPT3(3, 1, amdq, cmamdq, cpamdq);
+    RPT3(3, 2, apdq, cmapdq, cpapdq);
+    if (m3 == 2) { /* maux > 0 here: cqxx is split with imp = 1 and imp = 2 (flux3.f:262-283) */
+        RPT3(2, 1, cqxx, bmcqxxm, bpcqxxm);
+        RPT3(2, 2, cqxx, bmcqxxp, bpcqxxp);
+        RPT3(3, 1, cqxx, cmcqxxm, cpcqxxm);
+        RPT3(3, 2, cqxx, cmcqxxp, cpcqxxp);
+    }
+    /* ---- G fluxes (y-like direction) ---- */
+    if (m4 == 1) {
+        for (int i = 0; i <= mx + 2; i++)
+            for (int m = 0; m < meqn; m++) {
+                Q2(cpapdq2, m, i) = Q2(cpapdq, m, i); Q2(cpamdq2, m, i) = Q2(cpamdq, m, i);
+                Q2(cmapdq2, m, i) = Q2(cmapdq, m, i); Q2(cmamdq2, m, i) = Q2(cmamdq, m, i);
+            }
+    } else if (m4 == 2) {
+        for (int i = 0; i <= mx + 2; i++)
+            for (int m = 0; m < meqn; m++) {
+                Q2(cpapdq2, m, i) = Q2(cpapdq, m, i) - 3.0 * Q2(cpcqxxp, m, i);
+                Q2(cpamdq2, m, i) = Q2(cpamdq, m, i) + 3.0 * Q2(cpcqxxm, m, i);
+                Q2(cmapdq2, m, i) = Q2(cmapdq, m, i) - 3.0 * Q2(cmcqxxp, m, i);
+                Q2(cmamdq2, m, i) = Q2(cmamdq, m, i) + 3.0 * Q2(cmcqxxm, m, i);
+            }
+    }
+    if (m4 > 0) {
+        RPTT3(2, 2, 2, cpapdq2, bmcpapdq, bpcpapdq);
+        RPTT3(2, 1, 2, cpamdq2, bmcpamdq, bpcpamdq);
+        RPTT3(2, 2, 1, cmapdq2, bmcmapdq, bpcmapdq);
+        RPTT3(2, 1, 1, cmamdq2, bmcmamdq, bpcmamdq);
+    }
+    const double sixth = 1.0 / 6.0;
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++) {
+            const double dl = dtdx1d[IX(i - 1)], dr = dtdx1d[IX(i)];
+            GH(gadd, m, 1, 0, i - 1) = GH(gadd, m, 1, 0, i - 1) - 0.5 * dl * Q2(bmamdq, m, i);
+            GH(gadd, m, 2, 0, i - 1) = GH(gadd, m, 2, 0, i - 1) - 0.5 * dl * Q2(bpamdq, m, i);
+            GH(gadd, m, 1, 0, i) = GH(gadd, m, 1, 0, i) - 0.5 * dr * Q2(bmapdq, m, i);
+            GH(gadd, m, 2, 0, i) = GH(gadd, m, 2, 0, i) - 0.5 * dr * Q2(bpapdq, m, i);
+            if (m4 > 0) {
+                GH(gadd, m, 2, 0, i) = GH(gadd, m, 2, 0, i) + sixth * dr * dtdz * (Q2(bpcpapdq, m, i) - Q2(bpcmapdq, m, i));
+                GH(gadd, m, 1, 0, i) = GH(gadd, m, 1, 0, i) + sixth * dr * dtdz * (Q2(bmcpapdq, m, i) - Q2(bmcmapdq, m, i));
+                GH(gadd, m, 2, 1, i) = GH(gadd, m, 2, 1, i) - sixth * dr * dtdz * Q2(bpcpapdq, m, i);
+                GH(gadd, m, 1, 1, i) = GH(gadd, m, 1, 1, i) - sixth * dr * dtdz * Q2(bmcpapdq, m, i);
+                GH(gadd, m, 2, -1, i) = GH(gadd, m, 2, -1, i) + sixth * dr * dtdz * Q2(bpcmapdq, m, i);
+                GH(gadd, m, 1, -1, i) = GH(gadd, m, 1, -1, i) + sixth * dr * dtdz * Q2(bmcmapdq, m, i);
+                GH(gadd, m, 2, 0, i - 1) = GH(gadd, m, 2, 0, i - 1) + sixth * dl * dtdz * (Q2(bpcpamdq, m, i) - Q2(bpcmamdq, m, i));
+                GH(gadd, m, 1, 0, i - 1) = GH(gadd, m, 1, 0, i - 1) + sixth * dl * dtdz * (Q2(bmcpamdq, m, i) - Q2(bmcmamdq, m, i));
+                GH(gadd, m, 2, 1, i - 1) = GH(gadd, m, 2, 1, i - 1) - sixth * dl * dtdz * Q2(bpcpamdq, m, i);
+                GH(gadd, m, 1, 1, i - 1) = GH(gadd, m, 1, 1, i - 1) - sixth * dl * dtdz * Q2(bmcpamdq, m, i);
+                GH(gadd, m, 2, -1, i - 1) = GH(gadd, m, 2, -1, i - 1) + sixth * dl * dtdz * Q2(bpcmamdq, m, i);
+                GH(gadd, m, 1, -1, i - 1) = GH(gadd, m, 1, -1, i - 1) + sixth * dl * dtdz * Q2(bmcmamdq, m, i);
+            }
+            if (m3 >= 2) {
+                GH(gadd, m, 2, 0, i) = GH(gadd, m, 2, 0, i) + dr * Q2(bpcqxxp, m, i);
+                GH(gadd, m, 1, 0, i) = GH(gadd, m, 1, 0, i) + dr * Q2(bmcqxxp, m, i);
+                GH(gadd, m, 2, 0, i - 1) = GH(gadd, m, 2, 0, i - 1) - dl * Q2(bpcqxxm, m, i);
+                GH(gadd, m, 1, 0, i - 1) = GH(gadd, m, 1, 0, i - 1) - dl * Q2(bmcqxxm, m, i);
+            }
+        }
+    /* ---- H fluxes (z-like direction) ---- */
+    if (m4 == 2) {
+        for (int i = 0; i <= mx + 2; i++)
+            for (int m = 0; m < meqn; m++) {
+                Q2(bpapdq, m, i) = Q2(bpapdq, m, i) - 3.0 * Q2(bpcqxxp, m, i);
+                Q2(bpamdq, m, i) = Q2(bpamdq, m, i) + 3.0 * Q2(bpcqxxm, m, i);
+                Q2(bmapdq, m, i) = Q2(bmapdq, m, i) - 3.0 * Q2(bmcqxxp, m, i);
+                Q2(bmamdq, m, i) = Q2(bmamdq, m, i) + 3.0 * Q2(bmcqxxm, m, i);
+            }
+    }
+    if (m4 > 0) {
+        RPTT3(3, 2, 2, bpapdq, bmcpapdq, bpcpapdq);
+        RPTT3(3, 1, 2, bpamdq, bmcpamdq, bpcpamdq);
+        RPTT3(3, 2, 1, bmapdq, bmcmapdq, bpcmapdq);
+        RPTT3(3, 1, 1, bmamdq, bmcmamdq, bpcmamdq);
+    }
+    for (int i = 1; i <= mx + 1; i++)
+        for (int m = 0; m < meqn; m++) {
+            const double dl = dtdx1d[IX(i - 1)], dr = dtdx1d[IX(i)];
+            GH(hadd, m, 1, 0, i - 1) = GH(hadd, m, 1, 0, i - 1) - 0.5 * dl * Q2(cmamdq, m, i);
+            GH(hadd, m, 2, 0, i - 1) = GH(hadd, m, 2, 0, i - 1) - 0.5 * dl * Q2(cpamdq, m, i);
+            GH(hadd, m, 1, 0, i) = GH(hadd, m, 1, 0, i) - 0.5 * dr * Q2(cmapdq, m, i);
+            GH(hadd, m, 2, 0, i) = GH(hadd, m, 2, 0, i) - 0.5 * dr * Q2(cpapdq, m, i);
+            if (m4 > 0) {
+                GH(hadd, m, 2, 0, i) = GH(hadd, m, 2, 0, i) + sixth * dr * dtdy * (Q2(bpcpapdq, m, i) - Q2(bpcmapdq, m, i));
+                GH(hadd, m, 1, 0, i) = GH(hadd, m, 1, 0, i) + sixth * dr * dtdy * (Q2(bmcpapdq, m, i) - Q2(bmcmapdq, m, i));
+                GH(hadd, m, 2, 1, i) = GH(hadd, m, 2, 1, i) - sixth * dr * dtdy * Q2(bpcpapdq, m, i);
+                GH(hadd, m, 1, 1, i) = GH(hadd, m, 1, 1, i) - sixth * dr * dtdy * Q2(bmcpapdq, m, i);
+                GH(hadd, m, 2, -1, i) = GH(hadd, m, 2, -1, i) + sixth * dr * dtdy * Q2(bpcmapdq, m, i);
+                GH(hadd, m, 1, -1, i) = GH(hadd, m, 1, -1, i) + sixth * dr * dtdy * Q2(bmcmapdq, m, i);
+                GH(hadd, m, 2, 0, i - 1) = GH(hadd, m, 2, 0, i - 1) + sixth * dl * dtdy * (Q2(bpcpamdq, m, i) - Q2(bpcmamdq, m, i));
+                GH(hadd, m, 1, 0, i - 1) = GH(hadd, m, 1, 0, i - 1) + sixth * dl * dtdy * (Q2(bmcpamdq, m, i) - Q2(bmcmamdq, m, i));
+                GH(hadd, m, 2, 1, i - 1) = GH(hadd, m, 2, 1, i - 1) - sixth * dl * dtdy * Q2(bpcpamdq, m, i);
+                GH(hadd, m, 1, 1, i - 1) = GH(hadd, m, 1, 1, i - 1) - sixth * dl * dtdy * Q2(bmcpamdq, m, i);
+                GH(hadd, m, 2, -1, i - 1) = GH(hadd, m, 2, -1, i - 1) + sixth * dl * dtdy * Q2(bpcmamdq, m, i);
+                GH(hadd, m, 1, -1, i - 1) = GH(hadd, m, 1, -1, i - 1) + sixth * dl * dtdy * Q2(bmcmamdq, m, i);
+            }
+            if (m3 >= 2) {
+                GH(hadd, m, 2, 0, i) = GH(hadd, m, 2, 0, i) + dr * Q2(cpcqxxp, m, i);
+                GH(hadd, m, 1, 0, i) = GH(hadd, m, 1, 0, i) + dr * Q2(cmcqxxp, m, i);
+                GH(hadd, m, 2, 0, i - 1) = GH(hadd, m, 2, 0, i - 1) - dl * Q2(cpcqxxm, m, i);
+                GH(hadd, m, 1, 0, i - 1) = GH(hadd, m, 1, 0, i - 1) - dl * Q2(cmcqxxm, m, i);
+            }
+        }
+#undef RPT3
+#undef RPTT3
+    return cfl1d;
+}
+
+/* step3.f:2-594.  qnew == qold on entry (clawpack.py:650-651); q(meqn, 1-mbc:mx+mbc, ...). */
+double oracle_step3(int rp_id, const double *rp_params, int meqn, int mwaves, int maux, int mbc,
+                    int mx, int my, int mz, const double *qold, double *qnew, const double *aux,
+                    double dx, double dy, double dz, double dt, const int *method, const int *mthlim)
+{
+    if (rp_id != RP_ACOUSTICS3D_VC || method[5] > 0 || maux < 2) return -1.0;
+    int maxm = mx > my ? mx : my;
+    if (mz > maxm) maxm = mz;
+    const int n1d = maxm + 2 * mbc;
+    rp_ctx c;
+    rp_ctx_init(&c, rp_id, rp_params, n1d);
+    c.ndim = 3; c.maux = maux;
+    work3 w;
+    work3_alloc(&w, n1d, meqn, mwaves, maux);
+    const size_t NXs = mx + 2 * mbc, NYs = my + 2 * mbc;
+#define Q4(arr, m, i, j, k) arr[(m) + (size_t)meqn * (((i) + mbc - 1) + NXs * (((j) + mbc - 1) + NYs * ((k) + mbc - 1)))]
+#define AUX4(ma, i, j, k) aux[(ma) + (size_t)maux * (((i) + mbc - 1) + NXs * (((j) + mbc - 1) + NYs * ((k) + mbc - 1)))]
+    const double dtd[3] = {dt / dx, dt / dy, dt / dz};
+    const int len[3] = {mx, my, mz};
+    double cfl = 0.0;
+    double *qadd = w.qadd, *fadd = w.fadd, *gadd = w.gadd, *hadd = w.hadd;
+    for (int d = 0; d < 3; d++) {
+        const int e = (d + 1) % 3, f = (d + 2) % 3; /* y-like, z-like directions of this sweep */
+        const int o1 = (d == 0) ? 1 : 0;            /* the two other directions: lower one is the inner loop */
+        const int o2 = (d == 2) ? 1 : 2;
+        const double dtde = dtd[e], dtdf = dtd[f];
+        int idx[3];
+        for (idx[o2] = 0; idx[o2] <= len[o2] + 1; idx[o2]++)
+            for (idx[o1] = 0; idx[o1] <= len[o1] + 1; idx[o1]++) {
+                for (int l = 1 - mbc; l <= len[d] + mbc; l++) {
+                    idx[d] = l;
+                    for (int m = 0; m < meqn; m++) Q2(w.q1d, m, l) = Q4(qold, m, idx[0], idx[1], idx[2]);
+                    w.dtdx1d[IX(l)] = dtd[d];
+                    /* auxN(ma, l, 2+a): N <-> y-like offset -1, 0, +1 ; a <-> z-like offset */
+                    for (int a = -1; a <= 1; a++) {
+                        int p[3] = {idx[0], idx[1], idx[2]};
+                        p[f] += a;
+                        for (int ma = 0; ma < maux; ma++) {
+                            p[e] = idx[e] - 1; AUXN3(w.aux1, ma, l, 2 + a) = AUX4(ma, p[0], p[1], p[2]);
+                            p[e] = idx[e];     AUXN3(w.aux2, ma, l, 2 + a) = AUX4(ma, p[0], p[1], p[2]);
+                            p[e] = idx[e] + 1; AUXN3(w.aux3, ma, l, 2 + a) = AUX4(ma, p[0], p[1], p[2]);
+                        }
+                    }
+                }
+                double cfl1d = flux3(&c, d + 1, meqn, mwaves, mbc, len[d], maux, dtde, dtdf, method, mthlim, &w);
+                cfl = dmax2(cfl, cfl1d);
+                /* step3.f:185-220 (x), 340-377 (y), 497-534 (z): the same nine statements with the
+                   roles of the directions rotated; (eo, fo) = offset in the y-like / z-like direction */
+                for (int l = 1; l <= len[d]; l++)
+                    for (int m = 0; m < meqn; m++) {
+                        int p[3];
+#define QN(eo, fo) (p[0] = idx[0], p[1] = idx[1], p[2] = idx[2], p[d] = l, p[e] += (eo), p[f] += (fo), &Q4(qnew, m, p[0], p[1], p[2]))
+                        double *t;
+                        t = QN(0, 0);
+                        *t = *t + Q2(qadd, m, l) - dtd[d] * (Q2(fadd, m, l + 1) - Q2(fadd, m, l))
+                             - dtde * (GH(gadd, m, 2, 0, l) - GH(gadd, m, 1, 0, l))
+                             - dtdf * (GH(hadd, m, 2, 0, l) - GH(hadd, m, 1, 0, l));
+                        t = QN(-1, 0);
+                        *t = *t - dtde * GH(gadd, m, 1, 0, l) - dtdf * (GH(hadd, m, 2, -1, l) - GH(hadd, m, 1, -1, l));
+                        t = QN(-1, -1);
+                        *t = *t - dtde * GH(gadd, m, 1, -1, l) - dtdf * GH(hadd, m, 1, -1, l);
+                        t = QN(0, -1);
+                        *t = *t - dtde * (GH(gadd, m, 2, -1, l) - GH(gadd, m, 1, -1, l)) - dtdf * GH(hadd, m, 1, 0, l);
+                        t = QN(1, -1);
+                        *t = *t + dtde * GH(gadd, m, 2, -1, l) - dtdf * GH(hadd, m, 1, 1, l);
+                        t = QN(1, 0);
+                        *t = *t + dtde * GH(gadd, m, 2, 0, l) - dtdf * (GH(hadd, m, 2, 1, l) - GH(hadd, m, 1, 1, l));
+                        t = QN(1, 1);
+                        *t = *t + dtde * GH(gadd, m, 2, 1, l) + dtdf * GH(hadd, m, 2, 1, l);
+                        t = QN(0, 1);
+                        *t = *t - dtde * (GH(gadd, m, 2, 1, l) - GH(gadd, m, 1, 1, l)) + dtdf * GH(hadd, m, 2, 0, l);
+                        t = QN(-1, 1);
+                        *t = *t - dtde * GH(gadd, m, 1, 1, l) + dtdf * GH(hadd, m, 2, -1, l);
+#undef QN
+                    }
+            }
+    }
+#undef Q4
+#undef AUX4
+    work3_free(&w);
+    ctx_free(&c);
+    return cfl;
+}
+#undef AUXN3
+#undef GH
+
+/* ------------------------------------------------------------------------- */
 /* step2.f:2-241 (unsplit, with transverse terms).  qnew == qold on entry.    */
 /* ------------------------------------------------------------------------- */
 double oracle_step2(int rp_id, const double *rp_params, int maxm, int meqn, int mwaves,

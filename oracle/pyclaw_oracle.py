@@ -57,6 +57,8 @@ def lib():
         L.oracle_set_weno_tables.argtypes = [i, _dp, _dp, _dp, _dp, _dp, d]
         L.oracle_step3ds.restype = d
         L.oracle_step3ds.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, d, _ip, _ip, i]
+        L.oracle_step3.restype = d
+        L.oracle_step3.argtypes = [i, _dp, i, i, i, i, i, i, i, _dp, _dp, _dp, d, d, d, d, _ip, _ip]
         L.oracle_sc_flux1.restype = d
         L.oracle_sc_flux1.argtypes = [i, _dp, i, i, i, i, _dp, _dp, d, d, i]
         L.oracle_sc_flux2.restype = d
@@ -169,6 +171,22 @@ def step3ds(rp_id, rp_params, mbc, mx, my, mz, qold, qnew, auxbc, dx, dy, dz, dt
     assert qold.flags["F_CONTIGUOUS"] and qnew.flags["F_CONTIGUOUS"]
     return lib().oracle_step3ds(rp_id, _p(_params(rp_params)), meqn, len(mthlim), maux, mbc, mx, my, mz,
                                 _p(qold), _p(qnew), _p(aux), dx, dy, dz, dt, _pi(method), _pi(mthlim), idir)
+
+
+def step3(rp_id, rp_params, mbc, mx, my, mz, qold, qnew, auxbc, dx, dy, dz, dt, method, mthlim):
+    """classic3.step3 (clawpack.py:680-682; step3.f + flux3.f): the unsplit 3-D step; qnew (== qold
+    on entry) is updated in place.  method[2] = 0 | 10 | 11 | 20 | 21 | 22."""
+    meqn = qold.shape[0]
+    maux = 0 if auxbc is None else auxbc.shape[0]
+    aux = np.zeros(1) if maux == 0 else auxbc
+    method = np.ascontiguousarray(method, dtype=np.int32)
+    mthlim = np.ascontiguousarray(mthlim, dtype=np.int32)
+    assert qold.flags["F_CONTIGUOUS"] and qnew.flags["F_CONTIGUOUS"]
+    cfl = lib().oracle_step3(rp_id, _p(_params(rp_params)), meqn, len(mthlim), maux, mbc, mx, my, mz,
+                             _p(qold), _p(qnew), _p(aux), dx, dy, dz, dt, _pi(method), _pi(mthlim))
+    if cfl < 0:
+        raise ValueError("oracle_step3: unsupported solver / capa")
+    return cfl
 
 
 def step2_slabs(rp_id, rp_params, mbc, mx, my, qold, qnew, auxbc, dx, dy, dt, method, mthlim,
@@ -372,13 +390,16 @@ class OracleSolver(object):
             cfl = step1(self.rp_id, self.rp_params, mbc, self.n[0], self.qbc, self.auxbc,
                         self.d[0], self.dt, self.method, self.mthlim)
         elif self.ndim == 3:
-            # clawpack.py:656-676: three aliased step3ds calls; only dim_split is restated
-            assert self.dim_split
+            # clawpack.py:656-682: three aliased step3ds calls, or one step3 call
             mx, my, mz = self.n
             dx, dy, dz = self.d
             q = self.qbc
             cfl = 0.0
-            for idir in (1, 2, 3):
+            if not self.dim_split:
+                qold = q.copy("F")
+                cfl = step3(self.rp_id, self.rp_params, mbc, mx, my, mz, qold, q, self.auxbc,
+                            dx, dy, dz, self.dt, self.method, self.mthlim)
+            for idir in ((1, 2, 3) if self.dim_split else ()):
                 qold = q.copy("F")
                 cfl = max(cfl, step3ds(self.rp_id, self.rp_params, mbc, mx, my, mz, qold, q, self.auxbc,
                                        dx, dy, dz, self.dt, self.method, self.mthlim, idir))

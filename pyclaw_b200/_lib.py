@@ -117,6 +117,8 @@ SIGNATURES = {
     "clawb200_step3ds": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dp, _vp],
     "clawb200_bc_fill3": [_pp, _i, _dp, _i, _i, _i, _i, _i, _vp],
     "clawb200_step3ds_host": [_pp, _i, _d, _dp, _dp, _dp, _d, _i, _dref],
+    "clawb200_step3": [_pp, _i, _d, _dp, _dp, _dp, _d, _dp, _dp, _vp],
+    "clawb200_step3_host": [_pp, _i, _d, _dp, _dp, _dp, _d, _dref],
     "clawb200_release_host_scratch": [],
     "clawb200_rp_solve": [_pp, _i, ctypes.c_longlong, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp],
     "clawb200_rp_transverse": [_pp, _i, ctypes.c_longlong, _dp, _dp, _i, _dp, _dp, _dp, _vp],
@@ -150,6 +152,8 @@ def load(variant=None):
         L.clawb200_weno_table_doubles.restype = ctypes.c_int
         L.clawb200_step2_launches.restype = ctypes.c_int
         L.clawb200_step2_launches.argtypes = [_pp]
+        L.clawb200_step3_scratch_doubles.restype = ctypes.c_longlong
+        L.clawb200_step3_scratch_doubles.argtypes = [_pp]
         L.clawb200_last_error.restype = ctypes.c_char_p
         for name, args in SIGNATURES.items():
             f = getattr(L, name)

@@ -35,6 +35,7 @@ UNITS = {
     "sweep_misc.cu": _COMMON,
     "sweep_fused.cu": _COMMON + ["fused.cuh"],
     "step1.cu": _COMMON,
+    "step3.cu": _COMMON,
     "rp_point.cu": _COMMON,
     "sharpclaw.cu": _COMMON + ["sharpclaw.cuh"],
     "sweep_user.cu": _COMMON + ["sharpclaw.cuh"],   # the user-supplied Riemann solver (a stub without one)

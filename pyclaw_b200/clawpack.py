@@ -275,9 +275,9 @@ class ClawSolver2D(ClawSolver):
 
 
 class ClawSolver3D(ClawSolver):
-    """clawpack.py:563-702.  Only the dimensionally split algorithm (``dim_split=True``, the
-    reference's default: three ``step3ds`` sweeps) is built; the unsplit ``step3`` with its
-    transverse and double-transverse solves raises NotImplementedError."""
+    """clawpack.py:563-702: the dimensionally split algorithm (``dim_split=True``, the reference's
+    default: three ``step3ds`` sweeps) and the unsplit one (``step3`` with the transverse and
+    double-transverse solves selected by ``order_trans``)."""
     no_trans = 0
     trans_inc = 11
     trans_cor = 22
@@ -287,12 +287,6 @@ class ClawSolver3D(ClawSolver):
         self.ndim = 3
         super(ClawSolver3D, self).__init__(data)
 
-    def setup(self, solution):
-        if not self.dim_split:
-            raise NotImplementedError("ClawSolver3D: only dim_split=True (step3ds) is implemented; the "
-                                      "unsplit step3 / flux3 with rpt3 and rptt3 is not")
-        super(ClawSolver3D, self).setup(solution)
-
     def step_hyperbolic(self, solution):
         state = solution.states[0]
         aux = _ptr(state._aux.cur if state._aux is not None else None)
@@ -300,8 +294,18 @@ class ClawSolver3D(ClawSolver):
         F = state._q
         qold, b1, b2 = F.cur, F.get_spare(), F.get_spare()
         mz, dz = int(self._mz), float(self._dz)
+        if not self.dim_split:
+            import torch
+            need = _lib.load().clawb200_step3_scratch_doubles(ctypes.byref(self._problem))
+            if getattr(self, '_scratch3', None) is None or self._scratch3.numel() < need:
+                self._scratch3 = torch.empty(need, dtype=torch.float64, device=state.device)
+            scratch = _ptr(self._scratch3)
 
         def launch(P, cfl, st):
+            if not self.dim_split:
+                # classic3.step3 (clawpack.py:680-682)
+                _lib.call("clawb200_step3", P, mz, dz, _ptr(qold), _ptr(b1), aux, dt, scratch, cfl, st)
+                return
             # step3ds three times (clawpack.py:656-676); the Fortran's aliased calls become a
             # rotation qold -> b1 (x) -> b2 (y) -> b1 (z)
             _lib.call("clawb200_step3ds", P, mz, dz, _ptr(qold), _ptr(b1), aux, dt, 1, cfl, st)

@@ -266,6 +266,47 @@ extern "C" int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, co
     return 0;
 }
 
+// classic3.step3 (step3.f:2-594 + flux3.f:5-595; clawpack.py:680-682): the unsplit 3-D step.
+// method[2] = 0 | 10 | 11 | 20 | 21 | 22 (ClawSolver3D.no_trans / trans_inc / trans_cor and the
+// intermediate settings of flux3.f:42-68).  `scratch` holds clawb200_step3_scratch_doubles() doubles.
+static int check_step3(const clawb200_problem *p, int mz, double dz, const double *aux)
+{
+    int rc = check_problem(p, 3);
+    if (rc) return rc;
+    if (p->rp_id != CLAWB200_RP_ACOUSTICS3D_VC)
+        return fail(CLAWB200_ERR_UNSUPPORTED, "no 3-D version of this Riemann solver");
+    if (p->meqn != 4 || p->mwaves != 2) return fail(CLAWB200_ERR_INVALID, "meqn/mwaves do not match the Riemann solver");
+    if (p->maux < 2 || !aux) return fail(CLAWB200_ERR_INVALID, "aux array required: {impedance, sound speed}");
+    if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for the 3-D sweeps");
+    if (p->mbc < 2) return fail(CLAWB200_ERR_INVALID, "classic solvers need mbc >= 2");
+    if (mz < 1 || !(dz > 0.0)) return fail(CLAWB200_ERR_INVALID, "mz, dz must be positive");
+    const int t = p->method[2];
+    if (t < 0) return fail(CLAWB200_ERR_INVALID, "method[2] < 0 means dimensional splitting: call step3ds");
+    if (t != 0 && t != 10 && t != 11 && t != 20 && t != 21 && t != 22)
+        return fail(CLAWB200_ERR_INVALID, "method[2] must be one of 0, 10, 11, 20, 21, 22 (flux3.f:42-68)");
+    if (t >= 20 && p->method[1] != 2)
+        return fail(CLAWB200_ERR_INVALID, "method[2] = 20, 21, 22 propagate the correction waves: method[1] must be 2 (flux3.f:57-63)");
+    const long long plane = (long long)p->pitch * (p->my + 2 * p->mbc);
+    if (p->mstride < plane * (mz + 2 * p->mbc)) return fail(CLAWB200_ERR_INVALID, "mstride smaller than the padded field");
+    return 0;
+}
+
+extern "C" long long clawb200_step3_scratch_doubles(const clawb200_problem *p)
+{
+    if (!p) return fail(CLAWB200_ERR_INVALID, "null problem");
+    return claw_step3_scratch_doubles(p->mstride);
+}
+
+extern "C" int clawb200_step3(const clawb200_problem *p, int mz, double dz, const double *qold, double *qnew,
+                              const double *aux, double dt, double *scratch, double *cfl_dev, void *stream)
+{
+    int rc = check_step3(p, mz, dz, aux);
+    if (rc) return rc;
+    if (!qold || !qnew || !scratch) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (qold == qnew) return fail(CLAWB200_ERR_INVALID, "qold and qnew must differ");
+    return claw_step3(p, mz, dz, qold, qnew, aux, dt, scratch, cfl_dev, (cudaStream_t)stream);
+}
+
 __global__ void bc_kernel(double *q, long long mstride, int pitch, int narr, int nx, int ny,
                           int mbc, int idim, int side, int bctype, int negate);
 
@@ -1095,6 +1136,33 @@ extern "C" int clawb200_rp_transverse_host(const clawb200_problem *p, int ixy, l
     if (imp != 1 && imp != 2) return fail(CLAWB200_ERR_INVALID, "imp must be 1 or 2");
     if (p && p->ndim != 2) return fail(CLAWB200_ERR_INVALID, "transverse solves exist in 2-D only");
     return rp_point_host(p, ixy, n, ql, qr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, imp, asdq, bmasdq, bpasdq);
+}
+
+// classic3.step3 with host arrays (clawpack.py:680-682); qnew receives the whole padded array
+extern "C" int clawb200_step3_host(const clawb200_problem *p, int mz, double dz, const double *qold,
+                                   double *qnew, const double *aux, double dt, double *cfl)
+{
+    if (!p || !qold || !qnew) return fail(CLAWB200_ERR_INVALID, "null argument");
+    if (p->ndim != 3 || mz < 1) return fail(CLAWB200_ERR_INVALID, "3-D problem expected");
+    clawb200_problem P = *p;
+    P.dt_dev = nullptr;
+    const int nx = p->mx + 2 * p->mbc, ny = p->my + 2 * p->mbc, nz = mz + 2 * p->mbc;
+    P.pitch = nx;
+    P.mstride = (long long)nx * ny * nz;
+    int rc = g_hs.ensure((size_t)(P.meqn > P.maux ? P.meqn : P.maux) * P.mstride);
+    if (rc) return rc;
+    if ((rc = host_upload(P, qold, g_hs.d_a))) return rc;
+    const double *d_aux;
+    if ((rc = host_upload_aux(P, aux, &d_aux))) return rc;
+    double *scratch = nullptr;
+    CUDA_OK(cudaMalloc(&scratch, sizeof(double) * (size_t)claw_step3_scratch_doubles(P.mstride)));
+    if (!(rc = clawb200_cfl_reset(g_hs.d_cfl, g_hs.st)))
+        rc = clawb200_step3(&P, mz, dz, g_hs.d_a, g_hs.d_b, d_aux, dt, scratch, g_hs.d_cfl, g_hs.st);
+    if (!rc) rc = host_download(P, g_hs.d_b, qnew);
+    if (!rc) rc = host_finish(cfl);
+    else cudaStreamSynchronize(g_hs.st);
+    cudaFree(scratch);
+    return rc;
 }
 
 // classic3.step3ds with host arrays q(meqn, mx+2mbc, my+2mbc, mz+2mbc) (clawpack.py:656-676)

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_ctypes_signatures_cover_the_header():
     declared = set(_declared_symbols()) - {"clawb200_version", "clawb200_last_error", "clawb200_weno_table_doubles",
-                                                "clawb200_step2_launches"}
+                                                "clawb200_step2_launches", "clawb200_step3_scratch_doubles"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 

@@ -182,6 +182,34 @@ def test_acoustics3d_homogeneous_scalar():
     assert abs(err - 0.00286) < 1e-4, err
 
 
+def test_acoustics3d_heterogeneous_unsplit_golden():
+    """test/test_examples.py:497-514 (test/acoustics/3d/acoustics.py, test='het'): the UNSPLIT 3-D
+    classic solver (step3.f + flux3.f, order_trans = 22) with rpn3 / rpt3 / rptt3_vc_acoustics in a
+    medium whose impedance and sound speed double at x = 0; 30^3 cells, reflecting lower and
+    periodic upper boundaries, t = 2.  The reference asks |p - golden|_2 < 1e-4; the restatement
+    reproduces every digit of pressure_3D.txt, which pins step3 / flux3 and the three recalled
+    Riemann solvers."""
+    mx = my = mz = 30
+    x = (np.arange(mx) + 0.5) * (2.0 / mx) - 1.0
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    aux = np.empty((2, mx, my, mz), order="F")
+    aux[0] = 1.0 * (X < 0.) + 2.0 * (X >= 0.)
+    aux[1] = 1.0 * (X < 0.) + 2.0 * (X >= 0.)
+    q0 = np.zeros((4, mx, my, mz), order="F")
+    r = np.sqrt((X + 0.5) ** 2 + Y ** 2 + Z ** 2)
+    q0[0] = (np.abs(r - 0.3) <= 0.1) * (1. + np.cos(np.pi * (r - 0.3) / 0.1))
+    s = po.OracleSolver("classic", 3, po.RP_ACOUSTICS3D_VC, [], 2)
+    s.limiters = 4
+    s.bc_lower = s.aux_bc_lower = [po.BC_REFLECTING] * 3
+    s.bc_upper = s.aux_bc_upper = [po.BC_PERIODIC] * 3
+    s.dim_split, s.order_trans = False, 22
+    qf = s.run(q0, aux, [2.0 / mx] * 3, 2.0, 10)[-1]
+    gold = np.loadtxt(os.path.join(GOLD, "pressure_3D.txt"))
+    p = qf[0].reshape(-1)
+    assert s.total == {"numsteps": 70, "rejected": 1}
+    assert np.linalg.norm(p - gold) < 1e-13 and np.abs(p - gold).max() < 1e-14
+
+
 def test_weno_tables_match_the_reference_literals():
     """The regenerated WENO coefficients against literals of the reference's generated code
     (src/fortran/1d/sharpclaw/weno.f90): weno5 :35-90, weno7 :139-215, weno17 :1779-2240."""
