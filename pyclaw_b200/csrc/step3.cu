@@ -56,11 +56,15 @@ __host__ __device__ constexpr int hslot(int k, int j) { return 8 + (k - 1) + 2 *
 
 // rpt3 / rptt3_vc_acoustics for one interface: asdq split in the direction whose velocity
 // component is `iu`, across the cells with impedances zm | zz | zp and sound speeds cm, cp.
-__device__ __forceinline__ void split3(const double (&asdq)[M], int iu, double zm, double zz, double zp,
-                                       double cm, double cp, double (&bm)[M], double (&bp)[M])
+// rlo / rhi are the (shared) reciprocals of zm + zz and zz + zp: every line of three cells is the
+// denominator of up to four splits (A+ dq, A- dq and the two correction fluxes).
+template <class AR>
+__device__ __forceinline__ void split3(AR &ar, const double (&asdq)[M], int iu, double zm, double zz, double zp,
+                                       const Recip &rlo, const Recip &rhi, double cm, double cp,
+                                       double (&bm)[M], double (&bp)[M])
 {
-    const double a1 = (-asdq[0] + asdq[iu] * zz) / (zm + zz);
-    const double a2 = (asdq[0] + asdq[iu] * zz) / (zz + zp);
+    const double a1 = ar.div(-asdq[0] + asdq[iu] * zz, rlo);
+    const double a2 = ar.div(asdq[0] + asdq[iu] * zz, rhi);
 #pragma unroll
     for (int m = 0; m < M; m++) { bm[m] = 0.0; bp[m] = 0.0; }
     bm[0] = cm * a1 * zm;
@@ -69,31 +73,48 @@ __device__ __forceinline__ void split3(const double (&asdq)[M], int iu, double z
     for (int m = 1; m < M; m++) {
         if (m == iu) { bm[m] = -cm * a1; bp[m] = cp * a2; }
     }
+    (void)zm; (void)zp;
 }
 
-__device__ __forceinline__ double philim3(double a, double b, int meth)
+// the material of the 3x3 cells around c in the (y-like, z-like) plane and the reciprocals of the
+// impedance sums of neighbouring cells along each of its six lines
+struct Mat3 {
+    double Z[3][3], C[3][3];
+    Recip re[3][2]; // y-like lines at z-like offset f-1, f, f+1: 1 / (Z[0][f] + Z[1][f]), 1 / (Z[1][f] + Z[2][f])
+    Recip rf[3][2]; // z-like lines at y-like offset e-1, e, e+1: 1 / (Z[e][0] + Z[e][1]), 1 / (Z[e][1] + Z[e][2])
+};
+// split in the y-like direction along the line at z-like offset fo (0..2) / in the z-like direction
+// along the line at y-like offset eo
+template <class AR>
+__device__ __forceinline__ void split_e(AR &ar, const Mat3 &X, int fo, const double (&asdq)[M], int iu,
+                                        double (&bm)[M], double (&bp)[M])
 {
-    ExactArith ar;
-    return philim(ar, a, b, meth);
+    split3(ar, asdq, iu, X.Z[0][fo], X.Z[1][fo], X.Z[2][fo], X.re[fo][0], X.re[fo][1], X.C[0][fo], X.C[2][fo], bm, bp);
+}
+template <class AR>
+__device__ __forceinline__ void split_f(AR &ar, const Mat3 &X, int eo, const double (&asdq)[M], int iu,
+                                        double (&bm)[M], double (&bp)[M])
+{
+    split3(ar, asdq, iu, X.Z[eo][0], X.Z[eo][1], X.Z[eo][2], X.rf[eo][0], X.rf[eo][1], X.C[eo][0], X.C[eo][2], bm, bp);
 }
 
 // One side (SIDE = +1: A+ dq of interface c with the correction cqxx(c); SIDE = -1: A- dq of
 // interface c+1 with cqxx(c+1)) of the transverse part of flux3.f:239-594 for cell c.  Z / C are the
 // impedance and sound speed of the 3x3 cells around c in the (y-like, z-like) plane, [e+1][f+1].
 // g / h accumulate in the order of the Fortran's statements.
-template <int SIDE>
-__device__ __forceinline__ void transverse_side(const double (&asdq)[M], const double (&cq)[M], int m3, int m4,
-                                                int iue, int iuf, const double (&Z)[3][3], const double (&C)[3][3],
+template <int SIDE, class AR>
+__device__ __forceinline__ void transverse_side(AR &ar, const double (&asdq)[M], const double (&cq)[M], int m3, int m4,
+                                                int iue, int iuf, const Mat3 &X,
                                                 double dtdx, double dtdy, double dtdz, double (&g)[2][3][M],
                                                 double (&h)[2][3][M])
 {
     double bm[M], bp[M], cm[M], cp[M];           // B-+ A* dq, C-+ A* dq
     double bmq[M], bpq[M], cmq[M], cpq[M];       // the same splits of cqxx
-    split3(asdq, iue, Z[0][1], Z[1][1], Z[2][1], C[0][1], C[2][1], bm, bp);
-    split3(asdq, iuf, Z[1][0], Z[1][1], Z[1][2], C[1][0], C[1][2], cm, cp);
+    split_e(ar, X, 1, asdq, iue, bm, bp);
+    split_f(ar, X, 1, asdq, iuf, cm, cp);
     if (m3 == 2) {
-        split3(cq, iue, Z[0][1], Z[1][1], Z[2][1], C[0][1], C[2][1], bmq, bpq);
-        split3(cq, iuf, Z[1][0], Z[1][1], Z[1][2], C[1][0], C[1][2], cmq, cpq);
+        split_e(ar, X, 1, cq, iue, bmq, bpq);
+        split_f(ar, X, 1, cq, iuf, cmq, cpq);
     } else {
 #pragma unroll
         for (int m = 0; m < M; m++) bmq[m] = bpq[m] = cmq[m] = cpq[m] = 0.0;
@@ -112,8 +133,8 @@ __device__ __forceinline__ void transverse_side(const double (&asdq)[M], const d
                 cp2[m] = cp[m]; cm2[m] = cm[m];
             }
         }
-        split3(cp2, iue, Z[0][2], Z[1][2], Z[2][2], C[0][2], C[2][2], bmcp, bpcp); // impt = 2: plane f+1
-        split3(cm2, iue, Z[0][0], Z[1][0], Z[2][0], C[0][0], C[2][0], bmcm, bpcm); // impt = 1: plane f-1
+        split_e(ar, X, 2, cp2, iue, bmcp, bpcp); // impt = 2: plane f+1
+        split_e(ar, X, 0, cm2, iue, bmcm, bpcm); // impt = 1: plane f-1
     }
 #pragma unroll
     for (int m = 0; m < M; m++) {
@@ -149,8 +170,8 @@ __device__ __forceinline__ void transverse_side(const double (&asdq)[M], const d
                 bp2[m] = bp[m]; bm2[m] = bm[m];
             }
         }
-        split3(bp2, iuf, Z[2][0], Z[2][1], Z[2][2], C[2][0], C[2][2], bmcp, bpcp); // impt = 2: row e+1
-        split3(bm2, iuf, Z[0][0], Z[0][1], Z[0][2], C[0][0], C[0][2], bmcm, bpcm); // impt = 1: row e-1
+        split_f(ar, X, 2, bp2, iuf, bmcp, bpcp); // impt = 2: row e+1
+        split_f(ar, X, 0, bm2, iuf, bmcm, bpcm); // impt = 1: row e-1
     }
 #pragma unroll
     for (int m = 0; m < M; m++) {
@@ -209,18 +230,35 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
         zl[o] = A.aux[pos + (o - 2) * sd];
         cl[o] = A.aux[A.mstride + pos + (o - 2) * sd];
     }
+    Mat3 X;
+    if (A.m3 > 0) {
+#pragma unroll
+        for (int eo = -1; eo <= 1; eo++)
+#pragma unroll
+            for (int fo = -1; fo <= 1; fo++) {
+                const long long p = pos + eo * se + fo * sf;
+                X.Z[eo + 1][fo + 1] = A.aux[p];
+                X.C[eo + 1][fo + 1] = A.aux[A.mstride + p];
+            }
+    }
+    constexpr int MU = D + 1;
+    unsigned long long smax = 0ULL;
+    double out[NV][M];
+    // Every quotient of flux3 for this cell (8 in the four normal solves, 32 in the sixteen
+    // transverse splits) is over a sum of two neighbouring impedances: 4 + 12 refined reciprocals,
+    // shared (arith.cuh), instead of 40 IEEE divisions with their branches.
+    with_arith([&](auto &ar) {
     // rpn3 at the interfaces c-1 .. c+2 (interface I lies between cells I-1 and I; local index
     // n <-> interface c-1+n between q[n] and q[n+1])
-    constexpr int MU = D + 1;
     double wave[4][M][2], s[4][2], amdq[4][M], apdq[4][M];
-    unsigned long long smax = 0ULL;
 #pragma unroll
     for (int n = 0; n < 4; n++) {
         const double zim = zl[n], zi = zl[n + 1];
         const double delta1 = q[n + 1][0] - q[n][0];
         const double delta2 = q[n + 1][MU] - q[n][MU];
-        const double a1 = (-delta1 + zi * delta2) / (zim + zi);
-        const double a2 = (delta1 + zim * delta2) / (zim + zi);
+        const Recip rz = ar.rcp(zim + zi);
+        const double a1 = ar.div(-delta1 + zi * delta2, rz);
+        const double a2 = ar.div(delta1 + zim * delta2, rz);
 #pragma unroll
         for (int m = 0; m < M; m++) { wave[n][m][0] = 0.0; wave[n][m][1] = 0.0; }
         wave[n][0][0] = -a1 * zim;
@@ -263,7 +301,7 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
                 }
                 double wlimitr = 1.0;
                 const bool lim = (A.mthlim[mw] != 0) && (wnorm2 != 0.0);
-                if (lim) wlimitr = philim3(wnorm2, (s[n][mw] > 0.0) ? dotl : dotr, A.mthlim[mw]);
+                if (lim) wlimitr = philim(ar, wnorm2, (s[n][mw] > 0.0) ? dotl : dotr, A.mthlim[mw]);
 #pragma unroll
                 for (int m = 0; m < M; m++) wl[a][m][mw] = lim ? wlimitr * wave[n][m][mw] : wave[n][m][mw];
             }
@@ -275,7 +313,6 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
                     cqxx[a][m] = cqxx[a][m] + 0.5 * fabs(s[n][mw]) * (1.0 - fabs(s[n][mw]) * dtdxave) * wl[a][m][mw];
         }
     }
-    double out[NV][M];
 #pragma unroll
     for (int m = 0; m < M; m++) {
         out[0][m] = (0.0 - dtdx * apdq[1][m]) - dtdx * amdq[2][m];       // qadd(c)
@@ -289,20 +326,17 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
 #pragma unroll
             for (int m = 0; m < M; m++) { g[kk][jj][m] = 0.0; h[kk][jj][m] = 0.0; }
     if (A.m3 > 0) {
-        // material of the 3x3 cells around c in the (y-like, z-like) plane
-        double Z[3][3], C[3][3];
 #pragma unroll
-        for (int eo = -1; eo <= 1; eo++)
-#pragma unroll
-            for (int fo = -1; fo <= 1; fo++) {
-                const long long p = pos + eo * se + fo * sf;
-                Z[eo + 1][fo + 1] = A.aux[p];
-                C[eo + 1][fo + 1] = A.aux[A.mstride + p];
+        for (int o = 0; o < 3; o++) {
+            if (o == 1 || A.m4 > 0) { // the outer lines are read by the double-transverse splits only
+                X.re[o][0] = ar.rcp(X.Z[0][o] + X.Z[1][o]); X.re[o][1] = ar.rcp(X.Z[1][o] + X.Z[2][o]);
+                X.rf[o][0] = ar.rcp(X.Z[o][0] + X.Z[o][1]); X.rf[o][1] = ar.rcp(X.Z[o][1] + X.Z[o][2]);
             }
+        }
         constexpr int IUE = E + 1, IUF = F + 1;
         // iteration i = c of the Fortran's loops 180 / 200 (plus side), then i = c+1 (minus side)
-        transverse_side<+1>(apdq[1], cqxx[0], A.m3, A.m4, IUE, IUF, Z, C, dtdx, dtdy, dtdz, g, h);
-        transverse_side<-1>(amdq[2], cqxx[1], A.m3, A.m4, IUE, IUF, Z, C, dtdx, dtdy, dtdz, g, h);
+        transverse_side<+1>(ar, apdq[1], cqxx[0], A.m3, A.m4, IUE, IUF, X, dtdx, dtdy, dtdz, g, h);
+        transverse_side<-1>(ar, amdq[2], cqxx[1], A.m3, A.m4, IUE, IUF, X, dtdx, dtdy, dtdz, g, h);
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++)
@@ -313,6 +347,7 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
                 out[gslot(kk + 1, jj - 1)][m] = g[kk][jj][m];
                 out[hslot(kk + 1, jj - 1)][m] = h[kk][jj][m];
             }
+    });
     if (active) {
 #pragma unroll
         for (int v = 0; v < NV; v++)
