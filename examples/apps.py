@@ -239,23 +239,43 @@ def psystem(cells_per_layer=20, petsc=False, tfinal=2.0, outdir=None):
     return _run(pyclaw, solver, state, tfinal, 10, outdir)
 
 
-def acoustics3d(mx=256, my=4, mz=4, petsc=False, tfinal=2.0, outdir=None):
-    """test/acoustics/3d/acoustics.py, homogeneous variant (dimensional splitting)"""
+def acoustics3d(mx=256, my=4, mz=4, petsc=False, tfinal=2.0, outdir=None, test='hom', upper_bc=None):
+    """test/acoustics/3d/acoustics.py: 'hom' (homogeneous medium, dimensional splitting, periodic) or
+    'het' (impedance and sound speed double at x = 0, unsplit with order_trans = 22, reflecting lower
+    boundaries; the reference runs it at 30^3 against test/pressure_3D.txt)"""
     pyclaw = _pc(petsc)
     solver = pyclaw.ClawSolver3D()
     for i in range(3):
         solver.bc_lower[i] = solver.bc_upper[i] = pyclaw.BC.periodic
         solver.aux_bc_lower[i] = solver.aux_bc_upper[i] = pyclaw.BC.periodic
     solver.dim_split, solver.mwaves, solver.limiters = True, 2, pyclaw.limiters.tvd.MC
+    zr = cr = 1.0
+    if test == 'het':
+        solver.dim_split = False
+        for i in range(3):
+            solver.bc_lower[i] = solver.aux_bc_lower[i] = pyclaw.BC.reflecting
+            # the reference's script keeps the upper boundaries periodic next to reflecting lower ones;
+            # a slab partition (like the reference's DMDA, petclaw/state.py:205-208) cannot wrap one
+            # side of the partitioned dimension only: upper_bc overrides
+            if upper_bc is not None:
+                solver.bc_upper[i] = solver.aux_bc_upper[i] = upper_bc
+        zr = cr = 2.0
     grid = pyclaw.Grid([pyclaw.Dimension('x', -1.0, 1.0, mx), pyclaw.Dimension('y', -1.0, 1.0, my),
                         pyclaw.Dimension('z', -1.0, 1.0, mz)])
     state = pyclaw.State(grid, 4, 2)
     grid.compute_c_center()
-    X = grid._c_center[0]
-    state.aux = np.ones((2,) + X.shape, order='F')
-    r = np.abs(X + 0.5)
+    X, Y, Z = grid._c_center
+    aux = np.empty((2,) + X.shape, order='F')
+    aux[0] = 1.0 * (X < 0.) + zr * (X >= 0.)
+    aux[1] = 1.0 * (X < 0.) + cr * (X >= 0.)
+    state.aux = aux
     q0 = np.zeros((4,) + X.shape, order='F')
-    q0[0] = (r <= 0.2) * (1. + np.cos(np.pi * r / 0.2))
+    if test == 'het':
+        r = np.sqrt((X + 0.5) ** 2 + Y ** 2 + Z ** 2)
+        q0[0] = (np.abs(r - 0.3) <= 0.1) * (1. + np.cos(np.pi * (r - 0.3) / 0.1))
+    else:
+        r = np.abs(X + 0.5)
+        q0[0] = (r <= 0.2) * (1. + np.cos(np.pi * r / 0.2))
     state.q[...] = q0
     return _run(pyclaw, solver, state, tfinal, 10, outdir)
 

@@ -77,6 +77,26 @@ def main():
     o = dict(time_integrator="SSP33", cfl_max=0.6, cfl_desired=0.5)
     r = both(lambda v: tg._shallow("sharpclaw", arithmetic=v, **o))
     out["shallow_sharpclaw_ssp33_60x60"] = {"rel_linf_fma_vs_strict": rel_linf(r["fma"], r["strict"])}
+    # conditioning of that run: the STRICT build on initial data moved by one unit in the last
+    # place (every other cell's depth times 1 + 2^-52).  If round-off of the input alone moves the
+    # result by as much as the fma build does, the 1e-12 bar is a statement about bit-exactness
+    # for this configuration, not about the quality of the arithmetic.
+    import problems as _pb
+    orig = _pb.shallow2d
+
+    def perturbed(mx, my):
+        pb = orig(mx, my)
+        q = np.array(pb["q"], copy=True)
+        q[0, ::2, ::2] *= (1.0 + 2.0 ** -52)
+        pb = dict(pb)
+        pb["q"] = q
+        return pb
+    _pb.shallow2d = perturbed
+    try:
+        rp = tg._shallow("sharpclaw", arithmetic="strict", **o)
+    finally:
+        _pb.shallow2d = orig
+    out["shallow_sharpclaw_ssp33_60x60"]["rel_linf_strict_1ulp_input_perturbation"] = rel_linf(rp, r["strict"])
     r = both(lambda v: tg._shallow("classic", arithmetic=v, dim_split=0, order_trans=2))
     out["shallow_classic_unsplit_60x60"] = {"rel_linf_fma_vs_strict": rel_linf(r["fma"], r["strict"])}
 

@@ -121,7 +121,11 @@ def main():
                      ("annulus", dict(mx=20, my=60, tfinal=0.2)),
                      ("vc_acoustics2d", dict(mx=48, my=40, tfinal=0.1)),
                      ("psystem", dict(cells_per_layer=8, tfinal=0.15)),
-                     ("acoustics3d", dict(mx=32, my=4, mz=8 * world, tfinal=0.3))):
+                     ("acoustics3d", dict(mx=32, my=4, mz=8 * world, tfinal=0.3)),
+                     # single-pass unsplit kernel under the row-range calls of the overlapped step
+                     ("acoustics2d", dict(mx=64, my=72, dim_split=False, tfinal=0.08)),
+                     # unsplit 3-D (step3 + flux3 + rpt3 / rptt3), z-slabs
+                     ("acoustics3d", dict(test='het', mx=14, my=12, mz=6 * world, tfinal=0.3, upper_bc=1))):
         cp = apps.APPS[name](petsc=True, **kw)
         st = cp.frames[-1].state
         qp = np.asarray(st._partition.gather_interior(st))
