@@ -85,6 +85,9 @@ struct RpAcoustics {
 #define CLAW_AC_X_MINB 5
 #define CLAW_AC_Y_MINB 3
 #endif
+#ifdef CLAW_AC_F_MINB
+    static constexpr int F_MINB = CLAW_AC_F_MINB;
+#endif
     static constexpr int X_MINB = CLAW_AC_X_MINB, Y_MINB = CLAW_AC_Y_MINB;
 #ifndef CLAW_AC_Y_REGS
 #define CLAW_AC_Y_REGS 1
