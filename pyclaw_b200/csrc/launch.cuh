@@ -92,15 +92,16 @@ static int launch_y(SweepArgs A, cudaStream_t st)
     return 0;
 }
 
-static inline int pick_rows(int nrows, int ncol_ctas)
+static inline int pick_rows(int nrows, int ncol_ctas, bool tall = true)
 {
     // enough CTAs to fill 148 SMs a few times over, but strips tall enough that the
     // start-up rows of the streaming engines stay a small fraction of the work
     static const int forced = [] { const char *e = getenv("CLAWB200_ROWS_PER_CTA"); return e ? atoi(e) : 0; }();
     if (forced > 0) return forced; // tuning experiments
     // very large grids: 128-row strips halve the start-up rows again and still leave ~10 waves of
-    // CTAs (Euler 8192^2: 9.10 -> 8.89 ms per step; 4096^2 and the sphere are flat or worse)
-    if ((long long)ncol_ctas * ((nrows + 127) / 128) >= 148 * 28) return 128;
+    // CTAs (Euler 8192^2: 9.10 -> 8.89 ms per step; 4096^2 and the sphere are flat or worse, the
+    // SharpClaw stage kernel too: tall = false)
+    if (tall && (long long)ncol_ctas * ((nrows + 127) / 128) >= 148 * 28) return 128;
     int h = 64;
     while (h > 8 && (long long)ncol_ctas * ((nrows + h - 1) / h) < 148 * 4) h /= 2;
     return h;

@@ -125,7 +125,7 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
         A.tab = reinterpret_cast<const WenoTab *>(p->weno_tab);
         if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for WENO orders above 5");
         if (p->ndim == 2) {
-            A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+            A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2), false);
             switch (p->rp_id) {
             case CLAWB200_RP_ACOUSTICS: return sc_launch2_tab<RpAcoustics<2, 1>, RpAcoustics<2, 2>>(A, wk, st);
             case CLAWB200_RP_ADVECTION: return sc_launch2_tab<RpAdvection<2, 1>, RpAdvection<2, 2>>(A, wk, st);
@@ -177,7 +177,7 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
     }
     if (p->rp_id == CLAWB200_RP_USER) {
         if (p->method[5] > 0) return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa is not compiled for the user solver in SharpClaw");
-        if (p->ndim == 2) A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+        if (p->ndim == 2) A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2), false);
         return claw_sc_user(p->ndim, old, A, st);
     }
     if (p->method[5] > 0) {
@@ -193,7 +193,7 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
             default: return fail(CLAWB200_ERR_UNSUPPORTED, "mcapa not compiled for this solver");
             }
         }
-        A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+        A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2), false);
         switch (p->rp_id) {
         case CLAWB200_RP_ACOUSTICS: return old ? sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, true, true>(A, st)
                                                : sc_launch2<RpAcoustics<2, 1>, RpAcoustics<2, 2>, false, true>(A, st);
@@ -221,7 +221,7 @@ int sharpclaw_launch(const clawb200_problem *p, const double *q, const double *q
         default: return fail(CLAWB200_ERR_UNSUPPORTED, "no 1-D version of this Riemann solver");
         }
     }
-    A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2));
+    A.rows_per_cta = pick_rows(p->my, (p->mx + SNT - 3) / (SNT - 2), false);
 #define SC2(RPT)                                                                         \
     return old ? sc_launch2<RPT, true>(A, st) : sc_launch2<RPT, false>(A, st)
     switch (p->rp_id) {

@@ -214,7 +214,10 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
     constexpr int E = (D + 1) % 3, F = (D + 2) % 3;
     int i, j, k;
     const bool active = thread_cell<D>(A, i, j, k);
-    if (!active) i = 1; // every thread reaches the warp reduction of the Courant number
+    // a warp with no cell at all leaves (a warp-uniform exit); the idle lanes of the last partly
+    // filled warp redo cell 1 so that every lane reaches the warp reduction of the Courant number
+    if (!__any_sync(0xffffffffu, active)) return;
+    if (!active) i = 1;
     const long long plane = (long long)A.nx * A.ny;
     const long long stride[3] = {1, A.nx, plane};
     const long long sd = stride[D], se = stride[E], sf = stride[F];
