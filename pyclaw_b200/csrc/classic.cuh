@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
     double *qs = qs0;
     double *ws = qs0 + 2 * MEQN * QS; // [MEQN*MW][NT]  unlimited waves
     double *xs = ws + MEQN * MW * NT; // [4*MEQN][NT]   amdq, F, bm(A-), bp(A-) of each interface
+    // Solvers that read many aux components per interface (the sphere: ~70 loads, two thirds of them
+    // L1 misses with 8 warps per SM to hide them): the aux rows r-1, r, r+1 live in a ring of four
+    // shared-memory rows, row r+2 arrives by cp.async during iteration r.  Column c <-> cell i0-2+c.
+    constexpr bool AUXS = rp_x_aux_smem<RP>::value && TRANS;
+    constexpr int AQS = NT + 2;
+    double *as = xs + 4 * MEQN * NT;  // [4][MAUX][NT+2] (AUXS only)
 
     const int t = threadIdx.x;
     const int i0 = A.ilo + blockIdx.x * NC;
@@ -206,6 +212,26 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
     const int cload = min(i0 - 2 + t, imax) + mbc - 1;      // array column this thread stages
     const int cload2 = min(i0 - 2 + NT, imax) + mbc - 1;    // extra column staged by thread 0
     const bool cell_ok = (t >= 1) && (t <= NC) && (ii <= A.ihi);
+    auto stage_aux_row = [&](int row) { // aux row `row` (clamped like aux_cell) into its ring slot
+        if constexpr (AUXS) {
+            const int jc = min(max(row, 1 - mbc), A.my + mbc) + mbc - 1;
+            double *dst = as + (row & 3) * (RP::MAUX * AQS);
+            const double *src = A.aux + (long long)A.pitch * jc;
+            const int c0 = min(max(i0 - 2 + t, 1 - mbc), imax) + mbc - 1;
+#pragma unroll
+            for (int ma = 0; ma < RP::MAUX; ma++) cp_async8(&dst[ma * AQS + t], &src[ma * A.amstride + c0]);
+            if (t < 2) {
+                const int c1 = min(i0 - 2 + NT + t, imax) + mbc - 1;
+#pragma unroll
+                for (int ma = 0; ma < RP::MAUX; ma++) cp_async8(&dst[ma * AQS + NT + t], &src[ma * A.amstride + c1]);
+            }
+        }
+    };
+    // the aux cell di columns right of cell ii (= column t+1+di of the ring) in row `row`
+    auto ax = [&](int di, int row) {
+        if constexpr (AUXS) return AuxCellS{as + (row & 3) * (RP::MAUX * AQS) + (t + 1 + di), AQS};
+        else return (AUXRP || CAPA) ? aux_cell(A, ii + di, row) : AuxCell{nullptr, 0};
+    };
     const bool iface_ok = (ii >= 1) && (ii <= A.mx + 1) && (t >= 1) && (t <= NT - 2);
     const bool order2 = (A.order != 1);
     const bool trans2 = order2 && (A.trans == 2);
@@ -231,12 +257,15 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
             cp_async8(&qs[m * QS + t], &A.qin[m * A.mstride + ro + cload]);
             if (t == 0) cp_async8(&qs[m * QS + NT], &A.qin[m * A.mstride + ro + cload2]);
         }
+        stage_aux_row(rbeg - 1);
+        stage_aux_row(rbeg);
+        stage_aux_row(rbeg + 1);
         cp_async_commit();
     }
     int qb = 0;
     for (int r = rbeg; r <= rend; r++) {
         const long long rowoff = (long long)A.pitch * (r + mbc - 1);
-        if (RP::MAUX >= 8) { // aux of row r+2 (first needed as the "row above" of iteration r+1)
+        if (RP::MAUX >= 8 && !AUXS) { // aux of row r+2 (first needed as the "row above" of iteration r+1)
             const int jp = min(r + 2, A.my + mbc) + mbc - 1;
             const double *ap = A.aux + (long long)A.pitch * jp + (min(max(ii, 1 - mbc), imax) + mbc - 1);
 #pragma unroll
@@ -253,6 +282,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                 cp_async8(&qsn[m * QS + t], &A.qin[m * A.mstride + ro + cload]);
                 if (t == 0) cp_async8(&qsn[m * QS + NT], &A.qin[m * A.mstride + ro + cload2]);
             }
+            stage_aux_row(r + 2); // replaces row r-2, last read in iteration r-1
             cp_async_commit();
         }
         qb ^= 1;
@@ -263,17 +293,17 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
         // capacity function: dtdx1d(i) = dtdx / capa(i,j)  (step2.f:91-95)
         double dtdx_c = dtdx, dtdx_l = dtdx, capa_c = 1.0, capa_m = 1.0, capa_p = 1.0;
         if (CAPA) {
-            capa_c = aux_cell(A, ii, r)(A.mcapa - 1);
+            capa_c = ax(0, r)(A.mcapa - 1);
             dtdx_c = div1(dtdx, capa_c);
-            dtdx_l = div1(dtdx, aux_cell(A, ii - 1, r)(A.mcapa - 1));
+            dtdx_l = div1(dtdx, ax(-1, r)(A.mcapa - 1));
             if (TRANS) {
-                capa_m = aux_cell(A, ii, r - 1)(A.mcapa - 1);
-                capa_p = aux_cell(A, ii, r + 1)(A.mcapa - 1);
+                capa_m = ax(0, r - 1)(A.mcapa - 1);
+                capa_p = ax(0, r + 1)(A.mcapa - 1);
             }
         }
         const double hdtdx = 0.5 * dtdx_c;
-        const AuxCell axl = AUXRP ? aux_cell(A, ii - 1, r) : nocell;
-        const AuxCell axr = AUXRP ? aux_cell(A, ii, r) : nocell;
+        const auto axl = ax(-1, r);
+        const auto axr = ax(0, r);
 
         double wave[MEQN][MW], s[MW], amdq[MEQN], apdq[MEQN], roe[NROE];
         with_arith([&](auto &ar) { RP::solve(ar, A.rp, l, rr, axl, axr, wave, s, amdq, apdq, roe); });
@@ -340,8 +370,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                         // at / above this one (aux1, aux2, aux3 of step2.f:99-107)
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (amdq[m] + cqxx[m]) : amdq[m];
-                        RP::transverse(ar, A.rp, roe, l, AUXRP ? aux_cell(A, ii - 1, r - 1) : nocell, axl,
-                                       AUXRP ? aux_cell(A, ii - 1, r + 1) : nocell, asdq, bmm, bpm);
+                        RP::transverse(ar, A.rp, roe, l, ax(-1, r - 1), axl, ax(-1, r + 1), asdq, bmm, bpm);
                         // hand the "goes into the left cell" parts to thread t-1 right away: they
                         // are dead in this thread, and the second solve needs the registers
 #pragma unroll
@@ -351,8 +380,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
                         }
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) asdq[m] = trans2 ? (apdq[m] - cqxx[m]) : apdq[m];
-                        RP::transverse(ar, A.rp, roe, rr, AUXRP ? aux_cell(A, ii, r - 1) : nocell, axr,
-                                       AUXRP ? aux_cell(A, ii, r + 1) : nocell, asdq, bmp, bpp);
+                        RP::transverse(ar, A.rp, roe, rr, ax(0, r - 1), axr, ax(0, r + 1), asdq, bmp, bpp);
                     } else { // flux2.f:151 -- gadd stays zero
 #pragma unroll
                         for (int m = 0; m < MEQN; m++) bmm[m] = bpm[m] = bmp[m] = bpp[m] = 0.0;
@@ -412,7 +440,7 @@ __global__ void __launch_bounds__(NT, RP::X_MINB) xsweep_kernel(const SweepArgs 
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) qcv[m] = 0.0;
                 if constexpr (RP::QCOR) { // apps/shallow-sphere/step2qcor.f:147
-                    with_arith([&](auto &ar) { RP::qcor(ar, A.rp, rr, axr, aux_cell(A, ii + 1, r), qcv); });
+                    with_arith([&](auto &ar) { RP::qcor(ar, A.rp, rr, axr, ax(1, r), qcv); });
                 }
 #pragma unroll
                 for (int m = 0; m < MEQN; m++) {

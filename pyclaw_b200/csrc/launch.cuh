@@ -66,7 +66,8 @@ template <class RP, bool TRANS, bool CAPA = false>
 static int launch_x(SweepArgs A, cudaStream_t st)
 {
     constexpr int NC = XNT - 3;
-    size_t smem = sizeof(double) * (2 * RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT);
+    size_t smem = sizeof(double) * (2 * RP::MEQN * (XNT + 1) + RP::MEQN * RP::MWAVES * XNT + 4 * RP::MEQN * XNT +
+                                    ((rp_x_aux_smem<RP>::value && TRANS) ? 4 * RP::MAUX * (XNT + 2) : 0));
     auto k = xsweep_kernel<RP, TRANS, CAPA, XNT>;
     CUDA_OK(set_smem(k, smem));
     if (RP::MAUX >= 8) hint_carveout(k, smem, RP::X_MINB);

@@ -69,6 +69,20 @@ struct AuxCell {
     __device__ __forceinline__ double operator()(int ma) const { return __ldg(p + ma * ms); }
 };
 
+// The same cell staged in shared memory (x-engine, solvers with RP::X_AUX_SMEM): component stride
+// = padded row length of the staging ring.
+struct AuxCellS {
+    const double *p;
+    int ms;
+    __device__ __forceinline__ double operator()(int ma) const { return p[ma * ms]; }
+};
+// solvers that read so many aux components per interface (the sphere: ~70) that the x-engine stages
+// the aux rows in shared memory with cp.async, like q
+template <class RP, class = void>
+struct rp_x_aux_smem { static constexpr bool value = false; };
+template <class RP>
+struct rp_x_aux_smem<RP, decltype((void)RP::X_AUX_SMEM)> { static constexpr bool value = RP::X_AUX_SMEM; };
+
 __device__ __forceinline__ double dmax2(double a, double b) { return (a > b) ? a : b; }
 __device__ __forceinline__ double dmin2(double a, double b) { return (a < b) ? a : b; }
 
@@ -584,14 +598,15 @@ struct RpSphere {
     static constexpr int X_MINB = 2, Y_MINB = 2;
     static constexpr int MAUX = 16;
     static constexpr bool QCOR = true;
+    static constexpr bool X_AUX_SMEM = true;
     static constexpr int IOFF = (IXY == 2) ? 7 : 1;   // edge data of the sweep direction
     static constexpr int IOFFT = (IXY == 2) ? 1 : 7;  // edge data of the transverse direction
     __host__ __device__ static constexpr bool nz(int m, int mw) { return !(m == 0 && mw == 1); }
 
     // axl = cell i-1 (its radial vector projects amdq), axr = cell i (owns the edge)
-    template <class AR>
+    template <class AR, class AX>
     __device__ __forceinline__ static void solve(AR &ar, const RpParams &P, const double (&l)[4],
-                                                 const double (&r)[4], const AuxCell &axl, const AuxCell &axr,
+                                                 const double (&r)[4], const AX &axl, const AX &axr,
                                                  double (&wave)[4][3], double (&s)[3], double (&amdq)[4],
                                                  double (&apdq)[4], double (&roe)[NROE])
     {
@@ -704,9 +719,9 @@ struct RpSphere {
     }
 
     // one side of rpt2: edge data from `axe`, radial vector from `axp`, state of the cell
-    template <class AR, bool UP>
+    template <class AR, bool UP, class AX>
     __device__ __forceinline__ static void side(AR &ar, double g, double dx, const double (&qc)[4],
-                                                const AuxCell &axe, const AuxCell &axp,
+                                                const AX &axe, const AX &axp,
                                                 const double (&asdq)[4], double (&b)[4])
     {
         const double enx = axe(IOFFT + 0), eny = axe(IOFFT + 1), enz = axe(IOFFT + 2);
@@ -759,22 +774,22 @@ struct RpSphere {
 
     // qc = state of the cell the fluctuation moves into; ax1/ax2/ax3 = that cell in the
     // previous / current / next slice
-    template <class AR>
+    template <class AR, class AX>
     __device__ __forceinline__ static void transverse(AR &ar, const RpParams &P, const double (&roe)[NROE],
-                                                      const double (&qc)[4], const AuxCell &ax1,
-                                                      const AuxCell &ax2, const AuxCell &ax3,
+                                                      const double (&qc)[4], const AX &ax1,
+                                                      const AX &ax2, const AX &ax3,
                                                       const double (&asdq)[4], double (&bm)[4], double (&bp)[4])
     {
         const double g = P.p[0];
         const double dx = (IXY == 2) ? P.p[2] : P.p[1];
-        side<AR, true>(ar, g, dx, qc, ax3, ax3, asdq, bp);
-        side<AR, false>(ar, g, dx, qc, ax2, ax1, asdq, bm);
+        side<AR, true, AX>(ar, g, dx, qc, ax3, ax3, asdq, bp);
+        side<AR, false, AX>(ar, g, dx, qc, ax2, ax1, asdq, bm);
     }
 
     // apps/shallow-sphere/qcor.f:2-72: axi = this cell, axn = the next cell along the sweep
-    template <class AR>
+    template <class AR, class AX>
     __device__ __forceinline__ static void qcor(AR &ar, const RpParams &P, const double (&q)[4],
-                                                const AuxCell &axi, const AuxCell &axn, double (&qcv)[4])
+                                                const AX &axi, const AX &axn, double (&qcv)[4])
     {
         const double g = P.p[0];
         const double dy = (IXY == 2) ? P.p[1] : P.p[2];
