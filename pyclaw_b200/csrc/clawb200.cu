@@ -229,6 +229,11 @@ extern "C" int clawb200_step3ds(const clawb200_problem *p, int mz, double dz, co
     const long long plane = (long long)nx * ny;
     if (p->mstride < plane * nz) return fail(CLAWB200_ERR_INVALID, "mstride smaller than the padded field");
     cudaStream_t st = (cudaStream_t)stream;
+    // One launch over the whole padded field (step3.cu): swept cells are updated, all others copied.
+    // CLAWB200_STEP3DS_PLANES=1 keeps round 1's composition from the 2-D engines (one launch per
+    // plane after a copy of the field) for A/B measurements.
+    static const bool planes = [] { const char *e = getenv("CLAWB200_STEP3DS_PLANES"); return e && atoi(e) != 0; }();
+    if (!planes) return claw_step3ds(p, mz, dz, q_in, q_out, aux, dt, idir, cfl_dev, st);
     // step3ds.f: "qold and qnew are identical on entry"; cells the sweep does not touch keep qold
     CUDA_OK(cudaMemcpyAsync(q_out, q_in, sizeof(double) * (size_t)p->meqn * p->mstride,
                             cudaMemcpyDeviceToDevice, st));

@@ -121,7 +121,9 @@ int claw_y_ac3d(int idir, const SweepArgs &A, cudaStream_t st); // 3-D acoustics
 // single-pass unsplit step (sweep_fused.cu): solvers without aux / capa whose windows fit in registers
 bool claw_fused_available(int rp_id, const SweepArgs &A);
 int claw_fused(int rp_id, const SweepArgs &A, cudaStream_t st);
-// unsplit 3-D step (step3.cu)
+// 3-D steps (step3.cu): one dimensionally split sweep in one launch; the unsplit step
+int claw_step3ds(const clawb200_problem *p, int mz, double dz, const double *q_in, double *q_out,
+                 const double *aux, double dt, int idir, double *cfl_dev, cudaStream_t st);
 long long claw_step3_scratch_doubles(long long mstride);
 int claw_step3(const clawb200_problem *p, int mz, double dz, const double *qold, double *qnew,
                const double *aux, double dt, double *scratch, double *cfl_dev, cudaStream_t st);

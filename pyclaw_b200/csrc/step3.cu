@@ -197,6 +197,82 @@ __device__ __forceinline__ void transverse_side(AR &ar, const double (&asdq)[M],
     }
 }
 
+// The normal part of flux3.f:176-241 for cell c of a slice in direction D: rpn3 at the interfaces
+// c-1 .. c+2 (interface I lies between cells I-1 and I; local index n <-> interface c-1+n between
+// q[n] and q[n+1]), the limiter and the correction fluxes of the interfaces c and c+1.  Returns
+// A+ dq of interface c, A- dq of interface c+1, cqxx of both, and the largest wave speed.
+template <int D, class AR>
+__device__ __forceinline__ void normal3(AR &ar, const Step3Args &A, const double (&q)[5][M], const double (&zl)[5],
+                                        const double (&cl)[5], double dtdx, double (&apdq_c)[M],
+                                        double (&amdq_n)[M], double (&cqxx)[2][M], unsigned long long &smax)
+{
+    constexpr int MU = D + 1;
+    double wave[4][M][2], s[4][2], amdq[4][M], apdq[4][M];
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        const double zim = zl[n], zi = zl[n + 1];
+        const double delta1 = q[n + 1][0] - q[n][0];
+        const double delta2 = q[n + 1][MU] - q[n][MU];
+        const Recip rz = ar.rcp(zim + zi);
+        const double a1 = ar.div(-delta1 + zi * delta2, rz);
+        const double a2 = ar.div(delta1 + zim * delta2, rz);
+#pragma unroll
+        for (int m = 0; m < M; m++) { wave[n][m][0] = 0.0; wave[n][m][1] = 0.0; }
+        wave[n][0][0] = -a1 * zim;
+        wave[n][MU][0] = a1;
+        s[n][0] = -cl[n];
+        wave[n][0][1] = a2 * zi;
+        wave[n][MU][1] = a2;
+        s[n][1] = cl[n + 1];
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            amdq[n][m] = s[n][0] * wave[n][m][0];
+            apdq[n][m] = s[n][1] * wave[n][m][1];
+        }
+    }
+    // Courant number: interfaces c and c+1 (flux3.f:208-216; every interface 1..n+1 of a slice is
+    // interface c or c+1 of one of its cells)
+    smax_update(smax, s[1][0]); smax_update(smax, s[1][1]);
+    smax_update(smax, s[2][0]); smax_update(smax, s[2][1]);
+
+    // limiter (limiter.f:29-55) and correction flux (flux3.f:226-241) of the interfaces c (n = 1)
+    // and c+1 (n = 2); the dot products use the unlimited waves of the neighbours
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int m = 0; m < M; m++) cqxx[a][m] = 0.0;
+    if (A.order != 1) {
+        double wl[2][M][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const int n = 1 + a;
+#pragma unroll
+            for (int mw = 0; mw < 2; mw++) {
+                double wnorm2 = 0.0, dotl = 0.0, dotr = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; m++) {
+                    wnorm2 = wnorm2 + wave[n][m][mw] * wave[n][m][mw];
+                    dotl = dotl + wave[n - 1][m][mw] * wave[n][m][mw];
+                    dotr = dotr + wave[n][m][mw] * wave[n + 1][m][mw];
+                }
+                double wlimitr = 1.0;
+                const bool lim = (A.mthlim[mw] != 0) && (wnorm2 != 0.0);
+                if (lim) wlimitr = philim(ar, wnorm2, (s[n][mw] > 0.0) ? dotl : dotr, A.mthlim[mw]);
+#pragma unroll
+                for (int m = 0; m < M; m++) wl[a][m][mw] = lim ? wlimitr * wave[n][m][mw] : wave[n][m][mw];
+            }
+            const double dtdxave = 0.5 * (dtdx + dtdx);
+#pragma unroll
+            for (int mw = 0; mw < 2; mw++)
+#pragma unroll
+                for (int m = 0; m < M; m++)
+                    cqxx[a][m] = cqxx[a][m] + 0.5 * fabs(s[n][mw]) * (1.0 - fabs(s[n][mw]) * dtdxave) * wl[a][m][mw];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < M; m++) { apdq_c[m] = apdq[1][m]; amdq_n[m] = amdq[2][m]; }
+}
+
 // Fortran index (i, j, k) of this thread for a launch that covers [lo, lo + n) per dimension
 template <int D>
 __device__ __forceinline__ bool thread_cell(const Step3Args &A, int &i, int &j, int &k)
@@ -244,81 +320,17 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
                 X.C[eo + 1][fo + 1] = A.aux[A.mstride + p];
             }
     }
-    constexpr int MU = D + 1;
     unsigned long long smax = 0ULL;
     double out[NV][M];
     // Every quotient of flux3 for this cell (8 in the four normal solves, 32 in the sixteen
     // transverse splits) is over a sum of two neighbouring impedances: 4 + 12 refined reciprocals,
     // shared (arith.cuh), instead of 40 IEEE divisions with their branches.
     with_arith([&](auto &ar) {
-    // rpn3 at the interfaces c-1 .. c+2 (interface I lies between cells I-1 and I; local index
-    // n <-> interface c-1+n between q[n] and q[n+1])
-    double wave[4][M][2], s[4][2], amdq[4][M], apdq[4][M];
-#pragma unroll
-    for (int n = 0; n < 4; n++) {
-        const double zim = zl[n], zi = zl[n + 1];
-        const double delta1 = q[n + 1][0] - q[n][0];
-        const double delta2 = q[n + 1][MU] - q[n][MU];
-        const Recip rz = ar.rcp(zim + zi);
-        const double a1 = ar.div(-delta1 + zi * delta2, rz);
-        const double a2 = ar.div(delta1 + zim * delta2, rz);
-#pragma unroll
-        for (int m = 0; m < M; m++) { wave[n][m][0] = 0.0; wave[n][m][1] = 0.0; }
-        wave[n][0][0] = -a1 * zim;
-        wave[n][MU][0] = a1;
-        s[n][0] = -cl[n];
-        wave[n][0][1] = a2 * zi;
-        wave[n][MU][1] = a2;
-        s[n][1] = cl[n + 1];
-#pragma unroll
-        for (int m = 0; m < M; m++) {
-            amdq[n][m] = s[n][0] * wave[n][m][0];
-            apdq[n][m] = s[n][1] * wave[n][m][1];
-        }
-    }
-    // Courant number: interfaces c and c+1 (flux3.f:208-216; every interface 1..n+1 of a slice is
-    // interface c or c+1 of one of its cells)
-    smax_update(smax, s[1][0]); smax_update(smax, s[1][1]);
-    smax_update(smax, s[2][0]); smax_update(smax, s[2][1]);
-
-    // limiter (limiter.f:29-55) and correction flux (flux3.f:226-241) of the interfaces c (n = 1)
-    // and c+1 (n = 2); the dot products use the unlimited waves of the neighbours
-    double cqxx[2][M];
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int m = 0; m < M; m++) cqxx[a][m] = 0.0;
-    if (A.order != 1) {
-        double wl[2][M][2];
-#pragma unroll
-        for (int a = 0; a < 2; a++) {
-            const int n = 1 + a;
-#pragma unroll
-            for (int mw = 0; mw < 2; mw++) {
-                double wnorm2 = 0.0, dotl = 0.0, dotr = 0.0;
-#pragma unroll
-                for (int m = 0; m < M; m++) {
-                    wnorm2 = wnorm2 + wave[n][m][mw] * wave[n][m][mw];
-                    dotl = dotl + wave[n - 1][m][mw] * wave[n][m][mw];
-                    dotr = dotr + wave[n][m][mw] * wave[n + 1][m][mw];
-                }
-                double wlimitr = 1.0;
-                const bool lim = (A.mthlim[mw] != 0) && (wnorm2 != 0.0);
-                if (lim) wlimitr = philim(ar, wnorm2, (s[n][mw] > 0.0) ? dotl : dotr, A.mthlim[mw]);
-#pragma unroll
-                for (int m = 0; m < M; m++) wl[a][m][mw] = lim ? wlimitr * wave[n][m][mw] : wave[n][m][mw];
-            }
-            const double dtdxave = 0.5 * (dtdx + dtdx);
-#pragma unroll
-            for (int mw = 0; mw < 2; mw++)
-#pragma unroll
-                for (int m = 0; m < M; m++)
-                    cqxx[a][m] = cqxx[a][m] + 0.5 * fabs(s[n][mw]) * (1.0 - fabs(s[n][mw]) * dtdxave) * wl[a][m][mw];
-        }
-    }
+    double apdq_c[M], amdq_n[M], cqxx[2][M];
+    normal3<D>(ar, A, q, zl, cl, dtdx, apdq_c, amdq_n, cqxx, smax);
 #pragma unroll
     for (int m = 0; m < M; m++) {
-        out[0][m] = (0.0 - dtdx * apdq[1][m]) - dtdx * amdq[2][m];       // qadd(c)
+        out[0][m] = (0.0 - dtdx * apdq_c[m]) - dtdx * amdq_n[m];         // qadd(c)
         out[1][m] = (0.0 + cqxx[1][m]) - (0.0 + cqxx[0][m]);             // fadd(c+1) - fadd(c)
     }
     double g[2][3][M], h[2][3][M];
@@ -338,8 +350,8 @@ __global__ void __launch_bounds__(128) flux3_kernel(const Step3Args A)
         }
         constexpr int IUE = E + 1, IUF = F + 1;
         // iteration i = c of the Fortran's loops 180 / 200 (plus side), then i = c+1 (minus side)
-        transverse_side<+1>(ar, apdq[1], cqxx[0], A.m3, A.m4, IUE, IUF, X, dtdx, dtdy, dtdz, g, h);
-        transverse_side<-1>(ar, amdq[2], cqxx[1], A.m3, A.m4, IUE, IUF, X, dtdx, dtdy, dtdz, g, h);
+        transverse_side<+1>(ar, apdq_c, cqxx[0], A.m3, A.m4, IUE, IUF, X, dtdx, dtdy, dtdz, g, h);
+        transverse_side<-1>(ar, amdq_n, cqxx[1], A.m3, A.m4, IUE, IUF, X, dtdx, dtdy, dtdz, g, h);
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++)
@@ -413,6 +425,59 @@ __global__ void __launch_bounds__(128) apply3_kernel(const Step3Args A)
 #undef SV
 }
 
+// step3ds.f:2-376 (one directional sweep of the dimensionally split algorithm) as ONE launch over
+// the whole padded field: cells of the swept slices (1..n along D, one ghost layer of slices in the
+// other two directions) get q + qadd - dtdx (fadd(c+1) - fadd(c)), every other cell a copy of q_in.
+template <int D>
+__global__ void __launch_bounds__(128) sweep3ds_kernel(const Step3Args A, int nzpad)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x; // padded indices, 0-based
+    const int jp = blockIdx.y, kp = blockIdx.z;
+    const bool inside = ip < A.nx;
+    if (!__any_sync(0xffffffffu, inside)) return;
+    const int mbc = A.mbc;
+    const int i = ip - mbc + 1, j = jp - mbc + 1, k = kp - mbc + 1; // Fortran indices
+    const int c[3] = {i, j, k};
+    constexpr int E = (D + 1) % 3, F = (D + 2) % 3;
+    const bool swept = inside && c[D] >= 1 && c[D] <= A.n[D] && c[E] >= 0 && c[E] <= A.n[E] + 1 &&
+                       c[F] >= 0 && c[F] <= A.n[F] + 1;
+    const long long plane = (long long)A.nx * A.ny;
+    const long long stride[3] = {1, A.nx, plane};
+    const long long sd = stride[D];
+    const long long pos = (long long)min(ip, A.nx - 1) + (long long)A.nx * jp + plane * kp;
+    const double dtdx = dtd_of(A, D);
+    unsigned long long smax = 0ULL;
+    double res[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) res[m] = A.qold[m * A.mstride + pos];
+    if (swept) {
+        double q[5][M], zl[5], cl[5];
+#pragma unroll
+        for (int o = 0; o < 5; o++) {
+#pragma unroll
+            for (int m = 0; m < M; m++) q[o][m] = A.qold[m * A.mstride + pos + (o - 2) * sd];
+            zl[o] = A.aux[pos + (o - 2) * sd];
+            cl[o] = A.aux[A.mstride + pos + (o - 2) * sd];
+        }
+        with_arith([&](auto &ar) {
+            double apdq_c[M], amdq_n[M], cqxx[2][M];
+            normal3<D>(ar, A, q, zl, cl, dtdx, apdq_c, amdq_n, cqxx, smax);
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                const double qadd = (0.0 - dtdx * apdq_c[m]) - dtdx * amdq_n[m];
+                const double fdiff = (0.0 + cqxx[1][m]) - (0.0 + cqxx[0][m]);
+                res[m] = (q[2][m] + qadd) - dtdx * fdiff;
+            }
+        });
+    }
+    if (inside) {
+#pragma unroll
+        for (int m = 0; m < M; m++) A.qnew[m * A.mstride + pos] = res[m];
+    }
+    cfl_commit(swept ? dtdx * __longlong_as_double((long long)smax) : 0.0, A.cfl_bits);
+    (void)nzpad;
+}
+
 template <int D>
 int sweep3(const Step3Args &A, cudaStream_t st)
 {
@@ -430,10 +495,8 @@ int sweep3(const Step3Args &A, cudaStream_t st)
 
 } // namespace
 
-long long claw_step3_scratch_doubles(long long mstride) { return (long long)NV * M * mstride; }
-
-int claw_step3(const clawb200_problem *p, int mz, double dz, const double *qold, double *qnew,
-               const double *aux, double dt, double *scratch, double *cfl_dev, cudaStream_t st)
+static Step3Args make_args3(const clawb200_problem *p, int mz, double dz, const double *qold, double *qnew,
+                            const double *aux, double dt, double *scratch, double *cfl_dev)
 {
     Step3Args A;
     memset(&A, 0, sizeof(A));
@@ -446,10 +509,34 @@ int claw_step3(const clawb200_problem *p, int mz, double dz, const double *qold,
     A.dt_dev = p->dt_dev;
     A.d[0] = p->dx; A.d[1] = p->dy; A.d[2] = dz;
     A.order = p->method[1];
-    A.m3 = p->method[2] / 10;
-    A.m4 = p->method[2] - 10 * A.m3;
+    A.m3 = (p->method[2] < 0) ? -1 : p->method[2] / 10;
+    A.m4 = (p->method[2] < 0) ? 0 : p->method[2] - 10 * A.m3;
     A.mthlim[0] = p->mthlim[0]; A.mthlim[1] = p->mthlim[1];
     A.cfl_bits = (unsigned long long *)cfl_dev;
+    return A;
+}
+
+// one sweep of the dimensionally split algorithm, idir = 1, 2, 3 (q_out receives the whole field)
+int claw_step3ds(const clawb200_problem *p, int mz, double dz, const double *q_in, double *q_out,
+                 const double *aux, double dt, int idir, double *cfl_dev, cudaStream_t st)
+{
+    const Step3Args A = make_args3(p, mz, dz, q_in, q_out, aux, dt, nullptr, cfl_dev);
+    const int nzpad = mz + 2 * p->mbc;
+    if (A.ny > 65535 || nzpad > 65535) return fail(CLAWB200_ERR_UNSUPPORTED, "my, mz must be below 65532");
+    dim3 grid((A.nx + 127) / 128, A.ny, nzpad);
+    if (idir == 1) sweep3ds_kernel<0><<<grid, 128, 0, st>>>(A, nzpad);
+    else if (idir == 2) sweep3ds_kernel<1><<<grid, 128, 0, st>>>(A, nzpad);
+    else sweep3ds_kernel<2><<<grid, 128, 0, st>>>(A, nzpad);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+long long claw_step3_scratch_doubles(long long mstride) { return (long long)NV * M * mstride; }
+
+int claw_step3(const clawb200_problem *p, int mz, double dz, const double *qold, double *qnew,
+               const double *aux, double dt, double *scratch, double *cfl_dev, cudaStream_t st)
+{
+    const Step3Args A = make_args3(p, mz, dz, qold, qnew, aux, dt, scratch, cfl_dev);
     if (A.n[1] + 2 > 65535 || A.n[2] + 2 > 65535) return fail(CLAWB200_ERR_UNSUPPORTED, "my, mz must be below 65534");
     // step3.f: qnew holds qold on entry and accumulates the three families of sweeps
     CUDA_OK(cudaMemcpyAsync(qnew, qold, sizeof(double) * (size_t)p->meqn * p->mstride, cudaMemcpyDeviceToDevice, st));

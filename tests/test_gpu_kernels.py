@@ -83,6 +83,27 @@ def test_step2_unsplit(rp, shape, order, trans, mode):
     assert cfl_g.value == cfl_o
 
 
+def test_step2_mode_2_needs_a_single_pass_kernel():
+    """problem.step2_mode = 2 asks for the single-pass kernel: compiled for acoustics, not for Euler."""
+    mx, my, mbc = 20, 12, 2
+    for rp, ok in (("acoustics", True), ("euler", False)):
+        rp_id, params, meqn, mwaves, lim = RPS[rp]
+        q = _random_padded(rp, mx, my, mbc, seed=3)
+        P = _lib.make_problem(2, meqn, mwaves, mbc, mx, my, 0.01, 0.01, rp_id, params, [1, 2, 2, 0, 0, 0, 0], lim)
+        P.step2_mode = 2
+        qn, cfl = q.copy("F"), ctypes.c_double()
+        args = (ctypes.byref(P), _ptr(q), _ptr(qn), None, 0.001, ctypes.byref(cfl))
+        if ok:
+            _lib.call("clawb200_step2_host", *args)
+            assert _lib.load().clawb200_step2_launches(ctypes.byref(P)) == 1 and cfl.value > 0
+        else:
+            with pytest.raises(_lib.ClawB200Error, match="single-pass"):
+                _lib.call("clawb200_step2_host", *args)
+    P.step2_mode = 7
+    with pytest.raises(_lib.ClawB200Error, match="step2_mode"):
+        _lib.call("clawb200_step2_host", *args)
+
+
 @pytest.mark.parametrize("rp", ["acoustics", "advection"])
 @pytest.mark.parametrize("mx", [5, 100, 800, 1001])
 @pytest.mark.parametrize("order", [1, 2])
