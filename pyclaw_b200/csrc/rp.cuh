@@ -237,22 +237,24 @@ struct RpEuler5 {
     {
         const double gamma = P.p[0], gamma1 = P.p[1];
         // :87-104
-        double rhsqrtl = ar.sqrt(l[0]);
-        double rhsqrtr = ar.sqrt(r[0]);
-        const Recip rl0 = ar.rcp(l[0]), rr0 = ar.rcp(r[0]);
+        double rhsqrtl, rhsqrtr;
+        Recip rsl, rsr, rl0, rr0; // 1 / sqrt(rho), 1 / rho of the two states
+        ar.sqrt_rcps(l[0], rhsqrtl, rsl, rl0);
+        ar.sqrt_rcps(r[0], rhsqrtr, rsr, rr0);
         double pl = gamma1 * (l[3] - ar.div(0.5 * (l[1] * l[1] + l[2] * l[2]), rl0));
         double pr = gamma1 * (r[3] - ar.div(0.5 * (r[1] * r[1] + r[2] * r[2]), rr0));
         double rhsq2 = rhsqrtl + rhsqrtr;
-        const Recip rsl = ar.rcp(rhsqrtl), rsr = ar.rcp(rhsqrtr), rs2 = ar.rcp(rhsq2);
+        const Recip rs2 = ar.rcp(rhsq2);
         double u = ar.div(ar.div(l[MU], rsl) + ar.div(r[MU], rsr), rs2);
         double v = ar.div(ar.div(l[MV], rsl) + ar.div(r[MV], rsr), rs2);
         double enth = ar.div((ar.div(l[3] + pl, rsl) + ar.div(r[3] + pr, rsr)), rs2);
         double u2v2 = u * u + v * v;
         double a2r = gamma1 * (enth - .5 * u2v2);
-        double a = ar.sqrt(a2r);
-        double g1a2 = ar.div(gamma1, a2r);
+        double a;
+        Recip r2a, ra2; // 1 / (2 a), 1 / a^2
+        ar.sqrt_rcp2s(a2r, a, r2a, ra2);
+        double g1a2 = ar.div(gamma1, ra2);
         double euv = enth - u2v2;
-        const Recip r2a = ar.rcp(2.0 * a);
         roe[0] = u2v2; roe[1] = u; roe[2] = v; roe[3] = enth; roe[4] = a; roe[5] = g1a2; roe[6] = euv;
         roe[7] = r2a.r;
         // :110-119
@@ -459,14 +461,18 @@ struct RpShallow {
     {
         const double grav = P.p[0];
         double h = (l[0] + r[0]) * 0.50;
-        double hsqrtl = ar.sqrt(l[0]);
-        double hsqrtr = ar.sqrt(r[0]);
+        double hsqrtl, hsqrtr;
+        Recip rsl, rsr;
+        ar.sqrt_rcp(l[0], hsqrtl, rsl);
+        ar.sqrt_rcp(r[0], hsqrtr, rsr);
         double hsq2 = hsqrtl + hsqrtr;
-        const Recip rsl = ar.rcp(hsqrtl), rsr = ar.rcp(hsqrtr), rs2 = ar.rcp(hsq2);
+        const Recip rs2 = ar.rcp(hsq2);
         double u = ar.div(ar.div(l[MU], rsl) + ar.div(r[MU], rsr), rs2);
         double v = ar.div(ar.div(l[MV], rsl) + ar.div(r[MV], rsr), rs2);
-        double a = ar.sqrt(grav * h);
-        double hoa = ar.div(0.50, a);
+        double a;
+        Recip ra;
+        ar.sqrt_rcp(grav * h, a, ra);
+        double hoa = ar.div(0.50, ra);
         roe[0] = u; roe[1] = v; roe[2] = a; roe[3] = hoa;
         double d1 = r[0] - l[0];
         double d2 = r[MU] - l[MU];
@@ -614,8 +620,9 @@ struct RpSphere {
         const double dy = (IXY == 2) ? P.p[1] : P.p[2];
         const double enx = axr(IOFF + 0), eny = axr(IOFF + 1), enz = axr(IOFF + 2);
         double etx = axr(IOFF + 3), ety = axr(IOFF + 4), etz = axr(IOFF + 5);
-        const double gamma = ar.sqrt(etx * etx + ety * ety + etz * etz);
-        const Recip rg = ar.rcp(gamma);
+        double gamma;
+        Recip rg;
+        ar.sqrt_rcp(etx * etx + ety * ety + etz * etz, gamma, rg);
         etx = ar.div(etx, rg); ety = ar.div(ety, rg); etz = ar.div(etz, rg);
         // "ql" of the Fortran is the right cell, "qr" the left cell
         double hunl = enx * r[1] + eny * r[2] + enz * r[3];
@@ -624,12 +631,18 @@ struct RpSphere {
         double hutr = etx * l[1] + ety * l[2] + etz * l[3];
         double hl = r[0], hr = l[0];
         double h = (hl + hr) * 0.50;
-        double hsqr = ar.sqrt(hr), hsql = ar.sqrt(hl), hsq = hsqr + hsql;
-        const Recip rsr = ar.rcp(hsqr), rsl = ar.rcp(hsql), rsq = ar.rcp(hsq);
+        double hsqr, hsql;
+        Recip rsr, rsl;
+        ar.sqrt_rcp(hr, hsqr, rsr);
+        ar.sqrt_rcp(hl, hsql, rsl);
+        double hsq = hsqr + hsql;
+        const Recip rsq = ar.rcp(hsq);
         double u = ar.div(ar.div(hunr, rsr) + ar.div(hunl, rsl), rsq);
         double v = ar.div(ar.div(hutr, rsr) + ar.div(hutl, rsl), rsq);
-        double a = ar.sqrt(g * h);
-        double hoa = ar.div(0.50, a);
+        double a;
+        Recip ra;
+        ar.sqrt_rcp(g * h, a, ra);
+        double hoa = ar.div(0.50, ra);
         double d1 = hl - hr, d2 = hunl - hunr, d3 = hutl - hutr;
         double a1 = ((u + a) * d1 - d2) * hoa;
         double a2 = -v * d1 + d3;
@@ -726,15 +739,18 @@ struct RpSphere {
     {
         const double enx = axe(IOFFT + 0), eny = axe(IOFFT + 1), enz = axe(IOFFT + 2);
         double etx = axe(IOFFT + 3), ety = axe(IOFFT + 4), etz = axe(IOFFT + 5);
-        const double gamma = ar.sqrt(etx * etx + ety * ety + etz * etz);
-        const Recip rg = ar.rcp(gamma);
+        double gamma;
+        Recip rg;
+        ar.sqrt_rcp(etx * etx + ety * ety + etz * etz, gamma, rg);
         etx = ar.div(etx, rg); ety = ar.div(ety, rg); etz = ar.div(etz, rg);
         const double h = qc[0];
         const Recip rh = ar.rcp(h);
         double u = ar.div(enx * qc[1] + eny * qc[2] + enz * qc[3], rh);
         double v = ar.div(etx * qc[1] + ety * qc[2] + etz * qc[3], rh);
-        double a = ar.sqrt(g * h);
-        double hoa = ar.div(0.50, a);
+        double a;
+        Recip ra;
+        ar.sqrt_rcp(g * h, a, ra);
+        double hoa = ar.div(0.50, ra);
         double d2 = enx * asdq[1] + eny * asdq[2] + enz * asdq[3];
         double d3 = etx * asdq[1] + ety * asdq[2] + etz * asdq[3];
         double d1 = asdq[0];
