@@ -88,28 +88,33 @@ __device__ __forceinline__ void weno5_pyweno(AR &ar, const ScArgs &A, double qm2
     const Recip e0 = ar.rcp((sigma0 + A.eps) * (sigma0 + A.eps));
     const Recip e1 = ar.rcp((sigma1 + A.eps) * (sigma1 + A.eps));
     const Recip e2 = ar.rcp((sigma2 + A.eps) * (sigma2 + A.eps));
+    // The twelve quotients need no validity tests of their own (div_nz): the numerators d0k are
+    // positive constants, each reciprocal has passed its window test (2^-500 <= r < 2^500, or the
+    // whole block is redone with the IEEE operators), so every omega lies in [2^-504, 2^500], acc in
+    // [2^-504, 2^502], and a normalised weight omega / acc in [2^-1006, 1] because acc is a sum of
+    // positive terms that contains omega: all normal, none zero.
     double acc = 0.0;
-    double omega0 = ar.div(A.d01, e0);
+    double omega0 = ar.div_nz(A.d01, e0);
     acc = acc + omega0;
-    double omega1 = ar.div(A.d06, e1);
+    double omega1 = ar.div_nz(A.d06, e1);
     acc = acc + omega1;
-    double omega2 = ar.div(A.d03, e2);
+    double omega2 = ar.div_nz(A.d03, e2);
     acc = acc + omega2;
     const Recip ra = ar.rcp(acc);
-    omega0 = ar.div(omega0, ra);
-    omega1 = ar.div(omega1, ra);
-    omega2 = ar.div(omega2, ra);
+    omega0 = ar.div_nz(omega0, ra);
+    omega1 = ar.div_nz(omega1, ra);
+    omega2 = ar.div_nz(omega2, ra);
     acc = 0.0;
-    double omega3 = ar.div(A.d03, e0);
+    double omega3 = ar.div_nz(A.d03, e0);
     acc = acc + omega3;
-    double omega4 = ar.div(A.d06, e1);
+    double omega4 = ar.div_nz(A.d06, e1);
     acc = acc + omega4;
-    double omega5 = ar.div(A.d01, e2);
+    double omega5 = ar.div_nz(A.d01, e2);
     acc = acc + omega5;
     const Recip rb = ar.rcp(acc);
-    omega3 = ar.div(omega3, rb);
-    omega4 = ar.div(omega4, rb);
-    omega5 = ar.div(omega5, rb);
+    omega3 = ar.div_nz(omega3, rb);
+    omega4 = ar.div_nz(omega4, rb);
+    omega5 = ar.div_nz(omega5, rb);
     double fr0 = (A.r183) * q0 + (-A.r116) * qp1 + (A.r0333) * qp2;
     double fr1 = (A.r0333) * qm1 + (A.r0833) * q0 + (-A.r0166) * qp1;
     double fr2 = (-A.r0166) * qm2 + (A.r0833) * qm1 + (A.r0333) * q0;
