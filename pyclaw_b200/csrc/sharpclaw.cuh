@@ -100,7 +100,7 @@ __device__ __forceinline__ void weno5_pyweno(AR &ar, const ScArgs &A, double qm2
     acc = acc + omega1;
     double omega2 = ar.div_nz(A.d03, e2);
     acc = acc + omega2;
-    const Recip ra = ar.rcp(acc);
+    const Recip ra = ar.rcp_nc(acc); // acc in [2^-504, 2^502]: its window test is implied
     omega0 = ar.div_nz(omega0, ra);
     omega1 = ar.div_nz(omega1, ra);
     omega2 = ar.div_nz(omega2, ra);
@@ -111,7 +111,7 @@ __device__ __forceinline__ void weno5_pyweno(AR &ar, const ScArgs &A, double qm2
     acc = acc + omega4;
     double omega5 = ar.div_nz(A.d01, e2);
     acc = acc + omega5;
-    const Recip rb = ar.rcp(acc);
+    const Recip rb = ar.rcp_nc(acc);
     omega3 = ar.div_nz(omega3, rb);
     omega4 = ar.div_nz(omega4, rb);
     omega5 = ar.div_nz(omega5, rb);
@@ -691,23 +691,27 @@ __device__ __forceinline__ void weno_tab(AR &ar, const WenoTab &c_weno, const do
             }
         sigma[r] = sg;
     }
+    // as in weno5_pyweno: the linear weights are positive, each reciprocal passes its window test,
+    // so the quotients (and the reciprocal of their sum) need none of their own
+    Recip re[9];
+    for (int r = 0; r < k; r++) re[r] = ar.rcp((sigma[r] + eps) * (sigma[r] + eps));
     double acc = 0.0;
     for (int r = 0; r < k; r++) {
-        omega[r] = ar.div(c_weno.WL[r], (sigma[r] + eps) * (sigma[r] + eps));
+        omega[r] = ar.div_nz(c_weno.WL[r], re[r]);
         acc = acc + omega[r];
     }
     {
-        const Recip ra = ar.rcp(acc);
-        for (int r = 0; r < k; r++) omega[r] = ar.div(omega[r], ra);
+        const Recip ra = ar.rcp_nc(acc);
+        for (int r = 0; r < k; r++) omega[r] = ar.div_nz(omega[r], ra);
     }
     acc = 0.0;
     for (int r = 0; r < k; r++) {
-        omega[k + r] = ar.div(c_weno.WR[r], (sigma[r] + eps) * (sigma[r] + eps));
+        omega[k + r] = ar.div_nz(c_weno.WR[r], re[r]);
         acc = acc + omega[k + r];
     }
     {
-        const Recip ra = ar.rcp(acc);
-        for (int r = 0; r < k; r++) omega[k + r] = ar.div(omega[k + r], ra);
+        const Recip ra = ar.rcp_nc(acc);
+        for (int r = 0; r < k; r++) omega[k + r] = ar.div_nz(omega[k + r], ra);
     }
     double fs0 = 0.0, fs1 = 0.0;
     for (int r = 0; r < k; r++) {
