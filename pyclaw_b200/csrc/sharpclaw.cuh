@@ -313,7 +313,7 @@ __device__ __forceinline__ void sc_xrow_solve(const ScArgs &A, const double (&ql
 // 2-D: thread t <-> column ic = i0-1+t, output columns t = 1 .. NT-2.
 // ---------------------------------------------------------------------------
 #ifndef CLAW_SC_MINB
-#define CLAW_SC_MINB 2
+#define CLAW_SC_MINB 3 // 168 registers, 44 B of spills: 35.96 -> 32.49 ms per step (strict), 25.8 -> 21.6 ms (fma) at 8192^2; 4 CTAs spill 270 B
 #endif
 template <class RPX, class RPY, bool OLD, int NT, bool CAPA = false>
 __global__ void __launch_bounds__(NT, (RPX::MEQN <= 3) ? CLAW_SC_MINB : 2) sc2d_kernel(const ScArgs A)
